@@ -1,0 +1,225 @@
+"""Generate tests/golden/*.npz by EXECUTING THE UNMODIFIED REFERENCE (build container only).
+
+The reference has no tests or fixtures of its own, so parity is pinned against the
+outputs this script records.  Usage:  python -m oracle.make_golden [names...]   (default: all fast sets;
+``config1`` runs the real U-Net DDIM-200 chain at B=8 and takes a few minutes.)
+
+Shared deterministic inputs live in oracle/fixtures.py so that tests regenerate them instead of storing them.
+"""
+import os
+import sys
+import types
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+sys.path.insert(0, ROOT)
+from oracle import ref_import  # noqa: E402
+from oracle import fixtures as fx  # noqa: E402
+
+ref_import.install()
+GOLD = os.path.join(ROOT, "tests", "golden")
+os.makedirs(GOLD, exist_ok=True)
+
+
+def save(name, **arrs):
+    out = {k: (v.detach().cpu().numpy() if isinstance(v, torch.Tensor) else np.asarray(v)) for k, v in arrs.items()}
+    np.savez_compressed(os.path.join(GOLD, name + ".npz"), **out)
+    print("wrote", name, {k: v.shape for k, v in out.items()})
+
+
+class NoisePatch:
+    """Feed the reference's global-RNG draws (torch.randn / torch.randn_like) from a supplied list."""
+
+    def __init__(self, noises):
+        self.noises = list(noises)
+        self.k = 0
+
+    def __enter__(self):
+        self._randn, self._randn_like = torch.randn, torch.randn_like
+
+        def take(*a, **k):
+            z = self.noises[self.k]
+            self.k += 1
+            return z.clone()
+
+        torch.randn = take
+        torch.randn_like = take
+        return self
+
+    def __exit__(self, *exc):
+        torch.randn, torch.randn_like = self._randn, self._randn_like
+
+
+def gen_schedule():
+    from model.diffusion import GaussianDiffusion
+    for T in (1000, 20):
+        gd = GaussianDiffusion(fx.FakeEps(), seq_length=(16, 128), timesteps=T, temporal=True, use_conv2d=True)
+        sd = {k: v for k, v in gd.state_dict().items() if not k.startswith("model.")}
+        save(f"schedule_T{T}", **sd)
+
+
+def gen_solver():
+    from data.generate_burgers import burgers_numeric_solve, burgers_numeric_solve_free
+    u0, f = fx.solver_inputs(16, seed=0)
+    traj = burgers_numeric_solve_free(u0, f, visc=0.01, T=1.0, dt=1e-4, num_t=10)
+    save("solver_free", traj=traj)
+    # stiff / diverging inputs: NaN and Inf must propagate exactly like the reference
+    u0b, fb = fx.solver_inputs_wild(4, seed=3)
+    trajb = burgers_numeric_solve_free(u0b, fb, visc=0.01, T=1.0, dt=1e-4, num_t=10)
+    save("solver_free_wild", traj=trajb)
+    u0c, fc = fx.solver_inputs(3, seed=5)
+    trajc = burgers_numeric_solve(u0c, fc[:2], visc=0.01, T=1.0, dt=1e-4, num_t=10)
+    save("solver_cartesian", traj=trajc)
+    # metrics on the first set, target = rolled trajectories
+    from utils.metrics import evaluate_samples
+    tgt = torch.roll(traj, 1, dims=0)
+    diffused = torch.zeros(16, 3, 16, 128)
+    m = evaluate_samples(diffused, traj, tgt, nt=11, u_bound=0.8)
+    m2 = evaluate_samples(diffused, traj, tgt, nt=11, u_bound=0.3)
+    save("metrics", **{f"b08_{i}": np.asarray(v, dtype=np.float64) for i, v in enumerate(m.values())},
+         **{f"b03_{i}": np.asarray(v, dtype=np.float64) for i, v in enumerate(m2.values())},
+         keys=np.array(list(m.keys())))
+
+
+def _diffusion(T, S, eta=1.0, model=None):
+    from model.diffusion import GaussianDiffusion
+    return GaussianDiffusion(model or fx.FakeEps(), seq_length=(16, 128), timesteps=T, sampling_timesteps=S,
+                             ddim_sampling_eta=eta, temporal=True, use_conv2d=True, is_condition_u0=True,
+                             is_condition_uT=True, condition_idx=10, train_on_padded_locations=False)
+
+
+def _guidance_fn(Q, w_score=500.0, use_max_safety=True):
+    from utils.guidance import get_finetune_guidance
+    cfg = types.SimpleNamespace(use_max_safety=use_max_safety, u_bound=0.8, guidance_weights={"w_score": w_score})
+    return lambda x: get_finetune_guidance(cfg, x, Q)
+
+
+def gen_chains():
+    B = 4
+    u_init, u_final, w_gt = fx.chain_conditions(B)
+    out = {}
+    for name, T, S, kw in fx.CHAIN_CASES:
+        gd = _diffusion(T, S)
+        noises = fx.chain_noise(B, fx.n_draws(T, S, kw["guidance_u0"]), seed=kw["seed"])
+        guide = _guidance_fn(kw["Q"], use_max_safety=kw.get("use_max_safety", True)) if kw["guided"] else None
+        with NoisePatch(noises) as npch:
+            res = gd.sample(batch_size=B, clip_denoised=True, u_init=u_init, u_final=u_final,
+                            guidance_u0=kw["guidance_u0"], nablaJ=guide, J_scheduler=None, w_scheduler=None,
+                            w_groundtruth=(w_gt if kw["w_gt"] else None), enable_grad=kw["enable_grad"], device="cpu")
+            assert npch.k == len(noises), (name, npch.k, len(noises))
+        out[name] = res
+    save("chains", **out)
+
+
+def gen_guidance():
+    from inference.guidance import get_weight, normalize_weights
+    from inference.conformal import ConformalCalculator
+    out = {}
+    x = fx.guidance_states(6)
+    for Q in (0.0, 0.05, -0.5):
+        for ums in (True, False):
+            out[f"grad_Q{Q}_{int(ums)}"] = _guidance_fn(Q, use_max_safety=ums)(x.clone().requires_grad_())
+            cfg = types.SimpleNamespace(use_max_safety=ums, u_bound=0.8, guidance_weights={"w_score": 500.0})
+            out[f"weight_Q{Q}_{int(ums)}"] = get_weight(x, Q, cfg)
+    for i, w in enumerate(fx.weight_vectors()):
+        out[f"norm_{i}"] = normalize_weights(w.clone())
+    cc = ConformalCalculator(None, types.SimpleNamespace(device="cpu"))
+    for i, (s, alpha) in enumerate(fx.score_vectors()):
+        out[f"quant_{i}"] = cc.calculate_quantile(s, None, None, alpha)
+    save("guidance", **out)
+
+
+def gen_conformal():
+    from inference.conformal import ConformalCalculator
+    B, nb = 6, 2
+    gd = _diffusion(1000, 6)
+    cfg = types.SimpleNamespace(device="cpu", num_cal_batch=nb, nt=11, InfFT_Q=None, use_max_safety=True, u_bound=0.8,
+                                guidance_weights={"w_score": 500.0})
+    states = fx.calibration_states(B * nb)
+    loader = iter([states[i * B:(i + 1) * B] for i in range(nb)])
+    noises = []
+    for i in range(nb):
+        noises += fx.chain_noise(B, fx.n_draws(1000, 6, False), seed=100 + i)
+    with NoisePatch(noises):
+        scores, weights, st = ConformalCalculator(gd, cfg).get_conformal_scores(loader, Q=0.02)
+    save("conformal", scores=scores, weights=weights)
+
+
+def _unet(dim):
+    from model.unet import Unet2D
+    torch.manual_seed(42)
+    return Unet2D(dim=dim, dim_mults=(1, 2, 4, 8), channels=3, resnet_block_groups=1).eval()
+
+
+def gen_unet():
+    for dim, B in ((32, 3), (128, 2)):
+        net = _unet(dim)
+        x, t = fx.unet_inputs(B)
+        taps = {}
+        hooks = []
+        for nm in ("init_conv", "downs.0.0", "downs.0.2", "downs.0.3", "mid_attn", "ups.0.3", "final_res_block"):
+            mod = dict(net.named_modules())[nm]
+            hooks.append(mod.register_forward_hook(lambda m, i, o, nm=nm: taps.__setitem__("tap_" + nm, o)))
+        with torch.no_grad():
+            eps = net(x, t)
+        for h in hooks:
+            h.remove()
+        if dim == 128:  # keep the fixture small: full eps only, plus a strided view of the taps
+            taps = {k: v[:, ::8] for k, v in taps.items()}
+        save(f"unet_dim{dim}", eps=eps, **taps)
+        sd = net.state_dict()
+        save(f"unet_dim{dim}_wsum", **{"sum": np.array([float(v.double().sum()) for v in sd.values()]),
+                                       "abssum": np.array([float(v.double().abs().sum()) for v in sd.values()]),
+                                       "keys": np.array(list(sd.keys()))})
+
+
+def gen_config1():
+    """BASELINE config 1: real U-Net (seed 42), B=8, DDIM-200 eta=1 guided (w_score 500, Q 0), then solver+metrics."""
+    from data.generate_burgers import burgers_numeric_solve_free
+    from utils.metrics import control_trajectories, evaluate_samples
+    B = 8
+    net = _unet(128)
+    gd = _diffusion(1000, 200, model=net)
+    u0, uT, tgt = fx.config1_conditions(B)
+    noises = fx.chain_noise(B, fx.n_draws(1000, 200, True), seed=1234)
+    keep = {}
+    steps = (0, 1, 60, 120, 199)
+    cnt = {"k": 0}
+    orig = net.forward
+
+    def spy(x, time, *a, **k):
+        o = orig(x, time, *a, **k)
+        if cnt["k"] in steps:
+            keep[f"x_{cnt['k']}"] = x.detach().clone()
+            keep[f"eps_{cnt['k']}"] = o.detach().clone()
+            keep[f"t_{cnt['k']}"] = time.detach().clone()
+        cnt["k"] += 1
+        return o
+
+    net.forward = spy
+    import time as _time
+    t0 = _time.time()
+    with NoisePatch(noises):
+        res = gd.sample(batch_size=B, clip_denoised=True, u_init=u0, u_final=uT, guidance_u0=True,
+                        nablaJ=_guidance_fn(0.0), J_scheduler=None, w_scheduler=None, enable_grad=False, device="cpu")
+    t_chain = _time.time() - t0
+    pred = res * 10.0
+    t0 = _time.time()
+    uc = control_trajectories(pred, 11)
+    t_solve = _time.time() - t0
+    m = evaluate_samples(pred, uc, tgt, nt=11, u_bound=0.8)
+    save("config1_ddim", sample=res, u_controlled=uc, J=m["control_mse_mean (J)"], Rp=m["point_exceed_ratio (R_p)"],
+         Rt=m["time_exceed_ratio (R_t)"], Rs=m["sample_exceed_ratio (R_s)"], t_chain=t_chain, t_solve=t_solve,
+         threads=torch.get_num_threads(), **keep)
+
+
+ALL = {"schedule": gen_schedule, "solver": gen_solver, "chains": gen_chains, "guidance": gen_guidance,
+       "conformal": gen_conformal, "unet": gen_unet, "config1": gen_config1}
+
+if __name__ == "__main__":
+    names = sys.argv[1:] or [k for k in ALL if k != "config1"]
+    for n in names:
+        ALL[n]()
