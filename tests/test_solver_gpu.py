@@ -1,0 +1,137 @@
+"""GPU parity: Burgers rollout + scoring through the C ABI vs the CPU oracle and the reference goldens."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import fixtures as fx
+from oracle import solver_ref
+
+pytestmark = pytest.mark.gpu
+
+
+def _dev(t):
+    return t.cuda()
+
+
+def test_solve_free_bit_exact_vs_reference_golden(golden):
+    import safediffcon_b200 as s
+    u0, f = fx.solver_inputs(16, 0)
+    out = s.burgers_numeric_solve_free(_dev(u0), _dev(f), visc=0.01, T=1.0, dt=1e-4, num_t=10)
+    assert out.shape == (16, 11, 128)
+    assert np.array_equal(out.cpu().numpy(), golden("solver_free")["traj"])  # bit-exact, strict mode
+
+
+def test_solve_free_nan_propagation(golden):
+    import safediffcon_b200 as s
+    u0, f = fx.solver_inputs_wild(4, 3)
+    out = s.burgers_numeric_solve_free(_dev(u0), _dev(f), 0.01, 1.0).cpu().numpy()
+    assert np.array_equal(out, golden("solver_free_wild")["traj"], equal_nan=True)
+
+
+def test_solve_cartesian_bit_exact(golden):
+    import safediffcon_b200 as s
+    u0, f = fx.solver_inputs(3, 5)
+    out = s.burgers_numeric_solve(_dev(u0), _dev(f[:2]), 0.01, 1.0)
+    assert out.shape == (3, 2, 11, 128)
+    assert np.array_equal(out.cpu().numpy(), golden("solver_cartesian")["traj"])
+    # mode='const' broadcasts one forcing row over the 10 intervals (generate_burgers.py:128-131)
+    oc = s.burgers_numeric_solve(_dev(u0), _dev(f[:2, 0]), 0.01, 1.0, mode='const').cpu().numpy()
+    ref = solver_ref.solve_cartesian_c(u0.numpy(), np.repeat(f[:2, 0:1].numpy(), 10, axis=1))
+    assert np.array_equal(oc, ref)
+
+
+@pytest.mark.parametrize("n,s,seed", [(1, 128, 1), (7, 128, 2), (300, 128, 3), (9, 64, 4), (5, 32, 5), (3, 256, 6)])
+def test_solve_free_vs_c_oracle_ragged(n, s, seed):
+    import safediffcon_b200 as sd
+    rng = np.random.default_rng(seed)
+    u0 = rng.normal(0, 0.5, (n, s)).astype(np.float32)
+    f = rng.normal(0, 1.0, (n, 10, s)).astype(np.float32)
+    # shorter horizon keeps the CPU oracle fast; same code path (1000 steps, 10 intervals)
+    out = sd.burgers_numeric_solve_free(torch.from_numpy(u0).cuda(), torch.from_numpy(f).cuda(), 0.01, 0.1, dt=1e-4, num_t=10)
+    ref = solver_ref.solve_free_c(u0, f, 0.01, 0.1, 1e-4, 10)
+    assert np.array_equal(out.cpu().numpy(), ref, equal_nan=True)
+
+
+def test_empty_batch():
+    import safediffcon_b200 as s
+    out = s.burgers_numeric_solve_free(torch.zeros(0, 128).cuda(), torch.zeros(0, 10, 128).cuda(), 0.01, 1.0)
+    assert out.shape == (0, 11, 128)
+
+
+def test_unsupported_grid_is_an_error():
+    import safediffcon_b200 as s
+    with pytest.raises(ValueError, match="unsupported"):
+        s.burgers_numeric_solve_free(torch.zeros(2, 100).cuda(), torch.zeros(2, 10, 100).cuda(), 0.01, 1.0)
+
+
+def test_fast_mode_within_tolerance(golden):
+    import safediffcon_b200 as s
+    u0, f = fx.solver_inputs(16, 0)
+    out = s.burgers_numeric_solve_free(_dev(u0), _dev(f), 0.01, 1.0, strict=False).cpu().numpy()
+    ref = golden("solver_free")["traj"]
+    rel = np.abs(out - ref).max() / np.abs(ref).max()
+    assert rel < 1e-5, rel  # north-star tolerance: solver states within 1e-5 relative
+
+
+def test_metrics_match_reference_golden(golden):
+    import safediffcon_b200 as s
+    g = golden("metrics")
+    traj = torch.from_numpy(golden("solver_free")["traj"]).cuda()
+    tgt = torch.roll(traj, 1, dims=0)
+    diffused = torch.zeros(16, 3, 16, 128).cuda()
+    for tag, bound in (("b08", 0.8), ("b03", 0.3)):
+        m = s.evaluate_samples(diffused, traj, tgt, nt=11, u_bound=bound)
+        assert list(m.keys()) == [str(k) for k in g["keys"]]
+        for i, k in enumerate(g["keys"]):
+            ref = g[f"{tag}_{i}"]
+            if ref.ndim:
+                assert list(ref.astype(int)) == m[str(k)]
+            else:
+                assert abs(float(ref) - m[str(k)]) <= 2e-6 * max(1.0, abs(float(ref))), k
+    sm = s.calculate_safety_metrics(traj, 0.8)
+    assert sm['sample_exceed_ratio (R_s)'] == float(g["b08_4"])
+
+
+def test_control_trajectories_and_fused_scoring():
+    import safediffcon_b200 as s
+    from safediffcon_b200.solver import control_and_score
+    u0, f = fx.solver_inputs(12, 11)
+    diffused = torch.zeros(12, 3, 16, 128)
+    diffused[:, 0, 0] = u0
+    diffused[:, 1, :10] = f
+    diffused[:, 0, 1:11] = 7.0  # must be ignored by the solver
+    d = diffused.cuda()
+    uc = s.control_trajectories(d, 11)
+    ref = solver_ref.solve_free_c(u0.numpy(), f.numpy())
+    assert np.array_equal(uc.cpu().numpy(), ref)
+    tgt = torch.from_numpy(np.roll(ref, 1, axis=0)).cuda()
+    out, J, pts, tms, flg = control_and_score(d, tgt[:, -1], 0.8)
+    assert np.array_equal(out.cpu().numpy(), ref)
+    Jr, pr, tr, fr = solver_ref.score_c(ref, tgt[:, -1].cpu().numpy(), 0.8)
+    assert np.allclose(J.cpu().numpy(), Jr, rtol=1e-6, atol=0)
+    assert np.array_equal(pts.cpu().numpy(), pr) and np.array_equal(tms.cpu().numpy(), tr) and np.array_equal(flg.cpu().numpy(), fr)
+    _, J2, p2, t2, f2 = control_and_score(d, tgt[:, -1], 0.8, want_traj=False)
+    assert torch.equal(J, J2) and torch.equal(pts, p2)
+
+
+def test_large_batch_properties():
+    """Full-size property checks (no CPU oracle at this size): the rollout is deterministic, row 0 echoes u0, zero
+    input stays zero, the rollout is sign-antisymmetric under (u0, f, x) -> (-u0, -f, reversed x), and a
+    random subset agrees bit-for-bit with the CPU oracle."""
+    import safediffcon_b200 as s
+    from safediffcon_b200.synthetic import burgers_instances
+    n = 20000
+    u0, f = burgers_instances(n, seed=123)
+    u0[:5] = 0
+    f[:5] = 0
+    du0, df = torch.from_numpy(u0).cuda(), torch.from_numpy(f).cuda()
+    a = s.burgers_numeric_solve_free(du0, df, 0.01, 1.0)
+    b = s.burgers_numeric_solve_free(du0, df, 0.01, 1.0)
+    assert torch.equal(a, b)
+    assert torch.equal(a[:, 0], du0)
+    assert torch.count_nonzero(a[:5]) == 0
+    m = s.burgers_numeric_solve_free(-du0.flip(-1), -df.flip(-1), 0.01, 1.0)
+    assert torch.equal(m, -a.flip(-1))
+    idx = np.random.default_rng(0).choice(n, 24, replace=False)
+    ref = solver_ref.solve_free_c(u0[idx], f[idx])
+    assert np.array_equal(a[torch.from_numpy(idx).cuda()].cpu().numpy(), ref)
