@@ -301,21 +301,25 @@ class GaussianDiffusion(nn.Module):
     @torch.no_grad()
     def p_sample_loop(self, shape, w_groundtruth=None, enable_grad=True, **kwargs):
         assert not self.is_ddim_sampling, 'wrong branch!'
-        device = self.betas.device
+        device = self._require_cuda()
         with torch.cuda.device(device):
             return self._run_chain(SAMPLER_DDPM, shape, w_groundtruth, enable_grad, False, kwargs)
 
     @torch.no_grad()
     def ddim_sample(self, shape, return_all_timesteps=False, w_groundtruth=None, enable_grad=False, **kwargs):
-        device = self.betas.device
+        device = self._require_cuda()
         with torch.cuda.device(device):
             return self._run_chain(SAMPLER_DDIM, shape, w_groundtruth, enable_grad, return_all_timesteps, kwargs)
 
-    def _run_chain(self, sampler, shape, w_groundtruth, enable_grad, return_all, kwargs):
+    def _require_cuda(self):
         device = self.betas.device
         if device.type != 'cuda':
             raise RuntimeError("safediffcon_b200.GaussianDiffusion.sample: module is on the CPU; move it to a CUDA device "
                                "(there is no CPU fallback)")
+        return device
+
+    def _run_chain(self, sampler, shape, w_groundtruth, enable_grad, return_all, kwargs):
+        device = self._require_cuda()
         table, times, rows = self._coef_table(sampler, kwargs.get('J_scheduler'))
         noise_iter, seed, offset = self._rng(kwargs, device)
         conds = self._conditions(kwargs, w_groundtruth, device)

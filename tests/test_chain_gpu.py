@@ -107,7 +107,8 @@ def test_ddim_step_bit_exact_teacher_forced(ums):
     c = (1 - an - sigma ** 2).sqrt()
     ref = x0_ref * an.sqrt() + c * e_ref + sigma * z
     dr.write_conditions(ref, u_init, u_final, None, 10)
-    on = (dr.safety_guidance_grad(x0_ref, Q, 500.0, 0.8, ums).abs().amax(dim=(1, 2, 3)) > 0)
+    x0_first = (bufs["sqrt_recip_alphas_cumprod"][t] * x - bufs["sqrt_recipm1_alphas_cumprod"][t] * eps).clamp(-1, 1)
+    on = (dr.safety_guidance_grad(x0_first, Q, 500.0, 0.8, ums).abs().amax(dim=(1, 2, 3)) > 0)
     if ums:
         assert 5 < int(on.sum()) < B - 5  # both branches exercised
     row = (bufs["sqrt_recip_alphas_cumprod"][t].item(), bufs["sqrt_recipm1_alphas_cumprod"][t].item(), an.sqrt().item(),

@@ -116,8 +116,9 @@ def test_control_trajectories_and_fused_scoring():
 
 def test_large_batch_properties():
     """Full-size property checks (no CPU oracle at this size): the rollout is deterministic, row 0 echoes u0, zero
-    input stays zero, the rollout is sign-antisymmetric under (u0, f, x) -> (-u0, -f, reversed x), and a
-    random subset agrees bit-for-bit with the CPU oracle."""
+    input stays zero, the rollout is antisymmetric under (u0, f, x) -> (-u0, -f, reversed x) up to rounding (the
+    reference's left-to-right tap association is not mirror symmetric), and a random subset agrees bit-for-bit
+    with the CPU oracle."""
     import safediffcon_b200 as s
     from safediffcon_b200.synthetic import burgers_instances
     n = 20000
@@ -131,7 +132,7 @@ def test_large_batch_properties():
     assert torch.equal(a[:, 0], du0)
     assert torch.count_nonzero(a[:5]) == 0
     m = s.burgers_numeric_solve_free(-du0.flip(-1), -df.flip(-1), 0.01, 1.0)
-    assert torch.equal(m, -a.flip(-1))
+    assert (m + a.flip(-1)).abs().max().item() < 1e-5 * a.abs().max().item()
     idx = np.random.default_rng(0).choice(n, 24, replace=False)
     ref = solver_ref.solve_free_c(u0[idx], f[idx])
     assert np.array_equal(a[torch.from_numpy(idx).cuda()].cpu().numpy(), ref)
