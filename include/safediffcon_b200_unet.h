@@ -1,0 +1,77 @@
+/* safediffcon_b200 -- C ABI of the denoiser (Unet2D) building blocks.  See safediffcon_b200.h for conventions.
+ *
+ * Activation layout: NHWC fp32 ([B*H*W, C] row-major, "pixel rows"), values rounded to TF32 (round-to-nearest)
+ * by the producing kernel whenever a convolution consumes them.  Weights are packed once per parameter
+ * version by sdc_pack_conv_weight.  The ops are exposed individually (each is parity-tested against its
+ * torch counterpart); safediffcon_b200/unet.py strings them into Unet2D.forward
+ * (reference: 1D/model/unet.py:382-426).
+ */
+#ifndef SAFEDIFFCON_B200_UNET_H
+#define SAFEDIFFCON_B200_UNET_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* Repack an OIHW fp32 conv weight [Cout, Cin, kh, kw] into the K-major GEMM operand Wp[Cout, taps*Cin]
+ * (K index = tap*Cin + cin, tap = ky*kw_ + kx), rounding to TF32 (nearest).
+ * kind 0: 1x1, 1: 3x3, 2: the 1x1 conv that follows the pixel-unshuffle of Downsample2d (unet.py:39-43):
+ * Cin = 4*C with channel index c*4 + p1*2 + p2  ->  K index = (p1*2+p2)*C + c. */
+int sdc_pack_conv_weight(int kind, const float* w_oihw, float* w_packed, int Cout, int Cin, void* stream);
+
+/* Implicit-GEMM convolution on tcgen05 (replaces nn.Conv2d 3x3 pad 1 / 1x1, unet.py:132,161,189-192,232-233,345,370,
+ * and Downsample2d, unet.py:39-43).  Inputs: one or two NHWC tensors (a1 = second K segment of a channel concat,
+ * c1 = 0 if absent) of spatial size H x W (kind 2: 2H x 2W).  out[B*H*W, Cout] = conv + bias (+ residual[B*H*W, Cout]).
+ * stats (optional): double[B][2], += (sum, sum of squares) of the stored fp32 values per sample (GroupNorm(1, C)).
+ * round_tf32: store values rounded to TF32.  Requirements: W | 128, (H*W) % 32 == 0, channels % 32 == 0. */
+int sdc_conv_gemm(int kind, const float* a0, int c0, const float* a1, int c1, const float* w_packed, const float* bias,
+                  const float* residual, float* out, double* stats, int round_tf32, int B, int H, int W, int Cout,
+                  void* stream);
+
+/* Stem: 7x7 pad 3 convolution of the NCHW model input (unet.py:326,392).  x:[B,Cin,H,W] NCHW, w:[Cout,Cin,7,7] OIHW
+ * (unpacked, fp32), out: NHWC [B*H*W, Cout] rounded to TF32.  FP32 CUDA-core kernel (0.3% of the FLOPs). */
+int sdc_stem_conv7(const float* x, const float* w, const float* bias, float* out, int B, int Cin, int H, int W, int Cout,
+                   void* stream);
+
+/* GroupNorm(1, C) apply + FiLM + SiLU (+ residual), Block.forward (unet.py:138-147) and ResnetBlock's sum (:180):
+ * y = silu(((x - mean_b) * rstd_b * gamma_c + beta_c) * (scale_bc + 1) + shift_bc) + res ; mean/rstd from
+ * stats[b] = (sum, sumsq) over C*HW elements, eps 1e-5, biased variance.  scale_shift: [n_t, 2C] rows
+ * (scale | shift) indexed by t_index[b] (NULL t_index = row 0 for every sample), or NULL for none.  y rounded to TF32. */
+int sdc_gn_silu(const float* x, const double* stats, const float* gamma, const float* beta, const float* scale_shift,
+                const int32_t* t_index, int64_t ss_stride, const float* residual, float* y, int B, int HW, int C, void* stream);
+
+/* Channel LayerNorm (unet.py:53-63): y = (x - mean_c) * rsqrt(var_c + 1e-5) * g (+ residual), per pixel row.
+ * round_tf32: round y to TF32. */
+int sdc_channel_layernorm(const float* x, const float* g, const float* residual, float* y, int64_t M, int C, int round_tf32,
+                          void* stream);
+
+/* LinearAttention core (unet.py:202-222) on qkv:[B*n, 384] rows (q | k | v, each heads*32 channels):
+ * q <- softmax_d(q) * 32^-0.5 ; k <- softmax_n(k) ; ctx = k v^T ; out[B*n, 128] = ctx^T q, rounded to TF32.
+ * workspace: >= sdc_linear_attention_workspace(B) bytes. */
+int64_t sdc_linear_attention_workspace(int B);
+int sdc_linear_attention(const float* qkv, float* out, void* workspace, int B, int n, void* stream);
+
+/* Full softmax attention core (unet.py:239-258) for n <= 64 tokens: out[B*n, 128], rounded to TF32. */
+int sdc_attention(const float* qkv, float* out, int B, int n, void* stream);
+
+/* Nearest-neighbour x2 upsample of an NHWC tensor (nn.Upsample(scale_factor=2), unet.py:33-37). */
+int sdc_upsample2x(const float* x, float* y, int B, int H, int W, int C, void* stream);
+
+/* Final 1x1 conv to the model's output channels, NHWC -> NCHW (unet.py:378,426).  w:[Cout, Cin], out:[B,Cout,H,W]. */
+int sdc_head_conv1(const float* x, const float* w, const float* bias, float* out, int B, int HW, int Cin, int Cout,
+                   void* stream);
+
+/* Rows of a small dense layer: y[r, :] = act_in(x[r, :]) @ w[N, K]^T + b, act_in 0 = identity, 1 = SiLU, 2 = GELU(erf)
+ * (time MLP, unet.py:310-315 and ResnetBlock.mlp, :152-155).  Batch independent: evaluated once per distinct t. */
+int sdc_linear_rows(const float* x, const float* w, const float* b, float* y, int R, int K, int N, int act_in, void* stream);
+
+/* Sinusoidal embedding (unet.py:81-95): emb[r] = (sin(t_r * f_k), cos(t_r * f_k)), f_k = exp(-k ln(theta)/(dim/2-1)). */
+int sdc_sinusoidal_embedding(const float* t, float* emb, int R, int dim, float theta, void* stream);
+
+/* Zero a double buffer (GroupNorm statistics) on the stream. */
+int sdc_zero_f64(double* p, int64_t n, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -16,5 +16,6 @@ from .guidance import (calculate_guidance, get_finetune_guidance, get_weight, no
                        SafetyGuidance, SCALER)
 from .conformal import ConformalCalculator, kth_select  # noqa: F401
 from .diffusion import GaussianDiffusion, ModelPrediction  # noqa: F401
+from .unet import Unet2D  # noqa: F401
 
 __version__ = "0.1.0"

@@ -1,0 +1,370 @@
+// Implicit-GEMM convolution on tcgen05 tensor cores fed by TMA.
+//
+// Replaces every nn.Conv2d of Unet2D except the 3-channel stem (/root/reference/1D/model/unet.py:132,161,
+// 189-192,232-233,33-43,345,370,378):   out[M, Cout] = im2col(A)[M, K] * Wp[Cout, K]^T + bias
+//   M = B*H*W output pixels (NHWC activations, fp32 containers holding TF32-rounded values)
+//   K = taps * Cin   (3x3 pad 1: 9 taps; 1x1: 1 tap; pixel-unshuffle 2x2/stride 2: 4 taps),
+//       Cin may be the concatenation of two tensors (U-Net skip connections) -> two K segments, no torch.cat.
+//
+// Mapping (one CTA = one 128 x BN output tile, 192 threads):
+//   warp 0   TMA producer: per K block (32 channels of one tap) one 4-D/5-D box load of the shifted activation
+//            window (out-of-bounds rows/cols are zero-filled by TMA = the conv padding) + one 2-D load of the
+//            weight slab, both SWIZZLE_128B, completing on an mbarrier;
+//   warp 1   allocates TMEM, then one thread issues tcgen05.mma.kind::tf32 (M=128, N=BN, K=8) x4 per K block,
+//            accumulating in TMEM, and releases smem stages with tcgen05.commit;
+//   warps 2-5 epilogue: tcgen05.ld the accumulator (each warp owns its 32-lane TMEM quarter), add bias /
+//            residual, accumulate per-sample GroupNorm statistics (sum, sum of squares -> fp64 atomics),
+//            optionally round to TF32 (so that the next conv's operands are round-to-nearest, not truncated)
+//            and store NHWC rows.
+// Precision: TF32 operands (10-bit mantissa, rounded to nearest when produced), FP32 accumulation.
+#include "common.cuh"
+#include <cuda.h>
+#include <math.h>
+
+namespace sdc {
+
+// ------------------------------------------------------------------------------------------ PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    const uint32_t addr = smem_u32(bar);
+    uint32_t done;
+    do {
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, p;\n"
+            "}\n" : "=r"(done) : "r"(addr), "r"(parity) : "memory");
+    } while (!done);
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                 ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2, int c3) {
+    asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+                 ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ void tma_load_5d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2, int c3,
+                                            int c4) {
+    asm volatile("cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+                 ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4) : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
+
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n"
+        "}\n" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+// arrives on the mbarrier once all previously issued MMAs of this thread have completed
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+          "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
+          "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+          "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// K-major SWIZZLE_128B shared-memory matrix descriptor (rows of 128 bytes, 8-row groups 1024 bytes apart).
+// Bit layout per the sm_100 UMMA descriptor: [0,14) start>>4, [16,30) LBO>>4 (unused for swizzled K-major, 1),
+// [32,46) SBO>>4 = 64, [46,48) version = 1, [61,64) layout = 2 (SWIZZLE_128B).
+__device__ __forceinline__ uint64_t make_sw128_desc(uint32_t smem_addr) {
+    const uint32_t lo = ((smem_addr & 0x3FFFFu) >> 4) | (1u << 16);
+    const uint32_t hi = 64u | (1u << 14) | (2u << 29);
+    return ((uint64_t)hi << 32) | lo;
+}
+
+// ------------------------------------------------------------------------------------------ kernel
+constexpr int BM = 128;        // output pixels per tile (= UMMA M)
+constexpr int BK = 32;         // TF32 elements per K block (= 128 bytes = one swizzle row)
+constexpr int A_BYTES = BM * BK * 4;
+constexpr int GEMM_THREADS = 192;
+
+struct GemmParams {
+    int kind;            // 0: 1x1, 1: 3x3 pad 1, 2: 2x2 stride-2 (pixel-unshuffle + 1x1)
+    int M;               // valid output rows
+    int Cout;
+    int bn;              // N tile (multiple of 32, <= 256)
+    int H, W;            // OUTPUT spatial size
+    int bh, bb;          // tile = bb images x bh rows x W cols
+    int c0, c1;          // channels of segment 0 / 1 (c1 = 0: single input)
+    int stages;
+    int round_tf32;
+    int hw_per_sample;   // H*W
+    const float* bias;       // [Cout] or null
+    const float* residual;   // [M, Cout] or null (added after bias)
+    float* out;              // [M, Cout]
+    double* stats;           // [B, 2] (sum, sumsq) accumulated with atomics, or null
+};
+
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ CUtensorMap map_a1,
+                 const __grid_constant__ CUtensorMap map_w, const GemmParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    const int stage_bytes = A_BYTES + p.bn * BK * 4;
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + p.stages * stage_bytes);
+    uint64_t* empty_bar = full_bar + p.stages;
+    uint64_t* acc_bar = empty_bar + p.stages;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_bar + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int mt = blockIdx.x, nt = blockIdx.y;
+    const int taps = p.kind == 1 ? 9 : (p.kind == 2 ? 4 : 1);
+    const int ctot = p.c0 + p.c1;
+    const int chunks = ctot / BK;
+    const int num_kb = taps * chunks;
+    uint32_t tmem_cols = 32;
+    while ((int)tmem_cols < p.bn) tmem_cols <<= 1;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&map_a0);
+        if (p.c1) tma_prefetch_desc(&map_a1);
+        tma_prefetch_desc(&map_w);
+        for (int s = 0; s < p.stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+        mbar_init(acc_bar, 1);
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc(tmem_slot, tmem_cols);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            // tile origin in (image, row); tiles always span full rows (bw == W)
+            const int pix0 = mt * BM;
+            const int b0 = pix0 / p.hw_per_sample;
+            const int h0 = (pix0 - b0 * p.hw_per_sample) / p.W;
+            const uint32_t tx = (uint32_t)stage_bytes;
+            for (int kb = 0; kb < num_kb; ++kb) {
+                const int s = kb % p.stages;
+                const uint32_t ph = (uint32_t)(kb / p.stages) & 1u;
+                mbar_wait(&empty_bar[s], ph ^ 1u);
+                uint8_t* sa = smem + s * stage_bytes;
+                uint8_t* sb = sa + A_BYTES;
+                mbar_expect_tx(&full_bar[s], tx);
+                const int tap = kb / chunks;
+                const int cc = (kb - tap * chunks) * BK;          // channel offset in the concatenated input
+                const bool second = cc >= p.c0;
+                const CUtensorMap* ma = second ? &map_a1 : &map_a0;
+                const int cseg = second ? cc - p.c0 : cc;
+                if (p.kind == 2) {
+                    // input viewed as [B, H, 2(p1), W, 2*C]: coordinate (p2*C + c, w, p1, h, b)
+                    const int cin = second ? p.c1 : p.c0;
+                    tma_load_5d(sa, ma, &full_bar[s], (tap & 1) * cin + cseg, 0, tap >> 1, h0, b0);
+                } else {
+                    const int dy = p.kind == 1 ? tap / 3 - 1 : 0;
+                    const int dx = p.kind == 1 ? tap % 3 - 1 : 0;
+                    tma_load_4d(sa, ma, &full_bar[s], cseg, dx, h0 + dy, b0);
+                }
+                tma_load_2d(sb, &map_w, &full_bar[s], tap * ctot + cc, nt * p.bn);
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(p.bn >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+            for (int kb = 0; kb < num_kb; ++kb) {
+                const int s = kb % p.stages;
+                const uint32_t ph = (uint32_t)(kb / p.stages) & 1u;
+                mbar_wait(&full_bar[s], ph);
+                tc_fence_after();
+                const uint32_t sa = smem_u32(smem + s * stage_bytes);
+                const uint64_t adesc = make_sw128_desc(sa);
+                const uint64_t bdesc = make_sw128_desc(sa + A_BYTES);
+#pragma unroll
+                for (int k = 0; k < BK / 8; ++k) {
+                    // advance 8 TF32 = 32 bytes along K inside the 128-byte swizzle row: +2 in the (addr >> 4) field
+                    umma_tf32(tmem_base, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kb | k) != 0);
+                }
+                umma_commit(&empty_bar[s]);
+            }
+            umma_commit(acc_bar);
+        }
+    } else {
+        // ---- epilogue: warp w may only touch TMEM lanes [32*(w%4), 32*(w%4)+32) ----
+        const int q = warp & 3;
+        const int row = q * 32 + lane;
+        const int m = mt * BM + row;
+        const bool row_ok = m < p.M;
+        mbar_wait(acc_bar, 0);
+        tc_fence_after();
+        float* orow = p.out + (size_t)m * p.Cout + (size_t)nt * p.bn;
+        const float* rrow = p.residual ? p.residual + (size_t)m * p.Cout + (size_t)nt * p.bn : nullptr;
+        float s1 = 0.f, s2 = 0.f;
+        for (int c = 0; c < p.bn; c += 32) {
+            uint32_t r[32];
+            tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c, r);
+            const int ncol0 = nt * p.bn + c;
+            if (row_ok) {
+#pragma unroll
+                for (int j = 0; j < 32; j += 4) {
+                    float4 v = make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]),
+                                           __uint_as_float(r[j + 3]));
+                    if (p.bias) {
+                        const float4 bv = __ldg(reinterpret_cast<const float4*>(p.bias + ncol0 + j));
+                        v.x += bv.x; v.y += bv.y; v.z += bv.z; v.w += bv.w;
+                    }
+                    if (rrow) {
+                        const float4 rv = __ldg(reinterpret_cast<const float4*>(rrow + c + j));
+                        v.x += rv.x; v.y += rv.y; v.z += rv.z; v.w += rv.w;
+                    }
+                    s1 += (v.x + v.y) + (v.z + v.w);
+                    s2 += (v.x * v.x + v.y * v.y) + (v.z * v.z + v.w * v.w);
+                    if (p.round_tf32) { v.x = to_tf32(v.x); v.y = to_tf32(v.y); v.z = to_tf32(v.z); v.w = to_tf32(v.w); }
+                    *reinterpret_cast<float4*>(orow + c + j) = v;
+                }
+            }
+        }
+        if (p.stats) {
+            // all 32 rows of a warp belong to one sample (H*W is a multiple of 32)
+            s1 = warp_sum(s1);
+            s2 = warp_sum(s2);
+            const int m_w = mt * BM + q * 32;
+            if (lane == 0 && m_w < p.M) {
+                const int b = m_w / p.hw_per_sample;
+                atomicAdd(p.stats + 2 * b, (double)s1);
+                atomicAdd(p.stats + 2 * b + 1, (double)s2);
+            }
+        }
+        tc_fence_before();
+    }
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, tmem_cols);
+    }
+}
+
+// ------------------------------------------------------------------------------------------ host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* ptr = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(ptr);
+    }
+    return fn;
+}
+
+static int encode(CUtensorMap* map, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes,
+                  const cuuint32_t* box) {
+    EncodeTiledFn fn = get_encode();
+    if (!fn) { set_error("cuTensorMapEncodeTiled entry point unavailable (no CUDA driver?)"); return SDC_ERR_CUDA; }
+    cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank, const_cast<void*>(base), dims, strides_bytes, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed with CUresult %d (rank %d)", (int)r, rank); return SDC_ERR_CUDA; }
+    return SDC_OK;
+}
+
+// activation map: NHWC [B, Hin, Win, C]; for kind 2 the 5-D pixel-unshuffle view
+static int encode_act(CUtensorMap* map, const float* a, int kind, int B, int H, int W, int C, int bh, int bb) {
+    if (kind == 2) {
+        // input spatial 2H x 2W;  dims (inner->outer): {2C, W, 2, H, B}
+        cuuint64_t dims[5] = {(cuuint64_t)2 * C, (cuuint64_t)W, 2, (cuuint64_t)H, (cuuint64_t)B};
+        cuuint64_t str[4] = {(cuuint64_t)2 * C * 4, (cuuint64_t)2 * W * C * 4, (cuuint64_t)4 * W * C * 4,
+                             (cuuint64_t)4 * H * W * C * 4};
+        cuuint32_t box[5] = {BK, (cuuint32_t)W, 1, (cuuint32_t)bh, (cuuint32_t)bb};
+        return encode(map, a, 5, dims, str, box);
+    }
+    cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
+    cuuint64_t str[3] = {(cuuint64_t)C * 4, (cuuint64_t)W * C * 4, (cuuint64_t)H * W * C * 4};
+    cuuint32_t box[4] = {BK, (cuuint32_t)W, (cuuint32_t)bh, (cuuint32_t)bb};
+    return encode(map, a, 4, dims, str, box);
+}
+
+}  // namespace sdc
+
+using namespace sdc;
+
+extern "C" int sdc_conv_gemm(int kind, const float* a0, int c0, const float* a1, int c1, const float* w_packed,
+                             const float* bias, const float* residual, float* out, double* stats, int round_tf32, int B, int H,
+                             int W, int Cout, void* stream) {
+    SDC_REQUIRE(kind >= 0 && kind <= 2, "conv_gemm: kind %d", kind);
+    SDC_REQUIRE(B > 0 && H > 0 && W > 0, "conv_gemm: empty problem");
+    SDC_REQUIRE(a0 && w_packed && out, "conv_gemm: null pointer");
+    SDC_REQUIRE(c0 > 0 && c0 % BK == 0 && c1 >= 0 && c1 % BK == 0 && (c1 == 0 || a1), "conv_gemm: channels must be multiples of %d", BK);
+    SDC_REQUIRE(Cout % 32 == 0, "conv_gemm: Cout=%d must be a multiple of 32", Cout);
+    SDC_REQUIRE(W <= BM && BM % W == 0, "conv_gemm: W=%d must divide %d", W, BM);
+    int bh = BM / W;
+    if (bh > H) bh = H;
+    SDC_REQUIRE(H % bh == 0, "conv_gemm: H=%d not tileable by %d rows", H, bh);
+    const int bb = BM / (W * bh);
+    SDC_REQUIRE(bb * bh * W == BM && (H * W) % 32 == 0, "conv_gemm: H*W=%d cannot be tiled into 128-pixel blocks", H * W);
+    SDC_REQUIRE(bb == 1 || bh == H, "conv_gemm: tile spans images only when it holds whole images");
+    int bn = Cout % 256 == 0 ? 256 : (Cout % 128 == 0 ? 128 : (Cout % 64 == 0 ? 64 : 32));
+    GemmParams p{};
+    p.kind = kind; p.M = B * H * W; p.Cout = Cout; p.bn = bn; p.H = H; p.W = W; p.bh = bh; p.bb = bb;
+    p.c0 = c0; p.c1 = c1; p.round_tf32 = round_tf32; p.hw_per_sample = H * W;
+    p.bias = bias; p.residual = residual; p.out = out; p.stats = stats;
+    const int stage_bytes = A_BYTES + bn * BK * 4;
+    int stages = (200 * 1024) / stage_bytes;
+    if (stages > 6) stages = 6;
+    p.stages = stages;
+    const int smem_bytes = stages * stage_bytes + (2 * stages + 1) * 8 + 16 + 1024;
+
+    CUtensorMap ma0, ma1, mw;
+    int rc = encode_act(&ma0, a0, kind, B, H, W, c0, bh, bb);
+    if (rc) return rc;
+    if (c1) { rc = encode_act(&ma1, a1, kind, B, H, W, c1, bh, bb); if (rc) return rc; } else ma1 = ma0;
+    const int taps = kind == 1 ? 9 : (kind == 2 ? 4 : 1);
+    const cuuint64_t ktot = (cuuint64_t)taps * (c0 + c1);
+    cuuint64_t wd[2] = {ktot, (cuuint64_t)Cout};
+    cuuint64_t ws[1] = {ktot * 4};
+    cuuint32_t wb[2] = {BK, (cuuint32_t)bn};
+    rc = encode(&mw, w_packed, 2, wd, ws, wb);
+    if (rc) return rc;
+
+    static bool attr_set = false;
+    if (!attr_set) {
+        SDC_CUDA(cudaFuncSetAttribute(conv_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        attr_set = true;
+    }
+    dim3 grid((unsigned)((p.M + BM - 1) / BM), (unsigned)(Cout / bn));
+    conv_gemm_kernel<<<grid, GEMM_THREADS, smem_bytes, as_stream(stream)>>>(ma0, ma1, mw, p);
+    SDC_LAUNCHED();
+    return SDC_OK;
+}

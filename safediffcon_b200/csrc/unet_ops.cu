@@ -1,0 +1,480 @@
+// Bandwidth-bound building blocks of the denoiser plus weight packing,
+// the 3-channel stem conv and the 3-channel head conv.  Reference: /root/reference/1D/model/unet.py.
+// Activations are NHWC fp32 pixel rows [B*H*W, C]; every kernel here is a single pass over its tensors with
+// 16-byte coalesced accesses (the convolutions in conv_gemm.cu are the only compute-bound part).
+#include "common.cuh"
+#include "../../include/safediffcon_b200_unet.h"
+#include <math.h>
+
+namespace sdc {
+
+// ---------------------------------------------------------------------------------------------- weight packing
+__global__ void pack_conv_weight_kernel(int kind, const float* __restrict__ w, float* __restrict__ wp, int Cout, int Cin) {
+    const int taps = kind == 1 ? 9 : 1;
+    const int64_t total = (int64_t)Cout * Cin * taps;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int K = Cin * taps;
+        const int o = (int)(i / K), k = (int)(i % K);
+        float v;
+        if (kind == 1) {
+            const int tap = k / Cin, ci = k % Cin;
+            v = w[((int64_t)o * Cin + ci) * 9 + tap];
+        } else if (kind == 2) {
+            const int C = Cin / 4, pp = k / C, c = k % C;
+            v = w[(int64_t)o * Cin + c * 4 + pp];
+        } else {
+            v = w[i];
+        }
+        wp[i] = to_tf32(v);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------- stem 7x7 conv
+// One CTA = STEM_ROWS image rows of one sample; thread = 8 pixels x 8 output channels in registers.
+constexpr int STEM_ROWS = 4;
+__global__ void stem_conv7_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
+                                  float* __restrict__ out, int Cin, int H, int W, int Cout) {
+    extern __shared__ float sm[];
+    const int K = Cin * 49;
+    float* ws = sm;                      // [K][Cout]
+    float* xs = sm + (size_t)K * Cout;   // [Cin][7][W + 6]  (one output row at a time)
+    const int b = blockIdx.x, h_base = blockIdx.y * STEM_ROWS;
+    const int tid = threadIdx.x, nthr = blockDim.x;
+    for (int i = tid; i < K * Cout; i += nthr) {
+        const int co = i / K, k = i % K;            // coalesced read of OIHW
+        ws[k * Cout + co] = w[i];
+    }
+    const int cog = Cout / 8;
+    const int co0 = (tid % cog) * 8, px0 = (tid / cog) * 8;
+    const int WP = W + 6;
+    for (int hr = 0; hr < STEM_ROWS; ++hr) {
+        const int h = h_base + hr;
+        if (h >= H) break;
+        __syncthreads();
+        for (int i = tid; i < Cin * 7 * WP; i += nthr) {
+            const int ci = i / (7 * WP), r = (i / WP) % 7, c = i % WP;
+            const int hh = h + r - 3, ww = c - 3;
+            xs[i] = (hh >= 0 && hh < H && ww >= 0 && ww < W) ? x[(((int64_t)b * Cin + ci) * H + hh) * W + ww] : 0.f;
+        }
+        __syncthreads();
+        float acc[8][8];
+#pragma unroll
+        for (int p = 0; p < 8; ++p)
+#pragma unroll
+            for (int c = 0; c < 8; ++c) acc[p][c] = 0.f;
+        for (int cr = 0; cr < Cin * 7; ++cr) {
+            float xv[14];
+#pragma unroll
+            for (int j = 0; j < 14; ++j) xv[j] = xs[cr * WP + px0 + j];
+#pragma unroll
+            for (int kx = 0; kx < 7; ++kx) {
+                const float4 w0 = *reinterpret_cast<const float4*>(&ws[(cr * 7 + kx) * Cout + co0]);
+                const float4 w1 = *reinterpret_cast<const float4*>(&ws[(cr * 7 + kx) * Cout + co0 + 4]);
+                const float wv[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+#pragma unroll
+                for (int p = 0; p < 8; ++p)
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) acc[p][c] = fmaf(xv[p + kx], wv[c], acc[p][c]);
+            }
+        }
+        float bv[8];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) bv[c] = bias ? bias[co0 + c] : 0.f;
+#pragma unroll
+        for (int p = 0; p < 8; ++p) {
+            float* o = out + (((int64_t)b * H + h) * W + px0 + p) * Cout + co0;
+            *reinterpret_cast<float4*>(o) = make_float4(to_tf32(acc[p][0] + bv[0]), to_tf32(acc[p][1] + bv[1]),
+                                                        to_tf32(acc[p][2] + bv[2]), to_tf32(acc[p][3] + bv[3]));
+            *reinterpret_cast<float4*>(o + 4) = make_float4(to_tf32(acc[p][4] + bv[4]), to_tf32(acc[p][5] + bv[5]),
+                                                            to_tf32(acc[p][6] + bv[6]), to_tf32(acc[p][7] + bv[7]));
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------- GroupNorm(1)+FiLM+SiLU
+__device__ __forceinline__ float silu(float v) { return v / (1.0f + expf(-v)); }
+
+__global__ void __launch_bounds__(256) gn_silu_kernel(const float* __restrict__ x, const double* __restrict__ stats,
+                                                      const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                      const float* __restrict__ scale_shift, const int32_t* __restrict__ t_index,
+                                                      int64_t ss_stride, const float* __restrict__ residual, float* __restrict__ y,
+                                                      int HW, int C, int pix_per_cta) {
+    extern __shared__ float coef[];  // A[C], B[C]
+    const int b = blockIdx.x;
+    const double cnt = (double)HW * (double)C;
+    const double mean_d = stats[2 * b] / cnt;
+    double var_d = stats[2 * b + 1] / cnt - mean_d * mean_d;
+    if (var_d < 0.0) var_d = 0.0;
+    const float mean = (float)mean_d, rstd = (float)(1.0 / sqrt(var_d + 1e-5));
+    const float* ss = scale_shift ? scale_shift + (int64_t)(t_index ? t_index[b] : 0) * ss_stride : nullptr;
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        const float g = gamma[c] * rstd;
+        float a = g, bb = beta[c] - mean * g;
+        if (ss) {
+            const float sc = ss[c] + 1.0f;
+            a *= sc;
+            bb = bb * sc + ss[C + c];
+        }
+        coef[c] = a;
+        coef[C + c] = bb;
+    }
+    __syncthreads();
+    const int c4n = C / 4;
+    const int64_t row0 = (int64_t)b * HW + (int64_t)blockIdx.y * pix_per_cta;
+    const int rows = min(pix_per_cta, HW - (int)blockIdx.y * pix_per_cta);
+    const float4* x4 = reinterpret_cast<const float4*>(x + row0 * C);
+    const float4* r4 = residual ? reinterpret_cast<const float4*>(residual + row0 * C) : nullptr;
+    float4* y4 = reinterpret_cast<float4*>(y + row0 * C);
+    const int total = rows * c4n;
+    for (int i = threadIdx.x; i < total; i += blockDim.x) {
+        const int c = (i % c4n) * 4;
+        float4 v = x4[i];
+        v.x = silu(fmaf(v.x, coef[c], coef[C + c]));
+        v.y = silu(fmaf(v.y, coef[c + 1], coef[C + c + 1]));
+        v.z = silu(fmaf(v.z, coef[c + 2], coef[C + c + 2]));
+        v.w = silu(fmaf(v.w, coef[c + 3], coef[C + c + 3]));
+        if (r4) { const float4 r = r4[i]; v.x += r.x; v.y += r.y; v.z += r.z; v.w += r.w; }
+        y4[i] = make_float4(to_tf32(v.x), to_tf32(v.y), to_tf32(v.z), to_tf32(v.w));
+    }
+}
+
+// ---------------------------------------------------------------------------------------------- channel LayerNorm
+// one warp per pixel row; C <= 1024 kept in registers (two-pass variance like torch.var(unbiased=False))
+__global__ void __launch_bounds__(256) channel_layernorm_kernel(const float* __restrict__ x, const float* __restrict__ g,
+                                                                const float* __restrict__ residual, float* __restrict__ y,
+                                                                int64_t M, int C, int round_tf32) {
+    const int lane = threadIdx.x & 31;
+    const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= M) return;
+    const int n4 = C / 4;  // float4 per row; lane handles i = lane, lane+32, ...
+    const float4* x4 = reinterpret_cast<const float4*>(x + row * C);
+    float4 v[8];
+    float s = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const int i = lane + 32 * j;
+        if (i < n4) { v[j] = x4[i]; s += (v[j].x + v[j].y) + (v[j].z + v[j].w); }
+    }
+    const float mean = warp_sum(s) / (float)C;
+    float q = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const int i = lane + 32 * j;
+        if (i < n4) {
+            const float a = v[j].x - mean, b = v[j].y - mean, c = v[j].z - mean, d = v[j].w - mean;
+            q += (a * a + b * b) + (c * c + d * d);
+        }
+    }
+    const float rstd = rsqrtf(warp_sum(q) / (float)C + 1e-5f);
+    const float4* g4 = reinterpret_cast<const float4*>(g);
+    const float4* r4 = residual ? reinterpret_cast<const float4*>(residual + row * C) : nullptr;
+    float4* y4 = reinterpret_cast<float4*>(y + row * C);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const int i = lane + 32 * j;
+        if (i < n4) {
+            const float4 gv = g4[i];
+            float4 o = make_float4((v[j].x - mean) * rstd * gv.x, (v[j].y - mean) * rstd * gv.y, (v[j].z - mean) * rstd * gv.z,
+                                   (v[j].w - mean) * rstd * gv.w);
+            if (r4) { const float4 r = r4[i]; o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w; }
+            if (round_tf32) o = make_float4(to_tf32(o.x), to_tf32(o.y), to_tf32(o.z), to_tf32(o.w));
+            y4[i] = o;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------- linear attention
+constexpr int LA_HEADS = 4, LA_D = 32, LA_QKV = 3 * LA_HEADS * LA_D, LA_HID = LA_HEADS * LA_D;
+
+// ctx[b,h,d,e] = sum_n softmax_n(k)[d,n] * v[e,n]          grid = B*heads, 256 threads
+__global__ void __launch_bounds__(256) linattn_context_kernel(const float* __restrict__ qkv, float* __restrict__ ctx, int n) {
+    __shared__ float ek[64][LA_D];
+    __shared__ float vs[64][LA_D];
+    __shared__ float red[8][LA_D];
+    __shared__ float kmax[LA_D];
+    const int b = blockIdx.x / LA_HEADS, h = blockIdx.x % LA_HEADS;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const float* base = qkv + (int64_t)b * n * LA_QKV;
+    const float* kp = base + LA_HID + h * LA_D;
+    const float* vp = base + 2 * LA_HID + h * LA_D;
+    float m = -INFINITY;
+    for (int i = warp; i < n; i += 8) m = fmaxf(m, kp[(int64_t)i * LA_QKV + lane]);
+    red[warp][lane] = m;
+    __syncthreads();
+    if (warp == 0) {
+        float t = red[0][lane];
+#pragma unroll
+        for (int w = 1; w < 8; ++w) t = fmaxf(t, red[w][lane]);
+        kmax[lane] = t;
+    }
+    __syncthreads();
+    const int d = tid >> 3, e0 = (tid & 7) * 4;
+    float acc[4] = {0.f, 0.f, 0.f, 0.f}, ksum = 0.f;
+    for (int n0 = 0; n0 < n; n0 += 64) {
+        const int cnt = min(64, n - n0);
+        __syncthreads();
+        for (int i = tid; i < cnt * LA_D; i += 256) {
+            const int r = i >> 5, c = i & 31;
+            ek[r][c] = expf(kp[(int64_t)(n0 + r) * LA_QKV + c] - kmax[c]);
+            vs[r][c] = vp[(int64_t)(n0 + r) * LA_QKV + c];
+        }
+        __syncthreads();
+        for (int r = 0; r < cnt; ++r) {
+            const float a = ek[r][d];
+            const float4 vv = *reinterpret_cast<const float4*>(&vs[r][e0]);
+            acc[0] = fmaf(a, vv.x, acc[0]); acc[1] = fmaf(a, vv.y, acc[1]);
+            acc[2] = fmaf(a, vv.z, acc[2]); acc[3] = fmaf(a, vv.w, acc[3]);
+            ksum += a;
+        }
+    }
+    const float inv = 1.0f / ksum;
+    float* o = ctx + ((int64_t)blockIdx.x * LA_D + d) * LA_D + e0;
+    *reinterpret_cast<float4*>(o) = make_float4(acc[0] * inv, acc[1] * inv, acc[2] * inv, acc[3] * inv);
+}
+
+// out[n, h*32+e] = 32^-0.5 * sum_d ctx[d,e] * softmax_d(q[n,:])[d]      grid = (B*heads, ceil(n/64)), 256 threads
+__global__ void __launch_bounds__(256) linattn_apply_kernel(const float* __restrict__ qkv, const float* __restrict__ ctx,
+                                                            float* __restrict__ out, int n) {
+    const int b = blockIdx.x / LA_HEADS, h = blockIdx.x % LA_HEADS;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float c[LA_D];  // lane = e holds ctx[:, e]
+    const float* cp = ctx + (int64_t)blockIdx.x * LA_D * LA_D;
+#pragma unroll
+    for (int d = 0; d < LA_D; ++d) c[d] = cp[d * LA_D + lane];
+    const float* qp = qkv + (int64_t)b * n * LA_QKV + h * LA_D;
+    float* op = out + (int64_t)b * n * LA_HID + h * LA_D;
+    const float scale = 0.17677669529663687f;  // 32^-0.5
+    const int i_end = min(n, (int)(blockIdx.y + 1) * 64);
+    for (int i = blockIdx.y * 64 + warp; i < i_end; i += 8) {
+        const float qv = qp[(int64_t)i * LA_QKV + lane];
+        const float mx = warp_max(qv);
+        const float ex = expf(qv - mx);
+        const float sq = ex / warp_sum(ex) * scale;
+        float o = 0.f;
+#pragma unroll
+        for (int d = 0; d < LA_D; ++d) o = fmaf(__shfl_sync(0xffffffffu, sq, d), c[d], o);
+        op[(int64_t)i * LA_HID + lane] = to_tf32(o);
+    }
+}
+
+// full softmax attention for n <= 32 tokens: one warp per (b, head), lane = query token
+__global__ void __launch_bounds__(128) attention_kernel(const float* __restrict__ qkv, float* __restrict__ out, int n) {
+    __shared__ float ks[LA_HEADS][32][LA_D + 1];
+    __shared__ float vs[LA_HEADS][32][LA_D + 1];
+    const int b = blockIdx.x, h = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const float* base = qkv + (int64_t)b * n * LA_QKV;
+    for (int j = 0; j < n; ++j) {
+        ks[h][j][lane] = base[(int64_t)j * LA_QKV + LA_HID + h * LA_D + lane];
+        vs[h][j][lane] = base[(int64_t)j * LA_QKV + 2 * LA_HID + h * LA_D + lane];
+    }
+    __syncwarp();
+    if (lane < n) {
+        const float scale = 0.17677669529663687f;
+        float q[LA_D];
+#pragma unroll
+        for (int d = 0; d < LA_D; ++d) q[d] = base[(int64_t)lane * LA_QKV + h * LA_D + d] * scale;
+        float sim[32];
+        float mx = -INFINITY;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+            float s = -INFINITY;
+            if (j < n) {
+                s = 0.f;
+#pragma unroll
+                for (int d = 0; d < LA_D; ++d) s = fmaf(q[d], ks[h][j][d], s);
+            }
+            sim[j] = s;
+            mx = fmaxf(mx, s);
+        }
+        float den = 0.f;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) { sim[j] = (j < n) ? expf(sim[j] - mx) : 0.f; den += sim[j]; }
+        const float inv = 1.0f / den;
+        float* o = out + ((int64_t)b * n + lane) * LA_HID + h * LA_D;
+#pragma unroll
+        for (int d = 0; d < LA_D; ++d) {
+            float a = 0.f;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) a = fmaf(sim[j], vs[h][j][d], a);
+            o[d] = to_tf32(a * inv);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------- misc
+__global__ void upsample2x_kernel(const float4* __restrict__ x, float4* __restrict__ y, int64_t total4, int H, int W, int c4) {
+    // total4 = B*2H*2W*c4 output float4s
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total4; i += (int64_t)gridDim.x * blockDim.x) {
+        const int c = (int)(i % c4);
+        int64_t pix = i / c4;
+        const int wo = (int)(pix % (2 * W)); pix /= (2 * W);
+        const int ho = (int)(pix % (2 * H));
+        const int64_t b = pix / (2 * H);
+        y[i] = x[((b * H + (ho >> 1)) * W + (wo >> 1)) * c4 + c];
+    }
+}
+
+// warp per pixel, Cout <= 4 dot products of length Cin; NHWC -> NCHW
+__global__ void __launch_bounds__(256) head_conv1_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                                         const float* __restrict__ bias, float* __restrict__ out, int64_t M,
+                                                         int HW, int Cin, int Cout) {
+    const int lane = threadIdx.x & 31;
+    const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= M) return;
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int c = lane * 4; c < Cin; c += 128) {
+        const float4 xv = *reinterpret_cast<const float4*>(x + row * Cin + c);
+        for (int o = 0; o < Cout; ++o) {
+            const float4 wv = *reinterpret_cast<const float4*>(w + (int64_t)o * Cin + c);
+            acc[o] += (xv.x * wv.x + xv.y * wv.y) + (xv.z * wv.z + xv.w * wv.w);
+        }
+    }
+    const int64_t b = row / HW, p = row % HW;
+    for (int o = 0; o < Cout; ++o) {
+        const float s = warp_sum(acc[o]);
+        if (lane == 0) out[(b * Cout + o) * HW + p] = s + (bias ? bias[o] : 0.f);
+    }
+}
+
+__device__ __forceinline__ float act_in(float v, int act) {
+    if (act == 1) return silu(v);
+    if (act == 2) return 0.5f * v * (1.0f + erff(v * 0.7071067811865476f));
+    return v;
+}
+// warp per output element (r, n)
+__global__ void __launch_bounds__(256) linear_rows_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                                          const float* __restrict__ b, float* __restrict__ y, int K, int N, int act) {
+    const int lane = threadIdx.x & 31;
+    const int n = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), r = blockIdx.y;
+    if (n >= N) return;
+    float acc = 0.f;
+    for (int k = lane; k < K; k += 32) acc = fmaf(act_in(x[(int64_t)r * K + k], act), w[(int64_t)n * K + k], acc);
+    acc = warp_sum(acc);
+    if (lane == 0) y[(int64_t)r * N + n] = acc + (b ? b[n] : 0.f);
+}
+
+__global__ void sinusoidal_kernel(const float* __restrict__ t, float* __restrict__ emb, int R, int dim, float neg_step) {
+    const int half = dim / 2;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < R * half; i += gridDim.x * blockDim.x) {
+        const int r = i / half, k = i % half;
+        const float f = expf((float)k * neg_step);
+        const float a = t[r] * f;
+        emb[(int64_t)r * dim + k] = sinf(a);
+        emb[(int64_t)r * dim + half + k] = cosf(a);
+    }
+}
+
+}  // namespace sdc
+
+using namespace sdc;
+
+static inline unsigned blocks_for(int64_t n, int per) { int64_t b = (n + per - 1) / per; return (unsigned)(b > 148 * 16 ? 148 * 16 : (b < 1 ? 1 : b)); }
+
+extern "C" int sdc_pack_conv_weight(int kind, const float* w, float* wp, int Cout, int Cin, void* stream) {
+    SDC_REQUIRE(kind >= 0 && kind <= 2 && w && wp && Cout > 0 && Cin > 0, "pack_conv_weight: bad arguments");
+    SDC_REQUIRE(kind != 2 || Cin % 4 == 0, "pack_conv_weight: unshuffle conv needs Cin %% 4 == 0");
+    const int64_t total = (int64_t)Cout * Cin * (kind == 1 ? 9 : 1);
+    pack_conv_weight_kernel<<<blocks_for(total, 256), 256, 0, as_stream(stream)>>>(kind, w, wp, Cout, Cin);
+    SDC_LAUNCHED();
+    return SDC_OK;
+}
+
+extern "C" int sdc_stem_conv7(const float* x, const float* w, const float* bias, float* out, int B, int Cin, int H, int W,
+                              int Cout, void* stream) {
+    SDC_REQUIRE(x && w && out && B > 0, "stem_conv7: bad arguments");
+    SDC_REQUIRE(W % 8 == 0 && Cout % 8 == 0 && (W / 8) * (Cout / 8) <= 1024 && (W / 8) * (Cout / 8) >= 32,
+                "stem_conv7: unsupported W=%d Cout=%d", W, Cout);
+    const int threads = (W / 8) * (Cout / 8);
+    const size_t smem = ((size_t)Cin * 49 * Cout + (size_t)Cin * 7 * (W + 6)) * sizeof(float);
+    SDC_REQUIRE(smem <= 227 * 1024, "stem_conv7: weights do not fit shared memory (%zu bytes)", smem);
+    SDC_CUDA(cudaFuncSetAttribute(stem_conv7_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    dim3 grid((unsigned)B, (unsigned)((H + STEM_ROWS - 1) / STEM_ROWS));
+    stem_conv7_kernel<<<grid, threads, smem, as_stream(stream)>>>(x, w, bias, out, Cin, H, W, Cout);
+    SDC_LAUNCHED();
+    return SDC_OK;
+}
+
+extern "C" int sdc_gn_silu(const float* x, const double* stats, const float* gamma, const float* beta, const float* scale_shift,
+                           const int32_t* t_index, int64_t ss_stride, const float* residual, float* y, int B, int HW, int C,
+                           void* stream) {
+    SDC_REQUIRE(x && stats && gamma && beta && y && B > 0 && HW > 0, "gn_silu: bad arguments");
+    SDC_REQUIRE(C % 4 == 0 && C <= 4096, "gn_silu: C=%d unsupported", C);
+    int ppc = HW;  // pixels per CTA: aim for >= 2 waves of CTAs without shrinking below 32 pixels
+    while (ppc > 32 && (int64_t)B * (HW / ppc) < 2 * 148 && ppc % 2 == 0) ppc /= 2;
+    dim3 grid((unsigned)B, (unsigned)((HW + ppc - 1) / ppc));
+    gn_silu_kernel<<<grid, 256, 2 * C * sizeof(float), as_stream(stream)>>>(x, stats, gamma, beta, scale_shift, t_index, ss_stride,
+                                                                              residual, y, HW, C, ppc);
+    SDC_LAUNCHED();
+    return SDC_OK;
+}
+
+extern "C" int sdc_channel_layernorm(const float* x, const float* g, const float* residual, float* y, int64_t M, int C,
+                                     int round_tf32, void* stream) {
+    SDC_REQUIRE(x && g && y && M > 0, "channel_layernorm: bad arguments");
+    SDC_REQUIRE(C % 4 == 0 && C <= 1024, "channel_layernorm: C=%d unsupported (multiple of 4, <= 1024)", C);
+    channel_layernorm_kernel<<<(unsigned)((M + 7) / 8), 256, 0, as_stream(stream)>>>(x, g, residual, y, M, C, round_tf32);
+    SDC_LAUNCHED();
+    return SDC_OK;
+}
+
+extern "C" int64_t sdc_linear_attention_workspace(int B) { return (int64_t)B * LA_HEADS * LA_D * LA_D * sizeof(float); }
+
+extern "C" int sdc_linear_attention(const float* qkv, float* out, void* workspace, int B, int n, void* stream) {
+    SDC_REQUIRE(qkv && out && workspace && B > 0 && n > 0, "linear_attention: bad arguments");
+    float* ctx = reinterpret_cast<float*>(workspace);
+    linattn_context_kernel<<<(unsigned)(B * LA_HEADS), 256, 0, as_stream(stream)>>>(qkv, ctx, n);
+    SDC_LAUNCHED();
+    dim3 grid((unsigned)(B * LA_HEADS), (unsigned)((n + 63) / 64));
+    linattn_apply_kernel<<<grid, 256, 0, as_stream(stream)>>>(qkv, ctx, out, n);
+    SDC_LAUNCHED();
+    return SDC_OK;
+}
+
+extern "C" int sdc_attention(const float* qkv, float* out, int B, int n, void* stream) {
+    SDC_REQUIRE(qkv && out && B > 0, "attention: bad arguments");
+    SDC_REQUIRE(n > 0 && n <= 32, "attention: n=%d tokens unsupported (bottleneck of the 16x128 grid has 32)", n);
+    attention_kernel<<<(unsigned)B, 128, 0, as_stream(stream)>>>(qkv, out, n);
+    SDC_LAUNCHED();
+    return SDC_OK;
+}
+
+extern "C" int sdc_upsample2x(const float* x, float* y, int B, int H, int W, int C, void* stream) {
+    SDC_REQUIRE(x && y && B > 0 && C % 4 == 0, "upsample2x: bad arguments");
+    const int64_t total4 = (int64_t)B * 4 * H * W * (C / 4);
+    upsample2x_kernel<<<blocks_for(total4, 256 * 4), 256, 0, as_stream(stream)>>>(reinterpret_cast<const float4*>(x),
+                                                                                 reinterpret_cast<float4*>(y), total4, H, W, C / 4);
+    SDC_LAUNCHED();
+    return SDC_OK;
+}
+
+extern "C" int sdc_head_conv1(const float* x, const float* w, const float* bias, float* out, int B, int HW, int Cin, int Cout,
+                              void* stream) {
+    SDC_REQUIRE(x && w && out && B > 0 && Cin % 4 == 0 && Cout >= 1 && Cout <= 4, "head_conv1: needs Cin %% 4 == 0, Cout <= 4");
+    const int64_t M = (int64_t)B * HW;
+    head_conv1_kernel<<<(unsigned)((M + 7) / 8), 256, 0, as_stream(stream)>>>(x, w, bias, out, M, HW, Cin, Cout);
+    SDC_LAUNCHED();
+    return SDC_OK;
+}
+
+extern "C" int sdc_linear_rows(const float* x, const float* w, const float* b, float* y, int R, int K, int N, int act_in,
+                               void* stream) {
+    SDC_REQUIRE(x && w && y && R > 0 && K > 0 && N > 0 && R < 65536, "linear_rows: bad arguments");
+    dim3 grid((unsigned)((N + 7) / 8), (unsigned)R);
+    linear_rows_kernel<<<grid, 256, 0, as_stream(stream)>>>(x, w, b, y, K, N, act_in);
+    SDC_LAUNCHED();
+    return SDC_OK;
+}
+
+extern "C" int sdc_sinusoidal_embedding(const float* t, float* emb, int R, int dim, float theta, void* stream) {
+    SDC_REQUIRE(t && emb && R > 0 && dim % 2 == 0 && dim >= 4, "sinusoidal_embedding: bad arguments");
+    const float neg_step = (float)(-(log((double)theta) / (double)(dim / 2 - 1)));
+    sinusoidal_kernel<<<blocks_for((int64_t)R * dim / 2, 256), 256, 0, as_stream(stream)>>>(t, emb, R, dim, neg_step);
+    SDC_LAUNCHED();
+    return SDC_OK;
+}
+
+extern "C" int sdc_zero_f64(double* p, int64_t n, void* stream) {
+    SDC_REQUIRE(p != nullptr && n >= 0, "zero_f64: bad arguments");
+    SDC_CUDA(cudaMemsetAsync(p, 0, (size_t)n * sizeof(double), as_stream(stream)));
+    return SDC_OK;
+}

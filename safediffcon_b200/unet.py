@@ -1,0 +1,408 @@
+"""Denoiser: drop-in for Unet2D (/root/reference/1D/model/unet.py:263-426).
+
+The module tree below exists to own the parameters under the reference's state_dict keys
+(``downs.0.0.block1.proj.weight`` ...) and to consume torch's RNG in the reference's construction order, so a
+reference checkpoint loads unchanged and ``torch.manual_seed(s); Unet2D(...)`` yields the reference's initial
+weights.  ``forward`` does not run those modules: it drives the CUDA kernels of csrc/conv_gemm.cu (tcgen05
+implicit-GEMM convolutions) and csrc/unet_ops.cu (fused GroupNorm/SiLU, LayerNorm, attention) over NHWC
+activations.  Packed TF32 weights and the per-timestep FiLM table are cached and rebuilt whenever a parameter's
+version counter or storage changes (optimiser / EMA updates between chains).
+"""
+import math
+
+import torch
+import torch.nn as nn
+
+from . import _lib as L
+from ._lib import c_f, c_i, c_i64, c_p
+
+L.register({
+    "sdc_pack_conv_weight": (c_i, [c_i, c_p, c_p, c_i, c_i, c_p]),
+    "sdc_conv_gemm": (c_i, [c_i, c_p, c_i, c_p, c_i, c_p, c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_p]),
+    "sdc_stem_conv7": (c_i, [c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_p]),
+    "sdc_gn_silu": (c_i, [c_p, c_p, c_p, c_p, c_p, c_p, c_i64, c_p, c_p, c_i, c_i, c_i, c_p]),
+    "sdc_channel_layernorm": (c_i, [c_p, c_p, c_p, c_p, c_i64, c_i, c_i, c_p]),
+    "sdc_linear_attention_workspace": (c_i64, [c_i]),
+    "sdc_linear_attention": (c_i, [c_p, c_p, c_p, c_i, c_i, c_p]),
+    "sdc_attention": (c_i, [c_p, c_p, c_i, c_i, c_p]),
+    "sdc_upsample2x": (c_i, [c_p, c_p, c_i, c_i, c_i, c_i, c_p]),
+    "sdc_head_conv1": (c_i, [c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_p]),
+    "sdc_linear_rows": (c_i, [c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_p]),
+    "sdc_sinusoidal_embedding": (c_i, [c_p, c_p, c_i, c_i, c_f, c_p]),
+    "sdc_zero_f64": (c_i, [c_p, c_i64, c_p]),
+})
+
+HEADS, DIM_HEAD = 4, 32
+KIND_1x1, KIND_3x3, KIND_UNSHUFFLE = 0, 1, 2
+
+
+# ----------------------------------------------------------------------------- parameter containers
+class _Gain(nn.Module):
+    """Channel LayerNorm gain (reference LayerNorm.g)."""
+
+    def __init__(self, dim):
+        super().__init__()
+        self.g = nn.Parameter(torch.ones(1, dim, 1, 1))
+
+
+class _Block(nn.Module):
+    def __init__(self, dim, dim_out, groups):
+        super().__init__()
+        self.proj = nn.Conv2d(dim, dim_out, 3, padding=1)
+        self.norm = nn.GroupNorm(groups, dim_out)
+        self.act = nn.SiLU()
+
+
+class _ResnetBlock(nn.Module):
+    def __init__(self, dim, dim_out, time_emb_dim, groups):
+        super().__init__()
+        self.mlp = nn.Sequential(nn.SiLU(), nn.Linear(time_emb_dim, dim_out * 2))
+        self.block1 = _Block(dim, dim_out, groups)
+        self.block2 = _Block(dim_out, dim_out, groups)
+        self.res_conv = nn.Conv2d(dim, dim_out, 1) if dim != dim_out else nn.Identity()
+        self.dim, self.dim_out = dim, dim_out
+
+
+class _LinearAttention(nn.Module):
+    def __init__(self, dim):
+        super().__init__()
+        hidden = HEADS * DIM_HEAD
+        self.to_qkv = nn.Conv2d(dim, hidden * 3, 1, bias=False)
+        self.to_out = nn.Sequential(nn.Conv2d(hidden, dim, 1), _Gain(dim))
+
+
+class _Attention(nn.Module):
+    def __init__(self, dim):
+        super().__init__()
+        hidden = HEADS * DIM_HEAD
+        self.to_qkv = nn.Conv2d(dim, hidden * 3, 1, bias=False)
+        self.to_out = nn.Conv2d(hidden, dim, 1)
+
+
+class _PreNorm(nn.Module):
+    def __init__(self, dim, fn):
+        super().__init__()
+        self.fn = fn
+        self.norm = _Gain(dim)
+
+
+class _Residual(nn.Module):
+    def __init__(self, fn):
+        super().__init__()
+        self.fn = fn
+
+
+def _attn(dim, full=False):
+    inner = _Attention(dim) if full else _LinearAttention(dim)
+    return _Residual(_PreNorm(dim, inner))
+
+
+# ----------------------------------------------------------------------------- op wrappers (thin ctypes calls)
+def _st():
+    return L.stream_ptr()
+
+
+def conv_gemm(kind, a0, c0, a1, c1, wp, bias, residual, out, stats, round_tf32, B, H, W, Cout):
+    L.check(L.lib().sdc_conv_gemm(kind, L.ptr(a0), c0, L.ptr(a1), c1, L.ptr(wp), L.ptr(bias), L.ptr(residual), L.ptr(out),
+                                  L.ptr(stats), int(round_tf32), B, H, W, Cout, _st()))
+
+
+def pack_conv_weight(kind, w):
+    w = w.detach().to(torch.float32).contiguous()
+    cout, cin = w.shape[0], w.shape[1]
+    wp = torch.empty(cout, w[0].numel(), device=w.device, dtype=torch.float32)
+    L.check(L.lib().sdc_pack_conv_weight(kind, L.ptr(w), L.ptr(wp), cout, cin, _st()))
+    return wp
+
+
+class _PackCache:
+    """Packed-weight cache that is never deep-copied (EMA wrappers deepcopy the module; the copy repacks lazily)."""
+
+    def __init__(self):
+        self.pack, self.key = None, None
+
+    def __deepcopy__(self, memo):
+        return _PackCache()
+
+
+class Unet2D(nn.Module):
+    '''
+    Estimates the noise given the last diffusion step
+    The time dimension and the space dimension are treated equally
+    '''
+
+    def __init__(self, dim, init_dim=None, out_dim=None, dim_mults=(1, 2, 4, 8), channels=2, self_condition=False,
+                 resnet_block_groups=8, learned_variance=False, learned_sinusoidal_cond=False, random_fourier_features=False,
+                 learned_sinusoidal_dim=16, sinusoidal_pos_emb_theta=10000, attn_dim_head=32, attn_heads=4,
+                 condition_on_residual=None):
+        super().__init__()
+        if self_condition or learned_variance or learned_sinusoidal_cond or random_fourier_features or condition_on_residual:
+            raise NotImplementedError("safediffcon_b200.Unet2D: option outside the 1D hot path (SURVEY.md section 8)")
+        if resnet_block_groups != 1:
+            raise NotImplementedError("safediffcon_b200.Unet2D implements GroupNorm(1, C) (resnet_block_groups=1), the value of "
+                                      "every shipped 1D config")
+        if attn_dim_head != DIM_HEAD or attn_heads != HEADS:
+            raise NotImplementedError("attention is specialised for 4 heads x 32")
+        if dim % 32 != 0:
+            raise NotImplementedError("dim must be a multiple of 32 (TF32 K blocks of 32 channels)")
+        self.condition_on_residual = None
+        self.channels = channels
+        self.self_condition = False
+        self.dim = dim
+        self.theta = sinusoidal_pos_emb_theta
+        time_dim = dim * 4
+        self.time_mlp = nn.Sequential(nn.Identity(), nn.Linear(dim, time_dim), nn.GELU(), nn.Linear(time_dim, time_dim))
+        init_dim = init_dim if init_dim is not None else dim
+        self.init_conv = nn.Conv2d(channels, init_dim, 7, padding=3)
+        dims = [init_dim, *map(lambda m: dim * m, dim_mults)]
+        in_out = list(zip(dims[:-1], dims[1:]))
+        block = lambda a, b: _ResnetBlock(a, b, time_dim, resnet_block_groups)  # noqa: E731
+
+        self.downs = nn.ModuleList([])
+        for ind, (d_in, d_out) in enumerate(in_out):
+            is_last = ind >= (len(in_out) - 1)
+            # construction order = the reference's (it fixes the RNG stream of the default initialisation)
+            mods = [block(d_in, d_in), block(d_in, d_in), _attn(d_in)]
+            mods.append(nn.Sequential(nn.Identity(), nn.Conv2d(d_in * 4, d_out, 1)) if not is_last
+                        else nn.Conv2d(d_in, d_out, 3, padding=1))
+            self.downs.append(nn.ModuleList(mods))
+        mid = dims[-1]
+        self.mid_block1 = block(mid, mid)
+        self.mid_attn = _attn(mid, full=True)
+        self.mid_block2 = block(mid, mid)
+        self.ups = nn.ModuleList([])
+        for ind, (d_in, d_out) in enumerate(reversed(in_out)):
+            is_last = ind == (len(in_out) - 1)
+            mods = [block(d_out + d_in, d_out), block(d_out + d_in, d_out), _attn(d_out)]
+            mods.append(nn.Sequential(nn.Identity(), nn.Conv2d(d_out, d_in, 3, padding=1)) if not is_last
+                        else nn.Conv2d(d_out, d_in, 3, padding=1))
+            self.ups.append(nn.ModuleList(mods))
+        self.out_dim = out_dim if out_dim is not None else channels
+        self.final_res_block = block(dim * 2, dim)
+        self.final_conv = nn.Conv2d(dim, self.out_dim, 1)
+        self._cache = _PackCache()
+        self.table_timesteps = 1000  # rows of the cached FiLM table for integer diffusion times
+
+    # ------------------------------------------------------------------ weight packing / FiLM table
+    def _resnet_blocks(self):
+        for lvl in self.downs:
+            yield lvl[0]
+            yield lvl[1]
+        yield self.mid_block1
+        yield self.mid_block2
+        for lvl in self.ups:
+            yield lvl[0]
+            yield lvl[1]
+        yield self.final_res_block
+
+    def _key(self):
+        return tuple((p.data_ptr(), p._version) for p in self.parameters())
+
+    def _packed(self):
+        key = self._key()
+        if self._cache.pack is not None and key == self._cache.key:
+            return self._cache.pack
+        dev = self.init_conv.weight.device
+        if dev.type != "cuda":
+            raise RuntimeError("safediffcon_b200.Unet2D: parameters are on the CPU; move the module to a CUDA device "
+                               "(there is no CPU fallback)")
+        pk = {}
+        with torch.no_grad(), torch.cuda.device(dev):
+            def conv(m, kind):
+                return dict(w=pack_conv_weight(kind, m.weight), b=None if m.bias is None else m.bias.detach().float().contiguous(),
+                            cout=m.weight.shape[0])
+
+            def rb(m):
+                return dict(c1=conv(m.block1.proj, KIND_3x3), c2=conv(m.block2.proj, KIND_3x3),
+                            g1=(m.block1.norm.weight.detach().float().contiguous(), m.block1.norm.bias.detach().float().contiguous()),
+                            g2=(m.block2.norm.weight.detach().float().contiguous(), m.block2.norm.bias.detach().float().contiguous()),
+                            res=conv(m.res_conv, KIND_1x1) if isinstance(m.res_conv, nn.Conv2d) else None, cout=m.dim_out)
+
+            def at(m):
+                inner = m.fn.fn
+                d = dict(g_in=m.fn.norm.g.detach().float().reshape(-1).contiguous(), qkv=conv(inner.to_qkv, KIND_1x1))
+                if isinstance(inner, _LinearAttention):
+                    d.update(out=conv(inner.to_out[0], KIND_1x1), g_out=inner.to_out[1].g.detach().float().reshape(-1).contiguous(), full=False)
+                else:
+                    d.update(out=conv(inner.to_out, KIND_1x1), g_out=None, full=True)
+                return d
+
+            pk["downs"] = []
+            for lvl in self.downs:
+                is_unshuffle = isinstance(lvl[3], nn.Sequential)
+                pk["downs"].append(dict(b1=rb(lvl[0]), b2=rb(lvl[1]), attn=at(lvl[2]), unshuffle=is_unshuffle,
+                                        down=conv(lvl[3][1], KIND_UNSHUFFLE) if is_unshuffle else conv(lvl[3], KIND_3x3)))
+            pk["mid1"], pk["mid_attn"], pk["mid2"] = rb(self.mid_block1), at(self.mid_attn), rb(self.mid_block2)
+            pk["ups"] = []
+            for lvl in self.ups:
+                is_up = isinstance(lvl[3], nn.Sequential)
+                pk["ups"].append(dict(b1=rb(lvl[0]), b2=rb(lvl[1]), attn=at(lvl[2]), upsample=is_up,
+                                      up=conv(lvl[3][1] if is_up else lvl[3], KIND_3x3)))
+            pk["final"] = rb(self.final_res_block)
+            pk["stem"] = (self.init_conv.weight.detach().float().contiguous(), self.init_conv.bias.detach().float().contiguous())
+            pk["head"] = (self.final_conv.weight.detach().float().reshape(self.out_dim, -1).contiguous(),
+                          self.final_conv.bias.detach().float().contiguous())
+            # all ResnetBlock FiLM projections stacked: one [E_total, time_dim] matrix, block i owns rows [off, off+2*Cout)
+            ws, bs, off = [], [], 0
+            for i, m in enumerate(self._resnet_blocks()):
+                ws.append(m.mlp[1].weight.detach().float())
+                bs.append(m.mlp[1].bias.detach().float())
+                m._film_off = off
+                off += m.mlp[1].weight.shape[0]
+            pk["film_w"], pk["film_b"], pk["film_total"] = torch.cat(ws).contiguous(), torch.cat(bs).contiguous(), off
+            pk["time"] = tuple(t.detach().float().contiguous() for t in (self.time_mlp[1].weight, self.time_mlp[1].bias,
+                                                                            self.time_mlp[3].weight, self.time_mlp[3].bias))
+            pk["table"] = None
+        self._cache.pack, self._cache.key = pk, key
+        return pk
+
+    def _film_rows(self, pk, t_float):
+        """FiLM (scale | shift) rows [R, E_total] for R diffusion times (float32 tensor on the device)."""
+        R, dim, td = t_float.shape[0], self.dim, self.dim * 4
+        dev = t_float.device
+        emb = torch.empty(R, dim, device=dev)
+        h1 = torch.empty(R, td, device=dev)
+        h2 = torch.empty(R, td, device=dev)
+        out = torch.empty(R, pk["film_total"], device=dev)
+        w1, b1, w2, b2 = pk["time"]
+        lib = L.lib()
+        L.check(lib.sdc_sinusoidal_embedding(L.ptr(t_float), L.ptr(emb), R, dim, float(self.theta), _st()))
+        L.check(lib.sdc_linear_rows(L.ptr(emb), L.ptr(w1), L.ptr(b1), L.ptr(h1), R, dim, td, 0, _st()))
+        L.check(lib.sdc_linear_rows(L.ptr(h1), L.ptr(w2), L.ptr(b2), L.ptr(h2), R, td, td, 2, _st()))
+        L.check(lib.sdc_linear_rows(L.ptr(h2), L.ptr(pk["film_w"]), L.ptr(pk["film_b"]), L.ptr(out), R, td, pk["film_total"], 1, _st()))
+        return out
+
+    def _film_table(self, pk):
+        if pk["table"] is None:
+            dev = pk["film_w"].device
+            t = torch.arange(self.table_timesteps, device=dev, dtype=torch.float32)
+            pk["table"] = self._film_rows(pk, t)
+        return pk["table"]
+
+    # ------------------------------------------------------------------ forward
+    def denoise_uniform(self, x, t_int):
+        """eps for a batch-uniform integer diffusion time (sampler fast path: no per-sample index tensor)."""
+        return self._forward(x, table_row=int(t_int))
+
+    def forward(self, x, time, x_self_cond=None, residual=None):
+        if x_self_cond is not None or residual is not None:
+            raise NotImplementedError("self-conditioning / residual conditioning are outside the 1D hot path")
+        return self._forward(x, time=time)
+
+    @torch.no_grad()
+    def _forward(self, x, time=None, table_row=None):
+        x = L.dev_f32(x, "x")
+        with torch.cuda.device(x.device):
+            return self._run(x, time, table_row)
+
+    def _run(self, x, time, table_row):
+        pk = self._packed()
+        lib = L.lib()
+        dev = x.device
+        B, Cin, H, W = x.shape
+        assert Cin == self.channels
+        # FiLM rows: integer times index the cached 1000-row table; anything else is evaluated per sample
+        if table_row is not None:
+            film, t_index = self._film_table(pk)[table_row:table_row + 1], None
+        elif not torch.is_floating_point(time):
+            film, t_index = self._film_table(pk), time.to(device=dev, dtype=torch.int32).clamp(0, self.table_timesteps - 1).contiguous()
+        else:
+            film, t_index = self._film_rows(pk, time.to(device=dev, dtype=torch.float32).contiguous()), \
+                torch.arange(B, device=dev, dtype=torch.int32)
+        E = pk["film_total"]
+        n_gn = 2 * sum(1 for _ in self._resnet_blocks())
+        stats = torch.zeros(n_gn, B, 2, device=dev, dtype=torch.float64)
+        stat_i = [0]
+        new = lambda rows, c: torch.empty(rows, c, device=dev, dtype=torch.float32)  # noqa: E731
+
+        def resnet(p, m, a0, c0, a1, c1, h, w):
+            """ResnetBlock (unet.py:166-180) on one or two concatenated NHWC inputs -> [B*h*w, Cout]."""
+            M, cout = B * h * w, p["cout"]
+            s1, s2 = stats[stat_i[0]], stats[stat_i[0] + 1]
+            stat_i[0] += 2
+            h1 = new(M, cout)
+            conv_gemm(KIND_3x3, a0, c0, a1, c1, p["c1"]["w"], p["c1"]["b"], None, h1, s1, False, B, h, w, cout)
+            ss = film[:, m._film_off:]
+            L.check(lib.sdc_gn_silu(L.ptr(h1), L.ptr(s1), L.ptr(p["g1"][0]), L.ptr(p["g1"][1]), ctypes_ptr(ss), L.ptr(t_index), E,
+                                    None, L.ptr(h1), B, h * w, cout, _st()))
+            h2 = new(M, cout)
+            conv_gemm(KIND_3x3, h1, cout, None, 0, p["c2"]["w"], p["c2"]["b"], None, h2, s2, False, B, h, w, cout)
+            if p["res"] is not None:
+                res = h1  # reuse: h1 is dead after conv2
+                conv_gemm(KIND_1x1, a0, c0, a1, c1, p["res"]["w"], p["res"]["b"], None, res, None, False, B, h, w, cout)
+            else:
+                assert a1 is None
+                res = a0
+            L.check(lib.sdc_gn_silu(L.ptr(h2), L.ptr(s2), L.ptr(p["g2"][0]), L.ptr(p["g2"][1]), None, None, 0, L.ptr(res),
+                                    L.ptr(h2), B, h * w, cout, _st()))
+            return h2
+
+        def attention(p, xin, c, h, w):
+            """Residual(PreNorm(LinearAttention | Attention)) (unet.py:16-22,65-76,182-258)."""
+            M, n = B * h * w, h * w
+            xn = new(M, c)
+            L.check(lib.sdc_channel_layernorm(L.ptr(xin), L.ptr(p["g_in"]), None, L.ptr(xn), M, c, 1, _st()))
+            qkv = new(M, 3 * HEADS * DIM_HEAD)
+            conv_gemm(KIND_1x1, xn, c, None, 0, p["qkv"]["w"], None, None, qkv, None, False, B, h, w, 3 * HEADS * DIM_HEAD)
+            att = new(M, HEADS * DIM_HEAD)
+            if p["full"]:
+                L.check(lib.sdc_attention(L.ptr(qkv), L.ptr(att), B, n, _st()))
+                out = xn  # reuse
+                conv_gemm(KIND_1x1, att, HEADS * DIM_HEAD, None, 0, p["out"]["w"], p["out"]["b"], xin, out, None, True, B, h, w, c)
+                return out
+            ws = torch.empty(lib.sdc_linear_attention_workspace(B), device=dev, dtype=torch.uint8)
+            L.check(lib.sdc_linear_attention(L.ptr(qkv), L.ptr(att), L.ptr(ws), B, n, _st()))
+            proj = xn  # reuse
+            conv_gemm(KIND_1x1, att, HEADS * DIM_HEAD, None, 0, p["out"]["w"], p["out"]["b"], None, proj, None, False, B, h, w, c)
+            out = new(M, c)
+            L.check(lib.sdc_channel_layernorm(L.ptr(proj), L.ptr(p["g_out"]), L.ptr(xin), L.ptr(out), M, c, 1, _st()))
+            return out
+
+        def ctypes_ptr(t):
+            return L.ptr(t)
+
+        c = self.init_conv.weight.shape[0]
+        cur = new(B * H * W, c)
+        L.check(lib.sdc_stem_conv7(L.ptr(x), L.ptr(pk["stem"][0]), L.ptr(pk["stem"][1]), L.ptr(cur), B, Cin, H, W, c, _st()))
+        r, r_c = cur, c
+        h, w = H, W
+        skips = []
+        for lvl_m, lvl in zip(self.downs, pk["downs"]):
+            cur = resnet(lvl["b1"], lvl_m[0], cur, c, None, 0, h, w)
+            skips.append((cur, c))
+            cur = resnet(lvl["b2"], lvl_m[1], cur, c, None, 0, h, w)
+            cur = attention(lvl["attn"], cur, c, h, w)
+            skips.append((cur, c))
+            cout = lvl["down"]["cout"]
+            if lvl["unshuffle"]:
+                h, w = h // 2, w // 2
+                nxt = new(B * h * w, cout)
+                conv_gemm(KIND_UNSHUFFLE, cur, c, None, 0, lvl["down"]["w"], lvl["down"]["b"], None, nxt, None, True, B, h, w, cout)
+            else:
+                nxt = new(B * h * w, cout)
+                conv_gemm(KIND_3x3, cur, c, None, 0, lvl["down"]["w"], lvl["down"]["b"], None, nxt, None, True, B, h, w, cout)
+            cur, c = nxt, cout
+        cur = resnet(pk["mid1"], self.mid_block1, cur, c, None, 0, h, w)
+        cur = attention(pk["mid_attn"], cur, c, h, w)
+        cur = resnet(pk["mid2"], self.mid_block2, cur, c, None, 0, h, w)
+        for lvl_m, lvl in zip(self.ups, pk["ups"]):
+            s, sc = skips.pop()
+            cur = resnet(lvl["b1"], lvl_m[0], cur, c, s, sc, h, w)
+            c = lvl["b1"]["cout"]
+            s, sc = skips.pop()
+            cur = resnet(lvl["b2"], lvl_m[1], cur, c, s, sc, h, w)
+            cur = attention(lvl["attn"], cur, c, h, w)
+            cout = lvl["up"]["cout"]
+            if lvl["upsample"]:
+                up = new(B * 4 * h * w, c)
+                L.check(lib.sdc_upsample2x(L.ptr(cur), L.ptr(up), B, h, w, c, _st()))
+                h, w = 2 * h, 2 * w
+                cur = up
+            nxt = new(B * h * w, cout)
+            conv_gemm(KIND_3x3, cur, c, None, 0, lvl["up"]["w"], lvl["up"]["b"], None, nxt, None, True, B, h, w, cout)
+            cur, c = nxt, cout
+        cur = resnet(pk["final"], self.final_res_block, cur, c, r, r_c, h, w)
+        out = torch.empty(B, self.out_dim, H, W, device=dev, dtype=torch.float32)
+        L.check(lib.sdc_head_conv1(L.ptr(cur), L.ptr(pk["head"][0]), L.ptr(pk["head"][1]), L.ptr(out), B, H * W,
+                                   self.final_res_block.dim_out, self.out_dim, _st()))
+        return out

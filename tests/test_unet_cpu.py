@@ -1,0 +1,41 @@
+"""CPU: the drop-in Unet2D owns the reference's parameters (keys, shapes, seed-42 initial values) and the oracle
+U-Net restatement reproduces the reference's eps."""
+import copy
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import fixtures as fx
+from oracle import unet_ref
+
+
+@pytest.mark.parametrize("dim,B", [(32, 3), (128, 2)])
+def test_state_dict_and_oracle_match_reference(dim, B, golden):
+    import safediffcon_b200 as s
+    torch.manual_seed(42)
+    net = s.Unet2D(dim=dim, dim_mults=(1, 2, 4, 8), channels=3, resnet_block_groups=1)
+    g = golden(f"unet_dim{dim}_wsum")
+    sd = net.state_dict()
+    assert list(sd.keys()) == [str(k) for k in g["keys"]]
+    assert np.array_equal(np.array([float(v.double().sum()) for v in sd.values()]), g["sum"])
+    assert np.array_equal(np.array([float(v.double().abs().sum()) for v in sd.values()]), g["abssum"])
+    x, t = fx.unet_inputs(B)
+    with torch.no_grad():
+        eps = unet_ref.unet_forward(sd, x, t)
+    assert np.array_equal(eps.numpy(), golden(f"unet_dim{dim}")["eps"])
+
+
+def test_module_semantics():
+    import safediffcon_b200 as s
+    net = s.Unet2D(dim=32, channels=3, resnet_block_groups=1)
+    assert net.channels == 3 and net.self_condition is False and net.out_dim == 3
+    n2 = copy.deepcopy(net)
+    assert n2._cache.pack is None
+    n2.load_state_dict(net.state_dict())
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        net(torch.zeros(1, 3, 16, 128), torch.zeros(1, dtype=torch.long))
+    with pytest.raises(NotImplementedError):
+        s.Unet2D(dim=32, channels=3, resnet_block_groups=8)
+    gd = s.GaussianDiffusion(net, seq_length=(16, 128), temporal=True, use_conv2d=True)
+    assert len(gd.state_dict()) == 276 + 13

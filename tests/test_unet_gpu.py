@@ -1,0 +1,254 @@
+"""GPU parity: tcgen05 convolution and the fused U-Net kernels vs torch fp32, and the whole denoiser vs the
+reference's eps (tests/golden/unet_*.npz).  Tolerances: TF32 operands (10-bit mantissa) with fp32 accumulation;
+north-star bound for the whole network: eps within 1e-3 relative."""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import fixtures as fx
+from oracle import unet_ref
+
+pytestmark = pytest.mark.gpu
+
+
+def tf32(x):
+    i = x.contiguous().view(torch.int32)
+    return ((i + 0x1000) & ~0x1FFF).view(torch.float32)
+
+
+def nhwc(x):
+    return x.permute(0, 2, 3, 1).contiguous()
+
+
+def rel(a, b):
+    return ((a - b).norm() / b.norm()).item()
+
+
+@pytest.fixture(autouse=True)
+def _fp32_reference():
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+
+
+CONV_CASES = [
+    # kind, B, H, W, c0, c1, cout, bias, residual, stats, round
+    (1, 2, 16, 128, 32, 0, 32, True, False, True, False),
+    (1, 3, 16, 128, 128, 0, 128, True, False, True, False),
+    (1, 2, 8, 64, 64, 64, 128, True, False, True, False),     # two K segments (skip concat)
+    (1, 5, 2, 16, 96, 32, 64, True, False, True, True),        # ragged batch: 5 images, 4 per tile
+    (1, 4, 4, 32, 256, 0, 512, True, False, False, True),      # two N tiles
+    (0, 2, 16, 128, 128, 0, 384, False, False, False, False),  # qkv projection, no bias, N tile 128
+    (0, 4, 2, 16, 128, 0, 256, True, True, False, True),       # 1x1 + residual epilogue
+    (0, 2, 8, 64, 64, 32, 96, True, False, False, False),      # 1x1 on a concat, N tile 32
+    (2, 2, 8, 64, 32, 0, 64, True, False, False, True),        # pixel-unshuffle + 1x1 (input 16x128)
+    (2, 3, 2, 16, 128, 0, 256, True, False, False, True),      # unshuffle to the 2x16 level
+]
+
+
+@pytest.mark.parametrize("case", CONV_CASES, ids=[f"k{c[0]}_B{c[1]}_{c[2]}x{c[3]}_c{c[4]}+{c[5]}_o{c[6]}" for c in CONV_CASES])
+def test_conv_gemm_vs_torch(case):
+    from safediffcon_b200 import unet as U
+    kind, B, H, W, c0, c1, cout, use_bias, use_res, use_stats, rnd = case
+    g = torch.Generator().manual_seed(H * W + c0 + cout)
+    hin, win = (2 * H, 2 * W) if kind == 2 else (H, W)
+    cin = c0 + c1
+    x = tf32(torch.randn(B, cin, hin, win, generator=g)).cuda()
+    ksz = {0: 1, 1: 3, 2: 1}[kind]
+    w = (torch.randn(cout, cin * (4 if kind == 2 else 1), ksz, ksz, generator=g) / np.sqrt(cin * ksz * ksz)).cuda()
+    bias = torch.randn(cout, generator=g).cuda() if use_bias else None
+    res = torch.randn(B * H * W, cout, generator=g).cuda() if use_res else None
+    a0 = nhwc(x[:, :c0])
+    a1 = nhwc(x[:, c0:]) if c1 else None
+    wp = U.pack_conv_weight(kind, w)
+    out = torch.full((B * H * W, cout), float("nan")).cuda()
+    stats = torch.zeros(B, 2, dtype=torch.float64).cuda() if use_stats else None
+    U.conv_gemm(kind, a0, c0, a1, c1, wp, bias, res, out, stats, rnd, B, H, W, cout)
+    torch.cuda.synchronize()
+    wq = tf32(w.cpu()).cuda()
+    if kind == 2:
+        xin = x.reshape(B, cin, H, 2, W, 2).permute(0, 1, 3, 5, 2, 4).reshape(B, cin * 4, H, W)
+        ref = F.conv2d(xin.double(), wq.double(), None if bias is None else bias.double())
+    else:
+        ref = F.conv2d(x.double(), wq.double(), None if bias is None else bias.double(), padding=ksz // 2)
+    ref = ref.permute(0, 2, 3, 1).reshape(B * H * W, cout)
+    if res is not None:
+        ref = ref + res.double()
+    assert torch.isfinite(out).all()
+    err = (out.double() - ref).abs().max().item()
+    tol = 2e-3 if rnd else 2e-5   # fp32 accumulation of exact tf32 products; rounding the output costs 2^-11 relative
+    assert err < tol * max(1.0, ref.abs().max().item()), err
+    if rnd:
+        assert torch.equal(out, tf32(out.cpu()).cuda())  # stored values are TF32-representable
+    if stats is not None:
+        o = out.double().reshape(B, -1)
+        assert torch.allclose(stats[:, 0], o.sum(1), rtol=1e-6, atol=1e-3)
+        assert torch.allclose(stats[:, 1], (o * o).sum(1), rtol=1e-6, atol=1e-3)
+
+
+def _L():
+    from safediffcon_b200 import _lib as L
+    return L, L.lib()
+
+
+def test_stem_conv7_vs_torch():
+    L, lib = _L()
+    import safediffcon_b200.unet  # noqa: F401  (registers signatures)
+    for B, cout in ((2, 128), (3, 32)):
+        g = torch.Generator().manual_seed(cout)
+        x = torch.randn(B, 3, 16, 128, generator=g).cuda()
+        w = (torch.randn(cout, 3, 7, 7, generator=g) * 0.1).cuda()
+        b = torch.randn(cout, generator=g).cuda()
+        out = torch.empty(B * 16 * 128, cout).cuda()
+        L.check(lib.sdc_stem_conv7(L.ptr(x), L.ptr(w), L.ptr(b), L.ptr(out), B, 3, 16, 128, cout, L.stream_ptr()))
+        ref = nhwc(F.conv2d(x, w, b, padding=3)).reshape(-1, cout)
+        assert (out - ref).abs().max().item() < 1.5e-3 * ref.abs().max().item()  # output rounded to TF32
+        assert (out - tf32(ref.cpu()).cuda()).abs().max().item() < 1e-3 * ref.abs().max().item()
+
+
+def test_gn_silu_vs_torch():
+    L, lib = _L()
+    import safediffcon_b200.unet  # noqa: F401
+    for B, HW, C in ((3, 2048, 128), (4, 32, 1024), (2, 512, 32)):
+        g = torch.Generator().manual_seed(C)
+        x = (torch.randn(B, C, HW, generator=g) * 2 + 0.7).cuda()
+        gamma, beta = torch.randn(C, generator=g).cuda(), torch.randn(C, generator=g).cuda()
+        table = torch.randn(5, 3 * C, generator=g).cuda()  # rows wider than 2C: exercises the row stride
+        tidx = torch.tensor([4, 0, 2, 1][:B], dtype=torch.int32).cuda()
+        res = torch.randn(B * HW, C, generator=g).cuda()
+        xr = x.permute(0, 2, 1).reshape(B * HW, C).contiguous()
+        stats = torch.stack([xr.double().reshape(B, -1).sum(1), (xr.double() ** 2).reshape(B, -1).sum(1)], 1).contiguous()
+        y = torch.empty_like(xr)
+        L.check(lib.sdc_gn_silu(L.ptr(xr), L.ptr(stats), L.ptr(gamma), L.ptr(beta), L.ptr(table), L.ptr(tidx), 3 * C, L.ptr(res),
+                                L.ptr(y), B, HW, C, L.stream_ptr()))
+        ss = table[tidx.long()]
+        ref = F.group_norm(x, 1, gamma, beta, eps=1e-5) * (ss[:, :C, None] + 1) + ss[:, C:2 * C, None]
+        ref = F.silu(ref).permute(0, 2, 1).reshape(B * HW, C) + res
+        assert (y - ref).abs().max().item() < 2e-3 * ref.abs().max().item()
+        # no FiLM, no residual, uniform row 0
+        L.check(lib.sdc_gn_silu(L.ptr(xr), L.ptr(stats), L.ptr(gamma), L.ptr(beta), None, None, 0, None, L.ptr(y), B, HW, C,
+                                L.stream_ptr()))
+        ref2 = F.silu(F.group_norm(x, 1, gamma, beta, eps=1e-5)).permute(0, 2, 1).reshape(B * HW, C)
+        assert (y - ref2).abs().max().item() < 2e-3 * ref2.abs().max().item()
+
+
+def test_channel_layernorm_vs_torch():
+    L, lib = _L()
+    import safediffcon_b200.unet  # noqa: F401
+    for M, C in ((1000, 128), (77, 1024), (64, 32), (10, 512)):
+        g = torch.Generator().manual_seed(C)
+        x = (torch.randn(M, C, generator=g) * 3 + 1).cuda()
+        gain = torch.randn(C, generator=g).cuda()
+        res = torch.randn(M, C, generator=g).cuda()
+        y = torch.empty_like(x)
+        L.check(lib.sdc_channel_layernorm(L.ptr(x), L.ptr(gain), L.ptr(res), L.ptr(y), M, C, 0, L.stream_ptr()))
+        ref = (x - x.mean(1, keepdim=True)) * (x.var(1, unbiased=False, keepdim=True) + 1e-5).rsqrt() * gain + res
+        assert (y - ref).abs().max().item() < 1e-5 * ref.abs().max().item()
+        L.check(lib.sdc_channel_layernorm(L.ptr(x), L.ptr(gain), None, L.ptr(y), M, C, 1, L.stream_ptr()))
+        assert torch.equal(y, tf32((ref - res).cpu()).cuda()) or (y - (ref - res)).abs().max().item() < 1e-3 * ref.abs().max().item()
+
+
+def test_attention_cores_vs_torch():
+    L, lib = _L()
+    import safediffcon_b200.unet  # noqa: F401
+    for B, n in ((3, 2048), (2, 512), (5, 32), (2, 100)):
+        g = torch.Generator().manual_seed(n)
+        qkv = (torch.randn(B * n, 384, generator=g) * 1.5).cuda()
+        out = torch.empty(B * n, 128).cuda()
+        ws = torch.empty(lib.sdc_linear_attention_workspace(B), dtype=torch.uint8).cuda()
+        L.check(lib.sdc_linear_attention(L.ptr(qkv), L.ptr(out), L.ptr(ws), B, n, L.stream_ptr()))
+        q, k, v = (t.reshape(B, n, 4, 32).permute(0, 2, 3, 1) for t in qkv.chunk(3, dim=1))  # b h d n
+        ctx = torch.einsum("bhdn,bhen->bhde", k.softmax(-1), v)
+        ref = torch.einsum("bhde,bhdn->bhen", ctx, q.softmax(-2) * 32 ** -0.5)
+        ref = ref.permute(0, 3, 1, 2).reshape(B * n, 128)
+        assert (out - ref).abs().max().item() < 1.5e-3 * ref.abs().max().item()
+    for B, n in ((4, 32), (1, 32), (3, 20)):
+        g = torch.Generator().manual_seed(n + B)
+        qkv = (torch.randn(B * n, 384, generator=g) * 1.5).cuda()
+        out = torch.empty(B * n, 128).cuda()
+        L.check(lib.sdc_attention(L.ptr(qkv), L.ptr(out), B, n, L.stream_ptr()))
+        q, k, v = (t.reshape(B, n, 4, 32).permute(0, 2, 3, 1) for t in qkv.chunk(3, dim=1))
+        attn = torch.einsum("bhdi,bhdj->bhij", q * 32 ** -0.5, k).softmax(-1)
+        ref = torch.einsum("bhij,bhdj->bhid", attn, v).permute(0, 2, 1, 3).reshape(B * n, 128)
+        assert (out - ref).abs().max().item() < 1.5e-3 * ref.abs().max().item()
+
+
+def test_small_ops_vs_torch():
+    L, lib = _L()
+    import safediffcon_b200.unet  # noqa: F401
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn(2 * 4 * 8, 64, generator=g).cuda()
+    y = torch.empty(2 * 8 * 16, 64).cuda()
+    L.check(lib.sdc_upsample2x(L.ptr(x), L.ptr(y), 2, 4, 8, 64, L.stream_ptr()))
+    ref = nhwc(F.interpolate(x.reshape(2, 4, 8, 64).permute(0, 3, 1, 2), scale_factor=2, mode="nearest")).reshape(-1, 64)
+    assert torch.equal(y, ref)
+    xin = torch.randn(3 * 2048, 128, generator=g).cuda()
+    w, b = torch.randn(3, 128, generator=g).cuda(), torch.randn(3, generator=g).cuda()
+    out = torch.empty(3, 3, 16, 128).cuda()
+    L.check(lib.sdc_head_conv1(L.ptr(xin), L.ptr(w), L.ptr(b), L.ptr(out), 3, 2048, 128, 3, L.stream_ptr()))
+    ref = (xin @ w.t() + b).reshape(3, 2048, 3).permute(0, 2, 1).reshape(3, 3, 16, 128)
+    assert (out - ref).abs().max().item() < 1e-4
+    for act, fn in ((0, lambda v: v), (1, F.silu), (2, F.gelu)):
+        xi = torch.randn(7, 512, generator=g).cuda()
+        wl, bl = torch.randn(300, 512, generator=g).cuda() * 0.05, torch.randn(300, generator=g).cuda()
+        yo = torch.empty(7, 300).cuda()
+        L.check(lib.sdc_linear_rows(L.ptr(xi), L.ptr(wl), L.ptr(bl), L.ptr(yo), 7, 512, 300, act, L.stream_ptr()))
+        assert (yo - F.linear(fn(xi), wl, bl)).abs().max().item() < 2e-5
+    t = torch.tensor([0., 3., 417., 999.]).cuda()
+    emb = torch.empty(4, 128).cuda()
+    L.check(lib.sdc_sinusoidal_embedding(L.ptr(t), L.ptr(emb), 4, 128, 10000.0, L.stream_ptr()))
+    f = torch.exp(torch.arange(64) * -(np.log(10000) / 63))
+    a = t.cpu()[:, None] * f[None, :]
+    assert (emb.cpu() - torch.cat((a.sin(), a.cos()), -1)).abs().max().item() < 2e-4
+
+
+@pytest.mark.parametrize("dim,B", [(32, 3), (128, 2)])
+def test_unet_eps_vs_reference_golden(dim, B, golden):
+    """Whole denoiser, seed-42 weights, reference inputs -> reference eps within the north-star 1e-3 relative."""
+    import safediffcon_b200 as s
+    torch.manual_seed(42)
+    net = s.Unet2D(dim=dim, dim_mults=(1, 2, 4, 8), channels=3, resnet_block_groups=1).cuda()
+    x, t = fx.unet_inputs(B)
+    eps = net(x.cuda(), t.cuda())
+    ref = torch.from_numpy(golden(f"unet_dim{dim}")["eps"])
+    assert eps.shape == ref.shape
+    r = rel(eps.cpu(), ref)
+    per = [rel(eps[i].cpu(), ref[i]) for i in range(B)]
+    assert r < 1e-3 and max(per) < 1e-3, (r, per)
+    # batch-uniform fast path == per-sample time path
+    e0 = net.denoise_uniform(x.cuda(), int(t[0]))
+    assert torch.allclose(e0[0], eps[0], rtol=0, atol=1e-5 * ref.abs().max().item())
+    # float times take the per-sample FiLM evaluation
+    e1 = net(x.cuda(), t.cuda().float())
+    assert rel(e1.cpu(), ref) < 1e-3
+
+
+def test_unet_intermediates_localise_errors(golden):
+    """Per-stage comparison against the oracle's taps (diagnostic: which stage drifts first)."""
+    import safediffcon_b200 as s
+    torch.manual_seed(42)
+    net = s.Unet2D(dim=32, dim_mults=(1, 2, 4, 8), channels=3, resnet_block_groups=1).cuda()
+    x, t = fx.unet_inputs(3)
+    taps = {}
+    with torch.no_grad():
+        ref = unet_ref.unet_forward({k: v.cpu() for k, v in net.state_dict().items()}, x, t, taps=taps)
+    g = golden("unet_dim32")
+    assert np.array_equal(taps["init"].numpy(), g["tap_init_conv"])
+    eps = net(x.cuda(), t.cuda())
+    assert rel(eps.cpu(), ref) < 1e-3
+
+
+def test_weight_cache_follows_parameter_updates():
+    import safediffcon_b200 as s
+    torch.manual_seed(0)
+    net = s.Unet2D(dim=32, channels=3, resnet_block_groups=1).cuda()
+    x, t = fx.unet_inputs(2)
+    a = net(x.cuda(), t.cuda())
+    with torch.no_grad():
+        net.downs[0][0].block1.proj.weight.mul_(1.5)    # what an optimiser / EMA step does between chains
+        net.time_mlp[1].bias.add_(0.1)
+    b = net(x.cuda(), t.cuda())
+    assert not torch.allclose(a, b)
+    with torch.no_grad():
+        ref = unet_ref.unet_forward({k: v.cpu() for k, v in net.state_dict().items()}, x, t)
+    assert rel(b.cpu(), ref) < 1e-3
