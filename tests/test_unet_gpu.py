@@ -82,8 +82,10 @@ def test_conv_gemm_vs_torch(case):
         assert torch.equal(out, tf32(out.cpu()).cuda())  # stored values are TF32-representable
     if stats is not None:
         o = out.double().reshape(B, -1)
-        assert torch.allclose(stats[:, 0], o.sum(1), rtol=1e-6, atol=1e-3)
-        assert torch.allclose(stats[:, 1], (o * o).sum(1), rtol=1e-6, atol=1e-3)
+        # statistics are taken on the fp32 values BEFORE the optional TF32 rounding of the stored tensor
+        rt, at = (1e-3, 0.5) if rnd else (1e-6, 1e-3)
+        assert torch.allclose(stats[:, 0], o.sum(1), rtol=rt, atol=at)
+        assert torch.allclose(stats[:, 1], (o * o).sum(1), rtol=rt, atol=at)
 
 
 def _L():
