@@ -1,0 +1,340 @@
+"""Benchmark of the SafeDiffCon 1D-Burgers hot path on B200 (contract: see the task statement / DESIGN.md section 6).
+
+Workload at N=1 = BASELINE.json configs[1]: guided (safety, w_score 500) DDPM-1000 reverse chain of the dim-128
+trajectory U-Net (seed-42 random-init weights), batch 1024 control instances per GPU, synthetic u0/uT, in-kernel
+Philox noise, then solver rollout + J/safety scoring.
+
+  step      = ONE reverse-diffusion step over the whole batch: U-Net evaluation + fused guided posterior update
+              (the chain is 1000 such steps of identical cost; timing whole chains would take minutes per step)
+  value     = samples/s of the full job = N*B / (1000 * step_time + rollout_and_scoring_time), device-timed
+  e2e       = samples/s of ONE full call through the public API with HOST buffers: pinned u0/uT/target -> H2D ->
+              GaussianDiffusion.sample (all 1000 steps) -> control_and_score -> all-gather -> metrics on the host
+  roofline  = the tcgen05 conv kernel: algorithmic conv FLOPs of its launches / their summed CUDA-event durations
+  cpu_baseline / --impl reference = the oracle port of the reference's PyTorch-CPU path on the host cores
+Multi-GPU (torchrun): weak scaling, B per rank fixed, independent shards, one all-gather of J/violation vectors.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+CHAIN_STEPS = 1000
+CONV_GFLOP_PER_SAMPLE = 27.811 - 0.0771 - 0.0016  # tcgen05 convs only: minus the 7x7 stem and the 3-channel head
+W_SCORE, U_BOUND, Q_GUIDE = 500.0, 0.8, 0.0
+
+
+class Cfg:
+    use_max_safety = True
+    u_bound = U_BOUND
+    guidance_weights = {"w_score": W_SCORE}
+    nt = 11
+    InfFT_Q = None
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return d, "measured"
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        sm = [float(r[0]) for r in self.rows if len(r) >= 7 and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) >= 7 and r[1].replace(".", "").isdigit()]
+        reasons = set()
+        for r in self.rows:
+            if len(r) >= 7:
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+        busy = sorted(sm)[len(sm) // 2:] if sm else []
+        return {"sm_mhz": float(np.median(busy)) if busy else None, "sm_max_mhz": mx[0] if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def dist_setup(n_gpus):
+    import torch.distributed as dist
+    ws = int(os.environ.get("WORLD_SIZE", "1"))
+    if ws > 1:
+        rank, local = int(os.environ["RANK"]), int(os.environ.get("LOCAL_RANK", "0"))
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        return dist, rank, ws, local
+    return None, 0, 1, 0
+
+
+def max_over_ranks(dist, x):
+    if dist is None:
+        return x
+    t = torch.tensor([x], device="cuda", dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return t.item()
+
+
+def barrier(dist):
+    if dist is not None:
+        dist.barrier()
+    torch.cuda.synchronize()
+
+
+# ------------------------------------------------------------------------------------------------ CPU baseline
+def cpu_chain_and_solver_sample(steps, B=8):
+    """Oracle port of the reference's PyTorch-CPU path (all host threads): `steps` guided DDPM reverse steps at batch B
+    with the fp32 torch U-Net + the 10,000-step torch rollout loop truncated to 1,000 steps (x10 extrapolated)."""
+    from oracle import diffusion_ref as dr, unet_ref, solver_ref
+    import safediffcon_b200 as s
+    from safediffcon_b200.synthetic import burgers_instances
+    torch.set_num_threads(os.cpu_count() or 1)
+    torch.manual_seed(42)
+    net = s.Unet2D(dim=128, dim_mults=(1, 2, 4, 8), channels=3, resnet_block_groups=1)
+    sd = {k: v.detach() for k, v in net.state_dict().items()}
+    bufs = dr.schedule_buffers(1000)
+    g = torch.Generator().manual_seed(1)
+    x = torch.randn(B, 3, 16, 128, generator=g)
+    guide = dict(Q=Q_GUIDE, w_score=W_SCORE, u_bound=U_BOUND, use_max_safety=True)
+    times = []
+    with torch.no_grad():
+        for i in range(steps + 1):
+            t = 999 - i
+            t0 = time.perf_counter()
+            e = unet_ref.unet_forward(sd, x, torch.full((B,), t, dtype=torch.long))
+            eps, x0 = dr.predictions(bufs, x, t, e, False, guide)
+            x0 = x0.clamp(-1, 1)
+            x = bufs["posterior_mean_coef1"][t] * x0 + bufs["posterior_mean_coef2"][t] * x + \
+                (0.5 * bufs["posterior_log_variance_clipped"][t]).exp() * torch.randn(x.shape, generator=g)
+            if i > 0:  # first step = warm-up
+                times.append(time.perf_counter() - t0)
+    t_step = float(np.mean(times))
+    u0, f = burgers_instances(1024, seed=2)
+    t0 = time.perf_counter()
+    solver_ref.solve_free_torch(torch.from_numpy(u0), torch.from_numpy(f), T=0.1, dt=1e-4, num_t=10)
+    t_solve_1024 = (time.perf_counter() - t0) * 10.0
+    return t_step, t_solve_1024
+
+
+def cpu_baseline_obj(steps=8):
+    B = 8
+    t_step, t_solve = cpu_chain_and_solver_sample(steps, B)
+    chain_s = CHAIN_STEPS * t_step
+    return {"value": B / (chain_s + t_solve * B / 1024.0), "unit": "samples/s", "cores": os.cpu_count(), "kind": "port",
+            "sample": f"{steps} guided DDPM reverse steps at B={B} (fp32 torch-CPU U-Net + posterior update, {t_step:.3f} s/step, "
+                      f"x{CHAIN_STEPS} steps extrapolated) + torch-CPU rollout loop of 1024 trajectories for 1,000 of 10,000 steps (x10)",
+            "rollouts_per_s": 1024.0 / t_solve, "torch_threads": torch.get_num_threads()}
+
+
+def run_reference_arm(args):
+    ws, rank = int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    B = 8
+    vals, tsteps = [], []
+    for k in range(args.warmup + args.steps):
+        t_step, t_solve = cpu_chain_and_solver_sample(2, B)
+        if k >= args.warmup:
+            vals.append(B / (CHAIN_STEPS * t_step + t_solve * B / 1024.0))
+            tsteps.append(t_step)
+    v = float(np.mean(vals))
+    line = {"impl": "reference", "metric": "guided_ddpm_chain_samples_per_s", "value": v, "unit": "samples/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": float(np.mean(tsteps)) * 1e3, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": workload_config(args, B_ref=B),
+            "cpu_baseline": {"value": v, "unit": "samples/s", "cores": os.cpu_count(), "kind": "port",
+                             "sample": "each step = 2 guided DDPM reverse steps at B=8 on the host cores (oracle port of the reference's "
+                                       "PyTorch-CPU path: /root/reference is absent on the GPU box) + 1/10 of a 1024-trajectory rollout"},
+            "e2e": {"value": v, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args, B_ref=None):
+    return {"workload": "BASELINE configs[1]: 1D Burgers guided sampling, full DDPM-1000 chain, U-Net dim=128 mults (1,2,4,8), "
+                        "safety guidance w_score=500 Q=0, + burgers rollout/J/safety scoring",
+            "batch_per_gpu": args.batch if B_ref is None else B_ref, "chain_steps": CHAIN_STEPS,
+            "step": "one reverse-diffusion step (U-Net eval + fused guided posterior update) over the whole batch",
+            "l2": "per-step working set (activations ~10 GB at B=1024) exceeds the 126 MB L2; no flush needed",
+            "parallelism": f"dp{args.gpus} (independent shards, all-gather of J/violation vectors only)"}
+
+
+# ------------------------------------------------------------------------------------------------ GPU arm
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--batch", type=int, default=1024, help="control instances per GPU")
+    ap.add_argument("--no-e2e", action="store_true", help="skip the full-chain end-to-end call")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg")
+    ap.add_argument("--solver-n", type=int, default=100000, help="trajectories of the rollout-only measurement (config 3)")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+    if args.impl == "reference":
+        return run_reference_arm(args)
+
+    import safediffcon_b200 as s
+    from safediffcon_b200 import _lib as L, runner, unet as U
+    from safediffcon_b200.synthetic import burgers_instances
+    dist, rank, ws, local = dist_setup(args.gpus)
+    if ws == 1:
+        torch.cuda.set_device(0)
+    dev = torch.device("cuda", torch.cuda.current_device())
+    B = args.batch
+    pk, pk_kind = peaks()
+
+    torch.manual_seed(42)
+    net = s.Unet2D(dim=128, dim_mults=(1, 2, 4, 8), channels=3, resnet_block_groups=1)
+    gd = s.GaussianDiffusion(net, seq_length=(16, 128), timesteps=1000, sampling_timesteps=1000, temporal=True, use_conv2d=True,
+                             is_condition_u0=True, is_condition_uT=True, condition_idx=10, train_on_padded_locations=False).to(dev)
+    # synthetic control instances of this rank's shard (global index = rank*B + i): u0 and target from the generator
+    u0_np, f_np = burgers_instances(B, seed=1000 + rank)
+    tgt_np, _ = burgers_instances(B, seed=5000 + rank)
+    u0_h = torch.from_numpy(u0_np / 10.0).pin_memory()
+    uT_h = torch.from_numpy(tgt_np / 10.0).pin_memory()
+    tgt_h = torch.from_numpy(tgt_np).pin_memory()
+    cfg = Cfg()
+    guide = s.safety_guidance(cfg, Q_GUIDE)
+
+    # ---- device-timed reverse steps (inputs resident in HBM) ----
+    u0_d, uT_d = u0_h.to(dev), uT_h.to(dev)
+    table, times, rows = gd._coef_table(1, None)
+    gs = guide.struct()
+    img = torch.empty(B, 3, 16, 128, device=dev)
+    nxt = torch.empty_like(img)
+    L.check(L.lib().sdc_fill_normal(L.ptr(img), B, img[0].numel(), 2024, rank * B, 0x7FFFFFFF, L.stream_ptr()))
+    L.check(L.lib().sdc_write_conditions(L.ptr(img), L.ptr(u0_d), L.ptr(uT_d), None, 10, 1, B, 16, 128, L.stream_ptr()))
+
+    def one_step(i):
+        nonlocal img, nxt
+        eps = net.denoise_uniform(img, times[i])
+        gd._step(1, img, eps, None, nxt, table, i, gs, None, (u0_d, uT_d, None), True, 2024, rank * B)
+        img, nxt = nxt, img
+
+    for i in range(args.warmup):
+        one_step(i)
+    barrier(dist)
+    sampler = ClockSampler(local)
+    sampler.start()
+    launches0 = L.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(args.steps):
+        one_step(args.warmup + i)
+    e1.record()
+    barrier(dist)
+    clocks = sampler.stop()
+    launches = L.launch_count() - launches0
+    ms_step = max_over_ranks(dist, e0.elapsed_time(e1) / args.steps)
+
+    # ---- rollout + scoring of this batch (device-timed) and the rollout-only measurement (config 3) ----
+    pred = img * 10.0
+    tgt_d = tgt_h.to(dev)
+    for _ in range(2):
+        runner.control_and_score(pred, tgt_d, U_BOUND, want_traj=False)
+    barrier(dist)
+    e0.record()
+    runner.control_and_score(pred, tgt_d, U_BOUND, want_traj=False)
+    e1.record()
+    barrier(dist)
+    ms_score = max_over_ranks(dist, e0.elapsed_time(e1))
+    n_loc = args.solver_n // ws
+    su0, sf = burgers_instances(n_loc, seed=77 + rank)
+    su0_d, sf_d = torch.from_numpy(su0).to(dev), torch.from_numpy(sf).to(dev)
+    for _ in range(2):
+        s.burgers_numeric_solve_free(su0_d, sf_d, 0.01, 1.0)
+    barrier(dist)
+    e0.record()
+    s.burgers_numeric_solve_free(su0_d, sf_d, 0.01, 1.0)
+    e1.record()
+    barrier(dist)
+    ms_solver = max_over_ranks(dist, e0.elapsed_time(e1))
+    del su0_d, sf_d
+
+    chain_s = CHAIN_STEPS * ms_step / 1e3 + ms_score / 1e3
+    value = ws * B / chain_s
+
+    # ---- roofline of the dominant kernel (tcgen05 conv): per-launch CUDA events over 2 instrumented steps ----
+    U.PROFILE = []
+    for i in range(2):
+        one_step(args.warmup + args.steps + i)
+    torch.cuda.synchronize()
+    prof, U.PROFILE = U.PROFILE, None
+    conv_ms = sum(a.elapsed_time(b) for a, b, _, _ in prof) / 2
+    conv_flops = sum(fl for _, _, fl, _ in prof) / 2
+    n_conv = len(prof) // 2
+    achieved = conv_flops / (conv_ms * 1e-3) / 1e12
+    peak = pk.get("bf16_tflops_sustained", pk.get("bf16_tflops"))
+    roof = {"bound": "tensor", "kernel": "sdc::conv_gemm_kernel (tcgen05.mma kind::tf32, TMA operands)", "achieved": achieved,
+            "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None,
+            "peak_source": f"{pk_kind} bf16_tflops_sustained (kernel timed inside a long step); the kernel computes in TF32 whose "
+                           "hardware rate is half the BF16 rate, so frac_of_tf32_rate = 2*frac",
+            "frac_of_tf32_rate": 2 * achieved / peak, "launches_per_step": n_conv, "conv_ms_per_step": conv_ms,
+            "conv_share_of_step": conv_ms / ms_step, "algorithmic_gflop_per_step": conv_flops / 1e9}
+
+    # ---- end to end through the public API with host buffers: one full chain + control + scoring ----
+    e2e = None
+    if not args.no_e2e:
+        barrier(dist)
+        t0 = time.perf_counter()
+        predicted = runner.sample_controls(gd, u0_h, uT_h, cfg, Q_GUIDE, sample_offset=rank * B, seed=2024)
+        metrics, _ = runner.evaluate_controls(predicted, tgt_h, U_BOUND, n_total=ws * B)
+        barrier(dist)
+        t_e2e = max_over_ranks(dist, time.perf_counter() - t0)
+        e2e = {"value": ws * B / t_e2e, "unit": "samples/s", "h2d_bytes_per_step": int(3 * B * 128 * 4),
+               "d2h_bytes_per_step": int(4 * ws * B * 4), "seconds": t_e2e, "chains": 1,
+               "what": "pinned host u0/uT/target -> GaussianDiffusion.sample (1000 DDPM steps, fused safety guidance) -> "
+                       "control_and_score -> all-gather -> metrics dict on the host",
+               "J": metrics["control_mse_mean (J)"], "R_p": metrics["point_exceed_ratio (R_p)"],
+               "R_s": metrics["sample_exceed_ratio (R_s)"]}
+
+    if rank == 0:
+        line = {"metric": "guided_ddpm_chain_samples_per_s", "value": value, "unit": "samples/s", "n_gpus": ws, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "tf32", "data": "synthetic", "config": workload_config(args), "clocks": clocks, "gpu_launches": int(launches),
+                "roofline": roof,
+                "solver": {"rollouts_per_s": ws * n_loc / (ms_solver / 1e3), "n": ws * n_loc, "ms": ms_solver, "mode": "strict fp32",
+                           "fp32_tflops_algorithmic": ws * n_loc * 17.92e6 / (ms_solver / 1e3) / 1e12,
+                           "score_ms_for_batch": ms_score},
+                "e2e": e2e if e2e is not None else {"value": None, "unit": "samples/s", "h2d_bytes_per_step": 0,
+                                                    "d2h_bytes_per_step": 0, "skipped": True}}
+        if not args.no_cpu and ws >= 1:
+            line["cpu_baseline"] = cpu_baseline_obj()
+        print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -102,9 +102,20 @@ def _st():
     return L.stream_ptr()
 
 
+PROFILE = None  # bench.py sets this to a list: every conv launch is then bracketed by CUDA events on its stream
+
+
 def conv_gemm(kind, a0, c0, a1, c1, wp, bias, residual, out, stats, round_tf32, B, H, W, Cout):
+    prof = PROFILE
+    if prof is not None:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
     L.check(L.lib().sdc_conv_gemm(kind, L.ptr(a0), c0, L.ptr(a1), c1, L.ptr(wp), L.ptr(bias), L.ptr(residual), L.ptr(out),
                                   L.ptr(stats), int(round_tf32), B, H, W, Cout, _st()))
+    if prof is not None:
+        e1.record()
+        taps = {KIND_1x1: 1, KIND_3x3: 9, KIND_UNSHUFFLE: 4}[kind]
+        prof.append((e0, e1, 2.0 * B * H * W * Cout * taps * (c0 + c1), (kind, B, H, W, c0 + c1, Cout)))
 
 
 def pack_conv_weight(kind, w):
