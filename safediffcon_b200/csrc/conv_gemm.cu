@@ -6,16 +6,17 @@
 //   K = taps * Cin   (3x3 pad 1: 9 taps; 1x1: 1 tap; pixel-unshuffle 2x2/stride 2: 4 taps),
 //       Cin may be the concatenation of two tensors (U-Net skip connections) -> two K segments, no torch.cat.
 //
-// Mapping (one CTA = one 128 x BN output tile, 192 threads):
+// Mapping (persistent: one CTA per SM walks a contiguous range of 128 x BN output tiles, 192 threads):
 //   warp 0   TMA producer: per K block (32 channels of one tap) one 4-D/5-D box load of the shifted activation
 //            window (out-of-bounds rows/cols are zero-filled by TMA = the conv padding) + one 2-D load of the
 //            weight slab, both SWIZZLE_128B, completing on an mbarrier;
 //   warp 1   allocates TMEM, then one thread issues tcgen05.mma.kind::tf32 (M=128, N=BN, K=8) x4 per K block,
 //            accumulating in TMEM, and releases smem stages with tcgen05.commit;
-//   warps 2-5 epilogue: tcgen05.ld the accumulator (each warp owns its 32-lane TMEM quarter), add bias /
+//   warps 2-5 epilogue: tcgen05.ld the accumulator (each warp owns its 32-lane TMEM quarter), transpose it through
+//            a padded smem staging tile so that global stores are full 128-byte row segments, add bias /
 //            residual, accumulate per-sample GroupNorm statistics (sum, sum of squares -> fp64 atomics),
-//            optionally round to TF32 (so that the next conv's operands are round-to-nearest, not truncated)
-//            and store NHWC rows.
+//            optionally round to TF32 (so that the next conv's operands are round-to-nearest, not truncated).
+//   The accumulator is double buffered in TMEM (2 x BN columns): the epilogue of tile i overlaps the MMAs of i+1.
 // Precision: TF32 operands (10-bit mantissa, rounded to nearest when produced), FP32 accumulation.
 #include "common.cuh"
 #include <cuda.h>
@@ -113,6 +114,8 @@ constexpr int BM = 128;        // output pixels per tile (= UMMA M)
 constexpr int BK = 32;         // TF32 elements per K block (= 128 bytes = one swizzle row)
 constexpr int A_BYTES = BM * BK * 4;
 constexpr int GEMM_THREADS = 192;
+constexpr int STG_LD = 36;     // staging row stride in floats (32 + 4: conflict-free 16-byte accesses)
+constexpr int STG_BYTES = 4 * 32 * STG_LD * 4;
 
 struct GemmParams {
     int kind;            // 0: 1x1, 1: 3x3 pad 1, 2: 2x2 stride-2 (pixel-unshuffle + 1x1)
@@ -125,41 +128,53 @@ struct GemmParams {
     int stages;
     int round_tf32;
     int hw_per_sample;   // H*W
+    int tiles_n;         // Cout / bn
+    int tiles_total;     // tiles_m * tiles_n, tile id = m * tiles_n + n (consecutive ids share the A window)
+    int tiles_per_cta;
     const float* bias;       // [Cout] or null
     const float* residual;   // [M, Cout] or null (added after bias)
     float* out;              // [M, Cout]
     double* stats;           // [B, 2] (sum, sumsq) accumulated with atomics, or null
 };
 
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+// Persistent kernel: one CTA per SM walks a contiguous range of output tiles.  The accumulator is double
+// buffered in TMEM so the epilogue of tile i overlaps the MMA main loop of tile i+1.
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ CUtensorMap map_a1,
                  const __grid_constant__ CUtensorMap map_w, const GemmParams p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     const int stage_bytes = A_BYTES + p.bn * BK * 4;
-    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + p.stages * stage_bytes);
+    float* staging = reinterpret_cast<float*>(smem + p.stages * stage_bytes);
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + p.stages * stage_bytes + STG_BYTES);
     uint64_t* empty_bar = full_bar + p.stages;
-    uint64_t* acc_bar = empty_bar + p.stages;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_bar + 1);
+    uint64_t* acc_full = empty_bar + p.stages;   // [2]
+    uint64_t* acc_empty = acc_full + 2;          // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int mt = blockIdx.x, nt = blockIdx.y;
     const int taps = p.kind == 1 ? 9 : (p.kind == 2 ? 4 : 1);
     const int ctot = p.c0 + p.c1;
     const int chunks = ctot / BK;
     const int num_kb = taps * chunks;
-    uint32_t tmem_cols = 32;
-    while ((int)tmem_cols < p.bn) tmem_cols <<= 1;
+    uint32_t acc_cols = 32;                      // TMEM columns per accumulator buffer (power of two >= bn)
+    while ((int)acc_cols < p.bn) acc_cols <<= 1;
+    const int tile_lo = blockIdx.x * p.tiles_per_cta;
+    const int tile_hi = min(p.tiles_total, tile_lo + p.tiles_per_cta);
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&map_a0);
         if (p.c1) tma_prefetch_desc(&map_a1);
         tma_prefetch_desc(&map_w);
         for (int s = 0; s < p.stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-        mbar_init(acc_bar, 1);
+        for (int b = 0; b < 2; ++b) { mbar_init(&acc_full[b], 1); mbar_init(&acc_empty[b], 4); }
         fence_barrier_init();
     }
-    if (warp == 1) tmem_alloc(tmem_slot, tmem_cols);
+    if (warp == 1) tmem_alloc(tmem_slot, 2 * acc_cols);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -167,99 +182,122 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_consta
 
     if (warp == 0) {
         if (lane == 0) {
-            // tile origin in (image, row); tiles always span full rows (bw == W)
-            const int pix0 = mt * BM;
-            const int b0 = pix0 / p.hw_per_sample;
-            const int h0 = (pix0 - b0 * p.hw_per_sample) / p.W;
             const uint32_t tx = (uint32_t)stage_bytes;
-            for (int kb = 0; kb < num_kb; ++kb) {
-                const int s = kb % p.stages;
-                const uint32_t ph = (uint32_t)(kb / p.stages) & 1u;
-                mbar_wait(&empty_bar[s], ph ^ 1u);
-                uint8_t* sa = smem + s * stage_bytes;
-                uint8_t* sb = sa + A_BYTES;
-                mbar_expect_tx(&full_bar[s], tx);
-                const int tap = kb / chunks;
-                const int cc = (kb - tap * chunks) * BK;          // channel offset in the concatenated input
-                const bool second = cc >= p.c0;
-                const CUtensorMap* ma = second ? &map_a1 : &map_a0;
-                const int cseg = second ? cc - p.c0 : cc;
-                if (p.kind == 2) {
-                    // input viewed as [B, H, 2(p1), W, 2*C]: coordinate (p2*C + c, w, p1, h, b)
-                    const int cin = second ? p.c1 : p.c0;
-                    tma_load_5d(sa, ma, &full_bar[s], (tap & 1) * cin + cseg, 0, tap >> 1, h0, b0);
-                } else {
-                    const int dy = p.kind == 1 ? tap / 3 - 1 : 0;
-                    const int dx = p.kind == 1 ? tap % 3 - 1 : 0;
-                    tma_load_4d(sa, ma, &full_bar[s], cseg, dx, h0 + dy, b0);
+            int g = 0;  // running K-block counter across tiles (smem ring position)
+            for (int tile = tile_lo; tile < tile_hi; ++tile) {
+                const int mt = tile / p.tiles_n, nt = tile - mt * p.tiles_n;
+                // tile origin in (image, row); tiles always span full rows (bw == W)
+                const int pix0 = mt * BM;
+                const int b0 = pix0 / p.hw_per_sample;
+                const int h0 = (pix0 - b0 * p.hw_per_sample) / p.W;
+                for (int kb = 0; kb < num_kb; ++kb, ++g) {
+                    const int s = g % p.stages;
+                    const uint32_t ph = (uint32_t)(g / p.stages) & 1u;
+                    mbar_wait(&empty_bar[s], ph ^ 1u);
+                    uint8_t* sa = smem + s * stage_bytes;
+                    uint8_t* sb = sa + A_BYTES;
+                    mbar_expect_tx(&full_bar[s], tx);
+                    const int tap = kb / chunks;
+                    const int cc = (kb - tap * chunks) * BK;          // channel offset in the concatenated input
+                    const bool second = cc >= p.c0;
+                    const CUtensorMap* ma = second ? &map_a1 : &map_a0;
+                    const int cseg = second ? cc - p.c0 : cc;
+                    if (p.kind == 2) {
+                        // input viewed as [B, H, 2(p1), W, 2*C]: coordinate (p2*C + c, w, p1, h, b)
+                        const int cin = second ? p.c1 : p.c0;
+                        tma_load_5d(sa, ma, &full_bar[s], (tap & 1) * cin + cseg, 0, tap >> 1, h0, b0);
+                    } else {
+                        const int dy = p.kind == 1 ? tap / 3 - 1 : 0;
+                        const int dx = p.kind == 1 ? tap % 3 - 1 : 0;
+                        tma_load_4d(sa, ma, &full_bar[s], cseg, dx, h0 + dy, b0);
+                    }
+                    tma_load_2d(sb, &map_w, &full_bar[s], tap * ctot + cc, nt * p.bn);
                 }
-                tma_load_2d(sb, &map_w, &full_bar[s], tap * ctot + cc, nt * p.bn);
             }
         }
     } else if (warp == 1) {
         if (lane == 0) {
             const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(p.bn >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
-            for (int kb = 0; kb < num_kb; ++kb) {
-                const int s = kb % p.stages;
-                const uint32_t ph = (uint32_t)(kb / p.stages) & 1u;
-                mbar_wait(&full_bar[s], ph);
+            int g = 0, it = 0;
+            for (int tile = tile_lo; tile < tile_hi; ++tile, ++it) {
+                const int buf = it & 1;
+                mbar_wait(&acc_empty[buf], ((uint32_t)(it >> 1) & 1u) ^ 1u);   // epilogue has drained this buffer
                 tc_fence_after();
-                const uint32_t sa = smem_u32(smem + s * stage_bytes);
-                const uint64_t adesc = make_sw128_desc(sa);
-                const uint64_t bdesc = make_sw128_desc(sa + A_BYTES);
+                const uint32_t tmem_d = tmem_base + (uint32_t)buf * acc_cols;
+                for (int kb = 0; kb < num_kb; ++kb, ++g) {
+                    const int s = g % p.stages;
+                    const uint32_t ph = (uint32_t)(g / p.stages) & 1u;
+                    mbar_wait(&full_bar[s], ph);
+                    tc_fence_after();
+                    const uint32_t sa = smem_u32(smem + s * stage_bytes);
+                    const uint64_t adesc = make_sw128_desc(sa);
+                    const uint64_t bdesc = make_sw128_desc(sa + A_BYTES);
 #pragma unroll
-                for (int k = 0; k < BK / 8; ++k) {
-                    // advance 8 TF32 = 32 bytes along K inside the 128-byte swizzle row: +2 in the (addr >> 4) field
-                    umma_tf32(tmem_base, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kb | k) != 0);
+                    for (int k = 0; k < BK / 8; ++k) {
+                        // advance 8 TF32 = 32 bytes along K inside the 128-byte swizzle row: +2 in the (addr >> 4) field
+                        umma_tf32(tmem_d, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kb | k) != 0);
+                    }
+                    umma_commit(&empty_bar[s]);
                 }
-                umma_commit(&empty_bar[s]);
+                umma_commit(&acc_full[buf]);
             }
-            umma_commit(acc_bar);
         }
     } else {
         // ---- epilogue: warp w may only touch TMEM lanes [32*(w%4), 32*(w%4)+32) ----
         const int q = warp & 3;
-        const int row = q * 32 + lane;
-        const int m = mt * BM + row;
-        const bool row_ok = m < p.M;
-        mbar_wait(acc_bar, 0);
-        tc_fence_after();
-        float* orow = p.out + (size_t)m * p.Cout + (size_t)nt * p.bn;
-        const float* rrow = p.residual ? p.residual + (size_t)m * p.Cout + (size_t)nt * p.bn : nullptr;
-        float s1 = 0.f, s2 = 0.f;
-        for (int c = 0; c < p.bn; c += 32) {
-            uint32_t r[32];
-            tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c, r);
-            const int ncol0 = nt * p.bn + c;
-            if (row_ok) {
+        float* stg = staging + q * 32 * STG_LD;
+        const int sub_r = lane >> 3, sub_c = (lane & 7) * 4;   // coalesced phase: 4 rows x 8 float4 per instruction
+        int it = 0;
+        for (int tile = tile_lo; tile < tile_hi; ++tile, ++it) {
+            const int mt = tile / p.tiles_n, nt = tile - mt * p.tiles_n;
+            const int buf = it & 1;
+            mbar_wait(&acc_full[buf], (uint32_t)(it >> 1) & 1u);
+            tc_fence_after();
+            const int m_w = mt * BM + q * 32;          // first row of this warp
+            float s1 = 0.f, s2 = 0.f;
+            for (int c = 0; c < p.bn; c += 32) {
+                uint32_t r[32];
+                tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)buf * acc_cols + (uint32_t)c, r);
 #pragma unroll
-                for (int j = 0; j < 32; j += 4) {
-                    float4 v = make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]),
-                                           __uint_as_float(r[j + 3]));
-                    if (p.bias) {
-                        const float4 bv = __ldg(reinterpret_cast<const float4*>(p.bias + ncol0 + j));
+                for (int j = 0; j < 32; j += 4)
+                    *reinterpret_cast<float4*>(stg + lane * STG_LD + j) =
+                        make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
+                __syncwarp();
+                const int col = nt * p.bn + c + sub_c;
+                float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (p.bias) bv = __ldg(reinterpret_cast<const float4*>(p.bias + col));
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const int rr = sub_r + 4 * i;
+                    const int m = m_w + rr;
+                    if (m < p.M) {
+                        float4 v = *reinterpret_cast<const float4*>(stg + rr * STG_LD + sub_c);
                         v.x += bv.x; v.y += bv.y; v.z += bv.z; v.w += bv.w;
+                        if (p.residual) {
+                            const float4 rv = __ldg(reinterpret_cast<const float4*>(p.residual + (size_t)m * p.Cout + col));
+                            v.x += rv.x; v.y += rv.y; v.z += rv.z; v.w += rv.w;
+                        }
+                        s1 += (v.x + v.y) + (v.z + v.w);
+                        s2 += (v.x * v.x + v.y * v.y) + (v.z * v.z + v.w * v.w);
+                        if (p.round_tf32) { v.x = to_tf32(v.x); v.y = to_tf32(v.y); v.z = to_tf32(v.z); v.w = to_tf32(v.w); }
+                        *reinterpret_cast<float4*>(p.out + (size_t)m * p.Cout + col) = v;
                     }
-                    if (rrow) {
-                        const float4 rv = __ldg(reinterpret_cast<const float4*>(rrow + c + j));
-                        v.x += rv.x; v.y += rv.y; v.z += rv.z; v.w += rv.w;
-                    }
-                    s1 += (v.x + v.y) + (v.z + v.w);
-                    s2 += (v.x * v.x + v.y * v.y) + (v.z * v.z + v.w * v.w);
-                    if (p.round_tf32) { v.x = to_tf32(v.x); v.y = to_tf32(v.y); v.z = to_tf32(v.z); v.w = to_tf32(v.w); }
-                    *reinterpret_cast<float4*>(orow + c + j) = v;
                 }
+                __syncwarp();
             }
-        }
-        if (p.stats) {
-            // all 32 rows of a warp belong to one sample (H*W is a multiple of 32)
-            s1 = warp_sum(s1);
-            s2 = warp_sum(s2);
-            const int m_w = mt * BM + q * 32;
-            if (lane == 0 && m_w < p.M) {
-                const int b = m_w / p.hw_per_sample;
-                atomicAdd(p.stats + 2 * b, (double)s1);
-                atomicAdd(p.stats + 2 * b + 1, (double)s2);
+            // accumulator buffer fully read -> hand it back to the MMA warp
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&acc_empty[buf]);
+            if (p.stats) {
+                // all 32 rows of a warp belong to one sample (H*W is a multiple of 32)
+                s1 = warp_sum(s1);
+                s2 = warp_sum(s2);
+                if (lane == 0 && m_w < p.M) {
+                    const int b = m_w / p.hw_per_sample;
+                    atomicAdd(p.stats + 2 * b, (double)s1);
+                    atomicAdd(p.stats + 2 * b + 1, (double)s2);
+                }
             }
         }
         tc_fence_before();
@@ -267,7 +305,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_consta
     __syncthreads();
     if (warp == 1) {
         tc_fence_after();
-        tmem_dealloc(tmem_base, tmem_cols);
+        tmem_dealloc(tmem_base, 2 * acc_cols);
     }
 }
 
@@ -341,10 +379,20 @@ extern "C" int sdc_conv_gemm(int kind, const float* a0, int c0, const float* a1,
     p.c0 = c0; p.c1 = c1; p.round_tf32 = round_tf32; p.hw_per_sample = H * W;
     p.bias = bias; p.residual = residual; p.out = out; p.stats = stats;
     const int stage_bytes = A_BYTES + bn * BK * 4;
-    int stages = (200 * 1024) / stage_bytes;
+    int stages = (190 * 1024) / stage_bytes;
     if (stages > 6) stages = 6;
     p.stages = stages;
-    const int smem_bytes = stages * stage_bytes + (2 * stages + 1) * 8 + 16 + 1024;
+    const int smem_bytes = stages * stage_bytes + STG_BYTES + (2 * stages + 4) * 8 + 16 + 1024;
+    int n_sm = 148;
+    {
+        int dev = 0;
+        SDC_CUDA(cudaGetDevice(&dev));
+        SDC_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
+    }
+    p.tiles_n = Cout / bn;
+    p.tiles_total = ((p.M + BM - 1) / BM) * p.tiles_n;
+    const int ctas = p.tiles_total < n_sm ? p.tiles_total : n_sm;
+    p.tiles_per_cta = (p.tiles_total + ctas - 1) / ctas;
 
     CUtensorMap ma0, ma1, mw;
     int rc = encode_act(&ma0, a0, kind, B, H, W, c0, bh, bb);
@@ -363,7 +411,7 @@ extern "C" int sdc_conv_gemm(int kind, const float* a0, int c0, const float* a1,
         SDC_CUDA(cudaFuncSetAttribute(conv_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         attr_set = true;
     }
-    dim3 grid((unsigned)((p.M + BM - 1) / BM), (unsigned)(Cout / bn));
+    const int grid = (p.tiles_total + p.tiles_per_cta - 1) / p.tiles_per_cta;
     conv_gemm_kernel<<<grid, GEMM_THREADS, smem_bytes, as_stream(stream)>>>(ma0, ma1, mw, p);
     SDC_LAUNCHED();
     return SDC_OK;
