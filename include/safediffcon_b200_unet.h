@@ -28,6 +28,13 @@ int sdc_conv_gemm(int kind, const float* a0, int c0, const float* a1, int c1, co
                   const float* residual, float* out, double* stats, int round_tf32, int B, int H, int W, int Cout,
                   void* stream);
 
+/* Same contract as sdc_conv_gemm(kind = 3x3) for the full-resolution level: W == 128 and Cout <= 128.  One CTA computes
+ * two image rows and loads the activation halo once per 32-channel chunk (the 9 taps are shifted UMMA descriptor views of
+ * it), cutting L2->SMEM operand traffic ~2.8x.  Returns -1 (and does nothing) when the shape is not eligible. */
+int sdc_conv3x3_row(const float* a0, int c0, const float* a1, int c1, const float* w_packed, const float* bias,
+                    const float* residual, float* out, double* stats, int round_tf32, int B, int H, int W, int Cout,
+                    void* stream);
+
 /* Stem: 7x7 pad 3 convolution of the NCHW model input (unet.py:326,392).  x:[B,Cin,H,W] NCHW, w:[Cout,Cin,7,7] OIHW
  * (unpacked, fp32), out: NHWC [B*H*W, Cout] rounded to TF32.  FP32 CUDA-core kernel (0.3% of the FLOPs). */
 int sdc_stem_conv7(const float* x, const float* w, const float* bias, float* out, int B, int Cin, int H, int W, int Cout,

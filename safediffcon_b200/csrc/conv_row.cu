@@ -1,0 +1,259 @@
+// 3x3 convolution for the full-resolution level (W = 128, Cout <= 128) with ACTIVATION-HALO REUSE.
+//
+// Same math as conv_gemm.cu kind 1 (reference: nn.Conv2d(C, C', 3, padding=1) inside Block / Upsample2d,
+// /root/reference/1D/model/unet.py:132,33-37,370), different data movement.  The generic implicit GEMM re-loads
+// the activation window once per tap (9x) and, with only 128 output channels, is bound by L2->SMEM operand
+// traffic (ncu: ~50 B/clk/SM, tensor pipe 30-39% active).  Here one CTA computes TWO image rows (M = 2 x 128
+// pixels) per tile and, per 32-channel chunk, loads the 4 x 130-pixel halo ONCE (66.5 KB, one TMA box with zero
+// fill = padding); the nine taps' A operands are row-shifted views of that halo, expressed purely through the
+// UMMA shared-memory descriptor start address (the 128B swizzle phase follows the absolute address).  Each weight tile is
+// used by both rows.  Operand traffic drops from 64 to ~23 KB per 128x128x32 MAC block.
+//
+//   warp 0   TMA producer: halo ring (2 stages) + weight-tile ring (4 stages)
+//   warp 1   MMA issuer: 9 taps x 2 rows x 4 (K=8) tcgen05.mma.kind::tf32 per chunk, accumulators in TMEM
+//            (2 rows x Cout columns, double buffered)
+//   warps 2-5 epilogue (same as conv_gemm.cu): TMEM -> smem transpose -> coalesced rows, bias, GN statistics
+#include "tc_ptx.cuh"
+#include <math.h>
+#include <stdlib.h>
+
+namespace sdc {
+
+constexpr int RW = 128;                      // image width handled by this kernel (= UMMA M)
+constexpr int HALO_W = RW + 2;
+constexpr int HALO_ROWS = 4 * HALO_W;        // 520 pixel rows of 128 bytes
+constexpr int HALO_BYTES = HALO_ROWS * 128;  // 66,560 = 65 * 1024 (keeps every stage 1024-byte aligned)
+constexpr int ROW_BSTAGES = 4;
+constexpr int ROW_THREADS = 192;
+constexpr int RSTG_LD = 36;
+constexpr int RSTG_BYTES = 4 * 32 * RSTG_LD * 4;
+
+struct RowParams {
+    int B, H, Cout, bn;      // bn = Cout (single N tile, multiple of 32, <= 128)
+    int c0, c1;
+    int pairs_total, pairs_per_cta, pairs_per_image;
+    int round_tf32;
+    const float* bias;
+    const float* residual;
+    float* out;
+    double* stats;
+};
+
+__global__ void __launch_bounds__(ROW_THREADS, 1)
+conv_row_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ CUtensorMap map_a1,
+                const __grid_constant__ CUtensorMap map_w, const RowParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    const int b_bytes = p.bn * 128;
+    uint8_t* halo = smem;                                   // [2][HALO_BYTES]
+    uint8_t* bring = smem + 2 * HALO_BYTES;                 // [ROW_BSTAGES][b_bytes] (b_bytes multiple of 4096)
+    float* staging = reinterpret_cast<float*>(bring + ROW_BSTAGES * b_bytes);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(staging) + RSTG_BYTES);
+    uint64_t* halo_full = bars;            // [2]
+    uint64_t* halo_empty = bars + 2;       // [2]
+    uint64_t* b_full = bars + 4;           // [ROW_BSTAGES]
+    uint64_t* b_empty = b_full + ROW_BSTAGES;
+    uint64_t* acc_full = b_empty + ROW_BSTAGES;   // [2]
+    uint64_t* acc_empty = acc_full + 2;           // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int ctot = p.c0 + p.c1;
+    const int chunks = ctot / 32;
+    uint32_t acc_cols = 32;
+    while ((int)acc_cols < p.bn) acc_cols <<= 1;
+    const int pair_lo = blockIdx.x * p.pairs_per_cta;
+    const int pair_hi = min(p.pairs_total, pair_lo + p.pairs_per_cta);
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&map_a0);
+        if (p.c1) tma_prefetch_desc(&map_a1);
+        tma_prefetch_desc(&map_w);
+        for (int s = 0; s < 2; ++s) { mbar_init(&halo_full[s], 1); mbar_init(&halo_empty[s], 1); }
+        for (int s = 0; s < ROW_BSTAGES; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); }
+        for (int b = 0; b < 2; ++b) { mbar_init(&acc_full[b], 1); mbar_init(&acc_empty[b], 4); }
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc(tmem_slot, 4 * acc_cols);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            // flat sequence of (pair, chunk) work items; the halo of item i+1 is requested after weight tap 3 of item i
+            const int items = (pair_hi - pair_lo) * chunks;
+            auto issue_halo = [&](int item) {
+                const int pair = pair_lo + item / chunks, ch = item % chunks;
+                const int b = pair / p.pairs_per_image, h0 = 2 * (pair - b * p.pairs_per_image);
+                const int cc = ch * 32;
+                const bool second = cc >= p.c0;
+                const int hs = item & 1;
+                mbar_wait(&halo_empty[hs], (((uint32_t)(item >> 1)) & 1u) ^ 1u);
+                mbar_expect_tx(&halo_full[hs], (uint32_t)HALO_BYTES);
+                tma_load_4d(halo + hs * HALO_BYTES, second ? &map_a1 : &map_a0, &halo_full[hs], second ? cc - p.c0 : cc, -1, h0 - 1, b);
+            };
+            if (items > 0) issue_halo(0);
+            int g = 0;
+            for (int item = 0; item < items; ++item) {
+                const int cc = (item % chunks) * 32;
+                for (int tap = 0; tap < 9; ++tap, ++g) {
+                    const int s = g % ROW_BSTAGES;
+                    mbar_wait(&b_empty[s], (((uint32_t)(g / ROW_BSTAGES)) & 1u) ^ 1u);
+                    mbar_expect_tx(&b_full[s], (uint32_t)b_bytes);
+                    tma_load_2d(bring + s * b_bytes, &map_w, &b_full[s], tap * ctot + cc, 0);
+                    if (tap == 3 && item + 1 < items) issue_halo(item + 1);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(p.bn >> 3) << 17) | ((uint32_t)(RW >> 4) << 24);
+            int g = 0, item = 0, it = 0;
+            for (int pair = pair_lo; pair < pair_hi; ++pair, ++it) {
+                const int buf = it & 1;
+                mbar_wait(&acc_empty[buf], ((uint32_t)(it >> 1) & 1u) ^ 1u);
+                tc_fence_after();
+                const uint32_t tmem_d = tmem_base + (uint32_t)buf * 2u * acc_cols;
+                for (int ch = 0; ch < chunks; ++ch, ++item) {
+                    const int hs = item & 1;
+                    mbar_wait(&halo_full[hs], ((uint32_t)(item >> 1)) & 1u);
+                    tc_fence_after();
+                    const uint32_t ha = smem_u32(halo + hs * HALO_BYTES);
+                    for (int tap = 0; tap < 9; ++tap, ++g) {
+                        const int s = g % ROW_BSTAGES;
+                        mbar_wait(&b_full[s], ((uint32_t)(g / ROW_BSTAGES)) & 1u);
+                        tc_fence_after();
+                        const uint32_t ba = smem_u32(bring + s * b_bytes);
+                        const int dy = tap / 3, dx = tap - 3 * dy;
+#pragma unroll
+                        for (int j = 0; j < 2; ++j) {
+                            // A operand = 128 consecutive halo pixels starting at (row j+dy, col dx)
+                            const uint32_t aa = ha + (uint32_t)(((j + dy) * HALO_W + dx) * 128);
+#pragma unroll
+                            for (int k = 0; k < 4; ++k)
+                                umma_tf32(tmem_d + (uint32_t)j * acc_cols, make_sw128_desc(aa + 32u * k), make_sw128_desc(ba + 32u * k),
+                                          idesc, (ch | tap | k) != 0);
+                        }
+                        umma_commit(&b_empty[s]);
+                    }
+                    umma_commit(&halo_empty[hs]);
+                }
+                umma_commit(&acc_full[buf]);
+            }
+        }
+    } else {
+        const int q = warp & 3;
+        float* stg = staging + q * 32 * RSTG_LD;
+        const int sub_r = lane >> 3, sub_c = (lane & 7) * 4;
+        int it = 0;
+        for (int pair = pair_lo; pair < pair_hi; ++pair, ++it) {
+            const int b = pair / p.pairs_per_image, h0 = 2 * (pair - b * p.pairs_per_image);
+            const int buf = it & 1;
+            mbar_wait(&acc_full[buf], (uint32_t)(it >> 1) & 1u);
+            tc_fence_after();
+            float s1 = 0.f, s2 = 0.f;
+            for (int j = 0; j < 2; ++j) {
+                const bool row_ok = h0 + j < p.H;
+                const size_t m_w = ((size_t)b * p.H + h0 + j) * RW + q * 32;
+                for (int c = 0; c < p.bn; c += 32) {
+                    uint32_t r[32];
+                    tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)buf * 2u * acc_cols + (uint32_t)j * acc_cols + (uint32_t)c, r);
+#pragma unroll
+                    for (int jj = 0; jj < 32; jj += 4)
+                        *reinterpret_cast<float4*>(stg + lane * RSTG_LD + jj) =
+                            make_float4(__uint_as_float(r[jj]), __uint_as_float(r[jj + 1]), __uint_as_float(r[jj + 2]), __uint_as_float(r[jj + 3]));
+                    __syncwarp();
+                    const int col = c + sub_c;
+                    float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (p.bias) bv = __ldg(reinterpret_cast<const float4*>(p.bias + col));
+                    if (row_ok) {
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            const int rr = sub_r + 4 * i;
+                            const size_t m = m_w + rr;
+                            float4 v = *reinterpret_cast<const float4*>(stg + rr * RSTG_LD + sub_c);
+                            v.x += bv.x; v.y += bv.y; v.z += bv.z; v.w += bv.w;
+                            if (p.residual) {
+                                const float4 rv = __ldg(reinterpret_cast<const float4*>(p.residual + m * p.Cout + col));
+                                v.x += rv.x; v.y += rv.y; v.z += rv.z; v.w += rv.w;
+                            }
+                            s1 += (v.x + v.y) + (v.z + v.w);
+                            s2 += (v.x * v.x + v.y * v.y) + (v.z * v.z + v.w * v.w);
+                            if (p.round_tf32) { v.x = to_tf32(v.x); v.y = to_tf32(v.y); v.z = to_tf32(v.z); v.w = to_tf32(v.w); }
+                            *reinterpret_cast<float4*>(p.out + m * p.Cout + col) = v;
+                        }
+                    }
+                    __syncwarp();
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&acc_empty[buf]);
+            if (p.stats) {
+                s1 = warp_sum(s1);
+                s2 = warp_sum(s2);
+                if (lane == 0) {
+                    atomicAdd(p.stats + 2 * b, (double)s1);
+                    atomicAdd(p.stats + 2 * b + 1, (double)s2);
+                }
+            }
+        }
+        tc_fence_before();
+    }
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, 4 * acc_cols);
+    }
+}
+
+}  // namespace sdc
+
+using namespace sdc;
+
+// Returns SDC_OK when the problem was handled here, -1 when the shape is not eligible (caller uses conv_gemm).
+extern "C" int sdc_conv3x3_row(const float* a0, int c0, const float* a1, int c1, const float* w_packed, const float* bias,
+                               const float* residual, float* out, double* stats, int round_tf32, int B, int H, int W, int Cout,
+                               void* stream) {
+    if (W != RW || Cout > 128 || Cout % 32 != 0 || c0 % 32 != 0 || c1 % 32 != 0 || c0 <= 0) return -1;
+    SDC_REQUIRE(a0 && w_packed && out && B > 0 && H > 0 && (c1 == 0 || a1), "conv3x3_row: bad arguments");
+    RowParams p{};
+    p.B = B; p.H = H; p.Cout = Cout; p.bn = Cout; p.c0 = c0; p.c1 = c1; p.round_tf32 = round_tf32;
+    p.bias = bias; p.residual = residual; p.out = out; p.stats = stats;
+    p.pairs_per_image = (H + 1) / 2;
+    p.pairs_total = B * p.pairs_per_image;
+    int n_sm = 148, dev = 0;
+    SDC_CUDA(cudaGetDevice(&dev));
+    SDC_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
+    const int ctas = p.pairs_total < n_sm ? p.pairs_total : n_sm;
+    p.pairs_per_cta = (p.pairs_total + ctas - 1) / ctas;
+    const int grid = (p.pairs_total + p.pairs_per_cta - 1) / p.pairs_per_cta;
+
+    CUtensorMap ma0, ma1, mw;
+    auto enc_act = [&](CUtensorMap* m, const float* a, int C) {
+        cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
+        cuuint64_t str[3] = {(cuuint64_t)C * 4, (cuuint64_t)W * C * 4, (cuuint64_t)H * W * C * 4};
+        cuuint32_t box[4] = {32, (cuuint32_t)HALO_W, 4, 1};
+        return encode_tmap(m, a, 4, dims, str, box);
+    };
+    int rc = enc_act(&ma0, a0, c0);
+    if (rc) return rc;
+    if (c1) { rc = enc_act(&ma1, a1, c1); if (rc) return rc; } else ma1 = ma0;
+    const cuuint64_t ktot = (cuuint64_t)9 * (c0 + c1);
+    cuuint64_t wd[2] = {ktot, (cuuint64_t)Cout};
+    cuuint64_t ws[1] = {ktot * 4};
+    cuuint32_t wb[2] = {32, (cuuint32_t)Cout};
+    rc = encode_tmap(&mw, w_packed, 2, wd, ws, wb);
+    if (rc) return rc;
+    const int smem_bytes = 2 * HALO_BYTES + ROW_BSTAGES * Cout * 128 + RSTG_BYTES + 16 * 8 + 16 + 1024;
+    static bool attr_set = false;
+    if (!attr_set) {
+        SDC_CUDA(cudaFuncSetAttribute(conv_row_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        attr_set = true;
+    }
+    conv_row_kernel<<<grid, ROW_THREADS, smem_bytes, as_stream(stream)>>>(ma0, ma1, mw, p);
+    SDC_LAUNCHED();
+    return SDC_OK;
+}

@@ -9,6 +9,7 @@ activations.  Packed TF32 weights and the per-timestep FiLM table are cached and
 version counter or storage changes (optimiser / EMA updates between chains).
 """
 import math
+import os
 
 import torch
 import torch.nn as nn
@@ -19,6 +20,7 @@ from ._lib import c_f, c_i, c_i64, c_p
 L.register({
     "sdc_pack_conv_weight": (c_i, [c_i, c_p, c_p, c_i, c_i, c_p]),
     "sdc_conv_gemm": (c_i, [c_i, c_p, c_i, c_p, c_i, c_p, c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_p]),
+    "sdc_conv3x3_row": (c_i, [c_p, c_i, c_p, c_i, c_p, c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_p]),
     "sdc_stem_conv7": (c_i, [c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_p]),
     "sdc_gn_silu": (c_i, [c_p, c_p, c_p, c_p, c_p, c_p, c_i64, c_p, c_p, c_i, c_i, c_i, c_p]),
     "sdc_channel_layernorm": (c_i, [c_p, c_p, c_p, c_p, c_i64, c_i, c_i, c_p]),
@@ -102,6 +104,7 @@ def _st():
     return L.stream_ptr()
 
 
+USE_ROW_KERNEL = os.environ.get("SDC_NO_ROW_KERNEL", "0") != "1"  # halo-reuse kernel for the 16x128 level
 PROFILE = None  # bench.py sets this to a list: every conv launch is then bracketed by CUDA events on its stream
 
 
@@ -110,8 +113,15 @@ def conv_gemm(kind, a0, c0, a1, c1, wp, bias, residual, out, stats, round_tf32, 
     if prof is not None:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-    L.check(L.lib().sdc_conv_gemm(kind, L.ptr(a0), c0, L.ptr(a1), c1, L.ptr(wp), L.ptr(bias), L.ptr(residual), L.ptr(out),
-                                  L.ptr(stats), int(round_tf32), B, H, W, Cout, _st()))
+    rc = -1
+    if kind == KIND_3x3 and USE_ROW_KERNEL and W == 128 and Cout <= 128:
+        rc = L.lib().sdc_conv3x3_row(L.ptr(a0), c0, L.ptr(a1), c1, L.ptr(wp), L.ptr(bias), L.ptr(residual), L.ptr(out),
+                                     L.ptr(stats), int(round_tf32), B, H, W, Cout, _st())
+        if rc > 0:
+            L.check(rc)
+    if rc != 0:
+        L.check(L.lib().sdc_conv_gemm(kind, L.ptr(a0), c0, L.ptr(a1), c1, L.ptr(wp), L.ptr(bias), L.ptr(residual), L.ptr(out),
+                                      L.ptr(stats), int(round_tf32), B, H, W, Cout, _st()))
     if prof is not None:
         e1.record()
         taps = {KIND_1x1: 1, KIND_3x3: 9, KIND_UNSHUFFLE: 4}[kind]

@@ -43,6 +43,9 @@ CONV_CASES = [
     (0, 2, 8, 64, 64, 32, 96, True, False, False, False),      # 1x1 on a concat, N tile 32
     (2, 2, 8, 64, 32, 0, 64, True, False, False, True),        # pixel-unshuffle + 1x1 (input 16x128)
     (2, 3, 2, 16, 128, 0, 256, True, False, False, True),      # unshuffle to the 2x16 level
+    (1, 3, 16, 128, 128, 128, 128, True, False, True, False),  # row kernel: two segments (256 -> 128)
+    (1, 2, 5, 128, 64, 0, 96, True, True, True, True),         # row kernel: odd H (half-empty last pair), residual
+    (1, 150, 16, 128, 32, 0, 64, True, False, True, False),    # row kernel: more tile pairs than SMs
 ]
 
 
