@@ -139,46 +139,56 @@ __global__ void __launch_bounds__(256) gn_silu_kernel(const float* __restrict__ 
 }
 
 // ---------------------------------------------------------------------------------------------- channel LayerNorm
-// one warp per pixel row; C <= 1024 kept in registers (two-pass variance like torch.var(unbiased=False))
+// one warp per RPW pixel rows (RPW = 4 for C <= 256 so that 4-8 independent 16-byte loads are in flight per lane);
+// C <= 1024 kept in registers, two-pass variance like torch.var(unbiased=False)
+template <int RPW, int NV>
 __global__ void __launch_bounds__(256) channel_layernorm_kernel(const float* __restrict__ x, const float* __restrict__ g,
                                                                 const float* __restrict__ residual, float* __restrict__ y,
                                                                 int64_t M, int C, int round_tf32) {
     const int lane = threadIdx.x & 31;
-    const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    if (row >= M) return;
+    const int64_t row0 = ((int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * RPW;
+    if (row0 >= M) return;
     const int n4 = C / 4;  // float4 per row; lane handles i = lane, lane+32, ...
-    const float4* x4 = reinterpret_cast<const float4*>(x + row * C);
-    float4 v[8];
-    float s = 0.f;
+    float4 v[RPW][NV];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-        const int i = lane + 32 * j;
-        if (i < n4) { v[j] = x4[i]; s += (v[j].x + v[j].y) + (v[j].z + v[j].w); }
-    }
-    const float mean = warp_sum(s) / (float)C;
-    float q = 0.f;
+    for (int r = 0; r < RPW; ++r) {
+        const float4* x4 = reinterpret_cast<const float4*>(x + (row0 + r) * C);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-        const int i = lane + 32 * j;
-        if (i < n4) {
-            const float a = v[j].x - mean, b = v[j].y - mean, c = v[j].z - mean, d = v[j].w - mean;
-            q += (a * a + b * b) + (c * c + d * d);
+        for (int j = 0; j < NV; ++j) {
+            const int i = lane + 32 * j;
+            v[r][j] = (i < n4 && row0 + r < M) ? x4[i] : make_float4(0.f, 0.f, 0.f, 0.f);
         }
     }
-    const float rstd = rsqrtf(warp_sum(q) / (float)C + 1e-5f);
     const float4* g4 = reinterpret_cast<const float4*>(g);
-    const float4* r4 = residual ? reinterpret_cast<const float4*>(residual + row * C) : nullptr;
-    float4* y4 = reinterpret_cast<float4*>(y + row * C);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-        const int i = lane + 32 * j;
-        if (i < n4) {
-            const float4 gv = g4[i];
-            float4 o = make_float4((v[j].x - mean) * rstd * gv.x, (v[j].y - mean) * rstd * gv.y, (v[j].z - mean) * rstd * gv.z,
-                                   (v[j].w - mean) * rstd * gv.w);
-            if (r4) { const float4 r = r4[i]; o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w; }
-            if (round_tf32) o = make_float4(to_tf32(o.x), to_tf32(o.y), to_tf32(o.z), to_tf32(o.w));
-            y4[i] = o;
+    for (int r = 0; r < RPW; ++r) {
+        if (row0 + r >= M) break;
+        float s = 0.f;
+#pragma unroll
+        for (int j = 0; j < NV; ++j) s += (v[r][j].x + v[r][j].y) + (v[r][j].z + v[r][j].w);
+        const float mean = warp_sum(s) / (float)C;
+        float q = 0.f;
+#pragma unroll
+        for (int j = 0; j < NV; ++j) {
+            if (lane + 32 * j < n4) {
+                const float a = v[r][j].x - mean, b = v[r][j].y - mean, c = v[r][j].z - mean, d = v[r][j].w - mean;
+                q += (a * a + b * b) + (c * c + d * d);
+            }
+        }
+        const float rstd = rsqrtf(warp_sum(q) / (float)C + 1e-5f);
+        const float4* r4 = residual ? reinterpret_cast<const float4*>(residual + (row0 + r) * C) : nullptr;
+        float4* y4 = reinterpret_cast<float4*>(y + (row0 + r) * C);
+#pragma unroll
+        for (int j = 0; j < NV; ++j) {
+            const int i = lane + 32 * j;
+            if (i < n4) {
+                const float4 gv = g4[i];
+                float4 o = make_float4((v[r][j].x - mean) * rstd * gv.x, (v[r][j].y - mean) * rstd * gv.y,
+                                       (v[r][j].z - mean) * rstd * gv.z, (v[r][j].w - mean) * rstd * gv.w);
+                if (r4) { const float4 rr = r4[i]; o.x += rr.x; o.y += rr.y; o.z += rr.z; o.w += rr.w; }
+                if (round_tf32) o = make_float4(to_tf32(o.x), to_tf32(o.y), to_tf32(o.z), to_tf32(o.w));
+                y4[i] = o;
+            }
         }
     }
 }
@@ -187,9 +197,12 @@ __global__ void __launch_bounds__(256) channel_layernorm_kernel(const float* __r
 constexpr int LA_HEADS = 4, LA_D = 32, LA_QKV = 3 * LA_HEADS * LA_D, LA_HID = LA_HEADS * LA_D;
 
 // ctx[b,h,d,e] = sum_n softmax_n(k)[d,n] * v[e,n]          grid = B*heads, 256 threads
+// 4 pixel groups x 64 threads; each thread owns a 4x4 block of the 32x32 context in registers (16 FMA per two
+// 16-byte shared loads).  k is read twice (column max, then exp-weighted accumulation), v once.
+constexpr int LA_CHUNK = 128;
 __global__ void __launch_bounds__(256) linattn_context_kernel(const float* __restrict__ qkv, float* __restrict__ ctx, int n) {
-    __shared__ float ek[64][LA_D];
-    __shared__ float vs[64][LA_D];
+    __shared__ __align__(16) float ek[LA_CHUNK][LA_D];
+    __shared__ __align__(16) float vs[LA_CHUNK][LA_D];
     __shared__ float red[8][LA_D];
     __shared__ float kmax[LA_D];
     const int b = blockIdx.x / LA_HEADS, h = blockIdx.x % LA_HEADS;
@@ -197,64 +210,133 @@ __global__ void __launch_bounds__(256) linattn_context_kernel(const float* __res
     const float* base = qkv + (int64_t)b * n * LA_QKV;
     const float* kp = base + LA_HID + h * LA_D;
     const float* vp = base + 2 * LA_HID + h * LA_D;
-    float m = -INFINITY;
-    for (int i = warp; i < n; i += 8) m = fmaxf(m, kp[(int64_t)i * LA_QKV + lane]);
-    red[warp][lane] = m;
-    __syncthreads();
-    if (warp == 0) {
-        float t = red[0][lane];
+    {   // column max of k over the n pixels: 8 pixels x 4 channels per thread and iteration (16-byte loads)
+        const int c4 = (tid & 7) * 4, r = tid >> 3;  // 32 pixel rows per pass
+        float4 m = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+        for (int i = r; i < n; i += 32) {
+            const float4 kv = *reinterpret_cast<const float4*>(kp + (int64_t)i * LA_QKV + c4);
+            m.x = fmaxf(m.x, kv.x); m.y = fmaxf(m.y, kv.y); m.z = fmaxf(m.z, kv.z); m.w = fmaxf(m.w, kv.w);
+        }
+        // reduce over the 4 pixel rows held by one warp (lanes with equal lane&7), then across the 8 warps
 #pragma unroll
-        for (int w = 1; w < 8; ++w) t = fmaxf(t, red[w][lane]);
-        kmax[lane] = t;
+        for (int o = 8; o < 32; o <<= 1) {
+            m.x = fmaxf(m.x, __shfl_xor_sync(0xffffffffu, m.x, o)); m.y = fmaxf(m.y, __shfl_xor_sync(0xffffffffu, m.y, o));
+            m.z = fmaxf(m.z, __shfl_xor_sync(0xffffffffu, m.z, o)); m.w = fmaxf(m.w, __shfl_xor_sync(0xffffffffu, m.w, o));
+        }
+        if (lane < 8) { red[warp][c4] = m.x; red[warp][c4 + 1] = m.y; red[warp][c4 + 2] = m.z; red[warp][c4 + 3] = m.w; }
+        __syncthreads();
+        if (tid < LA_D) {
+            float t = red[0][tid];
+#pragma unroll
+            for (int w = 1; w < 8; ++w) t = fmaxf(t, red[w][tid]);
+            kmax[tid] = t;
+        }
+        __syncthreads();
+    }
+    const int ng = tid >> 6, t64 = tid & 63;
+    const int d0 = (t64 >> 3) * 4, e0 = (t64 & 7) * 4;
+    float acc[4][4], ksum[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { ksum[i] = 0.f; for (int j = 0; j < 4; ++j) acc[i][j] = 0.f; }
+    const int lc4 = (tid & 7) * 4, lr = tid >> 3;
+    const float4 km = *reinterpret_cast<const float4*>(&kmax[lc4]);
+    for (int n0 = 0; n0 < n; n0 += LA_CHUNK) {
+        const int cnt = min(LA_CHUNK, n - n0);
+        __syncthreads();
+#pragma unroll
+        for (int rr = 0; rr < LA_CHUNK; rr += 32) {
+            const int r = rr + lr;
+            float4 kv = make_float4(0.f, 0.f, 0.f, 0.f), vv = kv;
+            if (r < cnt) {
+                kv = *reinterpret_cast<const float4*>(kp + (int64_t)(n0 + r) * LA_QKV + lc4);
+                vv = *reinterpret_cast<const float4*>(vp + (int64_t)(n0 + r) * LA_QKV + lc4);
+                kv = make_float4(expf(kv.x - km.x), expf(kv.y - km.y), expf(kv.z - km.z), expf(kv.w - km.w));
+            }
+            *reinterpret_cast<float4*>(&ek[r][lc4]) = kv;   // rows >= cnt hold zeros: they add nothing
+            *reinterpret_cast<float4*>(&vs[r][lc4]) = vv;
+        }
+        __syncthreads();
+#pragma unroll 8
+        for (int r = ng * (LA_CHUNK / 4); r < (ng + 1) * (LA_CHUNK / 4); ++r) {
+            const float4 a = *reinterpret_cast<const float4*>(&ek[r][d0]);
+            const float4 vv = *reinterpret_cast<const float4*>(&vs[r][e0]);
+            const float av[4] = {a.x, a.y, a.z, a.w}, vv4[4] = {vv.x, vv.y, vv.z, vv.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                ksum[i] += av[i];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], vv4[j], acc[i][j]);
+            }
+        }
+    }
+    // reduce the 4 pixel groups through shared memory (reusing the staging tiles)
+    __syncthreads();
+    float* racc = &ek[0][0];   // [4][64][16] floats = 16 KB
+    float* rsum = &vs[0][0];   // [4][64][4]
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        rsum[(ng * 64 + t64) * 4 + i] = ksum[i];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) racc[(ng * 64 + t64) * 16 + i * 4 + j] = acc[i][j];
     }
     __syncthreads();
-    const int d = tid >> 3, e0 = (tid & 7) * 4;
-    float acc[4] = {0.f, 0.f, 0.f, 0.f}, ksum = 0.f;
-    for (int n0 = 0; n0 < n; n0 += 64) {
-        const int cnt = min(64, n - n0);
-        __syncthreads();
-        for (int i = tid; i < cnt * LA_D; i += 256) {
-            const int r = i >> 5, c = i & 31;
-            ek[r][c] = expf(kp[(int64_t)(n0 + r) * LA_QKV + c] - kmax[c]);
-            vs[r][c] = vp[(int64_t)(n0 + r) * LA_QKV + c];
-        }
-        __syncthreads();
-        for (int r = 0; r < cnt; ++r) {
-            const float a = ek[r][d];
-            const float4 vv = *reinterpret_cast<const float4*>(&vs[r][e0]);
-            acc[0] = fmaf(a, vv.x, acc[0]); acc[1] = fmaf(a, vv.y, acc[1]);
-            acc[2] = fmaf(a, vv.z, acc[2]); acc[3] = fmaf(a, vv.w, acc[3]);
-            ksum += a;
+    if (ng == 0) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            float ks = 0.f, o[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+            for (int gq = 0; gq < 4; ++gq) {
+                ks += rsum[(gq * 64 + t64) * 4 + i];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) o[j] += racc[(gq * 64 + t64) * 16 + i * 4 + j];
+            }
+            const float inv = 1.0f / ks;
+            *reinterpret_cast<float4*>(ctx + ((int64_t)blockIdx.x * LA_D + d0 + i) * LA_D + e0) =
+                make_float4(o[0] * inv, o[1] * inv, o[2] * inv, o[3] * inv);
         }
     }
-    const float inv = 1.0f / ksum;
-    float* o = ctx + ((int64_t)blockIdx.x * LA_D + d) * LA_D + e0;
-    *reinterpret_cast<float4*>(o) = make_float4(acc[0] * inv, acc[1] * inv, acc[2] * inv, acc[3] * inv);
 }
 
-// out[n, h*32+e] = 32^-0.5 * sum_d ctx[d,e] * softmax_d(q[n,:])[d]      grid = (B*heads, ceil(n/64)), 256 threads
+// out[n, h*32+e] = 32^-0.5 * sum_d ctx[d,e] * softmax_d(q[n,:])[d]      grid = (B*heads, ceil(n/256)), thread per pixel
 __global__ void __launch_bounds__(256) linattn_apply_kernel(const float* __restrict__ qkv, const float* __restrict__ ctx,
                                                             float* __restrict__ out, int n) {
+    __shared__ __align__(16) float cs[LA_D][LA_D];
     const int b = blockIdx.x / LA_HEADS, h = blockIdx.x % LA_HEADS;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    float c[LA_D];  // lane = e holds ctx[:, e]
-    const float* cp = ctx + (int64_t)blockIdx.x * LA_D * LA_D;
+    for (int i = threadIdx.x; i < LA_D * LA_D; i += blockDim.x) cs[i >> 5][i & 31] = ctx[(int64_t)blockIdx.x * LA_D * LA_D + i];
+    __syncthreads();
+    const int i = blockIdx.y * 256 + threadIdx.x;
+    if (i >= n) return;
+    const float* qp = qkv + ((int64_t)b * n + i) * LA_QKV + h * LA_D;
+    float q[LA_D];
 #pragma unroll
-    for (int d = 0; d < LA_D; ++d) c[d] = cp[d * LA_D + lane];
-    const float* qp = qkv + (int64_t)b * n * LA_QKV + h * LA_D;
-    float* op = out + (int64_t)b * n * LA_HID + h * LA_D;
-    const float scale = 0.17677669529663687f;  // 32^-0.5
-    const int i_end = min(n, (int)(blockIdx.y + 1) * 64);
-    for (int i = blockIdx.y * 64 + warp; i < i_end; i += 8) {
-        const float qv = qp[(int64_t)i * LA_QKV + lane];
-        const float mx = warp_max(qv);
-        const float ex = expf(qv - mx);
-        const float sq = ex / warp_sum(ex) * scale;
-        float o = 0.f;
-#pragma unroll
-        for (int d = 0; d < LA_D; ++d) o = fmaf(__shfl_sync(0xffffffffu, sq, d), c[d], o);
-        op[(int64_t)i * LA_HID + lane] = to_tf32(o);
+    for (int j = 0; j < LA_D; j += 4) {
+        const float4 t = *reinterpret_cast<const float4*>(qp + j);
+        q[j] = t.x; q[j + 1] = t.y; q[j + 2] = t.z; q[j + 3] = t.w;
     }
+    float mx = q[0];
+#pragma unroll
+    for (int j = 1; j < LA_D; ++j) mx = fmaxf(mx, q[j]);
+    float den = 0.f;
+#pragma unroll
+    for (int j = 0; j < LA_D; ++j) { q[j] = expf(q[j] - mx); den += q[j]; }
+    const float sc = 0.17677669529663687f / den;  // 32^-0.5 / sum
+    float o[LA_D];
+#pragma unroll
+    for (int e = 0; e < LA_D; ++e) o[e] = 0.f;
+#pragma unroll
+    for (int d = 0; d < LA_D; ++d) {
+        const float w = q[d] * sc;
+#pragma unroll
+        for (int e = 0; e < LA_D; e += 4) {
+            const float4 c4 = *reinterpret_cast<const float4*>(&cs[d][e]);
+            o[e] = fmaf(w, c4.x, o[e]); o[e + 1] = fmaf(w, c4.y, o[e + 1]);
+            o[e + 2] = fmaf(w, c4.z, o[e + 2]); o[e + 3] = fmaf(w, c4.w, o[e + 3]);
+        }
+    }
+    float* op = out + ((int64_t)b * n + i) * LA_HID + h * LA_D;
+#pragma unroll
+    for (int e = 0; e < LA_D; e += 4)
+        *reinterpret_cast<float4*>(op + e) = make_float4(to_tf32(o[e]), to_tf32(o[e + 1]), to_tf32(o[e + 2]), to_tf32(o[e + 3]));
 }
 
 // full softmax attention for n <= 32 tokens: one warp per (b, head), lane = query token
@@ -412,7 +494,14 @@ extern "C" int sdc_channel_layernorm(const float* x, const float* g, const float
                                      int round_tf32, void* stream) {
     SDC_REQUIRE(x && g && y && M > 0, "channel_layernorm: bad arguments");
     SDC_REQUIRE(C % 4 == 0 && C <= 1024, "channel_layernorm: C=%d unsupported (multiple of 4, <= 1024)", C);
-    channel_layernorm_kernel<<<(unsigned)((M + 7) / 8), 256, 0, as_stream(stream)>>>(x, g, residual, y, M, C, round_tf32);
+    if (C <= 128)
+        channel_layernorm_kernel<4, 1><<<(unsigned)((M + 31) / 32), 256, 0, as_stream(stream)>>>(x, g, residual, y, M, C, round_tf32);
+    else if (C <= 256)
+        channel_layernorm_kernel<4, 2><<<(unsigned)((M + 31) / 32), 256, 0, as_stream(stream)>>>(x, g, residual, y, M, C, round_tf32);
+    else if (C <= 512)
+        channel_layernorm_kernel<2, 4><<<(unsigned)((M + 15) / 16), 256, 0, as_stream(stream)>>>(x, g, residual, y, M, C, round_tf32);
+    else
+        channel_layernorm_kernel<1, 8><<<(unsigned)((M + 7) / 8), 256, 0, as_stream(stream)>>>(x, g, residual, y, M, C, round_tf32);
     SDC_LAUNCHED();
     return SDC_OK;
 }
@@ -424,7 +513,7 @@ extern "C" int sdc_linear_attention(const float* qkv, float* out, void* workspac
     float* ctx = reinterpret_cast<float*>(workspace);
     linattn_context_kernel<<<(unsigned)(B * LA_HEADS), 256, 0, as_stream(stream)>>>(qkv, ctx, n);
     SDC_LAUNCHED();
-    dim3 grid((unsigned)(B * LA_HEADS), (unsigned)((n + 63) / 64));
+    dim3 grid((unsigned)(B * LA_HEADS), (unsigned)((n + 255) / 256));
     linattn_apply_kernel<<<grid, 256, 0, as_stream(stream)>>>(qkv, ctx, out, n);
     SDC_LAUNCHED();
     return SDC_OK;
