@@ -20,6 +20,7 @@
 // Precision: TF32 operands (10-bit mantissa, rounded to nearest when produced), FP32 accumulation.
 #include "tc_ptx.cuh"
 #include <math.h>
+#include <stdlib.h>
 
 namespace sdc {
 
@@ -219,6 +220,179 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_consta
     }
 }
 
+// ------------------------------------------------------------------------------------------ CTA-pair kernel
+// Same computation with cta_group::2: a cluster of two CTAs (one SM pair) computes a 256 x BN tile.  Each CTA loads
+// its own 128 activation rows but only HALF of the weight slab (BN/2 rows); tcgen05.mma.cta_group::2 (issued by the
+// leader CTA) reads A and B from both CTAs' shared memory and writes each CTA's 128 accumulator rows into its own
+// TMEM.  Per-SM operand traffic per K block drops from 16 KB + BN*128 B to 16 KB + BN*64 B, which is what bounds
+// the 1-CTA kernel (bytes in flight per SM / L2 latency).  Barriers: TMA of both CTAs credits the leader's `full`;
+// the MMA commit multicasts to both CTAs' `empty` / `acc_full`; both epilogues arrive on the leader's `acc_empty`.
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
+conv_gemm2_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ CUtensorMap map_a1,
+                  const __grid_constant__ CUtensorMap map_w, const GemmParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    const int half_n = p.bn / 2;
+    const int stage_bytes = A_BYTES + half_n * BK * 4;
+    float* staging = reinterpret_cast<float*>(smem + p.stages * stage_bytes);
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + p.stages * stage_bytes + STG_BYTES);
+    uint64_t* empty_bar = full_bar + p.stages;
+    uint64_t* acc_full = empty_bar + p.stages;   // [2]
+    uint64_t* acc_empty = acc_full + 2;          // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const bool leader = rank == 0;
+    const int taps = p.kind == 1 ? 9 : (p.kind == 2 ? 4 : 1);
+    const int ctot = p.c0 + p.c1;
+    const int chunks = ctot / BK;
+    const int num_kb = taps * chunks;
+    uint32_t acc_cols = 32;
+    while ((int)acc_cols < p.bn) acc_cols <<= 1;
+    const int cluster_id = blockIdx.x >> 1;
+    const int tile_lo = cluster_id * p.tiles_per_cta;             // pair tiles: id = m2 * tiles_n + n
+    const int tile_hi = min(p.tiles_total, tile_lo + p.tiles_per_cta);
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&map_a0);
+        if (p.c1) tma_prefetch_desc(&map_a1);
+        tma_prefetch_desc(&map_w);
+        for (int s = 0; s < p.stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+        for (int b = 0; b < 2; ++b) { mbar_init(&acc_full[b], 1); mbar_init(&acc_empty[b], 8); }
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc_2sm(tmem_slot, 2 * acc_cols);
+    tc_fence_before();
+    cluster_sync_all();   // barriers of both CTAs initialised, TMEM allocated, before any remote signalling
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            int g = 0;
+            for (int tile = tile_lo; tile < tile_hi; ++tile) {
+                const int m2 = tile / p.tiles_n, nt = tile - m2 * p.tiles_n;
+                const int mt = 2 * m2 + (int)rank;
+                const int pix0 = mt * BM;
+                const int b0 = pix0 / p.hw_per_sample;
+                const int h0 = (pix0 - b0 * p.hw_per_sample) / p.W;
+                for (int kb = 0; kb < num_kb; ++kb, ++g) {
+                    const int s = g % p.stages;
+                    const uint32_t ph = (uint32_t)(g / p.stages) & 1u;
+                    mbar_wait(&empty_bar[s], ph ^ 1u);
+                    uint8_t* sa = smem + s * stage_bytes;
+                    uint8_t* sb = sa + A_BYTES;
+                    if (leader) mbar_expect_tx(&full_bar[s], (uint32_t)(2 * stage_bytes));   // bytes of BOTH CTAs
+                    const int tap = kb / chunks;
+                    const int cc = (kb - tap * chunks) * BK;
+                    const bool second = cc >= p.c0;
+                    const CUtensorMap* ma = second ? &map_a1 : &map_a0;
+                    const int cseg = second ? cc - p.c0 : cc;
+                    if (p.kind == 2) {
+                        const int cin = second ? p.c1 : p.c0;
+                        tma_load_5d_2sm(sa, ma, &full_bar[s], (tap & 1) * cin + cseg, 0, tap >> 1, h0, b0);
+                    } else {
+                        const int dy = p.kind == 1 ? tap / 3 - 1 : 0;
+                        const int dx = p.kind == 1 ? tap % 3 - 1 : 0;
+                        tma_load_4d_2sm(sa, ma, &full_bar[s], cseg, dx, h0 + dy, b0);
+                    }
+                    tma_load_2d_2sm(sb, &map_w, &full_bar[s], tap * ctot + cc, nt * p.bn + (int)rank * half_n);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (leader && lane == 0) {
+            const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(p.bn >> 3) << 17) | ((uint32_t)((2 * BM) >> 4) << 24);
+            int g = 0, it = 0;
+            for (int tile = tile_lo; tile < tile_hi; ++tile, ++it) {
+                const int buf = it & 1;
+                mbar_wait(&acc_empty[buf], ((uint32_t)(it >> 1) & 1u) ^ 1u);   // both CTAs' epilogues drained this buffer
+                tc_fence_after();
+                const uint32_t tmem_d = tmem_base + (uint32_t)buf * acc_cols;
+                for (int kb = 0; kb < num_kb; ++kb, ++g) {
+                    const int s = g % p.stages;
+                    const uint32_t ph = (uint32_t)(g / p.stages) & 1u;
+                    mbar_wait(&full_bar[s], ph);
+                    tc_fence_after();
+                    const uint32_t sa = smem_u32(smem + s * stage_bytes);
+                    const uint64_t adesc = make_sw128_desc(sa);
+                    const uint64_t bdesc = make_sw128_desc(sa + A_BYTES);
+#pragma unroll
+                    for (int k = 0; k < BK / 8; ++k)
+                        umma_tf32_2sm(tmem_d, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kb | k) != 0);
+                    umma_commit_2sm(&empty_bar[s]);
+                }
+                umma_commit_2sm(&acc_full[buf]);
+            }
+        }
+    } else {
+        const int q = warp & 3;
+        float* stg = staging + q * 32 * STG_LD;
+        const int sub_r = lane >> 3, sub_c = (lane & 7) * 4;
+        int it = 0;
+        for (int tile = tile_lo; tile < tile_hi; ++tile, ++it) {
+            const int m2 = tile / p.tiles_n, nt = tile - m2 * p.tiles_n;
+            const int mt = 2 * m2 + (int)rank;
+            const int buf = it & 1;
+            mbar_wait(&acc_full[buf], (uint32_t)(it >> 1) & 1u);
+            tc_fence_after();
+            const int m_w = mt * BM + q * 32;
+            float s1 = 0.f, s2 = 0.f;
+            for (int c = 0; c < p.bn; c += 32) {
+                uint32_t r[32];
+                tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)buf * acc_cols + (uint32_t)c, r);
+#pragma unroll
+                for (int j = 0; j < 32; j += 4)
+                    *reinterpret_cast<float4*>(stg + lane * STG_LD + j) =
+                        make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
+                __syncwarp();
+                const int col = nt * p.bn + c + sub_c;
+                float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (p.bias) bv = __ldg(reinterpret_cast<const float4*>(p.bias + col));
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const int rr = sub_r + 4 * i;
+                    const int m = m_w + rr;
+                    if (m < p.M) {
+                        float4 v = *reinterpret_cast<const float4*>(stg + rr * STG_LD + sub_c);
+                        v.x += bv.x; v.y += bv.y; v.z += bv.z; v.w += bv.w;
+                        if (p.residual) {
+                            const float4 rv = __ldg(reinterpret_cast<const float4*>(p.residual + (size_t)m * p.Cout + col));
+                            v.x += rv.x; v.y += rv.y; v.z += rv.z; v.w += rv.w;
+                        }
+                        s1 += (v.x + v.y) + (v.z + v.w);
+                        s2 += (v.x * v.x + v.y * v.y) + (v.z * v.z + v.w * v.w);
+                        if (p.round_tf32) { v.x = to_tf32(v.x); v.y = to_tf32(v.y); v.z = to_tf32(v.z); v.w = to_tf32(v.w); }
+                        *reinterpret_cast<float4*>(p.out + (size_t)m * p.Cout + col) = v;
+                    }
+                }
+                __syncwarp();
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_leader(&acc_empty[buf]);
+            if (p.stats) {
+                s1 = warp_sum(s1);
+                s2 = warp_sum(s2);
+                if (lane == 0 && m_w < p.M) {
+                    const int b = m_w / p.hw_per_sample;
+                    atomicAdd(p.stats + 2 * b, (double)s1);
+                    atomicAdd(p.stats + 2 * b + 1, (double)s2);
+                }
+            }
+        }
+        tc_fence_before();
+    }
+    // neither CTA may exit (or free TMEM) while its partner can still read its shared memory / signal its barriers
+    __syncthreads();
+    cluster_sync_all();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc_2sm(tmem_base, 2 * acc_cols);
+    }
+}
+
 // ------------------------------------------------------------------------------------------ host side
 // activation map: NHWC [B, Hin, Win, C]; for kind 2 the 5-D pixel-unshuffle view
 static int encode_act(CUtensorMap* map, const float* a, int kind, int B, int H, int W, int C, int bh, int bb) {
@@ -260,20 +434,25 @@ extern "C" int sdc_conv_gemm(int kind, const float* a0, int c0, const float* a1,
     p.kind = kind; p.M = B * H * W; p.Cout = Cout; p.bn = bn; p.H = H; p.W = W; p.bh = bh; p.bb = bb;
     p.c0 = c0; p.c1 = c1; p.round_tf32 = round_tf32; p.hw_per_sample = H * W;
     p.bias = bias; p.residual = residual; p.out = out; p.stats = stats;
-    const int stage_bytes = A_BYTES + bn * BK * 4;
-    int stages = (190 * 1024) / stage_bytes;
-    if (stages > 6) stages = 6;
-    p.stages = stages;
-    const int smem_bytes = stages * stage_bytes + STG_BYTES + (2 * stages + 4) * 8 + 16 + 1024;
     int n_sm = 148;
     {
         int dev = 0;
         SDC_CUDA(cudaGetDevice(&dev));
         SDC_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
     }
+    static const bool allow_pair = []() { const char* e = getenv("SDC_NO_2CTA"); return !(e && e[0] == '1'); }();
+    const int tiles_m = (p.M + BM - 1) / BM;
+    // CTA pairs (cta_group::2) whenever there are at least as many 256-row pair tiles as SM pairs
+    const bool pair = allow_pair && ((tiles_m + 1) / 2) * (Cout / bn) >= n_sm / 2;
+    const int stage_bytes = A_BYTES + (pair ? bn / 2 : bn) * BK * 4;
+    int stages = (190 * 1024) / stage_bytes;
+    if (stages > 8) stages = 8;
+    p.stages = stages;
+    const int smem_bytes = stages * stage_bytes + STG_BYTES + (2 * stages + 4) * 8 + 16 + 1024;
     p.tiles_n = Cout / bn;
-    p.tiles_total = ((p.M + BM - 1) / BM) * p.tiles_n;
-    const int ctas = p.tiles_total < n_sm ? p.tiles_total : n_sm;
+    p.tiles_total = (pair ? (tiles_m + 1) / 2 : tiles_m) * p.tiles_n;
+    const int workers = pair ? n_sm / 2 : n_sm;
+    const int ctas = p.tiles_total < workers ? p.tiles_total : workers;
     p.tiles_per_cta = (p.tiles_total + ctas - 1) / ctas;
 
     CUtensorMap ma0, ma1, mw;
@@ -284,17 +463,21 @@ extern "C" int sdc_conv_gemm(int kind, const float* a0, int c0, const float* a1,
     const cuuint64_t ktot = (cuuint64_t)taps * (c0 + c1);
     cuuint64_t wd[2] = {ktot, (cuuint64_t)Cout};
     cuuint64_t ws[1] = {ktot * 4};
-    cuuint32_t wb[2] = {BK, (cuuint32_t)bn};
+    cuuint32_t wb[2] = {BK, (cuuint32_t)(pair ? bn / 2 : bn)};
     rc = encode_tmap(&mw, w_packed, 2, wd, ws, wb);
     if (rc) return rc;
 
     static bool attr_set = false;
     if (!attr_set) {
         SDC_CUDA(cudaFuncSetAttribute(conv_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        SDC_CUDA(cudaFuncSetAttribute(conv_gemm2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         attr_set = true;
     }
     const int grid = (p.tiles_total + p.tiles_per_cta - 1) / p.tiles_per_cta;
-    conv_gemm_kernel<<<grid, GEMM_THREADS, smem_bytes, as_stream(stream)>>>(ma0, ma1, mw, p);
+    if (pair)
+        conv_gemm2_kernel<<<2 * grid, GEMM_THREADS, smem_bytes, as_stream(stream)>>>(ma0, ma1, mw, p);
+    else
+        conv_gemm_kernel<<<grid, GEMM_THREADS, smem_bytes, as_stream(stream)>>>(ma0, ma1, mw, p);
     SDC_LAUNCHED();
     return SDC_OK;
 }

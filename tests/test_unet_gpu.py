@@ -46,6 +46,11 @@ CONV_CASES = [
     (1, 3, 16, 128, 128, 128, 128, True, False, True, False),  # row kernel: two segments (256 -> 128)
     (1, 2, 5, 128, 64, 0, 96, True, True, True, True),         # row kernel: odd H (half-empty last pair), residual
     (1, 150, 16, 128, 32, 0, 64, True, False, True, False),    # row kernel: more tile pairs than SMs
+    (1, 40, 8, 64, 64, 32, 128, True, False, True, False),     # CTA-pair kernel (cta_group::2): 160 M tiles, 2 segments
+    (1, 149, 4, 32, 64, 0, 256, True, True, True, True),       # CTA-pair: odd tile count (phantom half), N=256, residual
+    (0, 80, 8, 64, 128, 0, 384, False, False, False, False),   # CTA-pair 1x1, three N tiles
+    (2, 598, 2, 16, 64, 0, 64, True, False, False, True),      # CTA-pair unshuffle, 4 images per tile, ragged last tile
+    (1, 600, 2, 16, 32, 32, 96, True, False, True, False),     # CTA-pair, N tile 32 -> half tiles of 16 rows
 ]
 
 
