@@ -127,7 +127,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_consta
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
+        {   // whole warp walks the loops (uniform control flow); one elected lane issues the MMAs and commits
             const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(p.bn >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
             int g = 0, it = 0;
             for (int tile = tile_lo; tile < tile_hi; ++tile, ++it) {
@@ -143,14 +143,17 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_consta
                     const uint32_t sa = smem_u32(smem + s * stage_bytes);
                     const uint64_t adesc = make_sw128_desc(sa);
                     const uint64_t bdesc = make_sw128_desc(sa + A_BYTES);
+                    if (elect_one()) {
 #pragma unroll
-                    for (int k = 0; k < BK / 8; ++k) {
-                        // advance 8 TF32 = 32 bytes along K inside the 128-byte swizzle row: +2 in the (addr >> 4) field
-                        umma_tf32(tmem_d, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kb | k) != 0);
+                        for (int k = 0; k < BK / 8; ++k) {
+                            // advance 8 TF32 = 32 bytes along K inside the 128-byte swizzle row: +2 in the (addr >> 4) field
+                            umma_tf32(tmem_d, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kb | k) != 0);
+                        }
+                        umma_commit(&empty_bar[s]);
+                        if (kb == num_kb - 1) umma_commit(&acc_full[buf]);
                     }
-                    umma_commit(&empty_bar[s]);
+                    __syncwarp();
                 }
-                umma_commit(&acc_full[buf]);
             }
         }
     } else {
@@ -302,7 +305,7 @@ conv_gemm2_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
             }
         }
     } else if (warp == 1) {
-        if (leader && lane == 0) {
+        if (leader) {
             const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(p.bn >> 3) << 17) | ((uint32_t)((2 * BM) >> 4) << 24);
             int g = 0, it = 0;
             for (int tile = tile_lo; tile < tile_hi; ++tile, ++it) {
@@ -318,12 +321,15 @@ conv_gemm2_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
                     const uint32_t sa = smem_u32(smem + s * stage_bytes);
                     const uint64_t adesc = make_sw128_desc(sa);
                     const uint64_t bdesc = make_sw128_desc(sa + A_BYTES);
+                    if (elect_one()) {
 #pragma unroll
-                    for (int k = 0; k < BK / 8; ++k)
-                        umma_tf32_2sm(tmem_d, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kb | k) != 0);
-                    umma_commit_2sm(&empty_bar[s]);
+                        for (int k = 0; k < BK / 8; ++k)
+                            umma_tf32_2sm(tmem_d, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kb | k) != 0);
+                        umma_commit_2sm(&empty_bar[s]);
+                        if (kb == num_kb - 1) umma_commit_2sm(&acc_full[buf]);
+                    }
+                    __syncwarp();
                 }
-                umma_commit_2sm(&acc_full[buf]);
             }
         }
     } else {

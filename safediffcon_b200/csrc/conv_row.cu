@@ -9,7 +9,7 @@
 // UMMA shared-memory descriptor start address (the 128B swizzle phase follows the absolute address).  Each weight tile is
 // used by both rows.  Operand traffic drops from 64 to ~23 KB per 128x128x32 MAC block.
 //
-//   warp 0   TMA producer: halo ring (2 stages) + weight-tile ring (4 stages)
+//   warp 0   TMA producer of the weight-tile ring (4 stages; 8 half tiles with CTA pairs);  warp 6: halo ring (2 stages)
 //   warp 1   MMA issuer: 9 taps x 2 rows x 4 (K=8) tcgen05.mma.kind::tf32 per chunk, accumulators in TMEM
 //            (2 rows x Cout columns, double buffered)
 //   warps 2-5 epilogue (same as conv_gemm.cu): TMEM -> smem transpose -> coalesced rows, bias, GN statistics
@@ -24,7 +24,7 @@ constexpr int HALO_W = RW + 2;
 constexpr int HALO_ROWS = 4 * HALO_W;        // 520 pixel rows of 128 bytes
 constexpr int HALO_BYTES = HALO_ROWS * 128;  // 66,560 = 65 * 1024 (keeps every stage 1024-byte aligned)
 constexpr int ROW_BSTAGES = 4;
-constexpr int ROW_THREADS = 192;
+constexpr int ROW_THREADS = 224;   // warp 0 weight TMA, 1 MMA, 2-5 epilogue, 6 halo TMA
 constexpr int RSTG_LD = 36;
 constexpr int RSTG_BYTES = 4 * 32 * RSTG_LD * 4;
 
@@ -33,27 +33,34 @@ struct RowParams {
     int c0, c1;
     int pairs_total, pairs_per_cta, pairs_per_image;
     int round_tf32;
+    int dbg;                 // experiments: bit0 = no TMA (MMA runs on whatever is in smem), bit1 = epilogue skips global stores
     const float* bias;
     const float* residual;
     float* out;
     double* stats;
 };
 
-__global__ void __launch_bounds__(ROW_THREADS, 1)
-conv_row_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ CUtensorMap map_a1,
-                const __grid_constant__ CUtensorMap map_w, const RowParams p) {
+// PAIR = true: cta_group::2.  A cluster of two CTAs computes FOUR image rows (CTA r: rows h0+2r, h0+2r+1); every MMA is
+// M = 256 (row j of both CTAs) and each CTA stages only half of each weight tile, so the weight ring is twice as deep
+// for the same shared memory and the per-SM operand traffic drops from 46 to 30 B/clk.
+template <bool PAIR>
+__device__ __forceinline__ void conv_row_body(const CUtensorMap& map_a0, const CUtensorMap& map_a1, const CUtensorMap& map_w,
+                                              const RowParams& p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-    const int b_bytes = p.bn * 128;
+    const int b_bytes = (PAIR ? p.bn / 2 : p.bn) * 128;   // weight rows staged by this CTA
+    constexpr int NB = PAIR ? 2 * ROW_BSTAGES : ROW_BSTAGES;
+    const uint32_t rank = PAIR ? cluster_ctarank() : 0u;
+    const bool leader = rank == 0;
     uint8_t* halo = smem;                                   // [2][HALO_BYTES]
-    uint8_t* bring = smem + 2 * HALO_BYTES;                 // [ROW_BSTAGES][b_bytes] (b_bytes multiple of 4096)
-    float* staging = reinterpret_cast<float*>(bring + ROW_BSTAGES * b_bytes);
+    uint8_t* bring = smem + 2 * HALO_BYTES;                 // [NB][b_bytes] (b_bytes multiple of 1024)
+    float* staging = reinterpret_cast<float*>(bring + NB * b_bytes);
     uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(staging) + RSTG_BYTES);
     uint64_t* halo_full = bars;            // [2]
     uint64_t* halo_empty = bars + 2;       // [2]
-    uint64_t* b_full = bars + 4;           // [ROW_BSTAGES]
-    uint64_t* b_empty = b_full + ROW_BSTAGES;
-    uint64_t* acc_full = b_empty + ROW_BSTAGES;   // [2]
+    uint64_t* b_full = bars + 4;           // [NB]
+    uint64_t* b_empty = b_full + NB;
+    uint64_t* acc_full = b_empty + NB;   // [2]
     uint64_t* acc_empty = acc_full + 2;           // [2]
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
 
@@ -62,7 +69,7 @@ conv_row_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constan
     const int chunks = ctot / 32;
     uint32_t acc_cols = 32;
     while ((int)acc_cols < p.bn) acc_cols <<= 1;
-    const int pair_lo = blockIdx.x * p.pairs_per_cta;
+    const int pair_lo = (PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x) * p.pairs_per_cta;   // work item = 2 (or 4) image rows
     const int pair_hi = min(p.pairs_total, pair_lo + p.pairs_per_cta);
 
     if (warp == 0 && lane == 0) {
@@ -70,46 +77,60 @@ conv_row_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constan
         if (p.c1) tma_prefetch_desc(&map_a1);
         tma_prefetch_desc(&map_w);
         for (int s = 0; s < 2; ++s) { mbar_init(&halo_full[s], 1); mbar_init(&halo_empty[s], 1); }
-        for (int s = 0; s < ROW_BSTAGES; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); }
-        for (int b = 0; b < 2; ++b) { mbar_init(&acc_full[b], 1); mbar_init(&acc_empty[b], 4); }
+        for (int s = 0; s < NB; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); }
+        for (int b = 0; b < 2; ++b) { mbar_init(&acc_full[b], 1); mbar_init(&acc_empty[b], PAIR ? 8 : 4); }
         fence_barrier_init();
     }
-    if (warp == 1) tmem_alloc(tmem_slot, 4 * acc_cols);
+    if (warp == 1) { if constexpr (PAIR) tmem_alloc_2sm(tmem_slot, 4 * acc_cols); else tmem_alloc(tmem_slot, 4 * acc_cols); }
     tc_fence_before();
-    __syncthreads();
+    if constexpr (PAIR) cluster_sync_all(); else __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp == 0) {
-        if (lane == 0) {
-            // flat sequence of (pair, chunk) work items; the halo of item i+1 is requested after weight tap 3 of item i
+        if (lane == 0 && !(p.dbg & 1)) {
+            // weight-tile producer: flat sequence of (pair, chunk, tap) over the weight ring
             const int items = (pair_hi - pair_lo) * chunks;
-            auto issue_halo = [&](int item) {
-                const int pair = pair_lo + item / chunks, ch = item % chunks;
-                const int b = pair / p.pairs_per_image, h0 = 2 * (pair - b * p.pairs_per_image);
-                const int cc = ch * 32;
-                const bool second = cc >= p.c0;
-                const int hs = item & 1;
-                mbar_wait(&halo_empty[hs], (((uint32_t)(item >> 1)) & 1u) ^ 1u);
-                mbar_expect_tx(&halo_full[hs], (uint32_t)HALO_BYTES);
-                tma_load_4d(halo + hs * HALO_BYTES, second ? &map_a1 : &map_a0, &halo_full[hs], second ? cc - p.c0 : cc, -1, h0 - 1, b);
-            };
-            if (items > 0) issue_halo(0);
             int g = 0;
             for (int item = 0; item < items; ++item) {
                 const int cc = (item % chunks) * 32;
                 for (int tap = 0; tap < 9; ++tap, ++g) {
-                    const int s = g % ROW_BSTAGES;
-                    mbar_wait(&b_empty[s], (((uint32_t)(g / ROW_BSTAGES)) & 1u) ^ 1u);
-                    mbar_expect_tx(&b_full[s], (uint32_t)b_bytes);
-                    tma_load_2d(bring + s * b_bytes, &map_w, &b_full[s], tap * ctot + cc, 0);
-                    if (tap == 3 && item + 1 < items) issue_halo(item + 1);
+                    const int s = g % NB;
+                    mbar_wait(&b_empty[s], (((uint32_t)(g / NB)) & 1u) ^ 1u);
+                    if constexpr (PAIR) {
+                        if (leader) mbar_expect_tx(&b_full[s], (uint32_t)(2 * b_bytes));
+                        tma_load_2d_2sm(bring + s * b_bytes, &map_w, &b_full[s], tap * ctot + cc, (int)rank * (p.bn / 2));
+                    } else {
+                        mbar_expect_tx(&b_full[s], (uint32_t)b_bytes);
+                        tma_load_2d(bring + s * b_bytes, &map_w, &b_full[s], tap * ctot + cc, 0);
+                    }
+                }
+            }
+        }
+    } else if (warp == 6) {
+        if (lane == 0 && !(p.dbg & 1)) {
+            // halo producer (own warp so that waiting for a free halo slot never stalls the weight ring): the halo of
+            // item i+1 is requested as soon as the MMAs of item i-1 have released its slot
+            const int items = (pair_hi - pair_lo) * chunks;
+            for (int item = 0; item < items; ++item) {
+                const int pair = pair_lo + item / chunks, ch = item % chunks;
+                const int b = pair / p.pairs_per_image, h0 = (PAIR ? 4 : 2) * (pair - b * p.pairs_per_image) + 2 * (int)rank;
+                const int cc = ch * 32;
+                const bool second = cc >= p.c0;
+                const int hs = item & 1;
+                mbar_wait(&halo_empty[hs], (((uint32_t)(item >> 1)) & 1u) ^ 1u);
+                if constexpr (PAIR) {
+                    if (leader) mbar_expect_tx(&halo_full[hs], (uint32_t)(2 * HALO_BYTES));
+                    tma_load_4d_2sm(halo + hs * HALO_BYTES, second ? &map_a1 : &map_a0, &halo_full[hs], second ? cc - p.c0 : cc, -1, h0 - 1, b);
+                } else {
+                    mbar_expect_tx(&halo_full[hs], (uint32_t)HALO_BYTES);
+                    tma_load_4d(halo + hs * HALO_BYTES, second ? &map_a1 : &map_a0, &halo_full[hs], second ? cc - p.c0 : cc, -1, h0 - 1, b);
                 }
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
-            const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(p.bn >> 3) << 17) | ((uint32_t)(RW >> 4) << 24);
+        if (leader) {   // whole warp: uniform control flow, one elected lane issues
+            const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(p.bn >> 3) << 17) | ((uint32_t)(((PAIR ? 2 : 1) * RW) >> 4) << 24);
             int g = 0, item = 0, it = 0;
             for (int pair = pair_lo; pair < pair_hi; ++pair, ++it) {
                 const int buf = it & 1;
@@ -118,29 +139,39 @@ conv_row_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constan
                 const uint32_t tmem_d = tmem_base + (uint32_t)buf * 2u * acc_cols;
                 for (int ch = 0; ch < chunks; ++ch, ++item) {
                     const int hs = item & 1;
-                    mbar_wait(&halo_full[hs], ((uint32_t)(item >> 1)) & 1u);
+                    if (!(p.dbg & 1)) mbar_wait(&halo_full[hs], ((uint32_t)(item >> 1)) & 1u);
                     tc_fence_after();
                     const uint32_t ha = smem_u32(halo + hs * HALO_BYTES);
                     for (int tap = 0; tap < 9; ++tap, ++g) {
-                        const int s = g % ROW_BSTAGES;
-                        mbar_wait(&b_full[s], ((uint32_t)(g / ROW_BSTAGES)) & 1u);
+                        const int s = g % NB;
+                        if (!(p.dbg & 1)) mbar_wait(&b_full[s], ((uint32_t)(g / NB)) & 1u);
                         tc_fence_after();
                         const uint32_t ba = smem_u32(bring + s * b_bytes);
                         const int dy = tap / 3, dx = tap - 3 * dy;
+                        if (elect_one()) {
 #pragma unroll
-                        for (int j = 0; j < 2; ++j) {
-                            // A operand = 128 consecutive halo pixels starting at (row j+dy, col dx)
-                            const uint32_t aa = ha + (uint32_t)(((j + dy) * HALO_W + dx) * 128);
+                            for (int j = 0; j < 2; ++j) {
+                                // A operand = 128 consecutive halo pixels starting at (row j+dy, col dx)
+                                const uint32_t aa = ha + (uint32_t)(((j + dy) * HALO_W + dx) * 128);
 #pragma unroll
-                            for (int k = 0; k < 4; ++k)
-                                umma_tf32(tmem_d + (uint32_t)j * acc_cols, make_sw128_desc(aa + 32u * k), make_sw128_desc(ba + 32u * k),
-                                          idesc, (ch | tap | k) != 0);
+                                for (int k = 0; k < 4; ++k) {
+                                    if constexpr (PAIR)
+                                        umma_tf32_2sm(tmem_d + (uint32_t)j * acc_cols, make_sw128_desc(aa + 32u * k), make_sw128_desc(ba + 32u * k),
+                                                      idesc, (ch | tap | k) != 0);
+                                    else
+                                        umma_tf32(tmem_d + (uint32_t)j * acc_cols, make_sw128_desc(aa + 32u * k), make_sw128_desc(ba + 32u * k),
+                                                  idesc, (ch | tap | k) != 0);
+                                }
+                            }
+                            if constexpr (PAIR) umma_commit_2sm(&b_empty[s]); else umma_commit(&b_empty[s]);
+                            if (tap == 8) {
+                                if constexpr (PAIR) umma_commit_2sm(&halo_empty[hs]); else umma_commit(&halo_empty[hs]);
+                                if (ch == chunks - 1) { if constexpr (PAIR) umma_commit_2sm(&acc_full[buf]); else umma_commit(&acc_full[buf]); }
+                            }
                         }
-                        umma_commit(&b_empty[s]);
+                        __syncwarp();
                     }
-                    umma_commit(&halo_empty[hs]);
                 }
-                umma_commit(&acc_full[buf]);
             }
         }
     } else {
@@ -149,7 +180,7 @@ conv_row_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constan
         const int sub_r = lane >> 3, sub_c = (lane & 7) * 4;
         int it = 0;
         for (int pair = pair_lo; pair < pair_hi; ++pair, ++it) {
-            const int b = pair / p.pairs_per_image, h0 = 2 * (pair - b * p.pairs_per_image);
+            const int b = pair / p.pairs_per_image, h0 = (PAIR ? 4 : 2) * (pair - b * p.pairs_per_image) + 2 * (int)rank;
             const int buf = it & 1;
             mbar_wait(&acc_full[buf], (uint32_t)(it >> 1) & 1u);
             tc_fence_after();
@@ -168,7 +199,7 @@ conv_row_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constan
                     const int col = c + sub_c;
                     float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
                     if (p.bias) bv = __ldg(reinterpret_cast<const float4*>(p.bias + col));
-                    if (row_ok) {
+                    if (row_ok && !(p.dbg & 2)) {
 #pragma unroll
                         for (int i = 0; i < 8; ++i) {
                             const int rr = sub_r + 4 * i;
@@ -190,11 +221,11 @@ conv_row_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constan
             }
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&acc_empty[buf]);
+            if (lane == 0) { if constexpr (PAIR) mbar_arrive_leader(&acc_empty[buf]); else mbar_arrive(&acc_empty[buf]); }
             if (p.stats) {
                 s1 = warp_sum(s1);
                 s2 = warp_sum(s2);
-                if (lane == 0) {
+                if (lane == 0 && h0 < p.H) {
                     atomicAdd(p.stats + 2 * b, (double)s1);
                     atomicAdd(p.stats + 2 * b + 1, (double)s2);
                 }
@@ -203,10 +234,22 @@ conv_row_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constan
         tc_fence_before();
     }
     __syncthreads();
+    if constexpr (PAIR) cluster_sync_all();
     if (warp == 1) {
         tc_fence_after();
-        tmem_dealloc(tmem_base, 4 * acc_cols);
+        if constexpr (PAIR) tmem_dealloc_2sm(tmem_base, 4 * acc_cols); else tmem_dealloc(tmem_base, 4 * acc_cols);
     }
+}
+
+__global__ void __launch_bounds__(ROW_THREADS, 1)
+conv_row_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ CUtensorMap map_a1,
+                const __grid_constant__ CUtensorMap map_w, const RowParams p) {
+    conv_row_body<false>(map_a0, map_a1, map_w, p);
+}
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(ROW_THREADS, 1)
+conv_row2_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ CUtensorMap map_a1,
+                 const __grid_constant__ CUtensorMap map_w, const RowParams p) {
+    conv_row_body<true>(map_a0, map_a1, map_w, p);
 }
 
 }  // namespace sdc
@@ -222,12 +265,16 @@ extern "C" int sdc_conv3x3_row(const float* a0, int c0, const float* a1, int c1,
     RowParams p{};
     p.B = B; p.H = H; p.Cout = Cout; p.bn = Cout; p.c0 = c0; p.c1 = c1; p.round_tf32 = round_tf32;
     p.bias = bias; p.residual = residual; p.out = out; p.stats = stats;
-    p.pairs_per_image = (H + 1) / 2;
-    p.pairs_total = B * p.pairs_per_image;
+    { const char* e = getenv("SDC_ROW_DBG"); p.dbg = e ? atoi(e) : 0; }
     int n_sm = 148, dev = 0;
     SDC_CUDA(cudaGetDevice(&dev));
     SDC_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
-    const int ctas = p.pairs_total < n_sm ? p.pairs_total : n_sm;
+    static const bool allow_pair = []() { const char* e = getenv("SDC_NO_2CTA"); return !(e && e[0] == '1'); }();
+    const bool pair = allow_pair && Cout % 32 == 0 && (Cout / 2) % 8 == 0 && B * ((H + 3) / 4) >= n_sm / 2;
+    p.pairs_per_image = pair ? (H + 3) / 4 : (H + 1) / 2;
+    p.pairs_total = B * p.pairs_per_image;
+    const int workers = pair ? n_sm / 2 : n_sm;
+    const int ctas = p.pairs_total < workers ? p.pairs_total : workers;
     p.pairs_per_cta = (p.pairs_total + ctas - 1) / ctas;
     const int grid = (p.pairs_total + p.pairs_per_cta - 1) / p.pairs_per_cta;
 
@@ -244,16 +291,20 @@ extern "C" int sdc_conv3x3_row(const float* a0, int c0, const float* a1, int c1,
     const cuuint64_t ktot = (cuuint64_t)9 * (c0 + c1);
     cuuint64_t wd[2] = {ktot, (cuuint64_t)Cout};
     cuuint64_t ws[1] = {ktot * 4};
-    cuuint32_t wb[2] = {32, (cuuint32_t)Cout};
+    cuuint32_t wb[2] = {32, (cuuint32_t)(pair ? Cout / 2 : Cout)};
     rc = encode_tmap(&mw, w_packed, 2, wd, ws, wb);
     if (rc) return rc;
-    const int smem_bytes = 2 * HALO_BYTES + ROW_BSTAGES * Cout * 128 + RSTG_BYTES + 16 * 8 + 16 + 1024;
+    const int smem_bytes = 2 * HALO_BYTES + ROW_BSTAGES * Cout * 128 + RSTG_BYTES + 24 * 8 + 16 + 1024;
     static bool attr_set = false;
     if (!attr_set) {
         SDC_CUDA(cudaFuncSetAttribute(conv_row_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        SDC_CUDA(cudaFuncSetAttribute(conv_row2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         attr_set = true;
     }
-    conv_row_kernel<<<grid, ROW_THREADS, smem_bytes, as_stream(stream)>>>(ma0, ma1, mw, p);
+    if (pair)
+        conv_row2_kernel<<<2 * grid, ROW_THREADS, smem_bytes, as_stream(stream)>>>(ma0, ma1, mw, p);
+    else
+        conv_row_kernel<<<grid, ROW_THREADS, smem_bytes, as_stream(stream)>>>(ma0, ma1, mw, p);
     SDC_LAUNCHED();
     return SDC_OK;
 }

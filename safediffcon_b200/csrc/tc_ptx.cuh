@@ -8,6 +8,18 @@ namespace sdc {
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
+// one lane of a fully converged warp (elect.sync): keeps the surrounding control flow warp-uniform so that ptxas holds
+// descriptors / addresses in uniform registers instead of wrapping every UTCHMMA / UTMALDG in an R2UR election loop
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "elect.sync _|p, 0xffffffff;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n" : "=r"(pred));
+    return pred != 0;
+}
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
 }

@@ -51,6 +51,8 @@ CONV_CASES = [
     (0, 80, 8, 64, 128, 0, 384, False, False, False, False),   # CTA-pair 1x1, three N tiles
     (2, 598, 2, 16, 64, 0, 64, True, False, False, True),      # CTA-pair unshuffle, 4 images per tile, ragged last tile
     (1, 600, 2, 16, 32, 32, 96, True, False, True, False),     # CTA-pair, N tile 32 -> half tiles of 16 rows
+    (1, 80, 6, 128, 32, 32, 64, True, True, True, True),       # row kernel, CTA pairs, H=6: phantom rows in the 2nd CTA
+    (1, 160, 16, 128, 128, 0, 128, True, False, True, False),  # row kernel, CTA pairs, production shape
 ]
 
 
