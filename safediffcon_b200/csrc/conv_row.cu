@@ -200,16 +200,19 @@ __device__ __forceinline__ void conv_row_body(const CUtensorMap& map_a0, const C
                     float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
                     if (p.bias) bv = __ldg(reinterpret_cast<const float4*>(p.bias + col));
                     if (row_ok && !(p.dbg & 2)) {
+                        float4 rv[8];
+                        if (p.residual) {
+#pragma unroll
+                            for (int i = 0; i < 8; ++i)
+                                rv[i] = __ldg(reinterpret_cast<const float4*>(p.residual + (m_w + sub_r + 4 * i) * p.Cout + col));
+                        }
 #pragma unroll
                         for (int i = 0; i < 8; ++i) {
                             const int rr = sub_r + 4 * i;
                             const size_t m = m_w + rr;
                             float4 v = *reinterpret_cast<const float4*>(stg + rr * RSTG_LD + sub_c);
                             v.x += bv.x; v.y += bv.y; v.z += bv.z; v.w += bv.w;
-                            if (p.residual) {
-                                const float4 rv = __ldg(reinterpret_cast<const float4*>(p.residual + m * p.Cout + col));
-                                v.x += rv.x; v.y += rv.y; v.z += rv.z; v.w += rv.w;
-                            }
+                            if (p.residual) { v.x += rv[i].x; v.y += rv[i].y; v.z += rv[i].z; v.w += rv[i].w; }
                             s1 += (v.x + v.y) + (v.z + v.w);
                             s2 += (v.x * v.x + v.y * v.y) + (v.z * v.z + v.w * v.w);
                             if (p.round_tf32) { v.x = to_tf32(v.x); v.y = to_tf32(v.y); v.z = to_tf32(v.z); v.w = to_tf32(v.w); }
