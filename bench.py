@@ -30,6 +30,7 @@ import torch  # noqa: E402
 CHAIN_STEPS = 1000
 CONV_GFLOP_PER_SAMPLE = 27.811 - 0.0771 - 0.0016  # tcgen05 convs only: minus the 7x7 stem and the 3-channel head
 W_SCORE, U_BOUND, Q_GUIDE = 500.0, 0.8, 0.0
+TRAFFIC_BYTES_PER_LAUNCH = None  # dram bytes per launch of the dominant kernel from the ncu --set full capture (profiles/), if taken
 
 
 class Cfg:
@@ -295,12 +296,16 @@ def main():
     n_conv = len(prof) // 2
     achieved = conv_flops / (conv_ms * 1e-3) / 1e12
     peak = pk.get("bf16_tflops_sustained", pk.get("bf16_tflops"))
-    roof = {"bound": "tensor", "kernel": "sdc::conv_gemm_kernel (tcgen05.mma kind::tf32, TMA operands)", "achieved": achieved,
-            "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None,
-            "peak_source": f"{pk_kind} bf16_tflops_sustained (kernel timed inside a long step); the kernel computes in TF32 whose "
-                           "hardware rate is half the BF16 rate, so frac_of_tf32_rate = 2*frac",
-            "frac_of_tf32_rate": 2 * achieved / peak, "launches_per_step": n_conv, "conv_ms_per_step": conv_ms,
+    f16 = net.precision == "f16"
+    roof = {"bound": "tensor", "kernel": f"sdc::conv_gemm2_kernel / conv_row2_kernel (tcgen05.mma cta_group::2 kind::{'f16' if f16 else 'tf32'}, "
+                                         "TMA operands, FP32 accumulate in TMEM)", "achieved": achieved,
+            "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": TRAFFIC_BYTES_PER_LAUNCH,
+            "peak_source": f"{pk_kind} bf16_tflops_sustained (kernel timed inside a long step; FP16 and BF16 share the kind::f16 rate)"
+                           + ("" if f16 else "; the kernel computes in TF32 whose hardware rate is half the BF16 rate"),
+            "launches_per_step": n_conv, "conv_ms_per_step": conv_ms,
             "conv_share_of_step": conv_ms / ms_step, "algorithmic_gflop_per_step": conv_flops / 1e9}
+    if not f16:
+        roof["frac_of_tf32_rate"] = 2 * achieved / peak
 
     # ---- end to end through the public API with host buffers: one full chain + control + scoring ----
     e2e = None
@@ -321,7 +326,7 @@ def main():
     if rank == 0:
         line = {"metric": "guided_ddpm_chain_samples_per_s", "value": value, "unit": "samples/s", "n_gpus": ws, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-                "dtype": "tf32", "data": "synthetic", "config": workload_config(args), "clocks": clocks, "gpu_launches": int(launches),
+                "dtype": net.precision, "data": "synthetic", "config": workload_config(args), "clocks": clocks, "gpu_launches": int(launches),
                 "roofline": roof,
                 "solver": {"rollouts_per_s": ws * n_loc / (ms_solver / 1e3), "n": ws * n_loc, "ms": ms_solver, "mode": "strict fp32",
                            "fp32_tflops_algorithmic": ws * n_loc * 17.92e6 / (ms_solver / 1e3) / 1e12,

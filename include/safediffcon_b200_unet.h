@@ -1,9 +1,13 @@
 /* safediffcon_b200 -- C ABI of the denoiser (Unet2D) building blocks.  See safediffcon_b200.h for conventions.
  *
- * Activation layout: NHWC fp32 ([B*H*W, C] row-major, "pixel rows"), values rounded to TF32 (round-to-nearest)
- * by the producing kernel whenever a convolution consumes them.  Weights are packed once per parameter
- * version by sdc_pack_conv_weight.  The ops are exposed individually (each is parity-tested against its
- * torch counterpart); safediffcon_b200/unet.py strings them into Unet2D.forward
+ * Activation layout: NHWC ([B*H*W, C] row-major, "pixel rows").  Tensors that feed a tensor-core convolution
+ * ("operands") are stored in the operand precision selected by `prec`, rounded to nearest by the producing kernel:
+ *   SDC_PREC_TF32: fp32 containers holding TF32 values (10-bit mantissa), tcgen05.mma.kind::tf32;
+ *   SDC_PREC_F16 : IEEE fp16 (same 10-bit mantissa, half the bytes, twice the tensor rate), tcgen05.mma.kind::f16.
+ * Accumulation is always FP32; tensors that feed normalisation statistics or softmax (conv outputs ahead of
+ * GroupNorm, qkv) stay fp32.  In the signatures below `const void*` operands are `float*` (TF32) or `__half*` (F16).
+ * Weights are packed once per parameter version by sdc_pack_conv_weight.  The ops are exposed individually (each
+ * is parity-tested against its torch counterpart); safediffcon_b200/unet.py strings them into Unet2D.forward
  * (reference: 1D/model/unet.py:382-426).
  */
 #ifndef SAFEDIFFCON_B200_UNET_H
@@ -13,59 +17,67 @@
 extern "C" {
 #endif
 
+#define SDC_PREC_TF32 0
+#define SDC_PREC_F16 1
+
 /* Repack an OIHW fp32 conv weight [Cout, Cin, kh, kw] into the K-major GEMM operand Wp[Cout, taps*Cin]
- * (K index = tap*Cin + cin, tap = ky*kw_ + kx), rounding to TF32 (nearest).
+ * (K index = tap*Cin + cin, tap = ky*kw_ + kx), rounded to the operand precision.
  * kind 0: 1x1, 1: 3x3, 2: the 1x1 conv that follows the pixel-unshuffle of Downsample2d (unet.py:39-43):
  * Cin = 4*C with channel index c*4 + p1*2 + p2  ->  K index = (p1*2+p2)*C + c. */
-int sdc_pack_conv_weight(int kind, const float* w_oihw, float* w_packed, int Cout, int Cin, void* stream);
+int sdc_pack_conv_weight(int prec, int kind, const float* w_oihw, void* w_packed, int Cout, int Cin, void* stream);
 
 /* Implicit-GEMM convolution on tcgen05 (replaces nn.Conv2d 3x3 pad 1 / 1x1, unet.py:132,161,189-192,232-233,345,370,
- * and Downsample2d, unet.py:39-43).  Inputs: one or two NHWC tensors (a1 = second K segment of a channel concat,
- * c1 = 0 if absent) of spatial size H x W (kind 2: 2H x 2W).  out[B*H*W, Cout] = conv + bias (+ residual[B*H*W, Cout]).
- * stats (optional): double[B][2], += (sum, sum of squares) of the stored fp32 values per sample (GroupNorm(1, C)).
- * round_tf32: store values rounded to TF32.  Requirements: W | 128, (H*W) % 32 == 0, channels % 32 == 0. */
-int sdc_conv_gemm(int kind, const float* a0, int c0, const float* a1, int c1, const float* w_packed, const float* bias,
-                  const float* residual, float* out, double* stats, int round_tf32, int B, int H, int W, int Cout,
+ * and Downsample2d, unet.py:39-43).  Inputs: one or two NHWC operand tensors (a1 = second K segment of a channel
+ * concat, c1 = 0 if absent) of spatial size H x W (kind 2: 2H x 2W).
+ * out[B*H*W, Cout] = conv + bias (+ residual[B*H*W, Cout], an operand-precision tensor).
+ * stats (optional): double[B][2], += (sum, sum of squares) of the fp32 results per sample (GroupNorm(1, C)).
+ * operand_out: 1 = store `out` in the operand precision (it feeds another convolution), 0 = plain fp32.
+ * Requirements: W | 128, (H*W) % 32 == 0, input channels % 32 (TF32) / % 64 (F16) == 0, Cout % 32 == 0. */
+int sdc_conv_gemm(int prec, int kind, const void* a0, int c0, const void* a1, int c1, const void* w_packed, const float* bias,
+                  const void* residual, void* out, double* stats, int operand_out, int B, int H, int W, int Cout,
                   void* stream);
 
 /* Same contract as sdc_conv_gemm(kind = 3x3) for the full-resolution level: W == 128 and Cout <= 128.  One CTA computes
- * two image rows and loads the activation halo once per 32-channel chunk (the 9 taps are shifted UMMA descriptor views of
- * it), cutting L2->SMEM operand traffic ~2.8x.  Returns -1 (and does nothing) when the shape is not eligible. */
-int sdc_conv3x3_row(const float* a0, int c0, const float* a1, int c1, const float* w_packed, const float* bias,
-                    const float* residual, float* out, double* stats, int round_tf32, int B, int H, int W, int Cout,
+ * two image rows and loads the activation halo once per 128-byte channel chunk (the 9 taps are shifted UMMA descriptor
+ * views of it), cutting L2->SMEM operand traffic ~2.8x.  Returns -1 (and does nothing) when the shape is not eligible. */
+int sdc_conv3x3_row(int prec, const void* a0, int c0, const void* a1, int c1, const void* w_packed, const float* bias,
+                    const void* residual, void* out, double* stats, int operand_out, int B, int H, int W, int Cout,
                     void* stream);
 
-/* Stem: 7x7 pad 3 convolution of the NCHW model input (unet.py:326,392).  x:[B,Cin,H,W] NCHW, w:[Cout,Cin,7,7] OIHW
- * (unpacked, fp32), out: NHWC [B*H*W, Cout] rounded to TF32.  FP32 CUDA-core kernel (0.3% of the FLOPs). */
-int sdc_stem_conv7(const float* x, const float* w, const float* bias, float* out, int B, int Cin, int H, int W, int Cout,
-                   void* stream);
+/* Stem: 7x7 pad 3 convolution of the NCHW model input (unet.py:326,392).  x:[B,Cin,H,W] NCHW fp32, w:[Cout,Cin,7,7] OIHW
+ * (unpacked, fp32), out: NHWC operand [B*H*W, Cout].  FP32 CUDA-core kernel (0.3% of the FLOPs). */
+int sdc_stem_conv7(int prec, const float* x, const float* w, const float* bias, void* out, int B, int Cin, int H, int W,
+                   int Cout, void* stream);
 
 /* GroupNorm(1, C) apply + FiLM + SiLU (+ residual), Block.forward (unet.py:138-147) and ResnetBlock's sum (:180):
  * y = silu(((x - mean_b) * rstd_b * gamma_c + beta_c) * (scale_bc + 1) + shift_bc) + res ; mean/rstd from
  * stats[b] = (sum, sumsq) over C*HW elements, eps 1e-5, biased variance.  scale_shift: [n_t, 2C] rows
- * (scale | shift) indexed by t_index[b] (NULL t_index = row 0 for every sample), or NULL for none.  y rounded to TF32. */
-int sdc_gn_silu(const float* x, const double* stats, const float* gamma, const float* beta, const float* scale_shift,
-                const int32_t* t_index, int64_t ss_stride, const float* residual, float* y, int B, int HW, int C, void* stream);
+ * (scale | shift) indexed by t_index[b] (NULL t_index = row 0 for every sample), or NULL for none.
+ * x: fp32 (a conv output).  residual: operand precision if residual_operand else fp32.  y: operand. */
+int sdc_gn_silu(int prec, const float* x, const double* stats, const float* gamma, const float* beta, const float* scale_shift,
+                const int32_t* t_index, int64_t ss_stride, const void* residual, int residual_operand, void* y, int B, int HW,
+                int C, void* stream);
 
 /* Channel LayerNorm (unet.py:53-63): y = (x - mean_c) * rsqrt(var_c + 1e-5) * g (+ residual), per pixel row.
- * round_tf32: round y to TF32. */
-int sdc_channel_layernorm(const float* x, const float* g, const float* residual, float* y, int64_t M, int C, int round_tf32,
-                          void* stream);
+ * x: operand precision if x_operand else fp32; residual and y: operand precision (TF32 mode: y is rounded to TF32
+ * only when operand_out is set; F16 mode: y is always fp16). */
+int sdc_channel_layernorm(int prec, const void* x, int x_operand, const float* g, const void* residual, void* y, int64_t M,
+                          int C, int operand_out, void* stream);
 
-/* LinearAttention core (unet.py:202-222) on qkv:[B*n, 384] rows (q | k | v, each heads*32 channels):
- * q <- softmax_d(q) * 32^-0.5 ; k <- softmax_n(k) ; ctx = k v^T ; out[B*n, 128] = ctx^T q, rounded to TF32.
+/* LinearAttention core (unet.py:202-222) on fp32 qkv:[B*n, 384] rows (q | k | v, each heads*32 channels):
+ * q <- softmax_d(q) * 32^-0.5 ; k <- softmax_n(k) ; ctx = k v^T ; out[B*n, 128] = ctx^T q, an operand.
  * workspace: >= sdc_linear_attention_workspace(B) bytes. */
 int64_t sdc_linear_attention_workspace(int B);
-int sdc_linear_attention(const float* qkv, float* out, void* workspace, int B, int n, void* stream);
+int sdc_linear_attention(int prec, const float* qkv, void* out, void* workspace, int B, int n, void* stream);
 
-/* Full softmax attention core (unet.py:239-258) for n <= 64 tokens: out[B*n, 128], rounded to TF32. */
-int sdc_attention(const float* qkv, float* out, int B, int n, void* stream);
+/* Full softmax attention core (unet.py:239-258) for n <= 32 tokens: out[B*n, 128], an operand. */
+int sdc_attention(int prec, const float* qkv, void* out, int B, int n, void* stream);
 
-/* Nearest-neighbour x2 upsample of an NHWC tensor (nn.Upsample(scale_factor=2), unet.py:33-37). */
-int sdc_upsample2x(const float* x, float* y, int B, int H, int W, int C, void* stream);
+/* Nearest-neighbour x2 upsample of an NHWC operand tensor (nn.Upsample(scale_factor=2), unet.py:33-37). */
+int sdc_upsample2x(int prec, const void* x, void* y, int B, int H, int W, int C, void* stream);
 
-/* Final 1x1 conv to the model's output channels, NHWC -> NCHW (unet.py:378,426).  w:[Cout, Cin], out:[B,Cout,H,W]. */
-int sdc_head_conv1(const float* x, const float* w, const float* bias, float* out, int B, int HW, int Cin, int Cout,
+/* Final 1x1 conv to the model's output channels, NHWC operand -> NCHW fp32 (unet.py:378,426).  w:[Cout, Cin] fp32. */
+int sdc_head_conv1(int prec, const void* x, const float* w, const float* bias, float* out, int B, int HW, int Cin, int Cout,
                    void* stream);
 
 /* Rows of a small dense layer: y[r, :] = act_in(x[r, :]) @ w[N, K]^T + b, act_in 0 = identity, 1 = SiLU, 2 = GELU(erf)

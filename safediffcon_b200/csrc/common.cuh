@@ -1,6 +1,7 @@
 // Shared helpers for the safediffcon_b200 C-ABI library (sm_100a only).
 #pragma once
 #include <cuda_runtime.h>
+#include <cuda_fp16.h>
 #include <stdint.h>
 #include <stdio.h>
 #include <atomic>
@@ -59,6 +60,36 @@ __device__ __forceinline__ float to_tf32(float x) {
     asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
     return __uint_as_float(r);
 }
+
+// 4-element loads / stores of activations in either operand precision (fp32 containers or fp16)
+__device__ __forceinline__ float4 load4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+__device__ __forceinline__ float4 load4(const __half* p) {
+    const uint2 u = *reinterpret_cast<const uint2*>(p);
+    const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&u.x)), b = __half22float2(*reinterpret_cast<const __half2*>(&u.y));
+    return make_float4(a.x, a.y, b.x, b.y);
+}
+__device__ __forceinline__ float4 load4_nc(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+__device__ __forceinline__ float4 load4_nc(const __half* p) {
+    const uint2 u = __ldg(reinterpret_cast<const uint2*>(p));
+    const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&u.x)), b = __half22float2(*reinterpret_cast<const __half2*>(&u.y));
+    return make_float4(a.x, a.y, b.x, b.y);
+}
+__device__ __forceinline__ void store4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
+// store as a tensor-core operand: TF32-rounded fp32 container, or fp16 (both round to nearest, 10-bit mantissa)
+__device__ __forceinline__ void store_operand4(float* p, float4 v) {
+    *reinterpret_cast<float4*>(p) = make_float4(to_tf32(v.x), to_tf32(v.y), to_tf32(v.z), to_tf32(v.w));
+}
+__device__ __forceinline__ void store_operand4(__half* p, float4 v) {
+    const __half2 a = __floats2half2_rn(v.x, v.y), b = __floats2half2_rn(v.z, v.w);
+    uint2 u;
+    u.x = *reinterpret_cast<const uint32_t*>(&a);
+    u.y = *reinterpret_cast<const uint32_t*>(&b);
+    *reinterpret_cast<uint2*>(p) = u;
+}
+__device__ __forceinline__ float to_operand(float v, float) { return to_tf32(v); }
+__device__ __forceinline__ __half to_operand(float v, __half) { return __float2half_rn(v); }
+template <bool HALF> struct ActT { using type = float; };
+template <> struct ActT<true> { using type = __half; };
 
 // Philox4x32-10 counter RNG (Salmon et al. 2011), written out here so the stream is ours and reproducible
 // independent of torch/cuRAND versions.

@@ -19,6 +19,7 @@
 //   The accumulator is double buffered in TMEM (2 x BN columns): the epilogue of tile i overlaps the MMAs of i+1.
 // Precision: TF32 operands (10-bit mantissa, rounded to nearest when produced), FP32 accumulation.
 #include "tc_ptx.cuh"
+#include "../../include/safediffcon_b200_unet.h"
 #include <math.h>
 #include <stdlib.h>
 
@@ -26,8 +27,7 @@ namespace sdc {
 
 // ------------------------------------------------------------------------------------------ kernel
 constexpr int BM = 128;        // output pixels per tile (= UMMA M)
-constexpr int BK = 32;         // TF32 elements per K block (= 128 bytes = one swizzle row)
-constexpr int A_BYTES = BM * BK * 4;
+constexpr int A_BYTES = BM * 128;   // one K block of activations: 128 rows of 128 bytes (32 TF32 or 64 FP16 channels)
 constexpr int GEMM_THREADS = 192;
 constexpr int STG_LD = 36;     // staging row stride in floats (32 + 4: conflict-free 16-byte accesses)
 constexpr int STG_BYTES = 4 * 32 * STG_LD * 4;
@@ -41,25 +41,36 @@ struct GemmParams {
     int bh, bb;          // tile = bb images x bh rows x W cols
     int c0, c1;          // channels of segment 0 / 1 (c1 = 0: single input)
     int stages;
-    int round_tf32;
+    int operand_out;     // 1: out feeds another tensor-core op -> TF32-rounded fp32 (TF32 mode) / fp16 (F16 mode); 0: plain fp32
     int hw_per_sample;   // H*W
     int tiles_n;         // Cout / bn
     int tiles_total;     // tiles_m * tiles_n, tile id = m * tiles_n + n (consecutive ids share the A window)
     int tiles_per_cta;
     const float* bias;       // [Cout] or null
-    const float* residual;   // [M, Cout] or null (added after bias)
-    float* out;              // [M, Cout]
+    const void* residual;    // [M, Cout] in the operand precision, or null (added after bias)
+    void* out;               // [M, Cout]
     double* stats;           // [B, 2] (sum, sumsq) accumulated with atomics, or null
 };
 
-// Persistent kernel: one CTA per SM walks a contiguous range of output tiles.  The accumulator is double
-// buffered in TMEM so the epilogue of tile i overlaps the MMA main loop of tile i+1.
-__global__ void __launch_bounds__(GEMM_THREADS, 1)
-conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ CUtensorMap map_a1,
-                 const __grid_constant__ CUtensorMap map_w, const GemmParams p) {
+// Persistent kernel: one CTA (PAIR = false) or one CTA pair (PAIR = true) per SM (pair) walks a contiguous range of
+// output tiles.  The accumulator is double buffered in TMEM so the epilogue of tile i overlaps the MMAs of tile i+1.
+//
+// PAIR (cta_group::2): a cluster of two CTAs computes a 256 x BN tile.  Each CTA loads its own 128 activation rows but
+// only HALF of the weight slab (BN/2 rows); tcgen05.mma.cta_group::2 (issued by the leader CTA) reads A and B from both
+// CTAs' shared memory and writes each CTA's 128 accumulator rows into its own TMEM.  Per-SM operand traffic per K block
+// drops from 16 KB + BN*128 B to 16 KB + BN*64 B, which is what bounds the 1-CTA kernel.  Barriers: TMA of both CTAs
+// credits the leader's `full`; the MMA commit multicasts to both CTAs' `empty` / `acc_full`; both epilogues arrive on
+// the leader's `acc_empty`.
+template <bool HALF, bool PAIR>
+__device__ __forceinline__ void conv_gemm_body(const CUtensorMap& map_a0, const CUtensorMap& map_a1, const CUtensorMap& map_w,
+                                               const GemmParams& p) {
+    using Op = Operand<HALF>;
+    using act_t = typename ActT<HALF>::type;
+    constexpr int BK = Op::kBK;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-    const int stage_bytes = A_BYTES + p.bn * BK * 4;
+    const int b_rows = PAIR ? p.bn / 2 : p.bn;            // weight rows staged by this CTA
+    const int stage_bytes = A_BYTES + b_rows * 128;
     float* staging = reinterpret_cast<float*>(smem + p.stages * stage_bytes);
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + p.stages * stage_bytes + STG_BYTES);
     uint64_t* empty_bar = full_bar + p.stages;
@@ -68,13 +79,16 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_consta
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = PAIR ? cluster_ctarank() : 0u;
+    const bool leader = rank == 0;
     const int taps = p.kind == 1 ? 9 : (p.kind == 2 ? 4 : 1);
     const int ctot = p.c0 + p.c1;
     const int chunks = ctot / BK;
     const int num_kb = taps * chunks;
     uint32_t acc_cols = 32;                      // TMEM columns per accumulator buffer (power of two >= bn)
     while ((int)acc_cols < p.bn) acc_cols <<= 1;
-    const int tile_lo = blockIdx.x * p.tiles_per_cta;
+    const int worker = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+    const int tile_lo = worker * p.tiles_per_cta;            // PAIR: pair tiles, id = m2 * tiles_n + n
     const int tile_hi = min(p.tiles_total, tile_lo + p.tiles_per_cta);
 
     if (warp == 0 && lane == 0) {
@@ -82,21 +96,22 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_consta
         if (p.c1) tma_prefetch_desc(&map_a1);
         tma_prefetch_desc(&map_w);
         for (int s = 0; s < p.stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-        for (int b = 0; b < 2; ++b) { mbar_init(&acc_full[b], 1); mbar_init(&acc_empty[b], 4); }
+        for (int b = 0; b < 2; ++b) { mbar_init(&acc_full[b], 1); mbar_init(&acc_empty[b], PAIR ? 8 : 4); }
         fence_barrier_init();
     }
-    if (warp == 1) tmem_alloc(tmem_slot, 2 * acc_cols);
+    if (warp == 1) { if constexpr (PAIR) tmem_alloc_2sm(tmem_slot, 2 * acc_cols); else tmem_alloc(tmem_slot, 2 * acc_cols); }
     tc_fence_before();
-    __syncthreads();
+    // PAIR: barriers of both CTAs initialised and TMEM allocated before any remote signalling
+    if constexpr (PAIR) cluster_sync_all(); else __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp == 0) {
         if (lane == 0) {
-            const uint32_t tx = (uint32_t)stage_bytes;
             int g = 0;  // running K-block counter across tiles (smem ring position)
             for (int tile = tile_lo; tile < tile_hi; ++tile) {
-                const int mt = tile / p.tiles_n, nt = tile - mt * p.tiles_n;
+                const int mq = tile / p.tiles_n, nt = tile - mq * p.tiles_n;
+                const int mt = PAIR ? 2 * mq + (int)rank : mq;
                 // tile origin in (image, row); tiles always span full rows (bw == W)
                 const int pix0 = mt * BM;
                 const int b0 = pix0 / p.hw_per_sample;
@@ -107,7 +122,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_consta
                     mbar_wait(&empty_bar[s], ph ^ 1u);
                     uint8_t* sa = smem + s * stage_bytes;
                     uint8_t* sb = sa + A_BYTES;
-                    mbar_expect_tx(&full_bar[s], tx);
+                    if constexpr (PAIR) { if (leader) mbar_expect_tx(&full_bar[s], (uint32_t)(2 * stage_bytes)); }   // bytes of BOTH CTAs
+                    else mbar_expect_tx(&full_bar[s], (uint32_t)stage_bytes);
                     const int tap = kb / chunks;
                     const int cc = (kb - tap * chunks) * BK;          // channel offset in the concatenated input
                     const bool second = cc >= p.c0;
@@ -116,23 +132,26 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_consta
                     if (p.kind == 2) {
                         // input viewed as [B, H, 2(p1), W, 2*C]: coordinate (p2*C + c, w, p1, h, b)
                         const int cin = second ? p.c1 : p.c0;
-                        tma_load_5d(sa, ma, &full_bar[s], (tap & 1) * cin + cseg, 0, tap >> 1, h0, b0);
+                        if constexpr (PAIR) tma_load_5d_2sm(sa, ma, &full_bar[s], (tap & 1) * cin + cseg, 0, tap >> 1, h0, b0);
+                        else tma_load_5d(sa, ma, &full_bar[s], (tap & 1) * cin + cseg, 0, tap >> 1, h0, b0);
                     } else {
                         const int dy = p.kind == 1 ? tap / 3 - 1 : 0;
                         const int dx = p.kind == 1 ? tap % 3 - 1 : 0;
-                        tma_load_4d(sa, ma, &full_bar[s], cseg, dx, h0 + dy, b0);
+                        if constexpr (PAIR) tma_load_4d_2sm(sa, ma, &full_bar[s], cseg, dx, h0 + dy, b0);
+                        else tma_load_4d(sa, ma, &full_bar[s], cseg, dx, h0 + dy, b0);
                     }
-                    tma_load_2d(sb, &map_w, &full_bar[s], tap * ctot + cc, nt * p.bn);
+                    if constexpr (PAIR) tma_load_2d_2sm(sb, &map_w, &full_bar[s], tap * ctot + cc, nt * p.bn + (int)rank * b_rows);
+                    else tma_load_2d(sb, &map_w, &full_bar[s], tap * ctot + cc, nt * p.bn);
                 }
             }
         }
     } else if (warp == 1) {
-        {   // whole warp walks the loops (uniform control flow); one elected lane issues the MMAs and commits
-            const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(p.bn >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+        if (leader) {   // whole warp walks the loops (uniform control flow); one elected lane issues the MMAs and commits
+            const uint32_t idesc = Op::idesc(p.bn, PAIR ? 2 * BM : BM);
             int g = 0, it = 0;
             for (int tile = tile_lo; tile < tile_hi; ++tile, ++it) {
                 const int buf = it & 1;
-                mbar_wait(&acc_empty[buf], ((uint32_t)(it >> 1) & 1u) ^ 1u);   // epilogue has drained this buffer
+                mbar_wait(&acc_empty[buf], ((uint32_t)(it >> 1) & 1u) ^ 1u);   // epilogue(s) drained this buffer
                 tc_fence_after();
                 const uint32_t tmem_d = tmem_base + (uint32_t)buf * acc_cols;
                 for (int kb = 0; kb < num_kb; ++kb, ++g) {
@@ -145,12 +164,12 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_consta
                     const uint64_t bdesc = make_sw128_desc(sa + A_BYTES);
                     if (elect_one()) {
 #pragma unroll
-                        for (int k = 0; k < BK / 8; ++k) {
-                            // advance 8 TF32 = 32 bytes along K inside the 128-byte swizzle row: +2 in the (addr >> 4) field
-                            umma_tf32(tmem_d, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kb | k) != 0);
+                        for (int k = 0; k < 4; ++k) {
+                            // advance 32 bytes (8 TF32 / 16 FP16) along K inside the 128-byte swizzle row: +2 in the (addr >> 4) field
+                            Op::template mma<PAIR>(tmem_d, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kb | k) != 0);
                         }
-                        umma_commit(&empty_bar[s]);
-                        if (kb == num_kb - 1) umma_commit(&acc_full[buf]);
+                        if constexpr (PAIR) umma_commit_2sm(&empty_bar[s]); else umma_commit(&empty_bar[s]);
+                        if (kb == num_kb - 1) { if constexpr (PAIR) umma_commit_2sm(&acc_full[buf]); else umma_commit(&acc_full[buf]); }
                     }
                     __syncwarp();
                 }
@@ -160,10 +179,12 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_consta
         // ---- epilogue: warp w may only touch TMEM lanes [32*(w%4), 32*(w%4)+32) ----
         const int q = warp & 3;
         float* stg = staging + q * 32 * STG_LD;
-        const int sub_r = lane >> 3, sub_c = (lane & 7) * 4;   // coalesced phase: 4 rows x 8 float4 per instruction
+        const int sub_r = lane >> 3, sub_c = (lane & 7) * 4;   // coalesced phase: 4 rows x 8 four-element groups per instruction
+        const act_t* resid = reinterpret_cast<const act_t*>(p.residual);
         int it = 0;
         for (int tile = tile_lo; tile < tile_hi; ++tile, ++it) {
-            const int mt = tile / p.tiles_n, nt = tile - mt * p.tiles_n;
+            const int mq = tile / p.tiles_n, nt = tile - mq * p.tiles_n;
+            const int mt = PAIR ? 2 * mq + (int)rank : mq;
             const int buf = it & 1;
             mbar_wait(&acc_full[buf], (uint32_t)(it >> 1) & 1u);
             tc_fence_after();
@@ -187,14 +208,15 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_consta
                     if (m < p.M) {
                         float4 v = *reinterpret_cast<const float4*>(stg + rr * STG_LD + sub_c);
                         v.x += bv.x; v.y += bv.y; v.z += bv.z; v.w += bv.w;
-                        if (p.residual) {
-                            const float4 rv = __ldg(reinterpret_cast<const float4*>(p.residual + (size_t)m * p.Cout + col));
+                        const size_t off = (size_t)m * p.Cout + col;
+                        if (resid) {
+                            const float4 rv = load4_nc(resid + off);
                             v.x += rv.x; v.y += rv.y; v.z += rv.z; v.w += rv.w;
                         }
                         s1 += (v.x + v.y) + (v.z + v.w);
                         s2 += (v.x * v.x + v.y * v.y) + (v.z * v.z + v.w * v.w);
-                        if (p.round_tf32) { v.x = to_tf32(v.x); v.y = to_tf32(v.y); v.z = to_tf32(v.z); v.w = to_tf32(v.w); }
-                        *reinterpret_cast<float4*>(p.out + (size_t)m * p.Cout + col) = v;
+                        if (p.operand_out) store_operand4(reinterpret_cast<act_t*>(p.out) + off, v);
+                        else store4(reinterpret_cast<float*>(p.out) + off, v);
                     }
                 }
                 __syncwarp();
@@ -202,7 +224,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_consta
             // accumulator buffer fully read -> hand it back to the MMA warp
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&acc_empty[buf]);
+            if (lane == 0) { if constexpr (PAIR) mbar_arrive_leader(&acc_empty[buf]); else mbar_arrive(&acc_empty[buf]); }
             if (p.stats) {
                 // all 32 rows of a warp belong to one sample (H*W is a multiple of 32)
                 s1 = warp_sum(s1);
@@ -216,213 +238,57 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_consta
         }
         tc_fence_before();
     }
+    // PAIR: neither CTA may exit (or free TMEM) while its partner can still read its shared memory / signal its barriers
     __syncthreads();
+    if constexpr (PAIR) cluster_sync_all();
     if (warp == 1) {
         tc_fence_after();
-        tmem_dealloc(tmem_base, 2 * acc_cols);
+        if constexpr (PAIR) tmem_dealloc_2sm(tmem_base, 2 * acc_cols); else tmem_dealloc(tmem_base, 2 * acc_cols);
     }
 }
 
-// ------------------------------------------------------------------------------------------ CTA-pair kernel
-// Same computation with cta_group::2: a cluster of two CTAs (one SM pair) computes a 256 x BN tile.  Each CTA loads
-// its own 128 activation rows but only HALF of the weight slab (BN/2 rows); tcgen05.mma.cta_group::2 (issued by the
-// leader CTA) reads A and B from both CTAs' shared memory and writes each CTA's 128 accumulator rows into its own
-// TMEM.  Per-SM operand traffic per K block drops from 16 KB + BN*128 B to 16 KB + BN*64 B, which is what bounds
-// the 1-CTA kernel (bytes in flight per SM / L2 latency).  Barriers: TMA of both CTAs credits the leader's `full`;
-// the MMA commit multicasts to both CTAs' `empty` / `acc_full`; both epilogues arrive on the leader's `acc_empty`.
+template <bool HALF>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ CUtensorMap map_a1,
+                 const __grid_constant__ CUtensorMap map_w, const GemmParams p) {
+    conv_gemm_body<HALF, false>(map_a0, map_a1, map_w, p);
+}
+template <bool HALF>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
 conv_gemm2_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ CUtensorMap map_a1,
                   const __grid_constant__ CUtensorMap map_w, const GemmParams p) {
-    extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-    const int half_n = p.bn / 2;
-    const int stage_bytes = A_BYTES + half_n * BK * 4;
-    float* staging = reinterpret_cast<float*>(smem + p.stages * stage_bytes);
-    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + p.stages * stage_bytes + STG_BYTES);
-    uint64_t* empty_bar = full_bar + p.stages;
-    uint64_t* acc_full = empty_bar + p.stages;   // [2]
-    uint64_t* acc_empty = acc_full + 2;          // [2]
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
-
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const uint32_t rank = cluster_ctarank();
-    const bool leader = rank == 0;
-    const int taps = p.kind == 1 ? 9 : (p.kind == 2 ? 4 : 1);
-    const int ctot = p.c0 + p.c1;
-    const int chunks = ctot / BK;
-    const int num_kb = taps * chunks;
-    uint32_t acc_cols = 32;
-    while ((int)acc_cols < p.bn) acc_cols <<= 1;
-    const int cluster_id = blockIdx.x >> 1;
-    const int tile_lo = cluster_id * p.tiles_per_cta;             // pair tiles: id = m2 * tiles_n + n
-    const int tile_hi = min(p.tiles_total, tile_lo + p.tiles_per_cta);
-
-    if (warp == 0 && lane == 0) {
-        tma_prefetch_desc(&map_a0);
-        if (p.c1) tma_prefetch_desc(&map_a1);
-        tma_prefetch_desc(&map_w);
-        for (int s = 0; s < p.stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-        for (int b = 0; b < 2; ++b) { mbar_init(&acc_full[b], 1); mbar_init(&acc_empty[b], 8); }
-        fence_barrier_init();
-    }
-    if (warp == 1) tmem_alloc_2sm(tmem_slot, 2 * acc_cols);
-    tc_fence_before();
-    cluster_sync_all();   // barriers of both CTAs initialised, TMEM allocated, before any remote signalling
-    tc_fence_after();
-    const uint32_t tmem_base = *tmem_slot;
-
-    if (warp == 0) {
-        if (lane == 0) {
-            int g = 0;
-            for (int tile = tile_lo; tile < tile_hi; ++tile) {
-                const int m2 = tile / p.tiles_n, nt = tile - m2 * p.tiles_n;
-                const int mt = 2 * m2 + (int)rank;
-                const int pix0 = mt * BM;
-                const int b0 = pix0 / p.hw_per_sample;
-                const int h0 = (pix0 - b0 * p.hw_per_sample) / p.W;
-                for (int kb = 0; kb < num_kb; ++kb, ++g) {
-                    const int s = g % p.stages;
-                    const uint32_t ph = (uint32_t)(g / p.stages) & 1u;
-                    mbar_wait(&empty_bar[s], ph ^ 1u);
-                    uint8_t* sa = smem + s * stage_bytes;
-                    uint8_t* sb = sa + A_BYTES;
-                    if (leader) mbar_expect_tx(&full_bar[s], (uint32_t)(2 * stage_bytes));   // bytes of BOTH CTAs
-                    const int tap = kb / chunks;
-                    const int cc = (kb - tap * chunks) * BK;
-                    const bool second = cc >= p.c0;
-                    const CUtensorMap* ma = second ? &map_a1 : &map_a0;
-                    const int cseg = second ? cc - p.c0 : cc;
-                    if (p.kind == 2) {
-                        const int cin = second ? p.c1 : p.c0;
-                        tma_load_5d_2sm(sa, ma, &full_bar[s], (tap & 1) * cin + cseg, 0, tap >> 1, h0, b0);
-                    } else {
-                        const int dy = p.kind == 1 ? tap / 3 - 1 : 0;
-                        const int dx = p.kind == 1 ? tap % 3 - 1 : 0;
-                        tma_load_4d_2sm(sa, ma, &full_bar[s], cseg, dx, h0 + dy, b0);
-                    }
-                    tma_load_2d_2sm(sb, &map_w, &full_bar[s], tap * ctot + cc, nt * p.bn + (int)rank * half_n);
-                }
-            }
-        }
-    } else if (warp == 1) {
-        if (leader) {
-            const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(p.bn >> 3) << 17) | ((uint32_t)((2 * BM) >> 4) << 24);
-            int g = 0, it = 0;
-            for (int tile = tile_lo; tile < tile_hi; ++tile, ++it) {
-                const int buf = it & 1;
-                mbar_wait(&acc_empty[buf], ((uint32_t)(it >> 1) & 1u) ^ 1u);   // both CTAs' epilogues drained this buffer
-                tc_fence_after();
-                const uint32_t tmem_d = tmem_base + (uint32_t)buf * acc_cols;
-                for (int kb = 0; kb < num_kb; ++kb, ++g) {
-                    const int s = g % p.stages;
-                    const uint32_t ph = (uint32_t)(g / p.stages) & 1u;
-                    mbar_wait(&full_bar[s], ph);
-                    tc_fence_after();
-                    const uint32_t sa = smem_u32(smem + s * stage_bytes);
-                    const uint64_t adesc = make_sw128_desc(sa);
-                    const uint64_t bdesc = make_sw128_desc(sa + A_BYTES);
-                    if (elect_one()) {
-#pragma unroll
-                        for (int k = 0; k < BK / 8; ++k)
-                            umma_tf32_2sm(tmem_d, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kb | k) != 0);
-                        umma_commit_2sm(&empty_bar[s]);
-                        if (kb == num_kb - 1) umma_commit_2sm(&acc_full[buf]);
-                    }
-                    __syncwarp();
-                }
-            }
-        }
-    } else {
-        const int q = warp & 3;
-        float* stg = staging + q * 32 * STG_LD;
-        const int sub_r = lane >> 3, sub_c = (lane & 7) * 4;
-        int it = 0;
-        for (int tile = tile_lo; tile < tile_hi; ++tile, ++it) {
-            const int m2 = tile / p.tiles_n, nt = tile - m2 * p.tiles_n;
-            const int mt = 2 * m2 + (int)rank;
-            const int buf = it & 1;
-            mbar_wait(&acc_full[buf], (uint32_t)(it >> 1) & 1u);
-            tc_fence_after();
-            const int m_w = mt * BM + q * 32;
-            float s1 = 0.f, s2 = 0.f;
-            for (int c = 0; c < p.bn; c += 32) {
-                uint32_t r[32];
-                tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)buf * acc_cols + (uint32_t)c, r);
-#pragma unroll
-                for (int j = 0; j < 32; j += 4)
-                    *reinterpret_cast<float4*>(stg + lane * STG_LD + j) =
-                        make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
-                __syncwarp();
-                const int col = nt * p.bn + c + sub_c;
-                float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (p.bias) bv = __ldg(reinterpret_cast<const float4*>(p.bias + col));
-#pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    const int rr = sub_r + 4 * i;
-                    const int m = m_w + rr;
-                    if (m < p.M) {
-                        float4 v = *reinterpret_cast<const float4*>(stg + rr * STG_LD + sub_c);
-                        v.x += bv.x; v.y += bv.y; v.z += bv.z; v.w += bv.w;
-                        if (p.residual) {
-                            const float4 rv = __ldg(reinterpret_cast<const float4*>(p.residual + (size_t)m * p.Cout + col));
-                            v.x += rv.x; v.y += rv.y; v.z += rv.z; v.w += rv.w;
-                        }
-                        s1 += (v.x + v.y) + (v.z + v.w);
-                        s2 += (v.x * v.x + v.y * v.y) + (v.z * v.z + v.w * v.w);
-                        if (p.round_tf32) { v.x = to_tf32(v.x); v.y = to_tf32(v.y); v.z = to_tf32(v.z); v.w = to_tf32(v.w); }
-                        *reinterpret_cast<float4*>(p.out + (size_t)m * p.Cout + col) = v;
-                    }
-                }
-                __syncwarp();
-            }
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive_leader(&acc_empty[buf]);
-            if (p.stats) {
-                s1 = warp_sum(s1);
-                s2 = warp_sum(s2);
-                if (lane == 0 && m_w < p.M) {
-                    const int b = m_w / p.hw_per_sample;
-                    atomicAdd(p.stats + 2 * b, (double)s1);
-                    atomicAdd(p.stats + 2 * b + 1, (double)s2);
-                }
-            }
-        }
-        tc_fence_before();
-    }
-    // neither CTA may exit (or free TMEM) while its partner can still read its shared memory / signal its barriers
-    __syncthreads();
-    cluster_sync_all();
-    if (warp == 1) {
-        tc_fence_after();
-        tmem_dealloc_2sm(tmem_base, 2 * acc_cols);
-    }
+    conv_gemm_body<HALF, true>(map_a0, map_a1, map_w, p);
 }
 
 // ------------------------------------------------------------------------------------------ host side
 // activation map: NHWC [B, Hin, Win, C]; for kind 2 the 5-D pixel-unshuffle view
-static int encode_act(CUtensorMap* map, const float* a, int kind, int B, int H, int W, int C, int bh, int bb) {
+static int encode_act(CUtensorMap* map, const void* a, int kind, int B, int H, int W, int C, int bh, int bb, bool half) {
+    const cuuint64_t eb = half ? 2 : 4;
+    const cuuint32_t bk = half ? 64 : 32;
     if (kind == 2) {
         // input spatial 2H x 2W;  dims (inner->outer): {2C, W, 2, H, B}
         cuuint64_t dims[5] = {(cuuint64_t)2 * C, (cuuint64_t)W, 2, (cuuint64_t)H, (cuuint64_t)B};
-        cuuint64_t str[4] = {(cuuint64_t)2 * C * 4, (cuuint64_t)2 * W * C * 4, (cuuint64_t)4 * W * C * 4,
-                             (cuuint64_t)4 * H * W * C * 4};
-        cuuint32_t box[5] = {BK, (cuuint32_t)W, 1, (cuuint32_t)bh, (cuuint32_t)bb};
-        return encode_tmap(map, a, 5, dims, str, box);
+        cuuint64_t str[4] = {(cuuint64_t)2 * C * eb, (cuuint64_t)2 * W * C * eb, (cuuint64_t)4 * W * C * eb,
+                             (cuuint64_t)4 * H * W * C * eb};
+        cuuint32_t box[5] = {bk, (cuuint32_t)W, 1, (cuuint32_t)bh, (cuuint32_t)bb};
+        return encode_tmap(map, a, 5, dims, str, box, half);
     }
     cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
-    cuuint64_t str[3] = {(cuuint64_t)C * 4, (cuuint64_t)W * C * 4, (cuuint64_t)H * W * C * 4};
-    cuuint32_t box[4] = {BK, (cuuint32_t)W, (cuuint32_t)bh, (cuuint32_t)bb};
-    return encode_tmap(map, a, 4, dims, str, box);
+    cuuint64_t str[3] = {(cuuint64_t)C * eb, (cuuint64_t)W * C * eb, (cuuint64_t)H * W * C * eb};
+    cuuint32_t box[4] = {bk, (cuuint32_t)W, (cuuint32_t)bh, (cuuint32_t)bb};
+    return encode_tmap(map, a, 4, dims, str, box, half);
 }
 
 }  // namespace sdc
 
 using namespace sdc;
 
-extern "C" int sdc_conv_gemm(int kind, const float* a0, int c0, const float* a1, int c1, const float* w_packed,
-                             const float* bias, const float* residual, float* out, double* stats, int round_tf32, int B, int H,
+extern "C" int sdc_conv_gemm(int prec, int kind, const void* a0, int c0, const void* a1, int c1, const void* w_packed,
+                             const float* bias, const void* residual, void* out, double* stats, int operand_out, int B, int H,
                              int W, int Cout, void* stream) {
+    SDC_REQUIRE(prec == SDC_PREC_TF32 || prec == SDC_PREC_F16, "conv_gemm: precision %d", prec);
+    const bool half = prec == SDC_PREC_F16;
+    const int BK = half ? 64 : 32;
     SDC_REQUIRE(kind >= 0 && kind <= 2, "conv_gemm: kind %d", kind);
     SDC_REQUIRE(B > 0 && H > 0 && W > 0, "conv_gemm: empty problem");
     SDC_REQUIRE(a0 && w_packed && out, "conv_gemm: null pointer");
@@ -438,7 +304,7 @@ extern "C" int sdc_conv_gemm(int kind, const float* a0, int c0, const float* a1,
     int bn = Cout % 256 == 0 ? 256 : (Cout % 128 == 0 ? 128 : (Cout % 64 == 0 ? 64 : 32));
     GemmParams p{};
     p.kind = kind; p.M = B * H * W; p.Cout = Cout; p.bn = bn; p.H = H; p.W = W; p.bh = bh; p.bb = bb;
-    p.c0 = c0; p.c1 = c1; p.round_tf32 = round_tf32; p.hw_per_sample = H * W;
+    p.c0 = c0; p.c1 = c1; p.operand_out = operand_out; p.hw_per_sample = H * W;
     p.bias = bias; p.residual = residual; p.out = out; p.stats = stats;
     int n_sm = 148;
     {
@@ -450,7 +316,7 @@ extern "C" int sdc_conv_gemm(int kind, const float* a0, int c0, const float* a1,
     const int tiles_m = (p.M + BM - 1) / BM;
     // CTA pairs (cta_group::2) whenever there are at least as many 256-row pair tiles as SM pairs
     const bool pair = allow_pair && ((tiles_m + 1) / 2) * (Cout / bn) >= n_sm / 2;
-    const int stage_bytes = A_BYTES + (pair ? bn / 2 : bn) * BK * 4;
+    const int stage_bytes = A_BYTES + (pair ? bn / 2 : bn) * 128;
     int stages = (190 * 1024) / stage_bytes;
     if (stages > 8) stages = 8;
     p.stages = stages;
@@ -462,28 +328,34 @@ extern "C" int sdc_conv_gemm(int kind, const float* a0, int c0, const float* a1,
     p.tiles_per_cta = (p.tiles_total + ctas - 1) / ctas;
 
     CUtensorMap ma0, ma1, mw;
-    int rc = encode_act(&ma0, a0, kind, B, H, W, c0, bh, bb);
+    int rc = encode_act(&ma0, a0, kind, B, H, W, c0, bh, bb, half);
     if (rc) return rc;
-    if (c1) { rc = encode_act(&ma1, a1, kind, B, H, W, c1, bh, bb); if (rc) return rc; } else ma1 = ma0;
+    if (c1) { rc = encode_act(&ma1, a1, kind, B, H, W, c1, bh, bb, half); if (rc) return rc; } else ma1 = ma0;
     const int taps = kind == 1 ? 9 : (kind == 2 ? 4 : 1);
     const cuuint64_t ktot = (cuuint64_t)taps * (c0 + c1);
     cuuint64_t wd[2] = {ktot, (cuuint64_t)Cout};
-    cuuint64_t ws[1] = {ktot * 4};
-    cuuint32_t wb[2] = {BK, (cuuint32_t)(pair ? bn / 2 : bn)};
-    rc = encode_tmap(&mw, w_packed, 2, wd, ws, wb);
+    cuuint64_t ws[1] = {ktot * (half ? 2 : 4)};
+    cuuint32_t wb[2] = {(cuuint32_t)BK, (cuuint32_t)(pair ? bn / 2 : bn)};
+    rc = encode_tmap(&mw, w_packed, 2, wd, ws, wb, half);
     if (rc) return rc;
 
     static bool attr_set = false;
     if (!attr_set) {
-        SDC_CUDA(cudaFuncSetAttribute(conv_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        SDC_CUDA(cudaFuncSetAttribute(conv_gemm2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        SDC_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        SDC_CUDA(cudaFuncSetAttribute(conv_gemm2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        SDC_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        SDC_CUDA(cudaFuncSetAttribute(conv_gemm2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         attr_set = true;
     }
     const int grid = (p.tiles_total + p.tiles_per_cta - 1) / p.tiles_per_cta;
-    if (pair)
-        conv_gemm2_kernel<<<2 * grid, GEMM_THREADS, smem_bytes, as_stream(stream)>>>(ma0, ma1, mw, p);
-    else
-        conv_gemm_kernel<<<grid, GEMM_THREADS, smem_bytes, as_stream(stream)>>>(ma0, ma1, mw, p);
+    cudaStream_t st = as_stream(stream);
+    if (pair) {
+        if (half) conv_gemm2_kernel<true><<<2 * grid, GEMM_THREADS, smem_bytes, st>>>(ma0, ma1, mw, p);
+        else conv_gemm2_kernel<false><<<2 * grid, GEMM_THREADS, smem_bytes, st>>>(ma0, ma1, mw, p);
+    } else {
+        if (half) conv_gemm_kernel<true><<<grid, GEMM_THREADS, smem_bytes, st>>>(ma0, ma1, mw, p);
+        else conv_gemm_kernel<false><<<grid, GEMM_THREADS, smem_bytes, st>>>(ma0, ma1, mw, p);
+    }
     SDC_LAUNCHED();
     return SDC_OK;
 }

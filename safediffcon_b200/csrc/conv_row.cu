@@ -14,6 +14,7 @@
 //            (2 rows x Cout columns, double buffered)
 //   warps 2-5 epilogue (same as conv_gemm.cu): TMEM -> smem transpose -> coalesced rows, bias, GN statistics
 #include "tc_ptx.cuh"
+#include "../../include/safediffcon_b200_unet.h"
 #include <math.h>
 #include <stdlib.h>
 
@@ -32,20 +33,23 @@ struct RowParams {
     int B, H, Cout, bn;      // bn = Cout (single N tile, multiple of 32, <= 128)
     int c0, c1;
     int pairs_total, pairs_per_cta, pairs_per_image;
-    int round_tf32;
+    int operand_out;         // 1: store as a tensor-core operand (TF32-rounded fp32 / fp16), 0: plain fp32
     int dbg;                 // experiments: bit0 = no TMA (MMA runs on whatever is in smem), bit1 = epilogue skips global stores
     const float* bias;
-    const float* residual;
-    float* out;
+    const void* residual;    // operand precision
+    void* out;
     double* stats;
 };
 
 // PAIR = true: cta_group::2.  A cluster of two CTAs computes FOUR image rows (CTA r: rows h0+2r, h0+2r+1); every MMA is
 // M = 256 (row j of both CTAs) and each CTA stages only half of each weight tile, so the weight ring is twice as deep
 // for the same shared memory and the per-SM operand traffic drops from 46 to 30 B/clk.
-template <bool PAIR>
+template <bool HALF, bool PAIR>
 __device__ __forceinline__ void conv_row_body(const CUtensorMap& map_a0, const CUtensorMap& map_a1, const CUtensorMap& map_w,
                                               const RowParams& p) {
+    using Op = Operand<HALF>;
+    using act_t = typename ActT<HALF>::type;
+    constexpr int BK = Op::kBK;   // channels per 128-byte chunk
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     const int b_bytes = (PAIR ? p.bn / 2 : p.bn) * 128;   // weight rows staged by this CTA
@@ -66,7 +70,7 @@ __device__ __forceinline__ void conv_row_body(const CUtensorMap& map_a0, const C
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int ctot = p.c0 + p.c1;
-    const int chunks = ctot / 32;
+    const int chunks = ctot / BK;
     uint32_t acc_cols = 32;
     while ((int)acc_cols < p.bn) acc_cols <<= 1;
     const int pair_lo = (PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x) * p.pairs_per_cta;   // work item = 2 (or 4) image rows
@@ -93,7 +97,7 @@ __device__ __forceinline__ void conv_row_body(const CUtensorMap& map_a0, const C
             const int items = (pair_hi - pair_lo) * chunks;
             int g = 0;
             for (int item = 0; item < items; ++item) {
-                const int cc = (item % chunks) * 32;
+                const int cc = (item % chunks) * BK;
                 for (int tap = 0; tap < 9; ++tap, ++g) {
                     const int s = g % NB;
                     mbar_wait(&b_empty[s], (((uint32_t)(g / NB)) & 1u) ^ 1u);
@@ -115,7 +119,7 @@ __device__ __forceinline__ void conv_row_body(const CUtensorMap& map_a0, const C
             for (int item = 0; item < items; ++item) {
                 const int pair = pair_lo + item / chunks, ch = item % chunks;
                 const int b = pair / p.pairs_per_image, h0 = (PAIR ? 4 : 2) * (pair - b * p.pairs_per_image) + 2 * (int)rank;
-                const int cc = ch * 32;
+                const int cc = ch * BK;
                 const bool second = cc >= p.c0;
                 const int hs = item & 1;
                 mbar_wait(&halo_empty[hs], (((uint32_t)(item >> 1)) & 1u) ^ 1u);
@@ -130,7 +134,7 @@ __device__ __forceinline__ void conv_row_body(const CUtensorMap& map_a0, const C
         }
     } else if (warp == 1) {
         if (leader) {   // whole warp: uniform control flow, one elected lane issues
-            const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(p.bn >> 3) << 17) | ((uint32_t)(((PAIR ? 2 : 1) * RW) >> 4) << 24);
+            const uint32_t idesc = Op::idesc(p.bn, (PAIR ? 2 : 1) * RW);
             int g = 0, item = 0, it = 0;
             for (int pair = pair_lo; pair < pair_hi; ++pair, ++it) {
                 const int buf = it & 1;
@@ -155,12 +159,8 @@ __device__ __forceinline__ void conv_row_body(const CUtensorMap& map_a0, const C
                                 const uint32_t aa = ha + (uint32_t)(((j + dy) * HALO_W + dx) * 128);
 #pragma unroll
                                 for (int k = 0; k < 4; ++k) {
-                                    if constexpr (PAIR)
-                                        umma_tf32_2sm(tmem_d + (uint32_t)j * acc_cols, make_sw128_desc(aa + 32u * k), make_sw128_desc(ba + 32u * k),
-                                                      idesc, (ch | tap | k) != 0);
-                                    else
-                                        umma_tf32(tmem_d + (uint32_t)j * acc_cols, make_sw128_desc(aa + 32u * k), make_sw128_desc(ba + 32u * k),
-                                                  idesc, (ch | tap | k) != 0);
+                                    Op::template mma<PAIR>(tmem_d + (uint32_t)j * acc_cols, make_sw128_desc(aa + 32u * k),
+                                                           make_sw128_desc(ba + 32u * k), idesc, (ch | tap | k) != 0);
                                 }
                             }
                             if constexpr (PAIR) umma_commit_2sm(&b_empty[s]); else umma_commit(&b_empty[s]);
@@ -178,6 +178,7 @@ __device__ __forceinline__ void conv_row_body(const CUtensorMap& map_a0, const C
         const int q = warp & 3;
         float* stg = staging + q * 32 * RSTG_LD;
         const int sub_r = lane >> 3, sub_c = (lane & 7) * 4;
+        const act_t* resid = reinterpret_cast<const act_t*>(p.residual);
         int it = 0;
         for (int pair = pair_lo; pair < pair_hi; ++pair, ++it) {
             const int b = pair / p.pairs_per_image, h0 = (PAIR ? 4 : 2) * (pair - b * p.pairs_per_image) + 2 * (int)rank;
@@ -201,10 +202,9 @@ __device__ __forceinline__ void conv_row_body(const CUtensorMap& map_a0, const C
                     if (p.bias) bv = __ldg(reinterpret_cast<const float4*>(p.bias + col));
                     if (row_ok && !(p.dbg & 2)) {
                         float4 rv[8];
-                        if (p.residual) {
+                        if (resid) {
 #pragma unroll
-                            for (int i = 0; i < 8; ++i)
-                                rv[i] = __ldg(reinterpret_cast<const float4*>(p.residual + (m_w + sub_r + 4 * i) * p.Cout + col));
+                            for (int i = 0; i < 8; ++i) rv[i] = load4_nc(resid + (m_w + sub_r + 4 * i) * p.Cout + col);
                         }
 #pragma unroll
                         for (int i = 0; i < 8; ++i) {
@@ -212,11 +212,11 @@ __device__ __forceinline__ void conv_row_body(const CUtensorMap& map_a0, const C
                             const size_t m = m_w + rr;
                             float4 v = *reinterpret_cast<const float4*>(stg + rr * RSTG_LD + sub_c);
                             v.x += bv.x; v.y += bv.y; v.z += bv.z; v.w += bv.w;
-                            if (p.residual) { v.x += rv[i].x; v.y += rv[i].y; v.z += rv[i].z; v.w += rv[i].w; }
+                            if (resid) { v.x += rv[i].x; v.y += rv[i].y; v.z += rv[i].z; v.w += rv[i].w; }
                             s1 += (v.x + v.y) + (v.z + v.w);
                             s2 += (v.x * v.x + v.y * v.y) + (v.z * v.z + v.w * v.w);
-                            if (p.round_tf32) { v.x = to_tf32(v.x); v.y = to_tf32(v.y); v.z = to_tf32(v.z); v.w = to_tf32(v.w); }
-                            *reinterpret_cast<float4*>(p.out + m * p.Cout + col) = v;
+                            if (p.operand_out) store_operand4(reinterpret_cast<act_t*>(p.out) + m * p.Cout + col, v);
+                            else store4(reinterpret_cast<float*>(p.out) + m * p.Cout + col, v);
                         }
                     }
                     __syncwarp();
@@ -244,15 +244,17 @@ __device__ __forceinline__ void conv_row_body(const CUtensorMap& map_a0, const C
     }
 }
 
+template <bool HALF>
 __global__ void __launch_bounds__(ROW_THREADS, 1)
 conv_row_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ CUtensorMap map_a1,
                 const __grid_constant__ CUtensorMap map_w, const RowParams p) {
-    conv_row_body<false>(map_a0, map_a1, map_w, p);
+    conv_row_body<HALF, false>(map_a0, map_a1, map_w, p);
 }
+template <bool HALF>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(ROW_THREADS, 1)
 conv_row2_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ CUtensorMap map_a1,
                  const __grid_constant__ CUtensorMap map_w, const RowParams p) {
-    conv_row_body<true>(map_a0, map_a1, map_w, p);
+    conv_row_body<HALF, true>(map_a0, map_a1, map_w, p);
 }
 
 }  // namespace sdc
@@ -260,13 +262,16 @@ conv_row2_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_consta
 using namespace sdc;
 
 // Returns SDC_OK when the problem was handled here, -1 when the shape is not eligible (caller uses conv_gemm).
-extern "C" int sdc_conv3x3_row(const float* a0, int c0, const float* a1, int c1, const float* w_packed, const float* bias,
-                               const float* residual, float* out, double* stats, int round_tf32, int B, int H, int W, int Cout,
+extern "C" int sdc_conv3x3_row(int prec, const void* a0, int c0, const void* a1, int c1, const void* w_packed, const float* bias,
+                               const void* residual, void* out, double* stats, int operand_out, int B, int H, int W, int Cout,
                                void* stream) {
-    if (W != RW || Cout > 128 || Cout % 32 != 0 || c0 % 32 != 0 || c1 % 32 != 0 || c0 <= 0) return -1;
+    SDC_REQUIRE(prec == SDC_PREC_TF32 || prec == SDC_PREC_F16, "conv3x3_row: precision %d", prec);
+    const bool half = prec == SDC_PREC_F16;
+    const int BK = half ? 64 : 32;
+    if (W != RW || Cout > 128 || Cout % 32 != 0 || c0 % BK != 0 || c1 % BK != 0 || c0 <= 0) return -1;
     SDC_REQUIRE(a0 && w_packed && out && B > 0 && H > 0 && (c1 == 0 || a1), "conv3x3_row: bad arguments");
     RowParams p{};
-    p.B = B; p.H = H; p.Cout = Cout; p.bn = Cout; p.c0 = c0; p.c1 = c1; p.round_tf32 = round_tf32;
+    p.B = B; p.H = H; p.Cout = Cout; p.bn = Cout; p.c0 = c0; p.c1 = c1; p.operand_out = operand_out;
     p.bias = bias; p.residual = residual; p.out = out; p.stats = stats;
     { const char* e = getenv("SDC_ROW_DBG"); p.dbg = e ? atoi(e) : 0; }
     int n_sm = 148, dev = 0;
@@ -282,32 +287,39 @@ extern "C" int sdc_conv3x3_row(const float* a0, int c0, const float* a1, int c1,
     const int grid = (p.pairs_total + p.pairs_per_cta - 1) / p.pairs_per_cta;
 
     CUtensorMap ma0, ma1, mw;
-    auto enc_act = [&](CUtensorMap* m, const float* a, int C) {
+    const cuuint64_t eb = half ? 2 : 4;
+    auto enc_act = [&](CUtensorMap* m, const void* a, int C) {
         cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
-        cuuint64_t str[3] = {(cuuint64_t)C * 4, (cuuint64_t)W * C * 4, (cuuint64_t)H * W * C * 4};
-        cuuint32_t box[4] = {32, (cuuint32_t)HALO_W, 4, 1};
-        return encode_tmap(m, a, 4, dims, str, box);
+        cuuint64_t str[3] = {(cuuint64_t)C * eb, (cuuint64_t)W * C * eb, (cuuint64_t)H * W * C * eb};
+        cuuint32_t box[4] = {(cuuint32_t)BK, (cuuint32_t)HALO_W, 4, 1};
+        return encode_tmap(m, a, 4, dims, str, box, half);
     };
     int rc = enc_act(&ma0, a0, c0);
     if (rc) return rc;
     if (c1) { rc = enc_act(&ma1, a1, c1); if (rc) return rc; } else ma1 = ma0;
     const cuuint64_t ktot = (cuuint64_t)9 * (c0 + c1);
     cuuint64_t wd[2] = {ktot, (cuuint64_t)Cout};
-    cuuint64_t ws[1] = {ktot * 4};
-    cuuint32_t wb[2] = {32, (cuuint32_t)(pair ? Cout / 2 : Cout)};
-    rc = encode_tmap(&mw, w_packed, 2, wd, ws, wb);
+    cuuint64_t ws[1] = {ktot * eb};
+    cuuint32_t wb[2] = {(cuuint32_t)BK, (cuuint32_t)(pair ? Cout / 2 : Cout)};
+    rc = encode_tmap(&mw, w_packed, 2, wd, ws, wb, half);
     if (rc) return rc;
     const int smem_bytes = 2 * HALO_BYTES + ROW_BSTAGES * Cout * 128 + RSTG_BYTES + 24 * 8 + 16 + 1024;
     static bool attr_set = false;
     if (!attr_set) {
-        SDC_CUDA(cudaFuncSetAttribute(conv_row_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        SDC_CUDA(cudaFuncSetAttribute(conv_row2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        SDC_CUDA(cudaFuncSetAttribute(conv_row_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        SDC_CUDA(cudaFuncSetAttribute(conv_row2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        SDC_CUDA(cudaFuncSetAttribute(conv_row_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        SDC_CUDA(cudaFuncSetAttribute(conv_row2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         attr_set = true;
     }
-    if (pair)
-        conv_row2_kernel<<<2 * grid, ROW_THREADS, smem_bytes, as_stream(stream)>>>(ma0, ma1, mw, p);
-    else
-        conv_row_kernel<<<grid, ROW_THREADS, smem_bytes, as_stream(stream)>>>(ma0, ma1, mw, p);
+    cudaStream_t st = as_stream(stream);
+    if (pair) {
+        if (half) conv_row2_kernel<true><<<2 * grid, ROW_THREADS, smem_bytes, st>>>(ma0, ma1, mw, p);
+        else conv_row2_kernel<false><<<2 * grid, ROW_THREADS, smem_bytes, st>>>(ma0, ma1, mw, p);
+    } else {
+        if (half) conv_row_kernel<true><<<grid, ROW_THREADS, smem_bytes, st>>>(ma0, ma1, mw, p);
+        else conv_row_kernel<false><<<grid, ROW_THREADS, smem_bytes, st>>>(ma0, ma1, mw, p);
+    }
     SDC_LAUNCHED();
     return SDC_OK;
 }

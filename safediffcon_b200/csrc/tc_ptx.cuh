@@ -76,6 +76,15 @@ __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint6
         "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n"
         "}\n" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
 }
+// FP16 operands (10-bit mantissa like TF32, but 2 bytes: twice the MMA rate and half the operand traffic), FP32 accumulate
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+        "}\n" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
 // arrives on the mbarrier once all previously issued MMAs of this thread have completed
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
@@ -151,6 +160,34 @@ __device__ __forceinline__ void umma_tf32_2sm(uint32_t tmem_d, uint64_t adesc, u
         "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n"
         "}\n" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
 }
+__device__ __forceinline__ void umma_f16_2sm(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n"
+        "}\n" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+// Operand precision of the tensor-core kernels.  HALF = false: TF32 (fp32 containers, 32 elements per 128-byte K block,
+// UMMA K = 8); HALF = true: FP16 (64 elements per K block, UMMA K = 16).  Both advance 32 bytes per MMA along K, so the
+// shared-memory tiles, swizzle and descriptors are byte-identical; only the instruction kind / descriptor formats differ.
+template <bool HALF>
+struct Operand {
+    static constexpr int kBytes = HALF ? 2 : 4;
+    static constexpr int kBK = 128 / kBytes;   // elements per 128-byte K block
+    // instruction descriptor: c_format F32 (bit 4), a/b format F16 = 0 or TF32 = 2 (bits 7, 10), N >> 3 at 17, M >> 4 at 24
+    __device__ __forceinline__ static uint32_t idesc(int n, int m) {
+        return (1u << 4) | ((HALF ? 0u : 2u) << 7) | ((HALF ? 0u : 2u) << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+    }
+    template <bool PAIR>
+    __device__ __forceinline__ static void mma(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc_, uint32_t accumulate) {
+        if constexpr (HALF) {
+            if constexpr (PAIR) umma_f16_2sm(tmem_d, adesc, bdesc, idesc_, accumulate); else umma_f16(tmem_d, adesc, bdesc, idesc_, accumulate);
+        } else {
+            if constexpr (PAIR) umma_tf32_2sm(tmem_d, adesc, bdesc, idesc_, accumulate); else umma_tf32(tmem_d, adesc, bdesc, idesc_, accumulate);
+        }
+    }
+};
 // arrive on the same-offset mbarrier of BOTH CTAs once all previously issued pair MMAs have completed
 __device__ __forceinline__ void umma_commit_2sm(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
@@ -179,11 +216,11 @@ inline EncodeTiledFn get_encode() {
 }
 
 inline int encode_tmap(CUtensorMap* map, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes,
-                  const cuuint32_t* box) {
+                  const cuuint32_t* box, bool half = false) {
     EncodeTiledFn fn = get_encode();
     if (!fn) { set_error("cuTensorMapEncodeTiled entry point unavailable (no CUDA driver?)"); return SDC_ERR_CUDA; }
     cuuint32_t estr[5] = {1, 1, 1, 1, 1};
-    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank, const_cast<void*>(base), dims, strides_bytes, box, estr,
+    CUresult r = fn(map, half ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank, const_cast<void*>(base), dims, strides_bytes, box, estr,
                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed with CUresult %d (rank %d)", (int)r, rank); return SDC_ERR_CUDA; }

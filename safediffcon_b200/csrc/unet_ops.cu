@@ -9,7 +9,8 @@
 namespace sdc {
 
 // ---------------------------------------------------------------------------------------------- weight packing
-__global__ void pack_conv_weight_kernel(int kind, const float* __restrict__ w, float* __restrict__ wp, int Cout, int Cin) {
+template <typename T>
+__global__ void pack_conv_weight_kernel(int kind, const float* __restrict__ w, T* __restrict__ wp, int Cout, int Cin) {
     const int taps = kind == 1 ? 9 : 1;
     const int64_t total = (int64_t)Cout * Cin * taps;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
@@ -25,15 +26,16 @@ __global__ void pack_conv_weight_kernel(int kind, const float* __restrict__ w, f
         } else {
             v = w[i];
         }
-        wp[i] = to_tf32(v);
+        wp[i] = to_operand(v, T());
     }
 }
 
 // ---------------------------------------------------------------------------------------------- stem 7x7 conv
 // One CTA = STEM_ROWS image rows of one sample; thread = 8 pixels x 8 output channels in registers.
 constexpr int STEM_ROWS = 4;
+template <typename T>
 __global__ void stem_conv7_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
-                                  float* __restrict__ out, int Cin, int H, int W, int Cout) {
+                                  T* __restrict__ out, int Cin, int H, int W, int Cout) {
     extern __shared__ float sm[];
     const int K = Cin * 49;
     float* ws = sm;                      // [K][Cout]
@@ -82,11 +84,9 @@ __global__ void stem_conv7_kernel(const float* __restrict__ x, const float* __re
         for (int c = 0; c < 8; ++c) bv[c] = bias ? bias[co0 + c] : 0.f;
 #pragma unroll
         for (int p = 0; p < 8; ++p) {
-            float* o = out + (((int64_t)b * H + h) * W + px0 + p) * Cout + co0;
-            *reinterpret_cast<float4*>(o) = make_float4(to_tf32(acc[p][0] + bv[0]), to_tf32(acc[p][1] + bv[1]),
-                                                        to_tf32(acc[p][2] + bv[2]), to_tf32(acc[p][3] + bv[3]));
-            *reinterpret_cast<float4*>(o + 4) = make_float4(to_tf32(acc[p][4] + bv[4]), to_tf32(acc[p][5] + bv[5]),
-                                                            to_tf32(acc[p][6] + bv[6]), to_tf32(acc[p][7] + bv[7]));
+            T* o = out + (((int64_t)b * H + h) * W + px0 + p) * Cout + co0;
+            store_operand4(o, make_float4(acc[p][0] + bv[0], acc[p][1] + bv[1], acc[p][2] + bv[2], acc[p][3] + bv[3]));
+            store_operand4(o + 4, make_float4(acc[p][4] + bv[4], acc[p][5] + bv[5], acc[p][6] + bv[6], acc[p][7] + bv[7]));
         }
     }
 }
@@ -94,10 +94,11 @@ __global__ void stem_conv7_kernel(const float* __restrict__ x, const float* __re
 // ---------------------------------------------------------------------------------------------- GroupNorm(1)+FiLM+SiLU
 __device__ __forceinline__ float silu(float v) { return v / (1.0f + expf(-v)); }
 
+template <typename TR, typename TY>
 __global__ void __launch_bounds__(256) gn_silu_kernel(const float* __restrict__ x, const double* __restrict__ stats,
                                                       const float* __restrict__ gamma, const float* __restrict__ beta,
                                                       const float* __restrict__ scale_shift, const int32_t* __restrict__ t_index,
-                                                      int64_t ss_stride, const float* __restrict__ residual, float* __restrict__ y,
+                                                      int64_t ss_stride, const TR* __restrict__ residual, TY* __restrict__ y,
                                                       int HW, int C, int pix_per_cta) {
     extern __shared__ float coef[];  // A[C], B[C]
     const int b = blockIdx.x;
@@ -123,8 +124,8 @@ __global__ void __launch_bounds__(256) gn_silu_kernel(const float* __restrict__ 
     const int64_t row0 = (int64_t)b * HW + (int64_t)blockIdx.y * pix_per_cta;
     const int rows = min(pix_per_cta, HW - (int)blockIdx.y * pix_per_cta);
     const float4* x4 = reinterpret_cast<const float4*>(x + row0 * C);
-    const float4* r4 = residual ? reinterpret_cast<const float4*>(residual + row0 * C) : nullptr;
-    float4* y4 = reinterpret_cast<float4*>(y + row0 * C);
+    const TR* r4 = residual ? residual + row0 * C : nullptr;
+    TY* y4 = y + row0 * C;
     const int total = rows * c4n;
     for (int i = threadIdx.x; i < total; i += blockDim.x) {
         const int c = (i % c4n) * 4;
@@ -133,18 +134,18 @@ __global__ void __launch_bounds__(256) gn_silu_kernel(const float* __restrict__ 
         v.y = silu(fmaf(v.y, coef[c + 1], coef[C + c + 1]));
         v.z = silu(fmaf(v.z, coef[c + 2], coef[C + c + 2]));
         v.w = silu(fmaf(v.w, coef[c + 3], coef[C + c + 3]));
-        if (r4) { const float4 r = r4[i]; v.x += r.x; v.y += r.y; v.z += r.z; v.w += r.w; }
-        y4[i] = make_float4(to_tf32(v.x), to_tf32(v.y), to_tf32(v.z), to_tf32(v.w));
+        if (r4) { const float4 r = load4(r4 + 4 * (int64_t)i); v.x += r.x; v.y += r.y; v.z += r.z; v.w += r.w; }
+        store_operand4(y4 + 4 * (int64_t)i, v);
     }
 }
 
 // ---------------------------------------------------------------------------------------------- channel LayerNorm
 // one warp per RPW pixel rows (RPW = 4 for C <= 256 so that 4-8 independent 16-byte loads are in flight per lane);
 // C <= 1024 kept in registers, two-pass variance like torch.var(unbiased=False)
-template <int RPW, int NV>
-__global__ void __launch_bounds__(256) channel_layernorm_kernel(const float* __restrict__ x, const float* __restrict__ g,
-                                                                const float* __restrict__ residual, float* __restrict__ y,
-                                                                int64_t M, int C, int round_tf32) {
+template <int RPW, int NV, typename TX, typename TY>
+__global__ void __launch_bounds__(256) channel_layernorm_kernel(const TX* __restrict__ x, const float* __restrict__ g,
+                                                                const TY* __restrict__ residual, TY* __restrict__ y,
+                                                                int64_t M, int C, int operand_out) {
     const int lane = threadIdx.x & 31;
     const int64_t row0 = ((int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * RPW;
     if (row0 >= M) return;
@@ -152,11 +153,11 @@ __global__ void __launch_bounds__(256) channel_layernorm_kernel(const float* __r
     float4 v[RPW][NV];
 #pragma unroll
     for (int r = 0; r < RPW; ++r) {
-        const float4* x4 = reinterpret_cast<const float4*>(x + (row0 + r) * C);
+        const TX* x4 = x + (row0 + r) * C;
 #pragma unroll
         for (int j = 0; j < NV; ++j) {
             const int i = lane + 32 * j;
-            v[r][j] = (i < n4 && row0 + r < M) ? x4[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+            v[r][j] = (i < n4 && row0 + r < M) ? load4(x4 + 4 * i) : make_float4(0.f, 0.f, 0.f, 0.f);
         }
     }
     const float4* g4 = reinterpret_cast<const float4*>(g);
@@ -176,8 +177,8 @@ __global__ void __launch_bounds__(256) channel_layernorm_kernel(const float* __r
             }
         }
         const float rstd = rsqrtf(warp_sum(q) / (float)C + 1e-5f);
-        const float4* r4 = residual ? reinterpret_cast<const float4*>(residual + (row0 + r) * C) : nullptr;
-        float4* y4 = reinterpret_cast<float4*>(y + (row0 + r) * C);
+        const TY* r4 = residual ? residual + (row0 + r) * C : nullptr;
+        TY* y4 = y + (row0 + r) * C;
 #pragma unroll
         for (int j = 0; j < NV; ++j) {
             const int i = lane + 32 * j;
@@ -185,9 +186,9 @@ __global__ void __launch_bounds__(256) channel_layernorm_kernel(const float* __r
                 const float4 gv = g4[i];
                 float4 o = make_float4((v[r][j].x - mean) * rstd * gv.x, (v[r][j].y - mean) * rstd * gv.y,
                                        (v[r][j].z - mean) * rstd * gv.z, (v[r][j].w - mean) * rstd * gv.w);
-                if (r4) { const float4 rr = r4[i]; o.x += rr.x; o.y += rr.y; o.z += rr.z; o.w += rr.w; }
-                if (round_tf32) o = make_float4(to_tf32(o.x), to_tf32(o.y), to_tf32(o.z), to_tf32(o.w));
-                y4[i] = o;
+                if (r4) { const float4 rr = load4(r4 + 4 * i); o.x += rr.x; o.y += rr.y; o.z += rr.z; o.w += rr.w; }
+                if constexpr (sizeof(TY) == 2) store_operand4(y4 + 4 * i, o);
+                else { if (operand_out) store_operand4(y4 + 4 * i, o); else store4(reinterpret_cast<float*>(y4) + 4 * i, o); }
             }
         }
     }
@@ -298,8 +299,9 @@ __global__ void __launch_bounds__(256) linattn_context_kernel(const float* __res
 }
 
 // out[n, h*32+e] = 32^-0.5 * sum_d ctx[d,e] * softmax_d(q[n,:])[d]      grid = (B*heads, ceil(n/256)), thread per pixel
+template <typename T>
 __global__ void __launch_bounds__(256) linattn_apply_kernel(const float* __restrict__ qkv, const float* __restrict__ ctx,
-                                                            float* __restrict__ out, int n) {
+                                                            T* __restrict__ out, int n) {
     __shared__ __align__(16) float cs[LA_D][LA_D];
     const int b = blockIdx.x / LA_HEADS, h = blockIdx.x % LA_HEADS;
     for (int i = threadIdx.x; i < LA_D * LA_D; i += blockDim.x) cs[i >> 5][i & 31] = ctx[(int64_t)blockIdx.x * LA_D * LA_D + i];
@@ -333,14 +335,14 @@ __global__ void __launch_bounds__(256) linattn_apply_kernel(const float* __restr
             o[e + 2] = fmaf(w, c4.z, o[e + 2]); o[e + 3] = fmaf(w, c4.w, o[e + 3]);
         }
     }
-    float* op = out + ((int64_t)b * n + i) * LA_HID + h * LA_D;
+    T* op = out + ((int64_t)b * n + i) * LA_HID + h * LA_D;
 #pragma unroll
-    for (int e = 0; e < LA_D; e += 4)
-        *reinterpret_cast<float4*>(op + e) = make_float4(to_tf32(o[e]), to_tf32(o[e + 1]), to_tf32(o[e + 2]), to_tf32(o[e + 3]));
+    for (int e = 0; e < LA_D; e += 4) store_operand4(op + e, make_float4(o[e], o[e + 1], o[e + 2], o[e + 3]));
 }
 
 // full softmax attention for n <= 32 tokens: one warp per (b, head), lane = query token
-__global__ void __launch_bounds__(128) attention_kernel(const float* __restrict__ qkv, float* __restrict__ out, int n) {
+template <typename T>
+__global__ void __launch_bounds__(128) attention_kernel(const float* __restrict__ qkv, T* __restrict__ out, int n) {
     __shared__ float ks[LA_HEADS][32][LA_D + 1];
     __shared__ float vs[LA_HEADS][32][LA_D + 1];
     const int b = blockIdx.x, h = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -372,13 +374,13 @@ __global__ void __launch_bounds__(128) attention_kernel(const float* __restrict_
 #pragma unroll
         for (int j = 0; j < 32; ++j) { sim[j] = (j < n) ? expf(sim[j] - mx) : 0.f; den += sim[j]; }
         const float inv = 1.0f / den;
-        float* o = out + ((int64_t)b * n + lane) * LA_HID + h * LA_D;
+        T* o = out + ((int64_t)b * n + lane) * LA_HID + h * LA_D;
 #pragma unroll
         for (int d = 0; d < LA_D; ++d) {
             float a = 0.f;
 #pragma unroll
             for (int j = 0; j < 32; ++j) a = fmaf(sim[j], vs[h][j][d], a);
-            o[d] = to_tf32(a * inv);
+            o[d] = to_operand(a * inv, T());
         }
     }
 }
@@ -397,7 +399,8 @@ __global__ void upsample2x_kernel(const float4* __restrict__ x, float4* __restri
 }
 
 // warp per pixel, Cout <= 4 dot products of length Cin; NHWC -> NCHW
-__global__ void __launch_bounds__(256) head_conv1_kernel(const float* __restrict__ x, const float* __restrict__ w,
+template <typename T>
+__global__ void __launch_bounds__(256) head_conv1_kernel(const T* __restrict__ x, const float* __restrict__ w,
                                                          const float* __restrict__ bias, float* __restrict__ out, int64_t M,
                                                          int HW, int Cin, int Cout) {
     const int lane = threadIdx.x & 31;
@@ -405,7 +408,7 @@ __global__ void __launch_bounds__(256) head_conv1_kernel(const float* __restrict
     if (row >= M) return;
     float acc[4] = {0.f, 0.f, 0.f, 0.f};
     for (int c = lane * 4; c < Cin; c += 128) {
-        const float4 xv = *reinterpret_cast<const float4*>(x + row * Cin + c);
+        const float4 xv = load4(x + row * Cin + c);
         for (int o = 0; o < Cout; ++o) {
             const float4 wv = *reinterpret_cast<const float4*>(w + (int64_t)o * Cin + c);
             acc[o] += (xv.x * wv.x + xv.y * wv.y) + (xv.z * wv.z + xv.w * wv.w);
@@ -452,95 +455,146 @@ using namespace sdc;
 
 static inline unsigned blocks_for(int64_t n, int per) { int64_t b = (n + per - 1) / per; return (unsigned)(b > 148 * 16 ? 148 * 16 : (b < 1 ? 1 : b)); }
 
-extern "C" int sdc_pack_conv_weight(int kind, const float* w, float* wp, int Cout, int Cin, void* stream) {
+#define SDC_CHECK_PREC(name) SDC_REQUIRE(prec == SDC_PREC_TF32 || prec == SDC_PREC_F16, name ": precision %d", prec)
+
+extern "C" int sdc_pack_conv_weight(int prec, int kind, const float* w, void* wp, int Cout, int Cin, void* stream) {
+    SDC_CHECK_PREC("pack_conv_weight");
     SDC_REQUIRE(kind >= 0 && kind <= 2 && w && wp && Cout > 0 && Cin > 0, "pack_conv_weight: bad arguments");
     SDC_REQUIRE(kind != 2 || Cin % 4 == 0, "pack_conv_weight: unshuffle conv needs Cin %% 4 == 0");
     const int64_t total = (int64_t)Cout * Cin * (kind == 1 ? 9 : 1);
-    pack_conv_weight_kernel<<<blocks_for(total, 256), 256, 0, as_stream(stream)>>>(kind, w, wp, Cout, Cin);
+    if (prec == SDC_PREC_F16)
+        pack_conv_weight_kernel<__half><<<blocks_for(total, 256), 256, 0, as_stream(stream)>>>(kind, w, (__half*)wp, Cout, Cin);
+    else
+        pack_conv_weight_kernel<float><<<blocks_for(total, 256), 256, 0, as_stream(stream)>>>(kind, w, (float*)wp, Cout, Cin);
     SDC_LAUNCHED();
     return SDC_OK;
 }
 
-extern "C" int sdc_stem_conv7(const float* x, const float* w, const float* bias, float* out, int B, int Cin, int H, int W,
+extern "C" int sdc_stem_conv7(int prec, const float* x, const float* w, const float* bias, void* out, int B, int Cin, int H, int W,
                               int Cout, void* stream) {
+    SDC_CHECK_PREC("stem_conv7");
     SDC_REQUIRE(x && w && out && B > 0, "stem_conv7: bad arguments");
     SDC_REQUIRE(W % 8 == 0 && Cout % 8 == 0 && (W / 8) * (Cout / 8) <= 1024 && (W / 8) * (Cout / 8) >= 32,
                 "stem_conv7: unsupported W=%d Cout=%d", W, Cout);
     const int threads = (W / 8) * (Cout / 8);
     const size_t smem = ((size_t)Cin * 49 * Cout + (size_t)Cin * 7 * (W + 6)) * sizeof(float);
     SDC_REQUIRE(smem <= 227 * 1024, "stem_conv7: weights do not fit shared memory (%zu bytes)", smem);
-    SDC_CUDA(cudaFuncSetAttribute(stem_conv7_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dim3 grid((unsigned)B, (unsigned)((H + STEM_ROWS - 1) / STEM_ROWS));
-    stem_conv7_kernel<<<grid, threads, smem, as_stream(stream)>>>(x, w, bias, out, Cin, H, W, Cout);
+    if (prec == SDC_PREC_F16) {
+        SDC_CUDA(cudaFuncSetAttribute(stem_conv7_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        stem_conv7_kernel<__half><<<grid, threads, smem, as_stream(stream)>>>(x, w, bias, (__half*)out, Cin, H, W, Cout);
+    } else {
+        SDC_CUDA(cudaFuncSetAttribute(stem_conv7_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        stem_conv7_kernel<float><<<grid, threads, smem, as_stream(stream)>>>(x, w, bias, (float*)out, Cin, H, W, Cout);
+    }
     SDC_LAUNCHED();
     return SDC_OK;
 }
 
-extern "C" int sdc_gn_silu(const float* x, const double* stats, const float* gamma, const float* beta, const float* scale_shift,
-                           const int32_t* t_index, int64_t ss_stride, const float* residual, float* y, int B, int HW, int C,
-                           void* stream) {
+extern "C" int sdc_gn_silu(int prec, const float* x, const double* stats, const float* gamma, const float* beta,
+                           const float* scale_shift, const int32_t* t_index, int64_t ss_stride, const void* residual,
+                           int residual_operand, void* y, int B, int HW, int C, void* stream) {
+    SDC_CHECK_PREC("gn_silu");
     SDC_REQUIRE(x && stats && gamma && beta && y && B > 0 && HW > 0, "gn_silu: bad arguments");
     SDC_REQUIRE(C % 4 == 0 && C <= 4096, "gn_silu: C=%d unsupported", C);
     int ppc = HW;  // pixels per CTA: aim for >= 2 waves of CTAs without shrinking below 32 pixels
     while (ppc > 32 && (int64_t)B * (HW / ppc) < 2 * 148 && ppc % 2 == 0) ppc /= 2;
     dim3 grid((unsigned)B, (unsigned)((HW + ppc - 1) / ppc));
-    gn_silu_kernel<<<grid, 256, 2 * C * sizeof(float), as_stream(stream)>>>(x, stats, gamma, beta, scale_shift, t_index, ss_stride,
-                                                                              residual, y, HW, C, ppc);
+    const size_t sm = 2 * C * sizeof(float);
+    cudaStream_t st = as_stream(stream);
+    if (prec == SDC_PREC_F16) {
+        if (residual_operand)
+            gn_silu_kernel<__half, __half><<<grid, 256, sm, st>>>(x, stats, gamma, beta, scale_shift, t_index, ss_stride,
+                                                                   (const __half*)residual, (__half*)y, HW, C, ppc);
+        else
+            gn_silu_kernel<float, __half><<<grid, 256, sm, st>>>(x, stats, gamma, beta, scale_shift, t_index, ss_stride,
+                                                                  (const float*)residual, (__half*)y, HW, C, ppc);
+    } else {
+        gn_silu_kernel<float, float><<<grid, 256, sm, st>>>(x, stats, gamma, beta, scale_shift, t_index, ss_stride,
+                                                             (const float*)residual, (float*)y, HW, C, ppc);
+    }
     SDC_LAUNCHED();
     return SDC_OK;
 }
 
-extern "C" int sdc_channel_layernorm(const float* x, const float* g, const float* residual, float* y, int64_t M, int C,
-                                     int round_tf32, void* stream) {
+template <typename TX, typename TY>
+static void launch_layernorm(const void* x, const float* g, const void* residual, void* y, int64_t M, int C, int operand_out,
+                             cudaStream_t st) {
+    const TX* xp = (const TX*)x;
+    const TY* rp = (const TY*)residual;
+    TY* yp = (TY*)y;
+    if (C <= 128)
+        channel_layernorm_kernel<4, 1, TX, TY><<<(unsigned)((M + 31) / 32), 256, 0, st>>>(xp, g, rp, yp, M, C, operand_out);
+    else if (C <= 256)
+        channel_layernorm_kernel<4, 2, TX, TY><<<(unsigned)((M + 31) / 32), 256, 0, st>>>(xp, g, rp, yp, M, C, operand_out);
+    else if (C <= 512)
+        channel_layernorm_kernel<2, 4, TX, TY><<<(unsigned)((M + 15) / 16), 256, 0, st>>>(xp, g, rp, yp, M, C, operand_out);
+    else
+        channel_layernorm_kernel<1, 8, TX, TY><<<(unsigned)((M + 7) / 8), 256, 0, st>>>(xp, g, rp, yp, M, C, operand_out);
+}
+
+extern "C" int sdc_channel_layernorm(int prec, const void* x, int x_operand, const float* g, const void* residual, void* y,
+                                     int64_t M, int C, int operand_out, void* stream) {
+    SDC_CHECK_PREC("channel_layernorm");
     SDC_REQUIRE(x && g && y && M > 0, "channel_layernorm: bad arguments");
     SDC_REQUIRE(C % 4 == 0 && C <= 1024, "channel_layernorm: C=%d unsupported (multiple of 4, <= 1024)", C);
-    if (C <= 128)
-        channel_layernorm_kernel<4, 1><<<(unsigned)((M + 31) / 32), 256, 0, as_stream(stream)>>>(x, g, residual, y, M, C, round_tf32);
-    else if (C <= 256)
-        channel_layernorm_kernel<4, 2><<<(unsigned)((M + 31) / 32), 256, 0, as_stream(stream)>>>(x, g, residual, y, M, C, round_tf32);
-    else if (C <= 512)
-        channel_layernorm_kernel<2, 4><<<(unsigned)((M + 15) / 16), 256, 0, as_stream(stream)>>>(x, g, residual, y, M, C, round_tf32);
-    else
-        channel_layernorm_kernel<1, 8><<<(unsigned)((M + 7) / 8), 256, 0, as_stream(stream)>>>(x, g, residual, y, M, C, round_tf32);
+    cudaStream_t st = as_stream(stream);
+    if (prec == SDC_PREC_F16) {
+        if (x_operand) launch_layernorm<__half, __half>(x, g, residual, y, M, C, 1, st);
+        else launch_layernorm<float, __half>(x, g, residual, y, M, C, 1, st);
+    } else {
+        launch_layernorm<float, float>(x, g, residual, y, M, C, operand_out, st);
+    }
     SDC_LAUNCHED();
     return SDC_OK;
 }
 
 extern "C" int64_t sdc_linear_attention_workspace(int B) { return (int64_t)B * LA_HEADS * LA_D * LA_D * sizeof(float); }
 
-extern "C" int sdc_linear_attention(const float* qkv, float* out, void* workspace, int B, int n, void* stream) {
+extern "C" int sdc_linear_attention(int prec, const float* qkv, void* out, void* workspace, int B, int n, void* stream) {
+    SDC_CHECK_PREC("linear_attention");
     SDC_REQUIRE(qkv && out && workspace && B > 0 && n > 0, "linear_attention: bad arguments");
     float* ctx = reinterpret_cast<float*>(workspace);
     linattn_context_kernel<<<(unsigned)(B * LA_HEADS), 256, 0, as_stream(stream)>>>(qkv, ctx, n);
     SDC_LAUNCHED();
     dim3 grid((unsigned)(B * LA_HEADS), (unsigned)((n + 255) / 256));
-    linattn_apply_kernel<<<grid, 256, 0, as_stream(stream)>>>(qkv, ctx, out, n);
+    if (prec == SDC_PREC_F16) linattn_apply_kernel<__half><<<grid, 256, 0, as_stream(stream)>>>(qkv, ctx, (__half*)out, n);
+    else linattn_apply_kernel<float><<<grid, 256, 0, as_stream(stream)>>>(qkv, ctx, (float*)out, n);
     SDC_LAUNCHED();
     return SDC_OK;
 }
 
-extern "C" int sdc_attention(const float* qkv, float* out, int B, int n, void* stream) {
+extern "C" int sdc_attention(int prec, const float* qkv, void* out, int B, int n, void* stream) {
+    SDC_CHECK_PREC("attention");
     SDC_REQUIRE(qkv && out && B > 0, "attention: bad arguments");
     SDC_REQUIRE(n > 0 && n <= 32, "attention: n=%d tokens unsupported (bottleneck of the 16x128 grid has 32)", n);
-    attention_kernel<<<(unsigned)B, 128, 0, as_stream(stream)>>>(qkv, out, n);
+    if (prec == SDC_PREC_F16) attention_kernel<__half><<<(unsigned)B, 128, 0, as_stream(stream)>>>(qkv, (__half*)out, n);
+    else attention_kernel<float><<<(unsigned)B, 128, 0, as_stream(stream)>>>(qkv, (float*)out, n);
     SDC_LAUNCHED();
     return SDC_OK;
 }
 
-extern "C" int sdc_upsample2x(const float* x, float* y, int B, int H, int W, int C, void* stream) {
-    SDC_REQUIRE(x && y && B > 0 && C % 4 == 0, "upsample2x: bad arguments");
-    const int64_t total4 = (int64_t)B * 4 * H * W * (C / 4);
+extern "C" int sdc_upsample2x(int prec, const void* x, void* y, int B, int H, int W, int C, void* stream) {
+    SDC_CHECK_PREC("upsample2x");
+    const int eb = prec == SDC_PREC_F16 ? 2 : 4;
+    SDC_REQUIRE(x && y && B > 0 && (C * eb) % 16 == 0, "upsample2x: bad arguments");
+    const int v16 = C * eb / 16;   // 16-byte vectors per pixel
+    const int64_t total4 = (int64_t)B * 4 * H * W * v16;
     upsample2x_kernel<<<blocks_for(total4, 256 * 4), 256, 0, as_stream(stream)>>>(reinterpret_cast<const float4*>(x),
-                                                                                 reinterpret_cast<float4*>(y), total4, H, W, C / 4);
+                                                                                 reinterpret_cast<float4*>(y), total4, H, W, v16);
     SDC_LAUNCHED();
     return SDC_OK;
 }
 
-extern "C" int sdc_head_conv1(const float* x, const float* w, const float* bias, float* out, int B, int HW, int Cin, int Cout,
-                              void* stream) {
+extern "C" int sdc_head_conv1(int prec, const void* x, const float* w, const float* bias, float* out, int B, int HW, int Cin,
+                              int Cout, void* stream) {
+    SDC_CHECK_PREC("head_conv1");
     SDC_REQUIRE(x && w && out && B > 0 && Cin % 4 == 0 && Cout >= 1 && Cout <= 4, "head_conv1: needs Cin %% 4 == 0, Cout <= 4");
     const int64_t M = (int64_t)B * HW;
-    head_conv1_kernel<<<(unsigned)((M + 7) / 8), 256, 0, as_stream(stream)>>>(x, w, bias, out, M, HW, Cin, Cout);
+    if (prec == SDC_PREC_F16)
+        head_conv1_kernel<__half><<<(unsigned)((M + 7) / 8), 256, 0, as_stream(stream)>>>((const __half*)x, w, bias, out, M, HW, Cin, Cout);
+    else
+        head_conv1_kernel<float><<<(unsigned)((M + 7) / 8), 256, 0, as_stream(stream)>>>((const float*)x, w, bias, out, M, HW, Cin, Cout);
     SDC_LAUNCHED();
     return SDC_OK;
 }

@@ -18,17 +18,17 @@ from . import _lib as L
 from ._lib import c_f, c_i, c_i64, c_p
 
 L.register({
-    "sdc_pack_conv_weight": (c_i, [c_i, c_p, c_p, c_i, c_i, c_p]),
-    "sdc_conv_gemm": (c_i, [c_i, c_p, c_i, c_p, c_i, c_p, c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_p]),
-    "sdc_conv3x3_row": (c_i, [c_p, c_i, c_p, c_i, c_p, c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_p]),
-    "sdc_stem_conv7": (c_i, [c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_p]),
-    "sdc_gn_silu": (c_i, [c_p, c_p, c_p, c_p, c_p, c_p, c_i64, c_p, c_p, c_i, c_i, c_i, c_p]),
-    "sdc_channel_layernorm": (c_i, [c_p, c_p, c_p, c_p, c_i64, c_i, c_i, c_p]),
+    "sdc_pack_conv_weight": (c_i, [c_i, c_i, c_p, c_p, c_i, c_i, c_p]),
+    "sdc_conv_gemm": (c_i, [c_i, c_i, c_p, c_i, c_p, c_i, c_p, c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_p]),
+    "sdc_conv3x3_row": (c_i, [c_i, c_p, c_i, c_p, c_i, c_p, c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_p]),
+    "sdc_stem_conv7": (c_i, [c_i, c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_p]),
+    "sdc_gn_silu": (c_i, [c_i, c_p, c_p, c_p, c_p, c_p, c_p, c_i64, c_p, c_i, c_p, c_i, c_i, c_i, c_p]),
+    "sdc_channel_layernorm": (c_i, [c_i, c_p, c_i, c_p, c_p, c_p, c_i64, c_i, c_i, c_p]),
     "sdc_linear_attention_workspace": (c_i64, [c_i]),
-    "sdc_linear_attention": (c_i, [c_p, c_p, c_p, c_i, c_i, c_p]),
-    "sdc_attention": (c_i, [c_p, c_p, c_i, c_i, c_p]),
-    "sdc_upsample2x": (c_i, [c_p, c_p, c_i, c_i, c_i, c_i, c_p]),
-    "sdc_head_conv1": (c_i, [c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_p]),
+    "sdc_linear_attention": (c_i, [c_i, c_p, c_p, c_p, c_i, c_i, c_p]),
+    "sdc_attention": (c_i, [c_i, c_p, c_p, c_i, c_i, c_p]),
+    "sdc_upsample2x": (c_i, [c_i, c_p, c_p, c_i, c_i, c_i, c_i, c_p]),
+    "sdc_head_conv1": (c_i, [c_i, c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_p]),
     "sdc_linear_rows": (c_i, [c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_p]),
     "sdc_sinusoidal_embedding": (c_i, [c_p, c_p, c_i, c_i, c_f, c_p]),
     "sdc_zero_f64": (c_i, [c_p, c_i64, c_p]),
@@ -36,6 +36,12 @@ L.register({
 
 HEADS, DIM_HEAD = 4, 32
 KIND_1x1, KIND_3x3, KIND_UNSHUFFLE = 0, 1, 2
+PREC_TF32, PREC_F16 = 0, 1   # operand precision of the tensor-core convolutions (include/safediffcon_b200_unet.h)
+PREC_NAMES = {"tf32": PREC_TF32, "f16": PREC_F16}
+
+
+def operand_dtype(prec):
+    return torch.float16 if prec == PREC_F16 else torch.float32
 
 
 # ----------------------------------------------------------------------------- parameter containers
@@ -108,31 +114,36 @@ USE_ROW_KERNEL = os.environ.get("SDC_NO_ROW_KERNEL", "0") != "1"  # halo-reuse k
 PROFILE = None  # bench.py sets this to a list: every conv launch is then bracketed by CUDA events on its stream
 
 
-def conv_gemm(kind, a0, c0, a1, c1, wp, bias, residual, out, stats, round_tf32, B, H, W, Cout):
+def conv_gemm(kind, a0, c0, a1, c1, wp, bias, residual, out, stats, operand_out, B, H, W, Cout, prec=PREC_TF32):
+    """out[B*H*W, Cout] = conv(a0 | a1) + bias (+ residual).  a0/a1/wp/residual are operand-precision tensors; `out` is an
+    operand-precision tensor when operand_out else fp32."""
+    od = operand_dtype(prec)
+    assert a0.dtype == od and wp.dtype == od and (a1 is None or a1.dtype == od) and (residual is None or residual.dtype == od)
+    assert out.dtype == (od if operand_out else torch.float32)
     prof = PROFILE
     if prof is not None:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
     rc = -1
     if kind == KIND_3x3 and USE_ROW_KERNEL and W == 128 and Cout <= 128:
-        rc = L.lib().sdc_conv3x3_row(L.ptr(a0), c0, L.ptr(a1), c1, L.ptr(wp), L.ptr(bias), L.ptr(residual), L.ptr(out),
-                                     L.ptr(stats), int(round_tf32), B, H, W, Cout, _st())
+        rc = L.lib().sdc_conv3x3_row(prec, L.ptr(a0), c0, L.ptr(a1), c1, L.ptr(wp), L.ptr(bias), L.ptr(residual), L.ptr(out),
+                                     L.ptr(stats), int(operand_out), B, H, W, Cout, _st())
         if rc > 0:
             L.check(rc)
     if rc != 0:
-        L.check(L.lib().sdc_conv_gemm(kind, L.ptr(a0), c0, L.ptr(a1), c1, L.ptr(wp), L.ptr(bias), L.ptr(residual), L.ptr(out),
-                                      L.ptr(stats), int(round_tf32), B, H, W, Cout, _st()))
+        L.check(L.lib().sdc_conv_gemm(prec, kind, L.ptr(a0), c0, L.ptr(a1), c1, L.ptr(wp), L.ptr(bias), L.ptr(residual),
+                                      L.ptr(out), L.ptr(stats), int(operand_out), B, H, W, Cout, _st()))
     if prof is not None:
         e1.record()
         taps = {KIND_1x1: 1, KIND_3x3: 9, KIND_UNSHUFFLE: 4}[kind]
         prof.append((e0, e1, 2.0 * B * H * W * Cout * taps * (c0 + c1), (kind, B, H, W, c0 + c1, Cout)))
 
 
-def pack_conv_weight(kind, w):
+def pack_conv_weight(kind, w, prec=PREC_TF32):
     w = w.detach().to(torch.float32).contiguous()
     cout, cin = w.shape[0], w.shape[1]
-    wp = torch.empty(cout, w[0].numel(), device=w.device, dtype=torch.float32)
-    L.check(L.lib().sdc_pack_conv_weight(kind, L.ptr(w), L.ptr(wp), cout, cin, _st()))
+    wp = torch.empty(cout, w[0].numel(), device=w.device, dtype=operand_dtype(prec))
+    L.check(L.lib().sdc_pack_conv_weight(prec, kind, L.ptr(w), L.ptr(wp), cout, cin, _st()))
     return wp
 
 
@@ -203,6 +214,12 @@ class Unet2D(nn.Module):
         self.final_conv = nn.Conv2d(dim, self.out_dim, 1)
         self._cache = _PackCache()
         self.table_timesteps = 1000  # rows of the cached FiLM table for integer diffusion times
+        # Operand precision of the tensor-core convolutions.  FP16 and TF32 carry the same 10-bit mantissa (identical
+        # rounding error on eps); FP16 runs at twice the tensor rate with half the operand bytes but needs every conv
+        # input channel count to be a multiple of 64 and activations within +-65504 (GroupNorm/LayerNorm-bounded here).
+        # Override with `net.precision = "tf32"` (or SDC_PRECISION=tf32) for checkpoints with extreme activation ranges.
+        default = "f16" if dim % 64 == 0 and init_dim % 64 == 0 else "tf32"
+        self.precision = os.environ.get("SDC_PRECISION", default)
 
     # ------------------------------------------------------------------ weight packing / FiLM table
     def _resnet_blocks(self):
@@ -216,8 +233,15 @@ class Unet2D(nn.Module):
             yield lvl[1]
         yield self.final_res_block
 
+    def _prec(self):
+        if self.precision not in PREC_NAMES:
+            raise ValueError(f"safediffcon_b200.Unet2D.precision must be 'f16' or 'tf32', got {self.precision!r}")
+        if self.precision == "f16" and (self.dim % 64 != 0 or self.init_conv.weight.shape[0] % 64 != 0):
+            raise ValueError("precision 'f16' needs dim and init_dim to be multiples of 64 (128-byte K blocks of fp16 channels)")
+        return PREC_NAMES[self.precision]
+
     def _key(self):
-        return tuple((p.data_ptr(), p._version) for p in self.parameters())
+        return (self.precision,) + tuple((p.data_ptr(), p._version) for p in self.parameters())
 
     def _packed(self):
         key = self._key()
@@ -227,10 +251,11 @@ class Unet2D(nn.Module):
         if dev.type != "cuda":
             raise RuntimeError("safediffcon_b200.Unet2D: parameters are on the CPU; move the module to a CUDA device "
                                "(there is no CPU fallback)")
-        pk = {}
+        prec = self._prec()
+        pk = {"prec": prec}
         with torch.no_grad(), torch.cuda.device(dev):
             def conv(m, kind):
-                return dict(w=pack_conv_weight(kind, m.weight), b=None if m.bias is None else m.bias.detach().float().contiguous(),
+                return dict(w=pack_conv_weight(kind, m.weight, prec), b=None if m.bias is None else m.bias.detach().float().contiguous(),
                             cout=m.weight.shape[0])
 
             def rb(m):
@@ -320,6 +345,8 @@ class Unet2D(nn.Module):
         pk = self._packed()
         lib = L.lib()
         dev = x.device
+        prec = pk["prec"]
+        od = operand_dtype(prec)
         B, Cin, H, W = x.shape
         assert Cin == self.channels
         # FiLM rows: integer times index the cached 1000-row table; anything else is evaluated per sample
@@ -334,57 +361,60 @@ class Unet2D(nn.Module):
         n_gn = 2 * sum(1 for _ in self._resnet_blocks())
         stats = torch.zeros(n_gn, B, 2, device=dev, dtype=torch.float64)
         stat_i = [0]
-        new = lambda rows, c: torch.empty(rows, c, device=dev, dtype=torch.float32)  # noqa: E731
+        f32 = lambda rows, c: torch.empty(rows, c, device=dev, dtype=torch.float32)  # noqa: E731  (conv outputs ahead of a norm)
+        opd = lambda rows, c: torch.empty(rows, c, device=dev, dtype=od)  # noqa: E731  (tensor-core operands)
+
+        def conv(kind, a0, c0, a1, c1, cw, residual, out, st, operand_out, h, w):
+            conv_gemm(kind, a0, c0, a1, c1, cw["w"], cw["b"], residual, out, st, operand_out, B, h, w, cw["cout"], prec)
 
         def resnet(p, m, a0, c0, a1, c1, h, w):
-            """ResnetBlock (unet.py:166-180) on one or two concatenated NHWC inputs -> [B*h*w, Cout]."""
+            """ResnetBlock (unet.py:166-180) on one or two concatenated NHWC inputs -> operand [B*h*w, Cout]."""
             M, cout = B * h * w, p["cout"]
             s1, s2 = stats[stat_i[0]], stats[stat_i[0] + 1]
             stat_i[0] += 2
-            h1 = new(M, cout)
-            conv_gemm(KIND_3x3, a0, c0, a1, c1, p["c1"]["w"], p["c1"]["b"], None, h1, s1, False, B, h, w, cout)
+            raw = f32(M, cout)
+            conv(KIND_3x3, a0, c0, a1, c1, p["c1"], None, raw, s1, False, h, w)
             ss = film[:, m._film_off:]
-            L.check(lib.sdc_gn_silu(L.ptr(h1), L.ptr(s1), L.ptr(p["g1"][0]), L.ptr(p["g1"][1]), ctypes_ptr(ss), L.ptr(t_index), E,
-                                    None, L.ptr(h1), B, h * w, cout, _st()))
-            h2 = new(M, cout)
-            conv_gemm(KIND_3x3, h1, cout, None, 0, p["c2"]["w"], p["c2"]["b"], None, h2, s2, False, B, h, w, cout)
+            h1 = raw if od == torch.float32 else opd(M, cout)   # TF32 mode: in place
+            L.check(lib.sdc_gn_silu(prec, L.ptr(raw), L.ptr(s1), L.ptr(p["g1"][0]), L.ptr(p["g1"][1]), L.ptr(ss), L.ptr(t_index), E,
+                                    None, 0, L.ptr(h1), B, h * w, cout, _st()))
+            raw2 = f32(M, cout)
+            conv(KIND_3x3, h1, cout, None, 0, p["c2"], None, raw2, s2, False, h, w)
             if p["res"] is not None:
-                res = h1  # reuse: h1 is dead after conv2
-                conv_gemm(KIND_1x1, a0, c0, a1, c1, p["res"]["w"], p["res"]["b"], None, res, None, False, B, h, w, cout)
+                res, res_operand = raw, 0   # fp32 scratch: conv1's output is dead once h1 exists (TF32 mode: h1 itself, dead after conv2)
+                conv(KIND_1x1, a0, c0, a1, c1, p["res"], None, res, None, False, h, w)
             else:
                 assert a1 is None
-                res = a0
-            L.check(lib.sdc_gn_silu(L.ptr(h2), L.ptr(s2), L.ptr(p["g2"][0]), L.ptr(p["g2"][1]), None, None, 0, L.ptr(res),
-                                    L.ptr(h2), B, h * w, cout, _st()))
-            return h2
+                res, res_operand = a0, 1
+            out = raw2 if od == torch.float32 else h1   # TF32 mode: in place; F16 mode: h1's buffer is dead after conv2
+            L.check(lib.sdc_gn_silu(prec, L.ptr(raw2), L.ptr(s2), L.ptr(p["g2"][0]), L.ptr(p["g2"][1]), None, None, 0, L.ptr(res),
+                                    res_operand, L.ptr(out), B, h * w, cout, _st()))
+            return out
 
         def attention(p, xin, c, h, w):
             """Residual(PreNorm(LinearAttention | Attention)) (unet.py:16-22,65-76,182-258)."""
             M, n = B * h * w, h * w
-            xn = new(M, c)
-            L.check(lib.sdc_channel_layernorm(L.ptr(xin), L.ptr(p["g_in"]), None, L.ptr(xn), M, c, 1, _st()))
-            qkv = new(M, 3 * HEADS * DIM_HEAD)
-            conv_gemm(KIND_1x1, xn, c, None, 0, p["qkv"]["w"], None, None, qkv, None, False, B, h, w, 3 * HEADS * DIM_HEAD)
-            att = new(M, HEADS * DIM_HEAD)
+            xn = opd(M, c)
+            L.check(lib.sdc_channel_layernorm(prec, L.ptr(xin), 1, L.ptr(p["g_in"]), None, L.ptr(xn), M, c, 1, _st()))
+            qkv = f32(M, 3 * HEADS * DIM_HEAD)
+            conv(KIND_1x1, xn, c, None, 0, p["qkv"], None, qkv, None, False, h, w)
+            att = opd(M, HEADS * DIM_HEAD)
             if p["full"]:
-                L.check(lib.sdc_attention(L.ptr(qkv), L.ptr(att), B, n, _st()))
+                L.check(lib.sdc_attention(prec, L.ptr(qkv), L.ptr(att), B, n, _st()))
                 out = xn  # reuse
-                conv_gemm(KIND_1x1, att, HEADS * DIM_HEAD, None, 0, p["out"]["w"], p["out"]["b"], xin, out, None, True, B, h, w, c)
+                conv(KIND_1x1, att, HEADS * DIM_HEAD, None, 0, p["out"], xin, out, None, True, h, w)
                 return out
             ws = torch.empty(lib.sdc_linear_attention_workspace(B), device=dev, dtype=torch.uint8)
-            L.check(lib.sdc_linear_attention(L.ptr(qkv), L.ptr(att), L.ptr(ws), B, n, _st()))
-            proj = xn  # reuse
-            conv_gemm(KIND_1x1, att, HEADS * DIM_HEAD, None, 0, p["out"]["w"], p["out"]["b"], None, proj, None, False, B, h, w, c)
-            out = new(M, c)
-            L.check(lib.sdc_channel_layernorm(L.ptr(proj), L.ptr(p["g_out"]), L.ptr(xin), L.ptr(out), M, c, 1, _st()))
+            L.check(lib.sdc_linear_attention(prec, L.ptr(qkv), L.ptr(att), L.ptr(ws), B, n, _st()))
+            proj = f32(M, c)
+            conv(KIND_1x1, att, HEADS * DIM_HEAD, None, 0, p["out"], None, proj, None, False, h, w)
+            out = xn  # reuse: LN1's output is dead once qkv exists
+            L.check(lib.sdc_channel_layernorm(prec, L.ptr(proj), 0, L.ptr(p["g_out"]), L.ptr(xin), L.ptr(out), M, c, 1, _st()))
             return out
 
-        def ctypes_ptr(t):
-            return L.ptr(t)
-
         c = self.init_conv.weight.shape[0]
-        cur = new(B * H * W, c)
-        L.check(lib.sdc_stem_conv7(L.ptr(x), L.ptr(pk["stem"][0]), L.ptr(pk["stem"][1]), L.ptr(cur), B, Cin, H, W, c, _st()))
+        cur = opd(B * H * W, c)
+        L.check(lib.sdc_stem_conv7(prec, L.ptr(x), L.ptr(pk["stem"][0]), L.ptr(pk["stem"][1]), L.ptr(cur), B, Cin, H, W, c, _st()))
         r, r_c = cur, c
         h, w = H, W
         skips = []
@@ -397,11 +427,11 @@ class Unet2D(nn.Module):
             cout = lvl["down"]["cout"]
             if lvl["unshuffle"]:
                 h, w = h // 2, w // 2
-                nxt = new(B * h * w, cout)
-                conv_gemm(KIND_UNSHUFFLE, cur, c, None, 0, lvl["down"]["w"], lvl["down"]["b"], None, nxt, None, True, B, h, w, cout)
+                nxt = opd(B * h * w, cout)
+                conv(KIND_UNSHUFFLE, cur, c, None, 0, lvl["down"], None, nxt, None, True, h, w)
             else:
-                nxt = new(B * h * w, cout)
-                conv_gemm(KIND_3x3, cur, c, None, 0, lvl["down"]["w"], lvl["down"]["b"], None, nxt, None, True, B, h, w, cout)
+                nxt = opd(B * h * w, cout)
+                conv(KIND_3x3, cur, c, None, 0, lvl["down"], None, nxt, None, True, h, w)
             cur, c = nxt, cout
         cur = resnet(pk["mid1"], self.mid_block1, cur, c, None, 0, h, w)
         cur = attention(pk["mid_attn"], cur, c, h, w)
@@ -415,15 +445,15 @@ class Unet2D(nn.Module):
             cur = attention(lvl["attn"], cur, c, h, w)
             cout = lvl["up"]["cout"]
             if lvl["upsample"]:
-                up = new(B * 4 * h * w, c)
-                L.check(lib.sdc_upsample2x(L.ptr(cur), L.ptr(up), B, h, w, c, _st()))
+                up = opd(B * 4 * h * w, c)
+                L.check(lib.sdc_upsample2x(prec, L.ptr(cur), L.ptr(up), B, h, w, c, _st()))
                 h, w = 2 * h, 2 * w
                 cur = up
-            nxt = new(B * h * w, cout)
-            conv_gemm(KIND_3x3, cur, c, None, 0, lvl["up"]["w"], lvl["up"]["b"], None, nxt, None, True, B, h, w, cout)
+            nxt = opd(B * h * w, cout)
+            conv(KIND_3x3, cur, c, None, 0, lvl["up"], None, nxt, None, True, h, w)
             cur, c = nxt, cout
         cur = resnet(pk["final"], self.final_res_block, cur, c, r, r_c, h, w)
         out = torch.empty(B, self.out_dim, H, W, device=dev, dtype=torch.float32)
-        L.check(lib.sdc_head_conv1(L.ptr(cur), L.ptr(pk["head"][0]), L.ptr(pk["head"][1]), L.ptr(out), B, H * W,
+        L.check(lib.sdc_head_conv1(prec, L.ptr(cur), L.ptr(pk["head"][0]), L.ptr(pk["head"][1]), L.ptr(out), B, H * W,
                                    self.final_res_block.dim_out, self.out_dim, _st()))
         return out

@@ -1,6 +1,6 @@
 """GPU parity: tcgen05 convolution and the fused U-Net kernels vs torch fp32, and the whole denoiser vs the
-reference's eps (tests/golden/unet_*.npz).  Tolerances: TF32 operands (10-bit mantissa) with fp32 accumulation;
-north-star bound for the whole network: eps within 1e-3 relative."""
+reference's eps (tests/golden/unet_*.npz), in both operand precisions (TF32 containers / FP16: 10-bit mantissa,
+round to nearest, fp32 accumulation).  North-star bound for the whole network: eps within 1e-3 relative."""
 import numpy as np
 import pytest
 import torch
@@ -15,6 +15,19 @@ pytestmark = pytest.mark.gpu
 def tf32(x):
     i = x.contiguous().view(torch.int32)
     return ((i + 0x1000) & ~0x1FFF).view(torch.float32)
+
+
+TF32, F16 = 0, 1
+
+
+def quant(x, prec):
+    """Round to the operand precision, result kept in fp32."""
+    return x.half().float() if prec == F16 else tf32(x)
+
+
+def as_operand(x, prec):
+    """fp32 tensor holding operand-representable values -> tensor of the operand dtype."""
+    return x.half() if prec == F16 else x
 
 
 def nhwc(x):
@@ -56,26 +69,31 @@ CONV_CASES = [
 ]
 
 
-@pytest.mark.parametrize("case", CONV_CASES, ids=[f"k{c[0]}_B{c[1]}_{c[2]}x{c[3]}_c{c[4]}+{c[5]}_o{c[6]}" for c in CONV_CASES])
-def test_conv_gemm_vs_torch(case):
+CONV_PARAMS = [(c, TF32) for c in CONV_CASES] + [(c, F16) for c in CONV_CASES if c[4] % 64 == 0 and c[5] % 64 == 0]
+
+
+@pytest.mark.parametrize("case,prec", CONV_PARAMS,
+                         ids=[f"{'f16' if pr else 'tf32'}_k{c[0]}_B{c[1]}_{c[2]}x{c[3]}_c{c[4]}+{c[5]}_o{c[6]}" for c, pr in CONV_PARAMS])
+def test_conv_gemm_vs_torch(case, prec):
     from safediffcon_b200 import unet as U
     kind, B, H, W, c0, c1, cout, use_bias, use_res, use_stats, rnd = case
     g = torch.Generator().manual_seed(H * W + c0 + cout)
     hin, win = (2 * H, 2 * W) if kind == 2 else (H, W)
     cin = c0 + c1
-    x = tf32(torch.randn(B, cin, hin, win, generator=g)).cuda()
+    x = quant(torch.randn(B, cin, hin, win, generator=g), prec).cuda()
     ksz = {0: 1, 1: 3, 2: 1}[kind]
     w = (torch.randn(cout, cin * (4 if kind == 2 else 1), ksz, ksz, generator=g) / np.sqrt(cin * ksz * ksz)).cuda()
     bias = torch.randn(cout, generator=g).cuda() if use_bias else None
-    res = torch.randn(B * H * W, cout, generator=g).cuda() if use_res else None
-    a0 = nhwc(x[:, :c0])
-    a1 = nhwc(x[:, c0:]) if c1 else None
-    wp = U.pack_conv_weight(kind, w)
-    out = torch.full((B * H * W, cout), float("nan")).cuda()
+    res = quant(torch.randn(B * H * W, cout, generator=g), prec).cuda() if use_res else None
+    a0 = as_operand(nhwc(x[:, :c0]), prec)
+    a1 = as_operand(nhwc(x[:, c0:]), prec) if c1 else None
+    wp = U.pack_conv_weight(kind, w, prec)
+    out = torch.full((B * H * W, cout), float("nan"), dtype=U.operand_dtype(prec) if rnd else torch.float32).cuda()
     stats = torch.zeros(B, 2, dtype=torch.float64).cuda() if use_stats else None
-    U.conv_gemm(kind, a0, c0, a1, c1, wp, bias, res, out, stats, rnd, B, H, W, cout)
+    U.conv_gemm(kind, a0, c0, a1, c1, wp, bias, None if res is None else as_operand(res, prec), out, stats, rnd, B, H, W, cout, prec)
     torch.cuda.synchronize()
-    wq = tf32(w.cpu()).cuda()
+    out = out.float()
+    wq = quant(w.cpu(), prec).cuda()
     if kind == 2:
         xin = x.reshape(B, cin, H, 2, W, 2).permute(0, 1, 3, 5, 2, 4).reshape(B, cin * 4, H, W)
         ref = F.conv2d(xin.double(), wq.double(), None if bias is None else bias.double())
@@ -89,7 +107,7 @@ def test_conv_gemm_vs_torch(case):
     tol = 2e-3 if rnd else 2e-5   # fp32 accumulation of exact tf32 products; rounding the output costs 2^-11 relative
     assert err < tol * max(1.0, ref.abs().max().item()), err
     if rnd:
-        assert torch.equal(out, tf32(out.cpu()).cuda())  # stored values are TF32-representable
+        assert torch.equal(out, quant(out.cpu(), prec).cuda())  # stored values are representable in the operand precision
     if stats is not None:
         o = out.double().reshape(B, -1)
         # statistics are taken on the fp32 values BEFORE the optional TF32 rounding of the stored tensor
@@ -103,24 +121,28 @@ def _L():
     return L, L.lib()
 
 
-def test_stem_conv7_vs_torch():
+@pytest.mark.parametrize("prec", [TF32, F16])
+def test_stem_conv7_vs_torch(prec):
     L, lib = _L()
-    import safediffcon_b200.unet  # noqa: F401  (registers signatures)
+    from safediffcon_b200 import unet as U
     for B, cout in ((2, 128), (3, 32)):
         g = torch.Generator().manual_seed(cout)
         x = torch.randn(B, 3, 16, 128, generator=g).cuda()
         w = (torch.randn(cout, 3, 7, 7, generator=g) * 0.1).cuda()
         b = torch.randn(cout, generator=g).cuda()
-        out = torch.empty(B * 16 * 128, cout).cuda()
-        L.check(lib.sdc_stem_conv7(L.ptr(x), L.ptr(w), L.ptr(b), L.ptr(out), B, 3, 16, 128, cout, L.stream_ptr()))
+        out = torch.empty(B * 16 * 128, cout, dtype=U.operand_dtype(prec)).cuda()
+        L.check(lib.sdc_stem_conv7(prec, L.ptr(x), L.ptr(w), L.ptr(b), L.ptr(out), B, 3, 16, 128, cout, L.stream_ptr()))
+        out = out.float()
         ref = nhwc(F.conv2d(x, w, b, padding=3)).reshape(-1, cout)
-        assert (out - ref).abs().max().item() < 1.5e-3 * ref.abs().max().item()  # output rounded to TF32
-        assert (out - tf32(ref.cpu()).cuda()).abs().max().item() < 1e-3 * ref.abs().max().item()
+        assert (out - ref).abs().max().item() < 1.5e-3 * ref.abs().max().item()  # output rounded to the operand precision
+        assert (out - quant(ref.cpu(), prec).cuda()).abs().max().item() < 1e-3 * ref.abs().max().item()
 
 
-def test_gn_silu_vs_torch():
+@pytest.mark.parametrize("prec", [TF32, F16])
+def test_gn_silu_vs_torch(prec):
     L, lib = _L()
-    import safediffcon_b200.unet  # noqa: F401
+    from safediffcon_b200 import unet as U
+    od = U.operand_dtype(prec)
     for B, HW, C in ((3, 2048, 128), (4, 32, 1024), (2, 512, 32)):
         g = torch.Generator().manual_seed(C)
         x = (torch.randn(B, C, HW, generator=g) * 2 + 0.7).cuda()
@@ -130,18 +152,22 @@ def test_gn_silu_vs_torch():
         res = torch.randn(B * HW, C, generator=g).cuda()
         xr = x.permute(0, 2, 1).reshape(B * HW, C).contiguous()
         stats = torch.stack([xr.double().reshape(B, -1).sum(1), (xr.double() ** 2).reshape(B, -1).sum(1)], 1).contiguous()
-        y = torch.empty_like(xr)
-        L.check(lib.sdc_gn_silu(L.ptr(xr), L.ptr(stats), L.ptr(gamma), L.ptr(beta), L.ptr(table), L.ptr(tidx), 3 * C, L.ptr(res),
-                                L.ptr(y), B, HW, C, L.stream_ptr()))
+        y = torch.empty(B * HW, C, dtype=od).cuda()
         ss = table[tidx.long()]
-        ref = F.group_norm(x, 1, gamma, beta, eps=1e-5) * (ss[:, :C, None] + 1) + ss[:, C:2 * C, None]
-        ref = F.silu(ref).permute(0, 2, 1).reshape(B * HW, C) + res
-        assert (y - ref).abs().max().item() < 2e-3 * ref.abs().max().item()
+        ref0 = F.group_norm(x, 1, gamma, beta, eps=1e-5) * (ss[:, :C, None] + 1) + ss[:, C:2 * C, None]
+        ref0 = F.silu(ref0).permute(0, 2, 1).reshape(B * HW, C)
+        # fp32 residual (the 1x1 res_conv output) and operand-precision residual (the block input)
+        for res_operand in (0, 1):
+            r_in = as_operand(quant(res.cpu(), prec).cuda(), prec) if res_operand else res
+            L.check(lib.sdc_gn_silu(prec, L.ptr(xr), L.ptr(stats), L.ptr(gamma), L.ptr(beta), L.ptr(table), L.ptr(tidx), 3 * C,
+                                    L.ptr(r_in), res_operand, L.ptr(y), B, HW, C, L.stream_ptr()))
+            ref = ref0 + r_in.float()
+            assert (y.float() - ref).abs().max().item() < 2e-3 * ref.abs().max().item()
         # no FiLM, no residual, uniform row 0
-        L.check(lib.sdc_gn_silu(L.ptr(xr), L.ptr(stats), L.ptr(gamma), L.ptr(beta), None, None, 0, None, L.ptr(y), B, HW, C,
+        L.check(lib.sdc_gn_silu(prec, L.ptr(xr), L.ptr(stats), L.ptr(gamma), L.ptr(beta), None, None, 0, None, 0, L.ptr(y), B, HW, C,
                                 L.stream_ptr()))
         ref2 = F.silu(F.group_norm(x, 1, gamma, beta, eps=1e-5)).permute(0, 2, 1).reshape(B * HW, C)
-        assert (y - ref2).abs().max().item() < 2e-3 * ref2.abs().max().item()
+        assert (y.float() - ref2).abs().max().item() < 2e-3 * ref2.abs().max().item()
 
 
 def test_channel_layernorm_vs_torch():
@@ -153,22 +179,32 @@ def test_channel_layernorm_vs_torch():
         gain = torch.randn(C, generator=g).cuda()
         res = torch.randn(M, C, generator=g).cuda()
         y = torch.empty_like(x)
-        L.check(lib.sdc_channel_layernorm(L.ptr(x), L.ptr(gain), L.ptr(res), L.ptr(y), M, C, 0, L.stream_ptr()))
+        L.check(lib.sdc_channel_layernorm(TF32, L.ptr(x), 1, L.ptr(gain), L.ptr(res), L.ptr(y), M, C, 0, L.stream_ptr()))
         ref = (x - x.mean(1, keepdim=True)) * (x.var(1, unbiased=False, keepdim=True) + 1e-5).rsqrt() * gain + res
         assert (y - ref).abs().max().item() < 1e-5 * ref.abs().max().item()
-        L.check(lib.sdc_channel_layernorm(L.ptr(x), L.ptr(gain), None, L.ptr(y), M, C, 1, L.stream_ptr()))
+        L.check(lib.sdc_channel_layernorm(TF32, L.ptr(x), 1, L.ptr(gain), None, L.ptr(y), M, C, 1, L.stream_ptr()))
         assert torch.equal(y, tf32((ref - res).cpu()).cuda()) or (y - (ref - res)).abs().max().item() < 1e-3 * ref.abs().max().item()
+        # FP16 mode: fp16 or fp32 input, fp16 residual and output
+        xh, rh, yh = x.half(), res.half(), torch.empty(M, C, dtype=torch.float16).cuda()
+        for x_in, x_operand in ((xh, 1), (x, 0)):
+            xf = x_in.float()
+            refh = (xf - xf.mean(1, keepdim=True)) * (xf.var(1, unbiased=False, keepdim=True) + 1e-5).rsqrt() * gain + rh.float()
+            L.check(lib.sdc_channel_layernorm(F16, L.ptr(x_in), x_operand, L.ptr(gain), L.ptr(rh), L.ptr(yh), M, C, 1, L.stream_ptr()))
+            assert (yh.float() - refh).abs().max().item() < 1e-3 * refh.abs().max().item()
 
 
-def test_attention_cores_vs_torch():
+@pytest.mark.parametrize("prec", [TF32, F16])
+def test_attention_cores_vs_torch(prec):
     L, lib = _L()
-    import safediffcon_b200.unet  # noqa: F401
+    from safediffcon_b200 import unet as U
+    od = U.operand_dtype(prec)
     for B, n in ((3, 2048), (2, 512), (5, 32), (2, 100)):
         g = torch.Generator().manual_seed(n)
         qkv = (torch.randn(B * n, 384, generator=g) * 1.5).cuda()
-        out = torch.empty(B * n, 128).cuda()
+        out = torch.empty(B * n, 128, dtype=od).cuda()
         ws = torch.empty(lib.sdc_linear_attention_workspace(B), dtype=torch.uint8).cuda()
-        L.check(lib.sdc_linear_attention(L.ptr(qkv), L.ptr(out), L.ptr(ws), B, n, L.stream_ptr()))
+        L.check(lib.sdc_linear_attention(prec, L.ptr(qkv), L.ptr(out), L.ptr(ws), B, n, L.stream_ptr()))
+        out = out.float()
         q, k, v = (t.reshape(B, n, 4, 32).permute(0, 2, 3, 1) for t in qkv.chunk(3, dim=1))  # b h d n
         ctx = torch.einsum("bhdn,bhen->bhde", k.softmax(-1), v)
         ref = torch.einsum("bhde,bhdn->bhen", ctx, q.softmax(-2) * 32 ** -0.5)
@@ -177,8 +213,9 @@ def test_attention_cores_vs_torch():
     for B, n in ((4, 32), (1, 32), (3, 20)):
         g = torch.Generator().manual_seed(n + B)
         qkv = (torch.randn(B * n, 384, generator=g) * 1.5).cuda()
-        out = torch.empty(B * n, 128).cuda()
-        L.check(lib.sdc_attention(L.ptr(qkv), L.ptr(out), B, n, L.stream_ptr()))
+        out = torch.empty(B * n, 128, dtype=od).cuda()
+        L.check(lib.sdc_attention(prec, L.ptr(qkv), L.ptr(out), B, n, L.stream_ptr()))
+        out = out.float()
         q, k, v = (t.reshape(B, n, 4, 32).permute(0, 2, 3, 1) for t in qkv.chunk(3, dim=1))
         attn = torch.einsum("bhdi,bhdj->bhij", q * 32 ** -0.5, k).softmax(-1)
         ref = torch.einsum("bhij,bhdj->bhid", attn, v).permute(0, 2, 1, 3).reshape(B * n, 128)
@@ -189,17 +226,18 @@ def test_small_ops_vs_torch():
     L, lib = _L()
     import safediffcon_b200.unet  # noqa: F401
     g = torch.Generator().manual_seed(3)
-    x = torch.randn(2 * 4 * 8, 64, generator=g).cuda()
-    y = torch.empty(2 * 8 * 16, 64).cuda()
-    L.check(lib.sdc_upsample2x(L.ptr(x), L.ptr(y), 2, 4, 8, 64, L.stream_ptr()))
-    ref = nhwc(F.interpolate(x.reshape(2, 4, 8, 64).permute(0, 3, 1, 2), scale_factor=2, mode="nearest")).reshape(-1, 64)
-    assert torch.equal(y, ref)
-    xin = torch.randn(3 * 2048, 128, generator=g).cuda()
-    w, b = torch.randn(3, 128, generator=g).cuda(), torch.randn(3, generator=g).cuda()
-    out = torch.empty(3, 3, 16, 128).cuda()
-    L.check(lib.sdc_head_conv1(L.ptr(xin), L.ptr(w), L.ptr(b), L.ptr(out), 3, 2048, 128, 3, L.stream_ptr()))
-    ref = (xin @ w.t() + b).reshape(3, 2048, 3).permute(0, 2, 1).reshape(3, 3, 16, 128)
-    assert (out - ref).abs().max().item() < 1e-4
+    for prec, dt in ((TF32, torch.float32), (F16, torch.float16)):
+        x = torch.randn(2 * 4 * 8, 64, generator=g).to(dt).cuda()
+        y = torch.empty(2 * 8 * 16, 64, dtype=dt).cuda()
+        L.check(lib.sdc_upsample2x(prec, L.ptr(x), L.ptr(y), 2, 4, 8, 64, L.stream_ptr()))
+        ref = nhwc(F.interpolate(x.float().reshape(2, 4, 8, 64).permute(0, 3, 1, 2), scale_factor=2, mode="nearest")).reshape(-1, 64)
+        assert torch.equal(y.float(), ref)
+        xin = torch.randn(3 * 2048, 128, generator=g).to(dt).cuda()
+        w, b = torch.randn(3, 128, generator=g).cuda(), torch.randn(3, generator=g).cuda()
+        out = torch.empty(3, 3, 16, 128).cuda()
+        L.check(lib.sdc_head_conv1(prec, L.ptr(xin), L.ptr(w), L.ptr(b), L.ptr(out), 3, 2048, 128, 3, L.stream_ptr()))
+        ref = (xin.float() @ w.t() + b).reshape(3, 2048, 3).permute(0, 2, 1).reshape(3, 3, 16, 128)
+        assert (out - ref).abs().max().item() < 1e-4
     for act, fn in ((0, lambda v: v), (1, F.silu), (2, F.gelu)):
         xi = torch.randn(7, 512, generator=g).cuda()
         wl, bl = torch.randn(300, 512, generator=g).cuda() * 0.05, torch.randn(300, generator=g).cuda()
@@ -214,12 +252,14 @@ def test_small_ops_vs_torch():
     assert (emb.cpu() - torch.cat((a.sin(), a.cos()), -1)).abs().max().item() < 2e-4
 
 
-@pytest.mark.parametrize("dim,B", [(32, 3), (128, 2)])
-def test_unet_eps_vs_reference_golden(dim, B, golden):
+@pytest.mark.parametrize("dim,B,precision", [(32, 3, "tf32"), (128, 2, "f16"), (128, 2, "tf32")])
+def test_unet_eps_vs_reference_golden(dim, B, precision, golden):
     """Whole denoiser, seed-42 weights, reference inputs -> reference eps within the north-star 1e-3 relative."""
     import safediffcon_b200 as s
     torch.manual_seed(42)
     net = s.Unet2D(dim=dim, dim_mults=(1, 2, 4, 8), channels=3, resnet_block_groups=1).cuda()
+    assert net.precision == ("f16" if dim % 64 == 0 else "tf32")   # default: FP16 operands whenever the channel counts allow
+    net.precision = precision
     x, t = fx.unet_inputs(B)
     eps = net(x.cuda(), t.cuda())
     ref = torch.from_numpy(golden(f"unet_dim{dim}")["eps"])
