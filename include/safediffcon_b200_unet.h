@@ -90,6 +90,55 @@ int sdc_sinusoidal_embedding(const float* t, float* emb, int R, int dim, float t
 /* Zero a double buffer (GroupNorm statistics) on the stream. */
 int sdc_zero_f64(double* p, int64_t n, void* stream);
 
+/* ---------------------------------------------------------------------------------------------------------------
+ * Backward-data (VJP with respect to the denoiser input x_t; reference: autograd through Unet2D.forward when a
+ * guidance callable differentiates eps_theta(x_t, t), 1D/model/diffusion.py:254-262).  Parameter gradients are not
+ * produced.  Gradients are fp32 tensors; "operand" gradients (inputs of a dgrad convolution) are TF32-rounded.  The
+ * dgrad of every convolution is sdc_conv_gemm / sdc_conv3x3_row in SDC_PREC_TF32 with weights packed by
+ * sdc_pack_conv_weight_dgrad.
+ * ------------------------------------------------------------------------------------------------------------- */
+
+/* Pack an OIHW conv weight for the data-gradient convolution: Wt[Cin, taps*Cout] (TF32-rounded fp32),
+ * kind 1: Wt[ci, tap'*Cout + co] = W[co, ci, 8 - tap'] (flipped taps); kind 0: Wt = W^T;
+ * kind 2: Wt[p*C + c, co] = W[co, c*4 + p] (row order of the pixel shuffle that follows the 1x1 dgrad). */
+int sdc_pack_conv_weight_dgrad(int kind, const float* w_oihw, float* w_packed, int Cout, int Cin, void* stream);
+
+/* Backward of sdc_gn_silu w.r.t. x: dx = d/dx silu(GN(x) FiLM), TF32-rounded.  dy: gradient w.r.t. the activation
+ * output (the residual branch is handled by the caller), x / stats / gamma / beta / scale_shift / t_index as in the
+ * forward call.  sums: double[B][2] scratch (zeroed and filled here). */
+int sdc_gn_silu_bwd(const float* dy, const float* x, const double* stats, const float* gamma, const float* beta,
+                    const float* scale_shift, const int32_t* t_index, int64_t ss_stride, double* sums, float* dx, int B, int HW,
+                    int C, void* stream);
+
+/* Backward of the channel LayerNorm: dx = LN'(x)^T (dy * g) (+ add).  x: the forward input (fp16 if x_half else fp32). */
+int sdc_channel_layernorm_bwd(const float* dy, const void* x, int x_half, const float* g, const float* add, float* dx, int64_t M,
+                              int C, int operand_out, void* stream);
+
+/* Backward of sdc_linear_attention: dqkv[B*n, 384] (TF32-rounded) from dout[B*n, 128], the forward qkv and the
+ * forward workspace (ctx | kmax | ksum per head).  workspace: >= sdc_linear_attention_bwd_workspace(B) bytes. */
+int64_t sdc_linear_attention_bwd_workspace(int B);
+int sdc_linear_attention_bwd(const float* qkv, const float* dout, const void* fwd_workspace, void* workspace, float* dqkv, int B,
+                             int n, void* stream);
+
+/* Backward of sdc_attention (n <= 32 tokens): dqkv[B*n, 384], TF32-rounded. */
+int sdc_attention_bwd(const float* qkv, const float* dout, float* dqkv, int B, int n, void* stream);
+
+/* Backward of the pixel-unshuffle view: dx[b, 2h+p1, 2w+p2, c] = t[b, h, w, (2 p1 + p2) C + c] (+ add); H, W = low-res size. */
+int sdc_pixel_shuffle_bwd(const float* t, const float* add, float* dx, int B, int H, int W, int C, int operand_out, void* stream);
+
+/* Backward of sdc_upsample2x: dx[b, h, w, c] = sum of the 2x2 block of dy; H, W = low-res size. */
+int sdc_upsample2x_bwd(const float* dy, float* dx, int B, int H, int W, int C, int operand_out, void* stream);
+
+/* a += b over n floats (n % 4 == 0), optionally rounding the sum to TF32. */
+int sdc_add_inplace(float* a, const float* b, int64_t n, int operand_out, void* stream);
+
+/* Backward of sdc_head_conv1: dx[B*HW, Cin] = g[B, Cout, HW]^T w[Cout, Cin]. */
+int sdc_head_conv1_bwd(const float* g, const float* w, float* dx, int B, int HW, int Cin, int Cout, int operand_out, void* stream);
+
+/* col2im half of the 7x7 stem backward: dx[B, Cin, H, W] (NCHW) gathered from t[B*H*W, ld] = dY * W[Cout, Cin*49]
+ * (computed by a 1x1 sdc_conv_gemm); column index ci*49 + ky*7 + kx. */
+int sdc_stem_col2im(const float* t, float* dx, int B, int Cin, int H, int W, int ld, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -111,6 +111,12 @@ def unet_inputs(B, seed=61):
     return x, t
 
 
+def unet_cotangent(B, seed=67):
+    """Cotangent g for the input-gradient tests: d<eps, g>/dx."""
+    g = torch.Generator().manual_seed(seed)
+    return torch.randn(B, 3, 16, 128, generator=g)
+
+
 def config1_conditions(B, seed=0):
     """u0 / target final state / full target trajectory for BASELINE config 1 (model units for u0,uT)."""
     from oracle import solver_ref

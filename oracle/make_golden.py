@@ -176,6 +176,18 @@ def gen_unet():
                                        "keys": np.array(list(sd.keys()))})
 
 
+def gen_unet_vjp():
+    """Input gradient of the unmodified reference denoiser: d<eps, g>/dx by autograd."""
+    for dim, B in ((32, 2), (64, 2)):
+        net = _unet(dim)
+        x, t = fx.unet_inputs(B)
+        g = fx.unet_cotangent(B)
+        x = x.clone().requires_grad_()
+        eps = net(x, t)
+        (gx,) = torch.autograd.grad(eps, x, g)
+        save(f"unet_dim{dim}_vjp", eps=eps.detach(), grad_x=gx)
+
+
 def gen_config1():
     """BASELINE config 1: real U-Net (seed 42), B=8, DDIM-200 eta=1 guided (w_score 500, Q 0), then solver+metrics."""
     from data.generate_burgers import burgers_numeric_solve_free
@@ -217,7 +229,7 @@ def gen_config1():
 
 
 ALL = {"schedule": gen_schedule, "solver": gen_solver, "chains": gen_chains, "guidance": gen_guidance,
-       "conformal": gen_conformal, "unet": gen_unet, "config1": gen_config1}
+       "conformal": gen_conformal, "unet": gen_unet, "unet_vjp": gen_unet_vjp, "config1": gen_config1}
 
 if __name__ == "__main__":
     names = sys.argv[1:] or [k for k in ALL if k != "config1"]

@@ -1,0 +1,685 @@
+// Backward-data (VJP with respect to the denoiser INPUT) building blocks: SURVEY.md section 8 rows A1/A7 — the pass that
+// autograd runs through Unet2D when a guidance callable or the `enable_grad` last step differentiates eps_theta(x_t, t)
+// with respect to x_t (/root/reference/1D/model/diffusion.py:254-262,524-551).  Parameter gradients are NOT produced.
+//
+// The dense part (dgrad of every convolution) reuses the tcgen05 implicit-GEMM kernels of conv_gemm.cu / conv_row.cu in
+// TF32 mode with weights re-packed by sdc_pack_conv_weight_dgrad (transposed, taps flipped): the data gradient of a
+// zero-padded 3x3 convolution is a zero-padded 3x3 convolution of dY.  Gradients live in fp32 containers (fp16 would
+// underflow) and are rounded to TF32 by the kernel that produces a dgrad operand.  This file holds the bandwidth-bound
+// backward kernels: GroupNorm+FiLM+SiLU, channel LayerNorm, linear / full attention, pixel-(un)shuffle, nearest-upsample,
+// the 3-channel head and the col2im of the 7x7 stem.  All tensors are NHWC pixel rows [B*H*W, C].
+#include "common.cuh"
+#include "../../include/safediffcon_b200_unet.h"
+#include <math.h>
+
+namespace sdc {
+
+__device__ __forceinline__ float sigmoidf_(float v) { return 1.0f / (1.0f + expf(-v)); }
+// d silu(z) / dz
+__device__ __forceinline__ float dsilu(float z) {
+    const float s = sigmoidf_(z);
+    return s * (1.0f + z * (1.0f - s));
+}
+
+// ---------------------------------------------------------------------------------------------- dgrad weight packing
+// kind 1: Wt[ci, tap'*Cout + co] = W[co, ci, 8 - tap']   (spatially flipped taps)
+// kind 0: Wt[ci, co] = W[co, ci]
+// kind 2: Wt[p*C + c, co] = W[co, c*4 + p]               (rows ordered for the pixel-shuffle that follows)
+__global__ void pack_dgrad_weight_kernel(int kind, const float* __restrict__ w, float* __restrict__ wt, int Cout, int Cin) {
+    const int taps = kind == 1 ? 9 : 1;
+    const int K = taps * Cout;
+    const int64_t total = (int64_t)Cin * K;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int r = (int)(i / K), k = (int)(i % K);
+        float v;
+        if (kind == 1) {
+            const int tp = k / Cout, co = k % Cout;
+            v = w[((int64_t)co * Cin + r) * 9 + (8 - tp)];
+        } else if (kind == 2) {
+            const int C = Cin / 4, p = r / C, c = r % C;
+            v = w[(int64_t)k * Cin + c * 4 + p];
+        } else {
+            v = w[(int64_t)k * Cin + r];
+        }
+        wt[i] = to_tf32(v);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------- GroupNorm(1)+FiLM+SiLU backward
+// forward: z = x * a_c + b_c, y = silu(z) with a_c = gamma_c rstd (sc_c + 1); xhat = (x - mean) rstd.
+// dxhat = dy silu'(z) a_c / rstd;  dx = rstd (dxhat - S1/N - xhat S2/N), S1 = sum dxhat, S2 = sum dxhat xhat per sample.
+struct GnCoef {
+    float mean, rstd;
+};
+__device__ __forceinline__ GnCoef gn_prepare(float* coef, const double* stats, const float* gamma, const float* beta,
+                                             const float* scale_shift, const int32_t* t_index, int64_t ss_stride, int b, int HW, int C) {
+    const double cnt = (double)HW * (double)C;
+    const double mean_d = stats[2 * b] / cnt;
+    double var_d = stats[2 * b + 1] / cnt - mean_d * mean_d;
+    if (var_d < 0.0) var_d = 0.0;
+    GnCoef g;
+    g.mean = (float)mean_d;
+    g.rstd = (float)(1.0 / sqrt(var_d + 1e-5));
+    const float* ss = scale_shift ? scale_shift + (int64_t)(t_index ? t_index[b] : 0) * ss_stride : nullptr;
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        const float gm = gamma[c] * g.rstd;
+        float a = gm, bb = beta[c] - g.mean * gm;
+        if (ss) {
+            const float sc = ss[c] + 1.0f;
+            a *= sc;
+            bb = bb * sc + ss[C + c];
+        }
+        coef[c] = a;
+        coef[C + c] = bb;
+    }
+    __syncthreads();
+    return g;
+}
+
+// pass 1: sums[b] += (S1, S2)
+__global__ void __launch_bounds__(256) gn_silu_bwd_reduce_kernel(const float* __restrict__ dy, const float* __restrict__ x,
+                                                                 const double* __restrict__ stats, const float* __restrict__ gamma,
+                                                                 const float* __restrict__ beta, const float* __restrict__ scale_shift,
+                                                                 const int32_t* __restrict__ t_index, int64_t ss_stride,
+                                                                 double* __restrict__ sums, int HW, int C, int pix_per_cta) {
+    extern __shared__ float coef[];
+    __shared__ float red[2][8];
+    const int b = blockIdx.x;
+    const GnCoef g = gn_prepare(coef, stats, gamma, beta, scale_shift, t_index, ss_stride, b, HW, C);
+    const int c4n = C / 4;
+    const int64_t row0 = (int64_t)b * HW + (int64_t)blockIdx.y * pix_per_cta;
+    const int rows = min(pix_per_cta, HW - (int)blockIdx.y * pix_per_cta);
+    const float4* x4 = reinterpret_cast<const float4*>(x + row0 * C);
+    const float4* d4 = reinterpret_cast<const float4*>(dy + row0 * C);
+    const int total = rows * c4n;
+    const float inv_rstd = 1.0f / g.rstd;
+    float s1 = 0.f, s2 = 0.f;
+    for (int i = threadIdx.x; i < total; i += blockDim.x) {
+        const int c = (i % c4n) * 4;
+        const float4 xv = x4[i], dv = d4[i];
+        const float xs[4] = {xv.x, xv.y, xv.z, xv.w}, ds[4] = {dv.x, dv.y, dv.z, dv.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const float a = coef[c + j];
+            const float z = fmaf(xs[j], a, coef[C + c + j]);
+            const float dxh = ds[j] * dsilu(z) * a * inv_rstd;
+            s1 += dxh;
+            s2 += dxh * (xs[j] - g.mean) * g.rstd;
+        }
+    }
+    s1 = warp_sum(s1);
+    s2 = warp_sum(s2);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (lane == 0) { red[0][warp] = s1; red[1][warp] = s2; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double a = 0.0, c = 0.0;
+        for (int w = 0; w < 8; ++w) { a += (double)red[0][w]; c += (double)red[1][w]; }
+        atomicAdd(sums + 2 * b, a);
+        atomicAdd(sums + 2 * b + 1, c);
+    }
+}
+
+// pass 2: dx (TF32-rounded: it feeds the dgrad convolution)
+__global__ void __launch_bounds__(256) gn_silu_bwd_apply_kernel(const float* __restrict__ dy, const float* __restrict__ x,
+                                                                const double* __restrict__ stats, const float* __restrict__ gamma,
+                                                                const float* __restrict__ beta, const float* __restrict__ scale_shift,
+                                                                const int32_t* __restrict__ t_index, int64_t ss_stride,
+                                                                const double* __restrict__ sums, float* __restrict__ dx, int HW, int C,
+                                                                int pix_per_cta) {
+    extern __shared__ float coef[];
+    const int b = blockIdx.x;
+    const GnCoef g = gn_prepare(coef, stats, gamma, beta, scale_shift, t_index, ss_stride, b, HW, C);
+    const double cnt = (double)HW * (double)C;
+    const float m1 = (float)(sums[2 * b] / cnt) * g.rstd, m2 = (float)(sums[2 * b + 1] / cnt) * g.rstd;
+    const int c4n = C / 4;
+    const int64_t row0 = (int64_t)b * HW + (int64_t)blockIdx.y * pix_per_cta;
+    const int rows = min(pix_per_cta, HW - (int)blockIdx.y * pix_per_cta);
+    const float4* x4 = reinterpret_cast<const float4*>(x + row0 * C);
+    const float4* d4 = reinterpret_cast<const float4*>(dy + row0 * C);
+    float* o = dx + row0 * C;
+    const int total = rows * c4n;
+    for (int i = threadIdx.x; i < total; i += blockDim.x) {
+        const int c = (i % c4n) * 4;
+        const float4 xv = x4[i], dv = d4[i];
+        const float xs[4] = {xv.x, xv.y, xv.z, xv.w}, ds[4] = {dv.x, dv.y, dv.z, dv.w};
+        float r[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const float a = coef[c + j];
+            const float z = fmaf(xs[j], a, coef[C + c + j]);
+            r[j] = ds[j] * dsilu(z) * a - m1 - (xs[j] - g.mean) * g.rstd * m2;
+        }
+        store_operand4(o + 4 * (int64_t)i, make_float4(r[0], r[1], r[2], r[3]));
+    }
+}
+
+// ---------------------------------------------------------------------------------------------- channel LayerNorm backward
+// forward: y = xhat * g, xhat = (x - mean) rsqrt(var + eps) per pixel row.  dx = rstd (dxhat - mean(dxhat) - xhat mean(dxhat xhat)) (+ add)
+template <int NV, typename TX>
+__global__ void __launch_bounds__(256) channel_layernorm_bwd_kernel(const float* __restrict__ dy, const TX* __restrict__ x,
+                                                                    const float* __restrict__ g, const float* __restrict__ add,
+                                                                    float* __restrict__ dx, int64_t M, int C, int operand_out) {
+    const int lane = threadIdx.x & 31;
+    const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= M) return;
+    const int n4 = C / 4;
+    float4 v[NV], d[NV];
+    float s = 0.f;
+#pragma unroll
+    for (int j = 0; j < NV; ++j) {
+        const int i = lane + 32 * j;
+        if (i < n4) {
+            v[j] = load4(x + row * C + 4 * i);
+            const float4 gv = *reinterpret_cast<const float4*>(g + 4 * i);
+            const float4 dv = *reinterpret_cast<const float4*>(dy + row * C + 4 * i);
+            d[j] = make_float4(dv.x * gv.x, dv.y * gv.y, dv.z * gv.z, dv.w * gv.w);
+        } else {
+            v[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+            d[j] = v[j];
+        }
+        s += (v[j].x + v[j].y) + (v[j].z + v[j].w);
+    }
+    const float mean = warp_sum(s) / (float)C;
+    float q = 0.f;
+#pragma unroll
+    for (int j = 0; j < NV; ++j) {
+        if (lane + 32 * j < n4) {
+            v[j].x -= mean; v[j].y -= mean; v[j].z -= mean; v[j].w -= mean;
+            q += (v[j].x * v[j].x + v[j].y * v[j].y) + (v[j].z * v[j].z + v[j].w * v[j].w);
+        }
+    }
+    const float rstd = rsqrtf(warp_sum(q) / (float)C + 1e-5f);
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int j = 0; j < NV; ++j) {
+        v[j].x *= rstd; v[j].y *= rstd; v[j].z *= rstd; v[j].w *= rstd;   // xhat (zero in the padded slots)
+        s1 += (d[j].x + d[j].y) + (d[j].z + d[j].w);
+        s2 += (d[j].x * v[j].x + d[j].y * v[j].y) + (d[j].z * v[j].z + d[j].w * v[j].w);
+    }
+    s1 = warp_sum(s1) / (float)C;
+    s2 = warp_sum(s2) / (float)C;
+#pragma unroll
+    for (int j = 0; j < NV; ++j) {
+        const int i = lane + 32 * j;
+        if (i < n4) {
+            float4 o = make_float4(rstd * (d[j].x - s1 - v[j].x * s2), rstd * (d[j].y - s1 - v[j].y * s2),
+                                   rstd * (d[j].z - s1 - v[j].z * s2), rstd * (d[j].w - s1 - v[j].w * s2));
+            if (add) { const float4 a = *reinterpret_cast<const float4*>(add + row * C + 4 * i); o.x += a.x; o.y += a.y; o.z += a.z; o.w += a.w; }
+            if (operand_out) store_operand4(dx + row * C + 4 * i, o); else store4(dx + row * C + 4 * i, o);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------- linear attention backward
+constexpr int LB_HEADS = 4, LB_D = 32, LB_QKV = 3 * LB_HEADS * LB_D, LB_HID = LB_HEADS * LB_D;
+constexpr int LB_CTX = LB_D * LB_D + 2 * LB_D;   // floats per (b, head) in the forward workspace: ctx | kmax | ksum
+constexpr int LB_CHUNK = 128;
+
+// dctx[b,h,d,e] = sum_n qs[d,n] dO[e,n],  qs = softmax_d(q) * 32^-0.5        grid = B*heads, 256 threads
+__global__ void __launch_bounds__(256) linattn_bwd_reduce_kernel(const float* __restrict__ qkv, const float* __restrict__ dout,
+                                                                 float* __restrict__ dctx, int n) {
+    __shared__ __align__(16) float qs[LB_CHUNK][LB_D];
+    __shared__ __align__(16) float ds[LB_CHUNK][LB_D];
+    const int b = blockIdx.x / LB_HEADS, h = blockIdx.x % LB_HEADS;
+    const int tid = threadIdx.x;
+    const float* qp = qkv + (int64_t)b * n * LB_QKV + h * LB_D;
+    const float* dp = dout + (int64_t)b * n * LB_HID + h * LB_D;
+    const int ng = tid >> 6, t64 = tid & 63;
+    const int d0 = (t64 >> 3) * 4, e0 = (t64 & 7) * 4;
+    float acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+    const int lc4 = (tid & 7) * 4, lr = tid >> 3;   // 8 consecutive lanes share one pixel
+    for (int n0 = 0; n0 < n; n0 += LB_CHUNK) {
+        const int cnt = min(LB_CHUNK, n - n0);
+        __syncthreads();
+#pragma unroll
+        for (int rr = 0; rr < LB_CHUNK; rr += 32) {
+            const int r = rr + lr;
+            float4 qv = make_float4(0.f, 0.f, 0.f, 0.f), dv = qv;
+            const bool ok = r < cnt;
+            if (ok) {
+                qv = *reinterpret_cast<const float4*>(qp + (int64_t)(n0 + r) * LB_QKV + lc4);
+                dv = *reinterpret_cast<const float4*>(dp + (int64_t)(n0 + r) * LB_HID + lc4);
+            }
+            float mx = fmaxf(fmaxf(qv.x, qv.y), fmaxf(qv.z, qv.w));
+#pragma unroll
+            for (int o = 1; o < 8; o <<= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+            qv = make_float4(expf(qv.x - mx), expf(qv.y - mx), expf(qv.z - mx), expf(qv.w - mx));
+            float sm = (qv.x + qv.y) + (qv.z + qv.w);
+#pragma unroll
+            for (int o = 1; o < 8; o <<= 1) sm += __shfl_xor_sync(0xffffffffu, sm, o);
+            const float sc = ok ? 0.17677669529663687f / sm : 0.f;
+            *reinterpret_cast<float4*>(&qs[r][lc4]) = make_float4(qv.x * sc, qv.y * sc, qv.z * sc, qv.w * sc);
+            *reinterpret_cast<float4*>(&ds[r][lc4]) = dv;
+        }
+        __syncthreads();
+#pragma unroll 8
+        for (int r = ng * (LB_CHUNK / 4); r < (ng + 1) * (LB_CHUNK / 4); ++r) {
+            const float4 a = *reinterpret_cast<const float4*>(&qs[r][d0]);
+            const float4 vv = *reinterpret_cast<const float4*>(&ds[r][e0]);
+            const float av[4] = {a.x, a.y, a.z, a.w}, vv4[4] = {vv.x, vv.y, vv.z, vv.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], vv4[j], acc[i][j]);
+        }
+    }
+    __syncthreads();
+    float* racc = &qs[0][0];   // [4][64][16]
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) racc[(ng * 64 + t64) * 16 + i * 4 + j] = acc[i][j];
+    __syncthreads();
+    if (ng == 0) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            float o[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+            for (int gq = 0; gq < 4; ++gq)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) o[j] += racc[(gq * 64 + t64) * 16 + i * 4 + j];
+            *reinterpret_cast<float4*>(dctx + ((int64_t)blockIdx.x * LB_D + d0 + i) * LB_D + e0) = make_float4(o[0], o[1], o[2], o[3]);
+        }
+    }
+}
+
+// per pixel: dq, dk, dv -> dqkv[B*n, 384] (TF32-rounded operand of the qkv dgrad)      grid = (B*heads, ceil(n/128)), 128 threads
+__global__ void __launch_bounds__(128) linattn_bwd_apply_kernel(const float* __restrict__ qkv, const float* __restrict__ dout,
+                                                                const float* __restrict__ fwd_ws, const float* __restrict__ dctx,
+                                                                float* __restrict__ dqkv, int n) {
+    __shared__ __align__(16) float cs[LB_D][LB_D];    // ctx[d][e]
+    __shared__ __align__(16) float dcs[LB_D][LB_D];   // dctx[d][e]
+    __shared__ float kmax[LB_D], kinv[LB_D], cdot[LB_D];
+    const int b = blockIdx.x / LB_HEADS, h = blockIdx.x % LB_HEADS;
+    const float* ws = fwd_ws + (int64_t)blockIdx.x * LB_CTX;
+    for (int i = threadIdx.x; i < LB_D * LB_D; i += blockDim.x) {
+        cs[i >> 5][i & 31] = ws[i];
+        dcs[i >> 5][i & 31] = dctx[(int64_t)blockIdx.x * LB_D * LB_D + i];
+    }
+    if (threadIdx.x < LB_D) {
+        kmax[threadIdx.x] = ws[LB_D * LB_D + threadIdx.x];
+        kinv[threadIdx.x] = 1.0f / ws[LB_D * LB_D + LB_D + threadIdx.x];
+    }
+    __syncthreads();
+    if (threadIdx.x < LB_D) {
+        float a = 0.f;
+        for (int e = 0; e < LB_D; ++e) a = fmaf(dcs[threadIdx.x][e], cs[threadIdx.x][e], a);
+        cdot[threadIdx.x] = a;   // = sum_n ks[d,n] dks[d,n]
+    }
+    __syncthreads();
+    const int i = blockIdx.y * 128 + threadIdx.x;
+    if (i >= n) return;
+    const int64_t pix = (int64_t)b * n + i;
+    const float* base = qkv + pix * LB_QKV + h * LB_D;
+    float* obase = dqkv + pix * LB_QKV + h * LB_D;
+    float a[LB_D], g[LB_D];
+    {   // ---- dq = p * (dp - sum p dp), p = softmax_d(q), dp[d] = 32^-0.5 * sum_e ctx[d,e] dO[e]
+        const float* dop = dout + pix * LB_HID + h * LB_D;
+#pragma unroll
+        for (int j = 0; j < LB_D; j += 4) {
+            const float4 t = *reinterpret_cast<const float4*>(base + j);
+            a[j] = t.x; a[j + 1] = t.y; a[j + 2] = t.z; a[j + 3] = t.w;
+            const float4 u = *reinterpret_cast<const float4*>(dop + j);
+            g[j] = u.x; g[j + 1] = u.y; g[j + 2] = u.z; g[j + 3] = u.w;
+        }
+        float mx = a[0];
+#pragma unroll
+        for (int j = 1; j < LB_D; ++j) mx = fmaxf(mx, a[j]);
+        float den = 0.f;
+#pragma unroll
+        for (int j = 0; j < LB_D; ++j) { a[j] = expf(a[j] - mx); den += a[j]; }
+        const float inv = 1.0f / den;
+        float dot = 0.f;
+        float dpv[LB_D];
+#pragma unroll
+        for (int d = 0; d < LB_D; ++d) {
+            float s = 0.f;
+#pragma unroll
+            for (int e = 0; e < LB_D; e += 4) {
+                const float4 c4 = *reinterpret_cast<const float4*>(&cs[d][e]);
+                s = fmaf(c4.x, g[e], s); s = fmaf(c4.y, g[e + 1], s); s = fmaf(c4.z, g[e + 2], s); s = fmaf(c4.w, g[e + 3], s);
+            }
+            a[d] *= inv;
+            dpv[d] = s * 0.17677669529663687f;
+            dot = fmaf(a[d], dpv[d], dot);
+        }
+#pragma unroll
+        for (int d = 0; d < LB_D; d += 4)
+            store_operand4(obase + d, make_float4(a[d] * (dpv[d] - dot), a[d + 1] * (dpv[d + 1] - dot), a[d + 2] * (dpv[d + 2] - dot),
+                                                  a[d + 3] * (dpv[d + 3] - dot)));
+    }
+    {   // ---- dk[d] = ks[d] (sum_e dctx[d,e] v[e] - cdot[d]),  dv[e] = sum_d ks[d] dctx[d,e],  ks = exp(k - kmax) / ksum
+#pragma unroll
+        for (int j = 0; j < LB_D; j += 4) {
+            const float4 t = *reinterpret_cast<const float4*>(base + LB_HID + j);
+            a[j] = expf(t.x - kmax[j]) * kinv[j]; a[j + 1] = expf(t.y - kmax[j + 1]) * kinv[j + 1];
+            a[j + 2] = expf(t.z - kmax[j + 2]) * kinv[j + 2]; a[j + 3] = expf(t.w - kmax[j + 3]) * kinv[j + 3];
+            const float4 u = *reinterpret_cast<const float4*>(base + 2 * LB_HID + j);
+            g[j] = u.x; g[j + 1] = u.y; g[j + 2] = u.z; g[j + 3] = u.w;
+        }
+        float dv[LB_D];
+#pragma unroll
+        for (int e = 0; e < LB_D; ++e) dv[e] = 0.f;
+        float dk[LB_D];
+#pragma unroll
+        for (int d = 0; d < LB_D; ++d) {
+            float s = 0.f;
+#pragma unroll
+            for (int e = 0; e < LB_D; e += 4) {
+                const float4 c4 = *reinterpret_cast<const float4*>(&dcs[d][e]);
+                s = fmaf(c4.x, g[e], s); s = fmaf(c4.y, g[e + 1], s); s = fmaf(c4.z, g[e + 2], s); s = fmaf(c4.w, g[e + 3], s);
+                dv[e] = fmaf(a[d], c4.x, dv[e]); dv[e + 1] = fmaf(a[d], c4.y, dv[e + 1]);
+                dv[e + 2] = fmaf(a[d], c4.z, dv[e + 2]); dv[e + 3] = fmaf(a[d], c4.w, dv[e + 3]);
+            }
+            dk[d] = a[d] * (s - cdot[d]);
+        }
+#pragma unroll
+        for (int d = 0; d < LB_D; d += 4) {
+            store_operand4(obase + LB_HID + d, make_float4(dk[d], dk[d + 1], dk[d + 2], dk[d + 3]));
+            store_operand4(obase + 2 * LB_HID + d, make_float4(dv[d], dv[d + 1], dv[d + 2], dv[d + 3]));
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------- full attention backward (n <= 32)
+// one warp per (b, head); lane = query i for the row quantities, lane = key j for dk / dv
+__global__ void __launch_bounds__(32) attention_bwd_kernel(const float* __restrict__ qkv, const float* __restrict__ dout,
+                                                           float* __restrict__ dqkv, int n) {
+    __shared__ float qs[1][32][LB_D + 1], ks[1][32][LB_D + 1], vs[1][32][LB_D + 1], gs[1][32][LB_D + 1];
+    __shared__ float Ps[1][32][33], Ss[1][32][33];
+    const int b = blockIdx.x / LB_HEADS, hh = blockIdx.x % LB_HEADS, lane = threadIdx.x;
+    constexpr int h = 0;   // one warp (= one head of one sample) per CTA
+    const float* base = qkv + (int64_t)b * n * LB_QKV;
+    const float scale = 0.17677669529663687f;
+    for (int j = 0; j < 32; ++j) {
+        const bool ok = j < n;
+        qs[h][j][lane] = ok ? base[(int64_t)j * LB_QKV + hh * LB_D + lane] : 0.f;
+        ks[h][j][lane] = ok ? base[(int64_t)j * LB_QKV + LB_HID + hh * LB_D + lane] : 0.f;
+        vs[h][j][lane] = ok ? base[(int64_t)j * LB_QKV + 2 * LB_HID + hh * LB_D + lane] : 0.f;
+        gs[h][j][lane] = ok ? dout[((int64_t)b * n + j) * LB_HID + hh * LB_D + lane] : 0.f;
+    }
+    __syncwarp();
+    {   // row i = lane: P[i,:], dS[i,:], dq_i
+        const int i = lane;
+        float sim[32];
+        float mx = -INFINITY;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+            float s = -INFINITY;
+            if (j < n) {
+                s = 0.f;
+#pragma unroll
+                for (int d = 0; d < LB_D; ++d) s = fmaf(qs[h][i][d] * scale, ks[h][j][d], s);
+            }
+            sim[j] = s;
+            mx = fmaxf(mx, s);
+        }
+        float den = 0.f;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) { sim[j] = (j < n) ? expf(sim[j] - mx) : 0.f; den += sim[j]; }
+        const float inv = 1.0f / den;
+        float dot = 0.f;
+        float dP[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+            sim[j] *= inv;
+            float s = 0.f;
+#pragma unroll
+            for (int d = 0; d < LB_D; ++d) s = fmaf(gs[h][i][d], vs[h][j][d], s);
+            dP[j] = s;
+            dot = fmaf(sim[j], s, dot);
+        }
+        float dq[LB_D];
+#pragma unroll
+        for (int d = 0; d < LB_D; ++d) dq[d] = 0.f;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+            const float dS = sim[j] * (dP[j] - dot);
+            Ps[h][i][j] = sim[j];
+            Ss[h][i][j] = dS;
+#pragma unroll
+            for (int d = 0; d < LB_D; ++d) dq[d] = fmaf(dS * scale, ks[h][j][d], dq[d]);
+        }
+        if (i < n) {
+            float* o = dqkv + ((int64_t)b * n + i) * LB_QKV + hh * LB_D;
+#pragma unroll
+            for (int d = 0; d < LB_D; ++d) o[d] = to_tf32(dq[d]);
+        }
+    }
+    __syncwarp();
+    {   // key j = lane: dk_j = scale sum_i dS[i,j] q_i,  dv_j = sum_i P[i,j] dO_i
+        const int j = lane;
+        float dk[LB_D], dv[LB_D];
+#pragma unroll
+        for (int d = 0; d < LB_D; ++d) { dk[d] = 0.f; dv[d] = 0.f; }
+        for (int i = 0; i < n; ++i) {
+            const float dS = Ss[h][i][j] * scale, P = Ps[h][i][j];
+#pragma unroll
+            for (int d = 0; d < LB_D; ++d) {
+                dk[d] = fmaf(dS, qs[h][i][d], dk[d]);
+                dv[d] = fmaf(P, gs[h][i][d], dv[d]);
+            }
+        }
+        if (j < n) {
+            float* o = dqkv + ((int64_t)b * n + j) * LB_QKV + hh * LB_D;
+#pragma unroll
+            for (int d = 0; d < LB_D; ++d) { o[LB_HID + d] = to_tf32(dk[d]); o[2 * LB_HID + d] = to_tf32(dv[d]); }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------- layout / small ops
+// dx[b, 2h+p1, 2w+p2, c] = t[b, h, w, (2 p1 + p2) C + c] (+ add)          (backward of the pixel-unshuffle view)
+__global__ void pixel_shuffle_bwd_kernel(const float4* __restrict__ t, const float4* __restrict__ add, float4* __restrict__ dx,
+                                         int64_t total4, int H, int W, int c4, int operand_out) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total4; i += (int64_t)gridDim.x * blockDim.x) {
+        const int c = (int)(i % c4);
+        int64_t pix = i / c4;
+        const int wo = (int)(pix % (2 * W)); pix /= (2 * W);
+        const int ho = (int)(pix % (2 * H));
+        const int64_t b = pix / (2 * H);
+        const int p = (ho & 1) * 2 + (wo & 1);
+        float4 v = t[(((b * H + (ho >> 1)) * W + (wo >> 1)) * 4 + p) * c4 + c];
+        if (add) { const float4 a = add[i]; v.x += a.x; v.y += a.y; v.z += a.z; v.w += a.w; }
+        if (operand_out) v = make_float4(to_tf32(v.x), to_tf32(v.y), to_tf32(v.z), to_tf32(v.w));
+        dx[i] = v;
+    }
+}
+
+// dx[b, h, w, c] = sum of the 2x2 block of dy[b, 2h.., 2w.., c]                (backward of nearest x2 upsample)
+__global__ void upsample2x_bwd_kernel(const float4* __restrict__ dy, float4* __restrict__ dx, int64_t total4, int H, int W, int c4,
+                                      int operand_out) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total4; i += (int64_t)gridDim.x * blockDim.x) {
+        const int c = (int)(i % c4);
+        int64_t pix = i / c4;
+        const int w = (int)(pix % W); pix /= W;
+        const int h = (int)(pix % H);
+        const int64_t b = pix / H;
+        const int64_t r0 = ((b * 2 * H + 2 * h) * 2 * W + 2 * w) * c4 + c;
+        const int64_t r1 = r0 + (int64_t)2 * W * c4;
+        const float4 a = dy[r0], bq = dy[r0 + c4], cq = dy[r1], d = dy[r1 + c4];
+        float4 v = make_float4((a.x + bq.x) + (cq.x + d.x), (a.y + bq.y) + (cq.y + d.y), (a.z + bq.z) + (cq.z + d.z), (a.w + bq.w) + (cq.w + d.w));
+        if (operand_out) v = make_float4(to_tf32(v.x), to_tf32(v.y), to_tf32(v.z), to_tf32(v.w));
+        dx[i] = v;
+    }
+}
+
+// a += b (optionally rounding the sum to TF32)
+__global__ void add_inplace_kernel(float4* __restrict__ a, const float4* __restrict__ b, int64_t n4, int operand_out) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+        float4 v = a[i];
+        const float4 u = b[i];
+        v.x += u.x; v.y += u.y; v.z += u.z; v.w += u.w;
+        if (operand_out) v = make_float4(to_tf32(v.x), to_tf32(v.y), to_tf32(v.z), to_tf32(v.w));
+        a[i] = v;
+    }
+}
+
+// head 1x1 conv backward: dx[m, c] = sum_o g[b, o, p] w[o, c]       (g NCHW fp32, dx NHWC fp32)
+__global__ void __launch_bounds__(256) head_conv1_bwd_kernel(const float* __restrict__ g, const float* __restrict__ w,
+                                                             float* __restrict__ dx, int64_t M, int HW, int Cin, int Cout, int operand_out) {
+    const int c4n = Cin / 4;
+    const int64_t total = M * c4n;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int c = (int)(i % c4n) * 4;
+        const int64_t m = i / c4n, b = m / HW, p = m % HW;
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int o = 0; o < Cout; ++o) {
+            const float gv = g[(b * Cout + o) * HW + p];
+            const float4 wv = *reinterpret_cast<const float4*>(w + (int64_t)o * Cin + c);
+            acc.x = fmaf(gv, wv.x, acc.x); acc.y = fmaf(gv, wv.y, acc.y); acc.z = fmaf(gv, wv.z, acc.z); acc.w = fmaf(gv, wv.w, acc.w);
+        }
+        if (operand_out) store_operand4(dx + m * Cin + c, acc); else store4(dx + m * Cin + c, acc);
+    }
+}
+
+// stem 7x7 backward, col2im half: dx[b, ci, h, w] = sum_{ky,kx} t[(b, h+3-ky, w+3-kx), ci*49 + ky*7 + kx]   (t: [B*H*W, ld])
+__global__ void __launch_bounds__(256) stem_col2im_kernel(const float* __restrict__ t, float* __restrict__ dx, int B, int Cin, int H,
+                                                          int W, int ld) {
+    const int64_t total = (int64_t)B * Cin * H * W;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int w = (int)(i % W);
+        int64_t r = i / W;
+        const int h = (int)(r % H); r /= H;
+        const int ci = (int)(r % Cin);
+        const int64_t b = r / Cin;
+        float acc = 0.f;
+        for (int ky = 0; ky < 7; ++ky) {
+            const int hh = h + 3 - ky;
+            if (hh < 0 || hh >= H) continue;
+#pragma unroll
+            for (int kx = 0; kx < 7; ++kx) {
+                const int ww = w + 3 - kx;
+                if (ww < 0 || ww >= W) continue;
+                acc += t[((b * H + hh) * W + ww) * ld + ci * 49 + ky * 7 + kx];
+            }
+        }
+        dx[i] = acc;
+    }
+}
+
+}  // namespace sdc
+
+using namespace sdc;
+
+static inline unsigned grid_for(int64_t n, int per) { int64_t b = (n + per - 1) / per; return (unsigned)(b > 148 * 16 ? 148 * 16 : (b < 1 ? 1 : b)); }
+
+extern "C" int sdc_pack_conv_weight_dgrad(int kind, const float* w, float* wt, int Cout, int Cin, void* stream) {
+    SDC_REQUIRE(kind >= 0 && kind <= 2 && w && wt && Cout > 0 && Cin > 0, "pack_conv_weight_dgrad: bad arguments");
+    SDC_REQUIRE(kind != 2 || Cin % 4 == 0, "pack_conv_weight_dgrad: unshuffle conv needs Cin %% 4 == 0");
+    const int64_t total = (int64_t)Cout * Cin * (kind == 1 ? 9 : 1);
+    pack_dgrad_weight_kernel<<<grid_for(total, 256), 256, 0, as_stream(stream)>>>(kind, w, wt, Cout, Cin);
+    SDC_LAUNCHED();
+    return SDC_OK;
+}
+
+extern "C" int sdc_gn_silu_bwd(const float* dy, const float* x, const double* stats, const float* gamma, const float* beta,
+                               const float* scale_shift, const int32_t* t_index, int64_t ss_stride, double* sums, float* dx, int B,
+                               int HW, int C, void* stream) {
+    SDC_REQUIRE(dy && x && stats && gamma && beta && sums && dx && B > 0 && HW > 0, "gn_silu_bwd: bad arguments");
+    SDC_REQUIRE(C % 4 == 0 && C <= 4096, "gn_silu_bwd: C=%d unsupported", C);
+    int ppc = HW;
+    while (ppc > 32 && (int64_t)B * (HW / ppc) < 2 * 148 && ppc % 2 == 0) ppc /= 2;
+    dim3 grid((unsigned)B, (unsigned)((HW + ppc - 1) / ppc));
+    const size_t sm = 2 * C * sizeof(float);
+    cudaStream_t st = as_stream(stream);
+    SDC_CUDA(cudaMemsetAsync(sums, 0, (size_t)B * 2 * sizeof(double), st));
+    gn_silu_bwd_reduce_kernel<<<grid, 256, sm, st>>>(dy, x, stats, gamma, beta, scale_shift, t_index, ss_stride, sums, HW, C, ppc);
+    SDC_LAUNCHED();
+    gn_silu_bwd_apply_kernel<<<grid, 256, sm, st>>>(dy, x, stats, gamma, beta, scale_shift, t_index, ss_stride, sums, dx, HW, C, ppc);
+    SDC_LAUNCHED();
+    return SDC_OK;
+}
+
+template <typename TX>
+static void launch_ln_bwd(const float* dy, const void* x, const float* g, const float* add, float* dx, int64_t M, int C,
+                          int operand_out, cudaStream_t st) {
+    const TX* xp = (const TX*)x;
+    const unsigned grid = (unsigned)((M + 7) / 8);
+    if (C <= 128) channel_layernorm_bwd_kernel<1, TX><<<grid, 256, 0, st>>>(dy, xp, g, add, dx, M, C, operand_out);
+    else if (C <= 256) channel_layernorm_bwd_kernel<2, TX><<<grid, 256, 0, st>>>(dy, xp, g, add, dx, M, C, operand_out);
+    else if (C <= 512) channel_layernorm_bwd_kernel<4, TX><<<grid, 256, 0, st>>>(dy, xp, g, add, dx, M, C, operand_out);
+    else channel_layernorm_bwd_kernel<8, TX><<<grid, 256, 0, st>>>(dy, xp, g, add, dx, M, C, operand_out);
+}
+
+extern "C" int sdc_channel_layernorm_bwd(const float* dy, const void* x, int x_half, const float* g, const float* add, float* dx,
+                                         int64_t M, int C, int operand_out, void* stream) {
+    SDC_REQUIRE(dy && x && g && dx && M > 0, "channel_layernorm_bwd: bad arguments");
+    SDC_REQUIRE(C % 4 == 0 && C <= 1024, "channel_layernorm_bwd: C=%d unsupported (multiple of 4, <= 1024)", C);
+    if (x_half) launch_ln_bwd<__half>(dy, x, g, add, dx, M, C, operand_out, as_stream(stream));
+    else launch_ln_bwd<float>(dy, x, g, add, dx, M, C, operand_out, as_stream(stream));
+    SDC_LAUNCHED();
+    return SDC_OK;
+}
+
+extern "C" int64_t sdc_linear_attention_bwd_workspace(int B) { return (int64_t)B * LB_HEADS * LB_D * LB_D * sizeof(float); }
+
+extern "C" int sdc_linear_attention_bwd(const float* qkv, const float* dout, const void* fwd_workspace, void* workspace, float* dqkv,
+                                        int B, int n, void* stream) {
+    SDC_REQUIRE(qkv && dout && fwd_workspace && workspace && dqkv && B > 0 && n > 0, "linear_attention_bwd: bad arguments");
+    float* dctx = reinterpret_cast<float*>(workspace);
+    linattn_bwd_reduce_kernel<<<(unsigned)(B * LB_HEADS), 256, 0, as_stream(stream)>>>(qkv, dout, dctx, n);
+    SDC_LAUNCHED();
+    dim3 grid((unsigned)(B * LB_HEADS), (unsigned)((n + 127) / 128));
+    linattn_bwd_apply_kernel<<<grid, 128, 0, as_stream(stream)>>>(qkv, dout, reinterpret_cast<const float*>(fwd_workspace), dctx, dqkv, n);
+    SDC_LAUNCHED();
+    return SDC_OK;
+}
+
+extern "C" int sdc_attention_bwd(const float* qkv, const float* dout, float* dqkv, int B, int n, void* stream) {
+    SDC_REQUIRE(qkv && dout && dqkv && B > 0, "attention_bwd: bad arguments");
+    SDC_REQUIRE(n > 0 && n <= 32, "attention_bwd: n=%d tokens unsupported", n);
+    attention_bwd_kernel<<<(unsigned)(B * LB_HEADS), 32, 0, as_stream(stream)>>>(qkv, dout, dqkv, n);
+    SDC_LAUNCHED();
+    return SDC_OK;
+}
+
+extern "C" int sdc_pixel_shuffle_bwd(const float* t, const float* add, float* dx, int B, int H, int W, int C, int operand_out,
+                                     void* stream) {
+    SDC_REQUIRE(t && dx && B > 0 && C % 4 == 0, "pixel_shuffle_bwd: bad arguments");
+    const int64_t total4 = (int64_t)B * 4 * H * W * (C / 4);
+    pixel_shuffle_bwd_kernel<<<grid_for(total4, 256 * 4), 256, 0, as_stream(stream)>>>(
+        reinterpret_cast<const float4*>(t), reinterpret_cast<const float4*>(add), reinterpret_cast<float4*>(dx), total4, H, W, C / 4,
+        operand_out);
+    SDC_LAUNCHED();
+    return SDC_OK;
+}
+
+extern "C" int sdc_upsample2x_bwd(const float* dy, float* dx, int B, int H, int W, int C, int operand_out, void* stream) {
+    SDC_REQUIRE(dy && dx && B > 0 && C % 4 == 0, "upsample2x_bwd: bad arguments");
+    const int64_t total4 = (int64_t)B * H * W * (C / 4);
+    upsample2x_bwd_kernel<<<grid_for(total4, 256 * 2), 256, 0, as_stream(stream)>>>(reinterpret_cast<const float4*>(dy),
+                                                                                  reinterpret_cast<float4*>(dx), total4, H, W, C / 4, operand_out);
+    SDC_LAUNCHED();
+    return SDC_OK;
+}
+
+extern "C" int sdc_add_inplace(float* a, const float* b, int64_t n, int operand_out, void* stream) {
+    SDC_REQUIRE(a && b && n > 0 && n % 4 == 0, "add_inplace: bad arguments");
+    add_inplace_kernel<<<grid_for(n / 4, 256 * 4), 256, 0, as_stream(stream)>>>(reinterpret_cast<float4*>(a),
+                                                                                reinterpret_cast<const float4*>(b), n / 4, operand_out);
+    SDC_LAUNCHED();
+    return SDC_OK;
+}
+
+extern "C" int sdc_head_conv1_bwd(const float* g, const float* w, float* dx, int B, int HW, int Cin, int Cout, int operand_out,
+                                  void* stream) {
+    SDC_REQUIRE(g && w && dx && B > 0 && Cin % 4 == 0 && Cout >= 1, "head_conv1_bwd: bad arguments");
+    const int64_t M = (int64_t)B * HW;
+    head_conv1_bwd_kernel<<<grid_for(M * (Cin / 4), 256), 256, 0, as_stream(stream)>>>(g, w, dx, M, HW, Cin, Cout, operand_out);
+    SDC_LAUNCHED();
+    return SDC_OK;
+}
+
+extern "C" int sdc_stem_col2im(const float* t, float* dx, int B, int Cin, int H, int W, int ld, void* stream) {
+    SDC_REQUIRE(t && dx && B > 0 && ld >= Cin * 49, "stem_col2im: bad arguments");
+    const int64_t total = (int64_t)B * Cin * H * W;
+    stem_col2im_kernel<<<grid_for(total, 256), 256, 0, as_stream(stream)>>>(t, dx, B, Cin, H, W, ld);
+    SDC_LAUNCHED();
+    return SDC_OK;
+}

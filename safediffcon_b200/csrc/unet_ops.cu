@@ -196,6 +196,8 @@ __global__ void __launch_bounds__(256) channel_layernorm_kernel(const TX* __rest
 
 // ---------------------------------------------------------------------------------------------- linear attention
 constexpr int LA_HEADS = 4, LA_D = 32, LA_QKV = 3 * LA_HEADS * LA_D, LA_HID = LA_HEADS * LA_D;
+// workspace floats per (b, head): ctx[32][32] | kmax[32] | ksum[32]  (the softmax_n(k) statistics are kept for the backward pass)
+constexpr int LA_CTX = LA_D * LA_D + 2 * LA_D;
 
 // ctx[b,h,d,e] = sum_n softmax_n(k)[d,n] * v[e,n]          grid = B*heads, 256 threads
 // 4 pixel groups x 64 threads; each thread owns a 4x4 block of the 32x32 context in registers (16 FMA per two
@@ -292,8 +294,9 @@ __global__ void __launch_bounds__(256) linattn_context_kernel(const float* __res
                 for (int j = 0; j < 4; ++j) o[j] += racc[(gq * 64 + t64) * 16 + i * 4 + j];
             }
             const float inv = 1.0f / ks;
-            *reinterpret_cast<float4*>(ctx + ((int64_t)blockIdx.x * LA_D + d0 + i) * LA_D + e0) =
-                make_float4(o[0] * inv, o[1] * inv, o[2] * inv, o[3] * inv);
+            float* cb = ctx + (int64_t)blockIdx.x * LA_CTX;
+            *reinterpret_cast<float4*>(cb + (d0 + i) * LA_D + e0) = make_float4(o[0] * inv, o[1] * inv, o[2] * inv, o[3] * inv);
+            if (e0 == 0) { cb[LA_D * LA_D + d0 + i] = kmax[d0 + i]; cb[LA_D * LA_D + LA_D + d0 + i] = ks; }
         }
     }
 }
@@ -304,7 +307,7 @@ __global__ void __launch_bounds__(256) linattn_apply_kernel(const float* __restr
                                                             T* __restrict__ out, int n) {
     __shared__ __align__(16) float cs[LA_D][LA_D];
     const int b = blockIdx.x / LA_HEADS, h = blockIdx.x % LA_HEADS;
-    for (int i = threadIdx.x; i < LA_D * LA_D; i += blockDim.x) cs[i >> 5][i & 31] = ctx[(int64_t)blockIdx.x * LA_D * LA_D + i];
+    for (int i = threadIdx.x; i < LA_D * LA_D; i += blockDim.x) cs[i >> 5][i & 31] = ctx[(int64_t)blockIdx.x * LA_CTX + i];
     __syncthreads();
     const int i = blockIdx.y * 256 + threadIdx.x;
     if (i >= n) return;
@@ -549,7 +552,7 @@ extern "C" int sdc_channel_layernorm(int prec, const void* x, int x_operand, con
     return SDC_OK;
 }
 
-extern "C" int64_t sdc_linear_attention_workspace(int B) { return (int64_t)B * LA_HEADS * LA_D * LA_D * sizeof(float); }
+extern "C" int64_t sdc_linear_attention_workspace(int B) { return (int64_t)B * LA_HEADS * LA_CTX * sizeof(float); }
 
 extern "C" int sdc_linear_attention(int prec, const float* qkv, void* out, void* workspace, int B, int n, void* stream) {
     SDC_CHECK_PREC("linear_attention");

@@ -32,6 +32,17 @@ L.register({
     "sdc_linear_rows": (c_i, [c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_p]),
     "sdc_sinusoidal_embedding": (c_i, [c_p, c_p, c_i, c_i, c_f, c_p]),
     "sdc_zero_f64": (c_i, [c_p, c_i64, c_p]),
+    "sdc_pack_conv_weight_dgrad": (c_i, [c_i, c_p, c_p, c_i, c_i, c_p]),
+    "sdc_gn_silu_bwd": (c_i, [c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_i64, c_p, c_p, c_i, c_i, c_i, c_p]),
+    "sdc_channel_layernorm_bwd": (c_i, [c_p, c_p, c_i, c_p, c_p, c_p, c_i64, c_i, c_i, c_p]),
+    "sdc_linear_attention_bwd_workspace": (c_i64, [c_i]),
+    "sdc_linear_attention_bwd": (c_i, [c_p, c_p, c_p, c_p, c_p, c_i, c_i, c_p]),
+    "sdc_attention_bwd": (c_i, [c_p, c_p, c_p, c_i, c_i, c_p]),
+    "sdc_pixel_shuffle_bwd": (c_i, [c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_p]),
+    "sdc_upsample2x_bwd": (c_i, [c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_p]),
+    "sdc_add_inplace": (c_i, [c_p, c_p, c_i64, c_i, c_p]),
+    "sdc_head_conv1_bwd": (c_i, [c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_p]),
+    "sdc_stem_col2im": (c_i, [c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_p]),
 })
 
 HEADS, DIM_HEAD = 4, 32
@@ -145,6 +156,34 @@ def pack_conv_weight(kind, w, prec=PREC_TF32):
     wp = torch.empty(cout, w[0].numel(), device=w.device, dtype=operand_dtype(prec))
     L.check(L.lib().sdc_pack_conv_weight(prec, kind, L.ptr(w), L.ptr(wp), cout, cin, _st()))
     return wp
+
+
+def pack_conv_weight_dgrad(kind, w):
+    """Weight of the data-gradient convolution: Wt[Cin, taps*Cout], TF32 (gradients are never fp16)."""
+    w = w.detach().to(torch.float32).contiguous()
+    cout, cin = w.shape[0], w.shape[1]
+    wt = torch.empty(cin, w[0].numel() // cin * cout, device=w.device, dtype=torch.float32)
+    L.check(L.lib().sdc_pack_conv_weight_dgrad(kind, L.ptr(w), L.ptr(wt), cout, cin, _st()))
+    return wt
+
+
+class _InputVJP(torch.autograd.Function):
+    """eps = Unet2D(x, t) with a backward that returns d<eps, g>/dx (backward-data only: no parameter gradients)."""
+
+    @staticmethod
+    def forward(ctx, x, net, time, table_row):
+        tape = []
+        with torch.cuda.device(x.device):
+            out = net._run(x.detach(), time, table_row, tape)
+        ctx.net, ctx.tape = net, tape
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        with torch.cuda.device(g.device):
+            gx = ctx.net._vjp(ctx.tape, L.dev_f32(g, "grad_eps"))
+        ctx.tape = None
+        return gx, None, None, None
 
 
 class _PackCache:
@@ -335,14 +374,31 @@ class Unet2D(nn.Module):
             raise NotImplementedError("self-conditioning / residual conditioning are outside the 1D hot path")
         return self._forward(x, time=time)
 
-    @torch.no_grad()
     def _forward(self, x, time=None, table_row=None):
         x = L.dev_f32(x, "x")
-        with torch.cuda.device(x.device):
+        if torch.is_grad_enabled() and x.requires_grad:
+            # autograd w.r.t. the INPUT (guidance callables that differentiate through the denoiser); parameters get no
+            # gradient from this path (fine-tuning is SURVEY.md section 8f)
+            return _InputVJP.apply(x, self, time, table_row)
+        with torch.no_grad(), torch.cuda.device(x.device):
             return self._run(x, time, table_row)
 
-    def _run(self, x, time, table_row):
+    def vjp(self, x, time, grad_eps):
+        """(eps, d<eps, grad_eps>/dx) in one call: forward with saved activations, then the backward-data pass."""
+        x = L.dev_f32(x, "x")
+        tape = []
+        with torch.no_grad(), torch.cuda.device(x.device):
+            if isinstance(time, int):
+                eps = self._run(x, None, time, tape)
+            else:
+                eps = self._run(x, time, None, tape)
+            return eps, self._vjp(tape, L.dev_f32(grad_eps, "grad_eps"))
+
+    def _run(self, x, time, table_row, tape=None):
+        """tape: None for inference (buffers are reused); a list to record what the backward-data pass needs (every
+        normalisation input is then kept in its own buffer)."""
         pk = self._packed()
+        keep = tape is not None
         lib = L.lib()
         dev = x.device
         prec = pk["prec"]
@@ -375,18 +431,22 @@ class Unet2D(nn.Module):
             raw = f32(M, cout)
             conv(KIND_3x3, a0, c0, a1, c1, p["c1"], None, raw, s1, False, h, w)
             ss = film[:, m._film_off:]
-            h1 = raw if od == torch.float32 else opd(M, cout)   # TF32 mode: in place
+            h1 = raw if (od == torch.float32 and not keep) else opd(M, cout)   # TF32 inference: in place
             L.check(lib.sdc_gn_silu(prec, L.ptr(raw), L.ptr(s1), L.ptr(p["g1"][0]), L.ptr(p["g1"][1]), L.ptr(ss), L.ptr(t_index), E,
                                     None, 0, L.ptr(h1), B, h * w, cout, _st()))
             raw2 = f32(M, cout)
             conv(KIND_3x3, h1, cout, None, 0, p["c2"], None, raw2, s2, False, h, w)
             if p["res"] is not None:
-                res, res_operand = raw, 0   # fp32 scratch: conv1's output is dead once h1 exists (TF32 mode: h1 itself, dead after conv2)
+                # fp32 scratch: conv1's output is dead once h1 exists (TF32 mode: h1 itself, dead after conv2)
+                res, res_operand = (f32(M, cout) if keep else raw), 0
                 conv(KIND_1x1, a0, c0, a1, c1, p["res"], None, res, None, False, h, w)
             else:
                 assert a1 is None
                 res, res_operand = a0, 1
-            out = raw2 if od == torch.float32 else h1   # TF32 mode: in place; F16 mode: h1's buffer is dead after conv2
+            # TF32 mode: in place; F16 mode: h1's buffer is dead after conv2
+            out = opd(M, cout) if keep else (raw2 if od == torch.float32 else h1)
+            if keep:
+                tape.append(("resnet", dict(p=p, c0=c0, c1=c1, h=h, w=w, raw1=raw, s1=s1, raw2=raw2, s2=s2, ss=ss)))
             L.check(lib.sdc_gn_silu(prec, L.ptr(raw2), L.ptr(s2), L.ptr(p["g2"][0]), L.ptr(p["g2"][1]), None, None, 0, L.ptr(res),
                                     res_operand, L.ptr(out), B, h * w, cout, _st()))
             return out
@@ -403,6 +463,8 @@ class Unet2D(nn.Module):
                 L.check(lib.sdc_attention(prec, L.ptr(qkv), L.ptr(att), B, n, _st()))
                 out = xn  # reuse
                 conv(KIND_1x1, att, HEADS * DIM_HEAD, None, 0, p["out"], xin, out, None, True, h, w)
+                if keep:
+                    tape.append(("attn", dict(p=p, c=c, h=h, w=w, xin=xin, qkv=qkv)))
                 return out
             ws = torch.empty(lib.sdc_linear_attention_workspace(B), device=dev, dtype=torch.uint8)
             L.check(lib.sdc_linear_attention(prec, L.ptr(qkv), L.ptr(att), L.ptr(ws), B, n, _st()))
@@ -410,6 +472,8 @@ class Unet2D(nn.Module):
             conv(KIND_1x1, att, HEADS * DIM_HEAD, None, 0, p["out"], None, proj, None, False, h, w)
             out = xn  # reuse: LN1's output is dead once qkv exists
             L.check(lib.sdc_channel_layernorm(prec, L.ptr(proj), 0, L.ptr(p["g_out"]), L.ptr(xin), L.ptr(out), M, c, 1, _st()))
+            if keep:
+                tape.append(("attn", dict(p=p, c=c, h=h, w=w, xin=xin, qkv=qkv, proj=proj, ws=ws)))
             return out
 
         c = self.init_conv.weight.shape[0]
@@ -418,12 +482,16 @@ class Unet2D(nn.Module):
         r, r_c = cur, c
         h, w = H, W
         skips = []
+        rec = tape.append if keep else (lambda item: None)
+        rec(("stem", dict(B=B, Cin=Cin, H=H, W=W, c=c, t_index=t_index, E=E)))
         for lvl_m, lvl in zip(self.downs, pk["downs"]):
             cur = resnet(lvl["b1"], lvl_m[0], cur, c, None, 0, h, w)
             skips.append((cur, c))
+            rec(("push", None))
             cur = resnet(lvl["b2"], lvl_m[1], cur, c, None, 0, h, w)
             cur = attention(lvl["attn"], cur, c, h, w)
             skips.append((cur, c))
+            rec(("push", None))
             cout = lvl["down"]["cout"]
             if lvl["unshuffle"]:
                 h, w = h // 2, w // 2
@@ -432,6 +500,7 @@ class Unet2D(nn.Module):
             else:
                 nxt = opd(B * h * w, cout)
                 conv(KIND_3x3, cur, c, None, 0, lvl["down"], None, nxt, None, True, h, w)
+            rec(("down", dict(p=lvl["down"], unshuffle=lvl["unshuffle"], c=c, h=h, w=w)))
             cur, c = nxt, cout
         cur = resnet(pk["mid1"], self.mid_block1, cur, c, None, 0, h, w)
         cur = attention(pk["mid_attn"], cur, c, h, w)
@@ -451,9 +520,174 @@ class Unet2D(nn.Module):
                 cur = up
             nxt = opd(B * h * w, cout)
             conv(KIND_3x3, cur, c, None, 0, lvl["up"], None, nxt, None, True, h, w)
+            rec(("up", dict(p=lvl["up"], upsample=lvl["upsample"], c=c, h=h, w=w)))
             cur, c = nxt, cout
         cur = resnet(pk["final"], self.final_res_block, cur, c, r, r_c, h, w)
         out = torch.empty(B, self.out_dim, H, W, device=dev, dtype=torch.float32)
         L.check(lib.sdc_head_conv1(prec, L.ptr(cur), L.ptr(pk["head"][0]), L.ptr(pk["head"][1]), L.ptr(out), B, H * W,
                                    self.final_res_block.dim_out, self.out_dim, _st()))
         return out
+
+    # ------------------------------------------------------------------ backward-data (VJP w.r.t. x)
+    def _dgrad_pack(self, pk):
+        """Transposed / tap-flipped TF32 weights of every convolution, built on first use per parameter version."""
+        if "dgrad" in pk:
+            return pk["dgrad"]
+        with torch.no_grad():
+            d = {}
+
+            def add(cw, m, kind):
+                d[id(cw)] = pack_conv_weight_dgrad(kind, m.weight)
+
+            def rb(p, m):
+                add(p["c1"], m.block1.proj, KIND_3x3)
+                add(p["c2"], m.block2.proj, KIND_3x3)
+                if p["res"] is not None:
+                    add(p["res"], m.res_conv, KIND_1x1)
+
+            def at(p, m):
+                inner = m.fn.fn
+                add(p["qkv"], inner.to_qkv, KIND_1x1)
+                add(p["out"], inner.to_out[0] if isinstance(inner, _LinearAttention) else inner.to_out, KIND_1x1)
+
+            for lvl_m, lvl in zip(self.downs, pk["downs"]):
+                rb(lvl["b1"], lvl_m[0]); rb(lvl["b2"], lvl_m[1]); at(lvl["attn"], lvl_m[2])
+                if lvl["unshuffle"]:
+                    add(lvl["down"], lvl_m[3][1], KIND_UNSHUFFLE)
+                else:
+                    add(lvl["down"], lvl_m[3], KIND_3x3)
+            rb(pk["mid1"], self.mid_block1); at(pk["mid_attn"], self.mid_attn); rb(pk["mid2"], self.mid_block2)
+            for lvl_m, lvl in zip(self.ups, pk["ups"]):
+                rb(lvl["b1"], lvl_m[0]); rb(lvl["b2"], lvl_m[1]); at(lvl["attn"], lvl_m[2])
+                add(lvl["up"], lvl_m[3][1] if lvl["upsample"] else lvl_m[3], KIND_3x3)
+            rb(pk["final"], self.final_res_block)
+            # stem: dY[M, c] x W[c, Cin*49] as a 1x1 convolution whose output rows are padded to a multiple of 64 columns
+            ws = self.init_conv.weight.detach().float()
+            c, k = ws.shape[0], ws[0].numel()
+            kp = (k + 63) // 64 * 64
+            wt = torch.zeros(kp, c, device=ws.device, dtype=torch.float32)
+            L.check(L.lib().sdc_pack_conv_weight_dgrad(KIND_1x1, L.ptr(ws.reshape(c, k).contiguous()), L.ptr(wt), c, k, _st()))
+            d["stem"] = (wt, kp)
+        pk["dgrad"] = d
+        return d
+
+    def _vjp(self, tape, g_eps):
+        """d<eps, g_eps>/dx for the forward recorded on `tape` (reverse walk)."""
+        pk = self._packed()
+        dg = self._dgrad_pack(pk)
+        lib = L.lib()
+        dev = g_eps.device
+        st0 = tape[0][1]
+        B, t_index, E = st0["B"], st0["t_index"], st0["E"]
+        f32 = lambda rows, c: torch.empty(rows, c, device=dev, dtype=torch.float32)  # noqa: E731
+        sums = torch.empty(B, 2, device=dev, dtype=torch.float64)
+
+        def dgrad(kind, g, cin_g, cw, rows, residual, out_c, operand_out, h, w):
+            """Data gradient of conv `cw` restricted to input channels `rows` = (lo, hi): conv of g with Wt[lo:hi]."""
+            wt = dg[id(cw)][rows[0]:rows[1]]
+            out = f32(B * h * w, out_c)
+            conv_gemm(kind, g, cin_g, None, 0, wt, None, residual, out, None, operand_out, B, h, w, out_c, PREC_TF32)
+            return out
+
+        def gn_bwd(dy, raw, stats, gb, ss, hw, c):
+            dx = torch.empty_like(raw)
+            L.check(lib.sdc_gn_silu_bwd(L.ptr(dy), L.ptr(raw), L.ptr(stats), L.ptr(gb[0]), L.ptr(gb[1]), L.ptr(ss),
+                                        L.ptr(t_index) if ss is not None else None, E if ss is not None else 0, L.ptr(sums),
+                                        L.ptr(dx), B, hw, c, _st()))
+            return dx
+
+        def resnet_bwd(r, g):
+            """-> (grad of input segment 0, grad of input segment 1 or None); g: TF32-rounded grad of the block output."""
+            p, c0, c1, h, w = r["p"], r["c0"], r["c1"], r["h"], r["w"]
+            cout = p["cout"]
+            d_raw2 = gn_bwd(g, r["raw2"], r["s2"], p["g2"], None, h * w, cout)
+            d_h1 = dgrad(KIND_3x3, d_raw2, cout, p["c2"], (0, cout), None, cout, False, h, w)
+            d_raw1 = gn_bwd(d_h1, r["raw1"], r["s1"], p["g1"], r["ss"], h * w, cout)
+            outs = []
+            for lo, hi in ((0, c0), (c0, c0 + c1)):
+                if hi == lo:
+                    outs.append(None)
+                    continue
+                if p["res"] is not None:
+                    side = dgrad(KIND_1x1, g, cout, p["res"], (lo, hi), None, hi - lo, False, h, w)
+                else:
+                    side = g   # identity residual (single input, c0 == cout)
+                outs.append(dgrad(KIND_3x3, d_raw1, cout, p["c1"], (lo, hi), side, hi - lo, True, h, w))
+            return outs[0], outs[1]
+
+        def attn_bwd(r, g):
+            p, c, h, w = r["p"], r["c"], r["h"], r["w"]
+            M, n, hid = B * h * w, h * w, HEADS * DIM_HEAD
+            xin = r["xin"]
+            d_qkv = f32(M, 3 * hid)
+            if p["full"]:
+                d_att = dgrad(KIND_1x1, g, c, p["out"], (0, hid), None, hid, False, h, w)
+                L.check(lib.sdc_attention_bwd(L.ptr(r["qkv"]), L.ptr(d_att), L.ptr(d_qkv), B, n, _st()))
+            else:
+                d_proj = f32(M, c)
+                L.check(lib.sdc_channel_layernorm_bwd(L.ptr(g), L.ptr(r["proj"]), 0, L.ptr(p["g_out"]), None, L.ptr(d_proj), M, c, 1, _st()))
+                d_att = dgrad(KIND_1x1, d_proj, c, p["out"], (0, hid), None, hid, False, h, w)
+                wsb = torch.empty(lib.sdc_linear_attention_bwd_workspace(B), device=dev, dtype=torch.uint8)
+                L.check(lib.sdc_linear_attention_bwd(L.ptr(r["qkv"]), L.ptr(d_att), L.ptr(r["ws"]), L.ptr(wsb), L.ptr(d_qkv), B, n, _st()))
+            d_xn = dgrad(KIND_1x1, d_qkv, 3 * hid, p["qkv"], (0, c), None, c, False, h, w)
+            d_x = f32(M, c)
+            L.check(lib.sdc_channel_layernorm_bwd(L.ptr(d_xn), L.ptr(xin), int(xin.dtype == torch.float16), L.ptr(p["g_in"]), L.ptr(g),
+                                                  L.ptr(d_x), M, c, 1, _st()))
+            return d_x
+
+        def add_(a, b):
+            L.check(lib.sdc_add_inplace(L.ptr(a), L.ptr(b), a.numel(), 1, _st()))
+            return a
+
+        # ---- reverse walk ----
+        i = len(tape) - 1
+        kind, r = tape[i]
+        assert kind == "resnet"   # final_res_block; the head is not on the tape (no saved state)
+        Hh, Ww = st0["H"], st0["W"]
+        cfin = self.final_res_block.dim_out
+        g = f32(B * Hh * Ww, cfin)
+        L.check(lib.sdc_head_conv1_bwd(L.ptr(g_eps), L.ptr(pk["head"][0]), L.ptr(g), B, Hh * Ww, cfin, self.out_dim, 1, _st()))
+        g, g_r = resnet_bwd(r, g)
+        i -= 1
+        skip_grads = []   # gradients of the skip tensors: filled by the up path in push order, consumed by the down path from the end
+        while i > 0:
+            kind, r = tape[i]
+            if kind == "up":
+                c, h, w = r["c"], r["h"], r["w"]
+                if r["upsample"]:
+                    g_hi = dgrad(KIND_3x3, g, r["p"]["cout"], r["p"], (0, c), None, c, False, h, w)
+                    g = f32(B * (h // 2) * (w // 2), c)
+                    L.check(lib.sdc_upsample2x_bwd(L.ptr(g_hi), L.ptr(g), B, h // 2, w // 2, c, 1, _st()))
+                else:
+                    g = dgrad(KIND_3x3, g, r["p"]["cout"], r["p"], (0, c), None, c, True, h, w)
+            elif kind == "attn":
+                g = attn_bwd(r, g)
+            elif kind == "resnet":
+                g, g_skip = resnet_bwd(r, g)
+                if g_skip is not None:
+                    skip_grads.append(g_skip)
+            elif kind == "down":
+                # the tensor entering the downsample was also pushed as a skip: its up-path gradient is the last entry
+                c, h, w = r["c"], r["h"], r["w"]
+                sg = skip_grads.pop()
+                if r["unshuffle"]:
+                    t = dgrad(KIND_1x1, g, r["p"]["cout"], r["p"], (0, 4 * c), None, 4 * c, False, h, w)
+                    g = f32(B * 4 * h * w, c)
+                    L.check(lib.sdc_pixel_shuffle_bwd(L.ptr(t), L.ptr(sg), L.ptr(g), B, h, w, c, 1, _st()))
+                else:
+                    g = dgrad(KIND_3x3, g, r["p"]["cout"], r["p"], (0, c), sg, c, True, h, w)
+            elif kind == "push":
+                # a "push" directly after an attention block is consumed by the following "down" record; a push after the
+                # first ResnetBlock of a level adds its skip gradient here
+                if tape[i + 1][0] != "down":
+                    g = add_(g, skip_grads.pop())
+            i -= 1
+        assert not skip_grads
+        g = add_(g, g_r)   # the stem output also feeds final_res_block (r = x.clone(), unet.py:393)
+        wt, kp = dg["stem"]
+        c = st0["c"]
+        t = f32(B * Hh * Ww, kp)
+        conv_gemm(KIND_1x1, g, c, None, 0, wt, None, None, t, None, False, B, Hh, Ww, kp, PREC_TF32)
+        gx = torch.empty(B, st0["Cin"], Hh, Ww, device=dev, dtype=torch.float32)
+        L.check(lib.sdc_stem_col2im(L.ptr(t), L.ptr(gx), B, st0["Cin"], Hh, Ww, kp, _st()))
+        return gx

@@ -39,3 +39,20 @@ def test_module_semantics():
         s.Unet2D(dim=32, channels=3, resnet_block_groups=8)
     gd = s.GaussianDiffusion(net, seq_length=(16, 128), temporal=True, use_conv2d=True)
     assert len(gd.state_dict()) == 276 + 13
+
+
+def test_oracle_input_gradient_matches_reference_golden(golden):
+    """The oracle's autograd VJP w.r.t. x (used by the GPU backward-data tests) equals the unmodified reference's."""
+    import safediffcon_b200 as s
+    from oracle import fixtures as fx, unet_ref
+    for dim in (32, 64):
+        torch.manual_seed(42)
+        net = s.Unet2D(dim=dim, dim_mults=(1, 2, 4, 8), channels=3, resnet_block_groups=1)
+        sd = {k: v.detach() for k, v in net.state_dict().items()}
+        x, t = fx.unet_inputs(2)
+        x = x.clone().requires_grad_()
+        eps = unet_ref.unet_forward(sd, x, t)
+        (gx,) = torch.autograd.grad(eps, x, fx.unet_cotangent(2))
+        g = golden(f"unet_dim{dim}_vjp")
+        assert np.allclose(eps.detach().numpy(), g["eps"], rtol=0, atol=1e-5 * np.abs(g["eps"]).max())
+        assert np.allclose(gx.numpy(), g["grad_x"], rtol=0, atol=1e-5 * np.abs(g["grad_x"]).max())
