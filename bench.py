@@ -30,7 +30,7 @@ import torch  # noqa: E402
 CHAIN_STEPS = 1000
 CONV_GFLOP_PER_SAMPLE = 27.811 - 0.0771 - 0.0016  # tcgen05 convs only: minus the 7x7 stem and the 3-channel head
 W_SCORE, U_BOUND, Q_GUIDE = 500.0, 0.8, 0.0
-TRAFFIC_BYTES_PER_LAUNCH = None  # dram bytes per launch of the dominant kernel from the ncu --set full capture (profiles/), if taken
+TRAFFIC_BYTES_PER_LAUNCH = 766.8e6  # mean dram read+write bytes per conv launch of one step at B=1024 (ncu, profiles/r01_conv_f16_per_launch_metrics.csv)
 
 
 class Cfg:
