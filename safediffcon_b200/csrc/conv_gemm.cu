@@ -2,22 +2,24 @@
 //
 // Replaces every nn.Conv2d of Unet2D except the 3-channel stem (/root/reference/1D/model/unet.py:132,161,
 // 189-192,232-233,33-43,345,370,378):   out[M, Cout] = im2col(A)[M, K] * Wp[Cout, K]^T + bias
-//   M = B*H*W output pixels (NHWC activations, fp32 containers holding TF32-rounded values)
+//   M = B*H*W output pixels (NHWC activations: fp16, or fp32 containers holding TF32-rounded values)
 //   K = taps * Cin   (3x3 pad 1: 9 taps; 1x1: 1 tap; pixel-unshuffle 2x2/stride 2: 4 taps),
 //       Cin may be the concatenation of two tensors (U-Net skip connections) -> two K segments, no torch.cat.
 //
 // Mapping (persistent: one CTA per SM walks a contiguous range of 128 x BN output tiles, 192 threads):
-//   warp 0   TMA producer: per K block (32 channels of one tap) one 4-D/5-D box load of the shifted activation
+//   warp 0   TMA producer: per K block (128 bytes of channels of one tap) one 4-D/5-D box load of the shifted activation
 //            window (out-of-bounds rows/cols are zero-filled by TMA = the conv padding) + one 2-D load of the
 //            weight slab, both SWIZZLE_128B, completing on an mbarrier;
-//   warp 1   allocates TMEM, then one thread issues tcgen05.mma.kind::tf32 (M=128, N=BN, K=8) x4 per K block,
+//   warp 1   allocates TMEM, then one thread issues tcgen05.mma.kind::f16|tf32 (M=128|256, N=BN, 32 bytes of K) x4 per K block,
 //            accumulating in TMEM, and releases smem stages with tcgen05.commit;
-//   warps 2-5 epilogue: tcgen05.ld the accumulator (each warp owns its 32-lane TMEM quarter), transpose it through
-//            a padded smem staging tile so that global stores are full 128-byte row segments, add bias /
-//            residual, accumulate per-sample GroupNorm statistics (sum, sum of squares -> fp64 atomics),
-//            optionally round to TF32 (so that the next conv's operands are round-to-nearest, not truncated).
+//   warps 2-5 epilogue: tcgen05.ld the accumulator (each warp owns its 32-lane TMEM quarter, lane = output row), add
+//            bias / residual in registers, accumulate per-sample GroupNorm statistics (sum, sum of squares -> fp64
+//            atomics), round to the operand precision if the output feeds another convolution, write the 32x32
+//            chunk into a swizzled shared staging buffer and hand it to ONE TMA store (tc_ptx.cuh: epilogue_chunk).
+//            A/B on B200 against a smem-transpose + st.global epilogue: 1x1 convolutions 1.7x faster (5 TB/s),
+//            3x3 convolutions equal or faster (profiles/r01_epilogue_ab.txt).
 //   The accumulator is double buffered in TMEM (2 x BN columns): the epilogue of tile i overlaps the MMAs of i+1.
-// Precision: TF32 operands (10-bit mantissa, rounded to nearest when produced), FP32 accumulation.
+// Precision: FP16 or TF32 operands (10-bit mantissa, rounded to nearest when produced; template HALF), FP32 accumulation.
 #include "tc_ptx.cuh"
 #include "../../include/safediffcon_b200_unet.h"
 #include <math.h>
@@ -29,8 +31,8 @@ namespace sdc {
 constexpr int BM = 128;        // output pixels per tile (= UMMA M)
 constexpr int A_BYTES = BM * 128;   // one K block of activations: 128 rows of 128 bytes (32 TF32 or 64 FP16 channels)
 constexpr int GEMM_THREADS = 192;
-constexpr int STG_LD = 36;     // staging row stride in floats (32 + 4: conflict-free 16-byte accesses)
-constexpr int STG_BYTES = 4 * 32 * STG_LD * 4;
+constexpr int STG_BUF = 4096;  // one epilogue staging buffer: 32 rows x 128 bytes (TMA-store box)
+constexpr int STG_BYTES = 4 * 2 * STG_BUF;   // 4 epilogue warps x double buffer
 
 struct GemmParams {
     int kind;            // 0: 1x1, 1: 3x3 pad 1, 2: 2x2 stride-2 (pixel-unshuffle + 1x1)
@@ -63,7 +65,7 @@ struct GemmParams {
 // the leader's `acc_empty`.
 template <bool HALF, bool PAIR>
 __device__ __forceinline__ void conv_gemm_body(const CUtensorMap& map_a0, const CUtensorMap& map_a1, const CUtensorMap& map_w,
-                                               const GemmParams& p) {
+                                               const CUtensorMap& map_out, const GemmParams& p) {
     using Op = Operand<HALF>;
     using act_t = typename ActT<HALF>::type;
     constexpr int BK = Op::kBK;
@@ -71,7 +73,7 @@ __device__ __forceinline__ void conv_gemm_body(const CUtensorMap& map_a0, const 
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     const int b_rows = PAIR ? p.bn / 2 : p.bn;            // weight rows staged by this CTA
     const int stage_bytes = A_BYTES + b_rows * 128;
-    float* staging = reinterpret_cast<float*>(smem + p.stages * stage_bytes);
+    uint8_t* staging = smem + p.stages * stage_bytes;   // 1024-byte aligned (stage_bytes is a multiple of 1024)
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + p.stages * stage_bytes + STG_BYTES);
     uint64_t* empty_bar = full_bar + p.stages;
     uint64_t* acc_full = empty_bar + p.stages;   // [2]
@@ -95,6 +97,7 @@ __device__ __forceinline__ void conv_gemm_body(const CUtensorMap& map_a0, const 
         tma_prefetch_desc(&map_a0);
         if (p.c1) tma_prefetch_desc(&map_a1);
         tma_prefetch_desc(&map_w);
+        tma_prefetch_desc(&map_out);
         for (int s = 0; s < p.stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
         for (int b = 0; b < 2; ++b) { mbar_init(&acc_full[b], 1); mbar_init(&acc_empty[b], PAIR ? 8 : 4); }
         fence_barrier_init();
@@ -176,12 +179,13 @@ __device__ __forceinline__ void conv_gemm_body(const CUtensorMap& map_a0, const 
             }
         }
     } else {
-        // ---- epilogue: warp w may only touch TMEM lanes [32*(w%4), 32*(w%4)+32) ----
+        // ---- epilogue: warp w may only touch TMEM lanes [32*(w%4), 32*(w%4)+32); lane = accumulator row ----
         const int q = warp & 3;
-        float* stg = staging + q * 32 * STG_LD;
-        const int sub_r = lane >> 3, sub_c = (lane & 7) * 4;   // coalesced phase: 4 rows x 8 four-element groups per instruction
+        const uint32_t stg = smem_u32(staging + q * 2 * STG_BUF);
         const act_t* resid = reinterpret_cast<const act_t*>(p.residual);
+        const bool out_half = HALF && p.operand_out;
         int it = 0;
+        uint32_t nchunk = 0;
         for (int tile = tile_lo; tile < tile_hi; ++tile, ++it) {
             const int mq = tile / p.tiles_n, nt = tile - mq * p.tiles_n;
             const int mt = PAIR ? 2 * mq + (int)rank : mq;
@@ -189,37 +193,21 @@ __device__ __forceinline__ void conv_gemm_body(const CUtensorMap& map_a0, const 
             mbar_wait(&acc_full[buf], (uint32_t)(it >> 1) & 1u);
             tc_fence_after();
             const int m_w = mt * BM + q * 32;          // first row of this warp
+            const int m = m_w + lane;
+            const bool row_ok = m < p.M;
             float s1 = 0.f, s2 = 0.f;
-            for (int c = 0; c < p.bn; c += 32) {
-                uint32_t r[32];
-                tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)buf * acc_cols + (uint32_t)c, r);
-#pragma unroll
-                for (int j = 0; j < 32; j += 4)
-                    *reinterpret_cast<float4*>(stg + lane * STG_LD + j) =
-                        make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
+            for (int c = 0; c < p.bn; c += 32, ++nchunk) {
+                // the bulk store that last read this staging buffer (two chunks ago) must have finished reading it
+                if (lane == 0) bulk_wait_read<1>();
                 __syncwarp();
-                const int col = nt * p.bn + c + sub_c;
-                float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (p.bias) bv = __ldg(reinterpret_cast<const float4*>(p.bias + col));
-#pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    const int rr = sub_r + 4 * i;
-                    const int m = m_w + rr;
-                    if (m < p.M) {
-                        float4 v = *reinterpret_cast<const float4*>(stg + rr * STG_LD + sub_c);
-                        v.x += bv.x; v.y += bv.y; v.z += bv.z; v.w += bv.w;
-                        const size_t off = (size_t)m * p.Cout + col;
-                        if (resid) {
-                            const float4 rv = load4_nc(resid + off);
-                            v.x += rv.x; v.y += rv.y; v.z += rv.z; v.w += rv.w;
-                        }
-                        s1 += (v.x + v.y) + (v.z + v.w);
-                        s2 += (v.x * v.x + v.y * v.y) + (v.z * v.z + v.w * v.w);
-                        if (p.operand_out) store_operand4(reinterpret_cast<act_t*>(p.out) + off, v);
-                        else store4(reinterpret_cast<float*>(p.out) + off, v);
-                    }
+                const int col = nt * p.bn + c;
+                const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)buf * acc_cols + (uint32_t)c;
+                const uint32_t sb = stg + (nchunk & 1u) * STG_BUF;
+                const act_t* rrow = resid ? resid + (size_t)m * p.Cout + col : nullptr;
+                if (m_w < p.M) {
+                    if (out_half) epilogue_chunk<true, act_t>(taddr, sb, &map_out, col, m_w, row_ok, p.bias, rrow, false, s1, s2, lane);
+                    else epilogue_chunk<false, act_t>(taddr, sb, &map_out, col, m_w, row_ok, p.bias, rrow, p.operand_out != 0, s1, s2, lane);
                 }
-                __syncwarp();
             }
             // accumulator buffer fully read -> hand it back to the MMA warp
             tc_fence_before();
@@ -236,6 +224,7 @@ __device__ __forceinline__ void conv_gemm_body(const CUtensorMap& map_a0, const 
                 }
             }
         }
+        if (lane == 0) bulk_wait<0>();   // all output stores complete before the CTA's shared memory goes away
         tc_fence_before();
     }
     // PAIR: neither CTA may exit (or free TMEM) while its partner can still read its shared memory / signal its barriers
@@ -250,14 +239,14 @@ __device__ __forceinline__ void conv_gemm_body(const CUtensorMap& map_a0, const 
 template <bool HALF>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ CUtensorMap map_a1,
-                 const __grid_constant__ CUtensorMap map_w, const GemmParams p) {
-    conv_gemm_body<HALF, false>(map_a0, map_a1, map_w, p);
+                 const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUtensorMap map_out, const GemmParams p) {
+    conv_gemm_body<HALF, false>(map_a0, map_a1, map_w, map_out, p);
 }
 template <bool HALF>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
 conv_gemm2_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ CUtensorMap map_a1,
-                  const __grid_constant__ CUtensorMap map_w, const GemmParams p) {
-    conv_gemm_body<HALF, true>(map_a0, map_a1, map_w, p);
+                  const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUtensorMap map_out, const GemmParams p) {
+    conv_gemm_body<HALF, true>(map_a0, map_a1, map_w, map_out, p);
 }
 
 // ------------------------------------------------------------------------------------------ host side
@@ -327,6 +316,7 @@ extern "C" int sdc_conv_gemm(int prec, int kind, const void* a0, int c0, const v
     const int ctas = p.tiles_total < workers ? p.tiles_total : workers;
     p.tiles_per_cta = (p.tiles_total + ctas - 1) / ctas;
 
+    SDC_REQUIRE((reinterpret_cast<uintptr_t>(out) & 15) == 0, "conv_gemm: out must be 16-byte aligned (TMA store)");
     CUtensorMap ma0, ma1, mw;
     int rc = encode_act(&ma0, a0, kind, B, H, W, c0, bh, bb, half);
     if (rc) return rc;
@@ -337,6 +327,9 @@ extern "C" int sdc_conv_gemm(int prec, int kind, const void* a0, int c0, const v
     cuuint64_t ws[1] = {ktot * (half ? 2 : 4)};
     cuuint32_t wb[2] = {(cuuint32_t)BK, (cuuint32_t)(pair ? bn / 2 : bn)};
     rc = encode_tmap(&mw, w_packed, 2, wd, ws, wb, half);
+    if (rc) return rc;
+    CUtensorMap mo;
+    rc = encode_out_tmap(&mo, out, p.M, Cout, half && operand_out);
     if (rc) return rc;
 
     static bool attr_set = false;
@@ -350,11 +343,11 @@ extern "C" int sdc_conv_gemm(int prec, int kind, const void* a0, int c0, const v
     const int grid = (p.tiles_total + p.tiles_per_cta - 1) / p.tiles_per_cta;
     cudaStream_t st = as_stream(stream);
     if (pair) {
-        if (half) conv_gemm2_kernel<true><<<2 * grid, GEMM_THREADS, smem_bytes, st>>>(ma0, ma1, mw, p);
-        else conv_gemm2_kernel<false><<<2 * grid, GEMM_THREADS, smem_bytes, st>>>(ma0, ma1, mw, p);
+        if (half) conv_gemm2_kernel<true><<<2 * grid, GEMM_THREADS, smem_bytes, st>>>(ma0, ma1, mw, mo, p);
+        else conv_gemm2_kernel<false><<<2 * grid, GEMM_THREADS, smem_bytes, st>>>(ma0, ma1, mw, mo, p);
     } else {
-        if (half) conv_gemm_kernel<true><<<grid, GEMM_THREADS, smem_bytes, st>>>(ma0, ma1, mw, p);
-        else conv_gemm_kernel<false><<<grid, GEMM_THREADS, smem_bytes, st>>>(ma0, ma1, mw, p);
+        if (half) conv_gemm_kernel<true><<<grid, GEMM_THREADS, smem_bytes, st>>>(ma0, ma1, mw, mo, p);
+        else conv_gemm_kernel<false><<<grid, GEMM_THREADS, smem_bytes, st>>>(ma0, ma1, mw, mo, p);
     }
     SDC_LAUNCHED();
     return SDC_OK;

@@ -4,15 +4,15 @@
 // /root/reference/1D/model/unet.py:132,33-37,370), different data movement.  The generic implicit GEMM re-loads
 // the activation window once per tap (9x) and, with only 128 output channels, is bound by L2->SMEM operand
 // traffic (ncu: ~50 B/clk/SM, tensor pipe 30-39% active).  Here one CTA computes TWO image rows (M = 2 x 128
-// pixels) per tile and, per 32-channel chunk, loads the 4 x 130-pixel halo ONCE (66.5 KB, one TMA box with zero
+// pixels) per tile and, per 128-byte channel chunk (64 fp16 / 32 tf32 channels), loads the 4 x 130-pixel halo ONCE (66.5 KB, one TMA box with zero
 // fill = padding); the nine taps' A operands are row-shifted views of that halo, expressed purely through the
 // UMMA shared-memory descriptor start address (the 128B swizzle phase follows the absolute address).  Each weight tile is
 // used by both rows.  Operand traffic drops from 64 to ~23 KB per 128x128x32 MAC block.
 //
 //   warp 0   TMA producer of the weight-tile ring (4 stages; 8 half tiles with CTA pairs);  warp 6: halo ring (2 stages)
-//   warp 1   MMA issuer: 9 taps x 2 rows x 4 (K=8) tcgen05.mma.kind::tf32 per chunk, accumulators in TMEM
+//   warp 1   MMA issuer: 9 taps x 2 rows x 4 (32 bytes of K) tcgen05.mma.kind::f16|tf32 per chunk, accumulators in TMEM
 //            (2 rows x Cout columns, double buffered)
-//   warps 2-5 epilogue (same as conv_gemm.cu): TMEM -> smem transpose -> coalesced rows, bias, GN statistics
+//   warps 2-5 epilogue (same as conv_gemm.cu): TMEM -> registers (bias, residual, GN statistics) -> swizzled smem -> TMA store
 #include "tc_ptx.cuh"
 #include "../../include/safediffcon_b200_unet.h"
 #include <math.h>
@@ -26,8 +26,8 @@ constexpr int HALO_ROWS = 4 * HALO_W;        // 520 pixel rows of 128 bytes
 constexpr int HALO_BYTES = HALO_ROWS * 128;  // 66,560 = 65 * 1024 (keeps every stage 1024-byte aligned)
 constexpr int ROW_BSTAGES = 4;
 constexpr int ROW_THREADS = 224;   // warp 0 weight TMA, 1 MMA, 2-5 epilogue, 6 halo TMA
-constexpr int RSTG_LD = 36;
-constexpr int RSTG_BYTES = 4 * 32 * RSTG_LD * 4;
+constexpr int RSTG_BUF = 4096;             // one staging buffer per epilogue warp (32 rows x 128 bytes, TMA-store box)
+constexpr int RSTG_BYTES = 4 * RSTG_BUF;   // single buffered: the halo + weight rings leave no room for a second set
 
 struct RowParams {
     int B, H, Cout, bn;      // bn = Cout (single N tile, multiple of 32, <= 128)
@@ -46,7 +46,7 @@ struct RowParams {
 // for the same shared memory and the per-SM operand traffic drops from 46 to 30 B/clk.
 template <bool HALF, bool PAIR>
 __device__ __forceinline__ void conv_row_body(const CUtensorMap& map_a0, const CUtensorMap& map_a1, const CUtensorMap& map_w,
-                                              const RowParams& p) {
+                                              const CUtensorMap& map_out, const RowParams& p) {
     using Op = Operand<HALF>;
     using act_t = typename ActT<HALF>::type;
     constexpr int BK = Op::kBK;   // channels per 128-byte chunk
@@ -58,8 +58,8 @@ __device__ __forceinline__ void conv_row_body(const CUtensorMap& map_a0, const C
     const bool leader = rank == 0;
     uint8_t* halo = smem;                                   // [2][HALO_BYTES]
     uint8_t* bring = smem + 2 * HALO_BYTES;                 // [NB][b_bytes] (b_bytes multiple of 1024)
-    float* staging = reinterpret_cast<float*>(bring + NB * b_bytes);
-    uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(staging) + RSTG_BYTES);
+    uint8_t* staging = bring + NB * b_bytes;   // 1024-byte aligned (b_bytes is a multiple of 1024)
+    uint64_t* bars = reinterpret_cast<uint64_t*>(staging + RSTG_BYTES);
     uint64_t* halo_full = bars;            // [2]
     uint64_t* halo_empty = bars + 2;       // [2]
     uint64_t* b_full = bars + 4;           // [NB]
@@ -80,6 +80,7 @@ __device__ __forceinline__ void conv_row_body(const CUtensorMap& map_a0, const C
         tma_prefetch_desc(&map_a0);
         if (p.c1) tma_prefetch_desc(&map_a1);
         tma_prefetch_desc(&map_w);
+        tma_prefetch_desc(&map_out);
         for (int s = 0; s < 2; ++s) { mbar_init(&halo_full[s], 1); mbar_init(&halo_empty[s], 1); }
         for (int s = 0; s < NB; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); }
         for (int b = 0; b < 2; ++b) { mbar_init(&acc_full[b], 1); mbar_init(&acc_empty[b], PAIR ? 8 : 4); }
@@ -176,9 +177,9 @@ __device__ __forceinline__ void conv_row_body(const CUtensorMap& map_a0, const C
         }
     } else {
         const int q = warp & 3;
-        float* stg = staging + q * 32 * RSTG_LD;
-        const int sub_r = lane >> 3, sub_c = (lane & 7) * 4;
+        const uint32_t stg = smem_u32(staging + q * RSTG_BUF);
         const act_t* resid = reinterpret_cast<const act_t*>(p.residual);
+        const bool out_half = HALF && p.operand_out;
         int it = 0;
         for (int pair = pair_lo; pair < pair_hi; ++pair, ++it) {
             const int b = pair / p.pairs_per_image, h0 = (PAIR ? 4 : 2) * (pair - b * p.pairs_per_image) + 2 * (int)rank;
@@ -187,39 +188,15 @@ __device__ __forceinline__ void conv_row_body(const CUtensorMap& map_a0, const C
             tc_fence_after();
             float s1 = 0.f, s2 = 0.f;
             for (int j = 0; j < 2; ++j) {
-                const bool row_ok = h0 + j < p.H;
-                const size_t m_w = ((size_t)b * p.H + h0 + j) * RW + q * 32;
+                if (h0 + j >= p.H || (p.dbg & 2)) continue;   // phantom row of an odd-height image (warp-uniform)
+                const int m_w = (b * p.H + h0 + j) * RW + q * 32;   // global output row of lane 0
                 for (int c = 0; c < p.bn; c += 32) {
-                    uint32_t r[32];
-                    tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)buf * 2u * acc_cols + (uint32_t)j * acc_cols + (uint32_t)c, r);
-#pragma unroll
-                    for (int jj = 0; jj < 32; jj += 4)
-                        *reinterpret_cast<float4*>(stg + lane * RSTG_LD + jj) =
-                            make_float4(__uint_as_float(r[jj]), __uint_as_float(r[jj + 1]), __uint_as_float(r[jj + 2]), __uint_as_float(r[jj + 3]));
+                    if (lane == 0) bulk_wait_read<0>();   // the previous store has finished reading the staging buffer
                     __syncwarp();
-                    const int col = c + sub_c;
-                    float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (p.bias) bv = __ldg(reinterpret_cast<const float4*>(p.bias + col));
-                    if (row_ok && !(p.dbg & 2)) {
-                        float4 rv[8];
-                        if (resid) {
-#pragma unroll
-                            for (int i = 0; i < 8; ++i) rv[i] = load4_nc(resid + (m_w + sub_r + 4 * i) * p.Cout + col);
-                        }
-#pragma unroll
-                        for (int i = 0; i < 8; ++i) {
-                            const int rr = sub_r + 4 * i;
-                            const size_t m = m_w + rr;
-                            float4 v = *reinterpret_cast<const float4*>(stg + rr * RSTG_LD + sub_c);
-                            v.x += bv.x; v.y += bv.y; v.z += bv.z; v.w += bv.w;
-                            if (resid) { v.x += rv[i].x; v.y += rv[i].y; v.z += rv[i].z; v.w += rv[i].w; }
-                            s1 += (v.x + v.y) + (v.z + v.w);
-                            s2 += (v.x * v.x + v.y * v.y) + (v.z * v.z + v.w * v.w);
-                            if (p.operand_out) store_operand4(reinterpret_cast<act_t*>(p.out) + m * p.Cout + col, v);
-                            else store4(reinterpret_cast<float*>(p.out) + m * p.Cout + col, v);
-                        }
-                    }
-                    __syncwarp();
+                    const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)buf * 2u * acc_cols + (uint32_t)j * acc_cols + (uint32_t)c;
+                    const act_t* rrow = resid ? resid + (size_t)(m_w + lane) * p.Cout + c : nullptr;
+                    if (out_half) epilogue_chunk<true, act_t>(taddr, stg, &map_out, c, m_w, true, p.bias, rrow, false, s1, s2, lane);
+                    else epilogue_chunk<false, act_t>(taddr, stg, &map_out, c, m_w, true, p.bias, rrow, p.operand_out != 0, s1, s2, lane);
                 }
             }
             tc_fence_before();
@@ -234,6 +211,7 @@ __device__ __forceinline__ void conv_row_body(const CUtensorMap& map_a0, const C
                 }
             }
         }
+        if (lane == 0) bulk_wait<0>();   // all output stores complete before the CTA's shared memory goes away
         tc_fence_before();
     }
     __syncthreads();
@@ -247,14 +225,14 @@ __device__ __forceinline__ void conv_row_body(const CUtensorMap& map_a0, const C
 template <bool HALF>
 __global__ void __launch_bounds__(ROW_THREADS, 1)
 conv_row_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ CUtensorMap map_a1,
-                const __grid_constant__ CUtensorMap map_w, const RowParams p) {
-    conv_row_body<HALF, false>(map_a0, map_a1, map_w, p);
+                const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUtensorMap map_out, const RowParams p) {
+    conv_row_body<HALF, false>(map_a0, map_a1, map_w, map_out, p);
 }
 template <bool HALF>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(ROW_THREADS, 1)
 conv_row2_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ CUtensorMap map_a1,
-                 const __grid_constant__ CUtensorMap map_w, const RowParams p) {
-    conv_row_body<HALF, true>(map_a0, map_a1, map_w, p);
+                 const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUtensorMap map_out, const RowParams p) {
+    conv_row_body<HALF, true>(map_a0, map_a1, map_w, map_out, p);
 }
 
 }  // namespace sdc
@@ -303,6 +281,10 @@ extern "C" int sdc_conv3x3_row(int prec, const void* a0, int c0, const void* a1,
     cuuint32_t wb[2] = {(cuuint32_t)BK, (cuuint32_t)(pair ? Cout / 2 : Cout)};
     rc = encode_tmap(&mw, w_packed, 2, wd, ws, wb, half);
     if (rc) return rc;
+    SDC_REQUIRE((reinterpret_cast<uintptr_t>(out) & 15) == 0, "conv3x3_row: out must be 16-byte aligned (TMA store)");
+    CUtensorMap mo;
+    rc = encode_out_tmap(&mo, out, (int64_t)B * H * W, Cout, half && operand_out);
+    if (rc) return rc;
     const int smem_bytes = 2 * HALO_BYTES + ROW_BSTAGES * Cout * 128 + RSTG_BYTES + 24 * 8 + 16 + 1024;
     static bool attr_set = false;
     if (!attr_set) {
@@ -314,11 +296,11 @@ extern "C" int sdc_conv3x3_row(int prec, const void* a0, int c0, const void* a1,
     }
     cudaStream_t st = as_stream(stream);
     if (pair) {
-        if (half) conv_row2_kernel<true><<<2 * grid, ROW_THREADS, smem_bytes, st>>>(ma0, ma1, mw, p);
-        else conv_row2_kernel<false><<<2 * grid, ROW_THREADS, smem_bytes, st>>>(ma0, ma1, mw, p);
+        if (half) conv_row2_kernel<true><<<2 * grid, ROW_THREADS, smem_bytes, st>>>(ma0, ma1, mw, mo, p);
+        else conv_row2_kernel<false><<<2 * grid, ROW_THREADS, smem_bytes, st>>>(ma0, ma1, mw, mo, p);
     } else {
-        if (half) conv_row_kernel<true><<<grid, ROW_THREADS, smem_bytes, st>>>(ma0, ma1, mw, p);
-        else conv_row_kernel<false><<<grid, ROW_THREADS, smem_bytes, st>>>(ma0, ma1, mw, p);
+        if (half) conv_row_kernel<true><<<grid, ROW_THREADS, smem_bytes, st>>>(ma0, ma1, mw, mo, p);
+        else conv_row_kernel<false><<<grid, ROW_THREADS, smem_bytes, st>>>(ma0, ma1, mw, mo, p);
     }
     SDC_LAUNCHED();
     return SDC_OK;

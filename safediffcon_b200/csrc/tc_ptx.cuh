@@ -113,6 +113,97 @@ __device__ __forceinline__ uint64_t make_sw128_desc(uint32_t smem_addr) {
     const uint32_t hi = 64u | (1u << 14) | (2u << 29);
     return ((uint64_t)hi << 32) | lo;
 }
+// explicit shared-window accesses for the epilogue staging tile: the dynamic-smem base is re-aligned through an integer
+// cast, after which the compiler no longer knows the address space and would emit generic LD.E / ST.E (long-scoreboard)
+__device__ __forceinline__ void sts128(uint32_t addr, float4 v) {
+    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+__device__ __forceinline__ float4 lds128(uint32_t addr) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");
+    return v;
+}
+// TMA store of a shared-memory box to global memory (bulk async-group completion)
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t src_smem, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+                 ::"l"(map), "r"(src_smem), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
+template <int N>
+__device__ __forceinline__ void bulk_wait() { asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory"); }
+
+// ---------------------------------------------------------------------------------------------- epilogue chunk
+// One 32-row x 32-column accumulator chunk of an epilogue warp (lane = row):
+//   tcgen05.ld -> registers (bias, residual, GroupNorm sums, rounding) -> swizzled shared staging -> ONE TMA store.
+// The thread-level work is ~40 instructions per chunk (the earlier smem-transpose + per-row st.global epilogue was ~390
+// and, with one epilogue warp per scheduler, issue-latency bound: 1x1 convolutions ran at 40% of HBM).
+//   OUT_HALF = false: fp32 rows of 128 bytes, SWIZZLE_128B box {32, 32}; `round` stores TF32-rounded values.
+//   OUT_HALF = true : fp16 rows of 64 bytes,  SWIZZLE_64B  box {32, 32}.
+// stg: 1024-byte aligned shared address of a 4 KB staging buffer that no in-flight bulk store is still reading.
+// res_row: this lane's residual row at column `col` (operand precision) or null.  Rows beyond the tensor are clipped by TMA;
+// `row_ok` keeps them out of the statistics.
+template <bool OUT_HALF, typename res_t>
+__device__ __forceinline__ void epilogue_chunk(uint32_t taddr, uint32_t stg, const CUtensorMap* map_out, int col, int row0,
+                                               bool row_ok, const float* __restrict__ bias, const res_t* __restrict__ res_row,
+                                               bool round, float& s1, float& s2, int lane) {
+    uint32_t r[32];
+    tmem_ld32(taddr, r);
+    float v[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+    if (bias) {
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+            const float4 b = __ldg(reinterpret_cast<const float4*>(bias + col + j));
+            v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
+        }
+    }
+    if (res_row && row_ok) {
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+            const float4 b = load4_nc(res_row + j);
+            v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
+        }
+    }
+    if (row_ok) {
+        float a1 = 0.f, a2 = 0.f;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) { a1 += v[j]; a2 = fmaf(v[j], v[j], a2); }
+        s1 += a1;
+        s2 += a2;
+    }
+    if constexpr (OUT_HALF) {
+        const uint32_t rowa = stg + (uint32_t)lane * 64u, sw = ((uint32_t)lane >> 1) & 3u;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            uint32_t w[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const __half2 h = __floats2half2_rn(v[8 * j + 2 * k], v[8 * j + 2 * k + 1]);
+                w[k] = *reinterpret_cast<const uint32_t*>(&h);
+            }
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(rowa + (((uint32_t)j ^ sw) << 4)), "r"(w[0]), "r"(w[1]),
+                         "r"(w[2]), "r"(w[3]) : "memory");
+        }
+    } else {
+        const uint32_t rowa = stg + (uint32_t)lane * 128u, sw = (uint32_t)lane & 7u;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            float4 o = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+            if (round) o = make_float4(to_tf32(o.x), to_tf32(o.y), to_tf32(o.z), to_tf32(o.w));
+            sts128(rowa + (((uint32_t)j ^ sw) << 4), o);
+        }
+    }
+    fence_proxy_async();   // generic-proxy writes above -> visible to the async proxy (TMA) below
+    __syncwarp();
+    if (lane == 0) {
+        tma_store_2d(map_out, stg, col, row0);
+        bulk_commit();
+    }
+}
+
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
@@ -216,16 +307,23 @@ inline EncodeTiledFn get_encode() {
 }
 
 inline int encode_tmap(CUtensorMap* map, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes,
-                  const cuuint32_t* box, bool half = false) {
+                  const cuuint32_t* box, bool half = false, CUtensorMapSwizzle swizzle = CU_TENSOR_MAP_SWIZZLE_128B) {
     EncodeTiledFn fn = get_encode();
     if (!fn) { set_error("cuTensorMapEncodeTiled entry point unavailable (no CUDA driver?)"); return SDC_ERR_CUDA; }
     cuuint32_t estr[5] = {1, 1, 1, 1, 1};
     CUresult r = fn(map, half ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank, const_cast<void*>(base), dims, strides_bytes, box, estr,
-                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed with CUresult %d (rank %d)", (int)r, rank); return SDC_ERR_CUDA; }
     return SDC_OK;
 }
 
+// output map of the TMA-store epilogue: out[M, Cout] row-major, box = 32 rows x 32 columns
+inline int encode_out_tmap(CUtensorMap* map, const void* out, int64_t M, int Cout, bool out_half) {
+    cuuint64_t dims[2] = {(cuuint64_t)Cout, (cuuint64_t)M};
+    cuuint64_t str[1] = {(cuuint64_t)Cout * (out_half ? 2 : 4)};
+    cuuint32_t box[2] = {32, 32};
+    return encode_tmap(map, out, 2, dims, str, box, out_half, out_half ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B);
+}
 
 }  // namespace sdc

@@ -93,7 +93,13 @@ __global__ void stem_conv7_kernel(const float* __restrict__ x, const float* __re
 
 // ---------------------------------------------------------------------------------------------- GroupNorm(1)+FiLM+SiLU
 __device__ __forceinline__ float silu(float v) { return v / (1.0f + expf(-v)); }
+// fast variant for the bandwidth-bound apply kernel: MUFU.EX2 + MUFU.RCP (relative error ~1e-6, far below the 2^-11 of the
+// operand rounding that follows)
+__device__ __forceinline__ float silu_fast(float v) { return __fdividef(v, 1.0f + __expf(-v)); }
 
+// One CTA = `pix_per_cta` pixels of one sample, 256 threads.  When 256 is a multiple of C/4 (every channel count of the
+// U-Net) a thread always meets the same 4 channels, so its scale/offset pairs live in registers and the loop is
+// 4 independent 16-byte loads -> 16 fma/ex2/rcp -> 4 stores per iteration.
 template <typename TR, typename TY>
 __global__ void __launch_bounds__(256) gn_silu_kernel(const float* __restrict__ x, const double* __restrict__ stats,
                                                       const float* __restrict__ gamma, const float* __restrict__ beta,
@@ -127,13 +133,43 @@ __global__ void __launch_bounds__(256) gn_silu_kernel(const float* __restrict__ 
     const TR* r4 = residual ? residual + row0 * C : nullptr;
     TY* y4 = y + row0 * C;
     const int total = rows * c4n;
+    if (256 % c4n == 0) {
+        const int c = (threadIdx.x % c4n) * 4;
+        const float a0 = coef[c], a1 = coef[c + 1], a2 = coef[c + 2], a3 = coef[c + 3];
+        const float b0 = coef[C + c], b1 = coef[C + c + 1], b2 = coef[C + c + 2], b3 = coef[C + c + 3];
+        int i = threadIdx.x;
+        for (; i + 3 * 256 < total; i += 4 * 256) {
+            float4 v[4], r[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) v[u] = __ldcs(x4 + i + u * 256);   // streamed once: evict first
+            if (r4) {
+#pragma unroll
+                for (int u = 0; u < 4; ++u) r[u] = load4(r4 + 4 * (int64_t)(i + u * 256));
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                v[u].x = silu_fast(fmaf(v[u].x, a0, b0)); v[u].y = silu_fast(fmaf(v[u].y, a1, b1));
+                v[u].z = silu_fast(fmaf(v[u].z, a2, b2)); v[u].w = silu_fast(fmaf(v[u].w, a3, b3));
+                if (r4) { v[u].x += r[u].x; v[u].y += r[u].y; v[u].z += r[u].z; v[u].w += r[u].w; }
+                store_operand4(y4 + 4 * (int64_t)(i + u * 256), v[u]);
+            }
+        }
+        for (; i < total; i += 256) {
+            float4 v = x4[i];
+            v.x = silu_fast(fmaf(v.x, a0, b0)); v.y = silu_fast(fmaf(v.y, a1, b1));
+            v.z = silu_fast(fmaf(v.z, a2, b2)); v.w = silu_fast(fmaf(v.w, a3, b3));
+            if (r4) { const float4 r = load4(r4 + 4 * (int64_t)i); v.x += r.x; v.y += r.y; v.z += r.z; v.w += r.w; }
+            store_operand4(y4 + 4 * (int64_t)i, v);
+        }
+        return;
+    }
     for (int i = threadIdx.x; i < total; i += blockDim.x) {
         const int c = (i % c4n) * 4;
         float4 v = x4[i];
-        v.x = silu(fmaf(v.x, coef[c], coef[C + c]));
-        v.y = silu(fmaf(v.y, coef[c + 1], coef[C + c + 1]));
-        v.z = silu(fmaf(v.z, coef[c + 2], coef[C + c + 2]));
-        v.w = silu(fmaf(v.w, coef[c + 3], coef[C + c + 3]));
+        v.x = silu_fast(fmaf(v.x, coef[c], coef[C + c]));
+        v.y = silu_fast(fmaf(v.y, coef[c + 1], coef[C + c + 1]));
+        v.z = silu_fast(fmaf(v.z, coef[c + 2], coef[C + c + 2]));
+        v.w = silu_fast(fmaf(v.w, coef[c + 3], coef[C + c + 3]));
         if (r4) { const float4 r = load4(r4 + 4 * (int64_t)i); v.x += r.x; v.y += r.y; v.z += r.z; v.w += r.w; }
         store_operand4(y4 + 4 * (int64_t)i, v);
     }
@@ -401,26 +437,36 @@ __global__ void upsample2x_kernel(const float4* __restrict__ x, float4* __restri
     }
 }
 
-// warp per pixel, Cout <= 4 dot products of length Cin; NHWC -> NCHW
+// 8 lanes per pixel (a warp covers 4 consecutive pixels), Cout <= 4 dot products of length Cin; NHWC -> NCHW
 template <typename T>
 __global__ void __launch_bounds__(256) head_conv1_kernel(const T* __restrict__ x, const float* __restrict__ w,
                                                          const float* __restrict__ bias, float* __restrict__ out, int64_t M,
                                                          int HW, int Cin, int Cout) {
-    const int lane = threadIdx.x & 31;
-    const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    if (row >= M) return;
-    float acc[4] = {0.f, 0.f, 0.f, 0.f};
-    for (int c = lane * 4; c < Cin; c += 128) {
-        const float4 xv = load4(x + row * Cin + c);
-        for (int o = 0; o < Cout; ++o) {
-            const float4 wv = *reinterpret_cast<const float4*>(w + (int64_t)o * Cin + c);
-            acc[o] += (xv.x * wv.x + xv.y * wv.y) + (xv.z * wv.z + xv.w * wv.w);
+    extern __shared__ float wsm[];   // [Cout][Cin]
+    for (int i = threadIdx.x; i < Cout * Cin; i += blockDim.x) wsm[i] = w[i];
+    __syncthreads();
+    const int sub = threadIdx.x & 7;
+    for (int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 3; row < M; row += ((int64_t)gridDim.x * blockDim.x) >> 3) {
+        float acc[4] = {0.f, 0.f, 0.f, 0.f};
+        for (int c = sub * 4; c < Cin; c += 32) {
+            const float4 xv = load4(x + row * Cin + c);
+#pragma unroll
+            for (int o = 0; o < 4; ++o) {
+                if (o < Cout) {
+                    const float4 wv = *reinterpret_cast<const float4*>(wsm + o * Cin + c);
+                    acc[o] += (xv.x * wv.x + xv.y * wv.y) + (xv.z * wv.z + xv.w * wv.w);
+                }
+            }
         }
-    }
-    const int64_t b = row / HW, p = row % HW;
-    for (int o = 0; o < Cout; ++o) {
-        const float s = warp_sum(acc[o]);
-        if (lane == 0) out[(b * Cout + o) * HW + p] = s + (bias ? bias[o] : 0.f);
+        const int64_t b = row / HW, p = row % HW;
+#pragma unroll
+        for (int o = 0; o < 4; ++o) {
+            if (o < Cout) {
+                float s = acc[o];
+                s += __shfl_xor_sync(0xffffffffu, s, 1); s += __shfl_xor_sync(0xffffffffu, s, 2); s += __shfl_xor_sync(0xffffffffu, s, 4);
+                if (sub == 0) out[(b * Cout + o) * HW + p] = s + (bias ? bias[o] : 0.f);
+            }
+        }
     }
 }
 
@@ -594,10 +640,13 @@ extern "C" int sdc_head_conv1(int prec, const void* x, const float* w, const flo
     SDC_CHECK_PREC("head_conv1");
     SDC_REQUIRE(x && w && out && B > 0 && Cin % 4 == 0 && Cout >= 1 && Cout <= 4, "head_conv1: needs Cin %% 4 == 0, Cout <= 4");
     const int64_t M = (int64_t)B * HW;
+    SDC_REQUIRE(M % 4 == 0, "head_conv1: B*HW must be a multiple of 4");   // a warp's 4 pixels are all valid or all absent
+    const unsigned grid = blocks_for(M * 8, 256);
+    const size_t sm = (size_t)Cout * Cin * sizeof(float);
     if (prec == SDC_PREC_F16)
-        head_conv1_kernel<__half><<<(unsigned)((M + 7) / 8), 256, 0, as_stream(stream)>>>((const __half*)x, w, bias, out, M, HW, Cin, Cout);
+        head_conv1_kernel<__half><<<grid, 256, sm, as_stream(stream)>>>((const __half*)x, w, bias, out, M, HW, Cin, Cout);
     else
-        head_conv1_kernel<float><<<(unsigned)((M + 7) / 8), 256, 0, as_stream(stream)>>>((const float*)x, w, bias, out, M, HW, Cin, Cout);
+        head_conv1_kernel<float><<<grid, 256, sm, as_stream(stream)>>>((const float*)x, w, bias, out, M, HW, Cin, Cout);
     SDC_LAUNCHED();
     return SDC_OK;
 }
