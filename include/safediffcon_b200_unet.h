@@ -49,6 +49,12 @@ int sdc_conv3x3_row(int prec, const void* a0, int c0, const void* a1, int c1, co
 int sdc_stem_conv7(int prec, const float* x, const float* w, const float* bias, void* out, int B, int Cin, int H, int W,
                    int Cout, void* stream);
 
+/* Tensor-core stem, step 1: im2col of the NCHW fp32 input for the 7x7 pad-3 convolution.  a:[B*H*W, kp] operand rows,
+ * columns [0, Cin*49) = high part of the patch (index ci*49 + ky*7 + kx), [kp/2, kp/2 + Cin*49) = low part
+ * (x - high), zeros elsewhere.  Step 2 is sdc_conv_gemm(kind 0, c0 = kp) with the stem weight repeated in both ranges:
+ * the product sees x to ~2^-22 with fp16 / tf32 operands. */
+int sdc_stem_im2col(int prec, const float* x, void* a, int B, int Cin, int H, int W, int kp, void* stream);
+
 /* GroupNorm(1, C) apply + FiLM + SiLU (+ residual), Block.forward (unet.py:138-147) and ResnetBlock's sum (:180):
  * y = silu(((x - mean_b) * rstd_b * gamma_c + beta_c) * (scale_bc + 1) + shift_bc) + res ; mean/rstd from
  * stats[b] = (sum, sumsq) over C*HW elements, eps 1e-5, biased variance.  scale_shift: [n_t, 2C] rows
@@ -66,9 +72,24 @@ int sdc_channel_layernorm(int prec, const void* x, int x_operand, const float* g
 
 /* LinearAttention core (unet.py:202-222) on fp32 qkv:[B*n, 384] rows (q | k | v, each heads*32 channels):
  * q <- softmax_d(q) * 32^-0.5 ; k <- softmax_n(k) ; ctx = k v^T ; out[B*n, 128] = ctx^T q, an operand.
- * workspace: >= sdc_linear_attention_workspace(B) bytes. */
+ * n (pixels per sample) must be a multiple of 32.  workspace: >= sdc_linear_attention_workspace(B) bytes; on return it
+ * holds per (sample, head) ctx[32][32] | kmax[32] | ksum[32], which sdc_linear_attention_bwd consumes. */
 int64_t sdc_linear_attention_workspace(int B);
 int sdc_linear_attention(int prec, const float* qkv, void* out, void* workspace, int B, int n, void* stream);
+
+/* Fused LinearAttention path (same math as sdc_conv_gemm(qkv) + sdc_linear_attention + sdc_conv_gemm(to_out), without ever
+ * materialising the [B*n, 128] attention tensor):
+ *   1. sdc_conv1x1_qkv: the bias-free qkv projection (unet.py:189,203) whose epilogue applies q <- softmax_d(q) * 32^-0.5 to
+ *      the q columns in registers; writes qs[B*H*W, hidden] (operand precision) and kv[B*H*W, 2*hidden] (fp32: k | v).
+ *   2. sdc_linear_attention_context: ctx = softmax_n(k) v^T per (sample, head) from rows k + i*ld, v + i*ld into the workspace.
+ *   3. sdc_linear_attention_fold: per-sample folded projection Wf_b[Cout, 128] = W_out (x) ctx_b (operand precision).
+ *   4. sdc_conv1x1_per_sample: out[B*H*W, Cout] = qs * Wf_b^T + bias (H*W must be a multiple of 128). */
+int sdc_conv1x1_qkv(int prec, const void* a, int c, const void* w_packed, void* q_out, float* kv_out, int B, int H, int W, int hidden,
+                    void* stream);
+int sdc_linear_attention_context(const float* k, const float* v, int ld, void* workspace, int B, int n, void* stream);
+int sdc_linear_attention_fold(int prec, const void* workspace, const float* w_out, void* w_folded, int B, int Cout, void* stream);
+int sdc_conv1x1_per_sample(int prec, const void* a, int c, const void* w_per_sample, const float* bias, void* out, int operand_out,
+                           int B, int H, int W, int Cout, void* stream);
 
 /* Full softmax attention core (unet.py:239-258) for n <= 32 tokens: out[B*n, 128], an operand. */
 int sdc_attention(int prec, const float* qkv, void* out, int B, int n, void* stream);

@@ -48,6 +48,9 @@ struct GemmParams {
     int tiles_n;         // Cout / bn
     int tiles_total;     // tiles_m * tiles_n, tile id = m * tiles_n + n (consecutive ids share the A window)
     int tiles_per_cta;
+    int q_cols;          // > 0: LinearAttention qkv mode -- output columns [0, q_cols) get softmax_d * 32^-0.5 per 32-column head and
+                         //      go to a second tensor (map_q, operand precision); columns [q_cols, Cout) go to `out` (fp32)
+    int w_sample_rows;   // > 0: per-sample weights -- sample b uses weight rows [b * w_sample_rows, (b + 1) * w_sample_rows)
     const float* bias;       // [Cout] or null
     const void* residual;    // [M, Cout] in the operand precision, or null (added after bias)
     void* out;               // [M, Cout]
@@ -65,7 +68,7 @@ struct GemmParams {
 // the leader's `acc_empty`.
 template <bool HALF, bool PAIR>
 __device__ __forceinline__ void conv_gemm_body(const CUtensorMap& map_a0, const CUtensorMap& map_a1, const CUtensorMap& map_w,
-                                               const CUtensorMap& map_out, const GemmParams& p) {
+                                               const CUtensorMap& map_out, const CUtensorMap& map_q, const GemmParams& p) {
     using Op = Operand<HALF>;
     using act_t = typename ActT<HALF>::type;
     constexpr int BK = Op::kBK;
@@ -98,6 +101,7 @@ __device__ __forceinline__ void conv_gemm_body(const CUtensorMap& map_a0, const 
         if (p.c1) tma_prefetch_desc(&map_a1);
         tma_prefetch_desc(&map_w);
         tma_prefetch_desc(&map_out);
+        if (p.q_cols) tma_prefetch_desc(&map_q);
         for (int s = 0; s < p.stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
         for (int b = 0; b < 2; ++b) { mbar_init(&acc_full[b], 1); mbar_init(&acc_empty[b], PAIR ? 8 : 4); }
         fence_barrier_init();
@@ -143,8 +147,9 @@ __device__ __forceinline__ void conv_gemm_body(const CUtensorMap& map_a0, const 
                         if constexpr (PAIR) tma_load_4d_2sm(sa, ma, &full_bar[s], cseg, dx, h0 + dy, b0);
                         else tma_load_4d(sa, ma, &full_bar[s], cseg, dx, h0 + dy, b0);
                     }
-                    if constexpr (PAIR) tma_load_2d_2sm(sb, &map_w, &full_bar[s], tap * ctot + cc, nt * p.bn + (int)rank * b_rows);
-                    else tma_load_2d(sb, &map_w, &full_bar[s], tap * ctot + cc, nt * p.bn);
+                    const int wrow = nt * p.bn + b0 * p.w_sample_rows;   // per-sample weights: tiles never straddle samples (host check)
+                    if constexpr (PAIR) tma_load_2d_2sm(sb, &map_w, &full_bar[s], tap * ctot + cc, wrow + (int)rank * b_rows);
+                    else tma_load_2d(sb, &map_w, &full_bar[s], tap * ctot + cc, wrow);
                 }
             }
         }
@@ -205,8 +210,9 @@ __device__ __forceinline__ void conv_gemm_body(const CUtensorMap& map_a0, const 
                 const uint32_t sb = stg + (nchunk & 1u) * STG_BUF;
                 const act_t* rrow = resid ? resid + (size_t)m * p.Cout + col : nullptr;
                 if (m_w < p.M) {
-                    if (out_half) epilogue_chunk<true, act_t>(taddr, sb, &map_out, col, m_w, row_ok, p.bias, rrow, false, s1, s2, lane);
-                    else epilogue_chunk<false, act_t>(taddr, sb, &map_out, col, m_w, row_ok, p.bias, rrow, p.operand_out != 0, s1, s2, lane);
+                    if (col < p.q_cols) epilogue_chunk_qsoftmax<HALF>(taddr, sb, &map_q, col, m_w, lane);
+                    else if (out_half) epilogue_chunk<true, act_t>(taddr, sb, &map_out, col - p.q_cols, m_w, row_ok, p.bias, rrow, false, s1, s2, lane);
+                    else epilogue_chunk<false, act_t>(taddr, sb, &map_out, col - p.q_cols, m_w, row_ok, p.bias, rrow, p.operand_out != 0, s1, s2, lane);
                 }
             }
             // accumulator buffer fully read -> hand it back to the MMA warp
@@ -239,14 +245,16 @@ __device__ __forceinline__ void conv_gemm_body(const CUtensorMap& map_a0, const 
 template <bool HALF>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ CUtensorMap map_a1,
-                 const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUtensorMap map_out, const GemmParams p) {
-    conv_gemm_body<HALF, false>(map_a0, map_a1, map_w, map_out, p);
+                 const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUtensorMap map_out,
+                 const __grid_constant__ CUtensorMap map_q, const GemmParams p) {
+    conv_gemm_body<HALF, false>(map_a0, map_a1, map_w, map_out, map_q, p);
 }
 template <bool HALF>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
 conv_gemm2_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ CUtensorMap map_a1,
-                  const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUtensorMap map_out, const GemmParams p) {
-    conv_gemm_body<HALF, true>(map_a0, map_a1, map_w, map_out, p);
+                  const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUtensorMap map_out,
+                  const __grid_constant__ CUtensorMap map_q, const GemmParams p) {
+    conv_gemm_body<HALF, true>(map_a0, map_a1, map_w, map_out, map_q, p);
 }
 
 // ------------------------------------------------------------------------------------------ host side
@@ -272,9 +280,9 @@ static int encode_act(CUtensorMap* map, const void* a, int kind, int B, int H, i
 
 using namespace sdc;
 
-extern "C" int sdc_conv_gemm(int prec, int kind, const void* a0, int c0, const void* a1, int c1, const void* w_packed,
-                             const float* bias, const void* residual, void* out, double* stats, int operand_out, int B, int H,
-                             int W, int Cout, void* stream) {
+static int conv_gemm_launch(int prec, int kind, const void* a0, int c0, const void* a1, int c1, const void* w_packed,
+                            const float* bias, const void* residual, void* out, double* stats, int operand_out, int B, int H,
+                            int W, int Cout, void* q_out, int q_cols, int per_sample_weights, void* stream) {
     SDC_REQUIRE(prec == SDC_PREC_TF32 || prec == SDC_PREC_F16, "conv_gemm: precision %d", prec);
     const bool half = prec == SDC_PREC_F16;
     const int BK = half ? 64 : 32;
@@ -291,7 +299,11 @@ extern "C" int sdc_conv_gemm(int prec, int kind, const void* a0, int c0, const v
     SDC_REQUIRE(bb * bh * W == BM && (H * W) % 32 == 0, "conv_gemm: H*W=%d cannot be tiled into 128-pixel blocks", H * W);
     SDC_REQUIRE(bb == 1 || bh == H, "conv_gemm: tile spans images only when it holds whole images");
     int bn = Cout % 256 == 0 ? 256 : (Cout % 128 == 0 ? 128 : (Cout % 64 == 0 ? 64 : 32));
+    SDC_REQUIRE(q_cols >= 0 && q_cols % 32 == 0 && q_cols < Cout && (q_cols == 0 || (q_out && !bias && !residual && !stats && !operand_out)),
+                "conv_gemm: qkv mode needs q_out, q_cols %% 32 == 0 and a plain fp32 kv output");
     GemmParams p{};
+    p.q_cols = q_cols;
+    p.w_sample_rows = per_sample_weights ? Cout : 0;
     p.kind = kind; p.M = B * H * W; p.Cout = Cout; p.bn = bn; p.H = H; p.W = W; p.bh = bh; p.bb = bb;
     p.c0 = c0; p.c1 = c1; p.operand_out = operand_out; p.hw_per_sample = H * W;
     p.bias = bias; p.residual = residual; p.out = out; p.stats = stats;
@@ -304,7 +316,9 @@ extern "C" int sdc_conv_gemm(int prec, int kind, const void* a0, int c0, const v
     static const bool allow_pair = []() { const char* e = getenv("SDC_NO_2CTA"); return !(e && e[0] == '1'); }();
     const int tiles_m = (p.M + BM - 1) / BM;
     // CTA pairs (cta_group::2) whenever there are at least as many 256-row pair tiles as SM pairs
-    const bool pair = allow_pair && ((tiles_m + 1) / 2) * (Cout / bn) >= n_sm / 2;
+    // per-sample weights: every (pair) tile must lie inside one sample
+    SDC_REQUIRE(!per_sample_weights || (H * W) % BM == 0, "conv_gemm: per-sample weights need H*W %% 128 == 0");
+    const bool pair = allow_pair && ((tiles_m + 1) / 2) * (Cout / bn) >= n_sm / 2 && (!per_sample_weights || (H * W) % (2 * BM) == 0);
     const int stage_bytes = A_BYTES + (pair ? bn / 2 : bn) * 128;
     int stages = (190 * 1024) / stage_bytes;
     if (stages > 8) stages = 8;
@@ -323,14 +337,15 @@ extern "C" int sdc_conv_gemm(int prec, int kind, const void* a0, int c0, const v
     if (c1) { rc = encode_act(&ma1, a1, kind, B, H, W, c1, bh, bb, half); if (rc) return rc; } else ma1 = ma0;
     const int taps = kind == 1 ? 9 : (kind == 2 ? 4 : 1);
     const cuuint64_t ktot = (cuuint64_t)taps * (c0 + c1);
-    cuuint64_t wd[2] = {ktot, (cuuint64_t)Cout};
+    cuuint64_t wd[2] = {ktot, (cuuint64_t)Cout * (cuuint64_t)(per_sample_weights ? B : 1)};
     cuuint64_t ws[1] = {ktot * (half ? 2 : 4)};
     cuuint32_t wb[2] = {(cuuint32_t)BK, (cuuint32_t)(pair ? bn / 2 : bn)};
     rc = encode_tmap(&mw, w_packed, 2, wd, ws, wb, half);
     if (rc) return rc;
-    CUtensorMap mo;
-    rc = encode_out_tmap(&mo, out, p.M, Cout, half && operand_out);
+    CUtensorMap mo, mq;
+    rc = encode_out_tmap(&mo, out, p.M, Cout - q_cols, half && operand_out);
     if (rc) return rc;
+    if (q_cols) { rc = encode_out_tmap(&mq, q_out, p.M, q_cols, half); if (rc) return rc; } else mq = mo;
 
     static bool attr_set = false;
     if (!attr_set) {
@@ -343,12 +358,32 @@ extern "C" int sdc_conv_gemm(int prec, int kind, const void* a0, int c0, const v
     const int grid = (p.tiles_total + p.tiles_per_cta - 1) / p.tiles_per_cta;
     cudaStream_t st = as_stream(stream);
     if (pair) {
-        if (half) conv_gemm2_kernel<true><<<2 * grid, GEMM_THREADS, smem_bytes, st>>>(ma0, ma1, mw, mo, p);
-        else conv_gemm2_kernel<false><<<2 * grid, GEMM_THREADS, smem_bytes, st>>>(ma0, ma1, mw, mo, p);
+        if (half) conv_gemm2_kernel<true><<<2 * grid, GEMM_THREADS, smem_bytes, st>>>(ma0, ma1, mw, mo, mq, p);
+        else conv_gemm2_kernel<false><<<2 * grid, GEMM_THREADS, smem_bytes, st>>>(ma0, ma1, mw, mo, mq, p);
     } else {
-        if (half) conv_gemm_kernel<true><<<grid, GEMM_THREADS, smem_bytes, st>>>(ma0, ma1, mw, mo, p);
-        else conv_gemm_kernel<false><<<grid, GEMM_THREADS, smem_bytes, st>>>(ma0, ma1, mw, mo, p);
+        if (half) conv_gemm_kernel<true><<<grid, GEMM_THREADS, smem_bytes, st>>>(ma0, ma1, mw, mo, mq, p);
+        else conv_gemm_kernel<false><<<grid, GEMM_THREADS, smem_bytes, st>>>(ma0, ma1, mw, mo, mq, p);
     }
     SDC_LAUNCHED();
     return SDC_OK;
+}
+
+extern "C" int sdc_conv_gemm(int prec, int kind, const void* a0, int c0, const void* a1, int c1, const void* w_packed,
+                             const float* bias, const void* residual, void* out, double* stats, int operand_out, int B, int H,
+                             int W, int Cout, void* stream) {
+    return conv_gemm_launch(prec, kind, a0, c0, a1, c1, w_packed, bias, residual, out, stats, operand_out, B, H, W, Cout, nullptr, 0, 0,
+                            stream);
+}
+
+extern "C" int sdc_conv1x1_qkv(int prec, const void* a, int c, const void* w_packed, void* q_out, float* kv_out, int B, int H, int W,
+                               int hidden, void* stream) {
+    SDC_REQUIRE(hidden > 0 && hidden % 32 == 0 && q_out && kv_out, "conv1x1_qkv: bad arguments");
+    return conv_gemm_launch(prec, 0, a, c, nullptr, 0, w_packed, nullptr, nullptr, kv_out, nullptr, 0, B, H, W, 3 * hidden, q_out, hidden, 0,
+                            stream);
+}
+
+extern "C" int sdc_conv1x1_per_sample(int prec, const void* a, int c, const void* w_per_sample, const float* bias, void* out,
+                                      int operand_out, int B, int H, int W, int Cout, void* stream) {
+    return conv_gemm_launch(prec, 0, a, c, nullptr, 0, w_per_sample, bias, nullptr, out, nullptr, operand_out, B, H, W, Cout, nullptr, 0, 1,
+                            stream);
 }

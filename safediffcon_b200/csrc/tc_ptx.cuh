@@ -204,6 +204,52 @@ __device__ __forceinline__ void epilogue_chunk(uint32_t taddr, uint32_t stg, con
     }
 }
 
+// Variant for the q columns of a LinearAttention qkv projection: the 32 accumulator columns of a chunk are exactly one head's
+// logits of this lane's pixel, so q <- softmax_d(q) * 32^-0.5 (/root/reference/1D/model/unet.py:206,209) is applied in
+// registers and stored in the operand precision (it is the A operand of the folded output projection).
+template <bool OUT_HALF>
+__device__ __forceinline__ void epilogue_chunk_qsoftmax(uint32_t taddr, uint32_t stg, const CUtensorMap* map_q, int col, int row0,
+                                                        int lane) {
+    uint32_t r[32];
+    tmem_ld32(taddr, r);
+    float v[32];
+    float mx = __uint_as_float(r[0]);
+#pragma unroll
+    for (int j = 0; j < 32; ++j) { v[j] = __uint_as_float(r[j]); mx = fmaxf(mx, v[j]); }
+    float den = 0.f;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) { v[j] = expf(v[j] - mx); den += v[j]; }
+    const float sc = 0.17677669529663687f / den;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] *= sc;
+    if constexpr (OUT_HALF) {
+        const uint32_t rowa = stg + (uint32_t)lane * 64u, sw = ((uint32_t)lane >> 1) & 3u;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            uint32_t w[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const __half2 h = __floats2half2_rn(v[8 * j + 2 * k], v[8 * j + 2 * k + 1]);
+                w[k] = *reinterpret_cast<const uint32_t*>(&h);
+            }
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(rowa + (((uint32_t)j ^ sw) << 4)), "r"(w[0]), "r"(w[1]),
+                         "r"(w[2]), "r"(w[3]) : "memory");
+        }
+    } else {
+        const uint32_t rowa = stg + (uint32_t)lane * 128u, sw = (uint32_t)lane & 7u;
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+            sts128(rowa + (((uint32_t)j ^ sw) << 4),
+                   make_float4(to_tf32(v[4 * j]), to_tf32(v[4 * j + 1]), to_tf32(v[4 * j + 2]), to_tf32(v[4 * j + 3])));
+    }
+    fence_proxy_async();
+    __syncwarp();
+    if (lane == 0) {
+        tma_store_2d(map_q, stg, col, row0);
+        bulk_commit();
+    }
+}
+
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }

@@ -91,6 +91,50 @@ __global__ void stem_conv7_kernel(const float* __restrict__ x, const float* __re
     }
 }
 
+// ---------------------------------------------------------------------------------------------- stem im2col (tensor-core stem)
+// A[m, :] for the 7x7 pad-3 stem as a GEMM operand: columns [0, K) hold the HIGH part of the patch (K = Cin*49, index
+// ci*49 + ky*7 + kx), columns [KH, KH+K) the LOW part (x - high, rounded to the operand precision), the rest zeros.
+// With the stem weights repeated in both column ranges the tcgen05 GEMM sees the fp32 input to ~2^-22 although its
+// operands are fp16 / tf32.  One CTA = one image row; the 7 input rows it needs are staged in shared memory.
+template <typename T>
+__global__ void __launch_bounds__(256) stem_im2col_kernel(const float* __restrict__ x, T* __restrict__ a, int Cin, int H, int W,
+                                                          int kp) {
+    extern __shared__ float xs[];   // [Cin][7][W + 6], then the patch-offset table int[K]
+    const int b = blockIdx.x / H, h = blockIdx.x % H;
+    const int WP = W + 6, K = Cin * 49, KH = kp / 2;
+    int* koff = reinterpret_cast<int*>(xs + Cin * 7 * WP);   // column k -> offset of (ci, ky, kx) inside the window
+    for (int k = threadIdx.x; k < K; k += blockDim.x) {
+        const int ci = k / 49, t = k - ci * 49, ky = t / 7, kx = t - ky * 7;
+        koff[k] = (ci * 7 + ky) * WP + kx;
+    }
+    for (int i = threadIdx.x; i < Cin * 7 * WP; i += blockDim.x) {
+        const int ci = i / (7 * WP), r = (i / WP) % 7, c = i % WP;
+        const int hh = h + r - 3, ww = c - 3;
+        xs[i] = (hh >= 0 && hh < H && ww >= 0 && ww < W) ? x[(((int64_t)b * Cin + ci) * H + hh) * W + ww] : 0.f;
+    }
+    __syncthreads();
+    const int vpr = kp / 4;   // 4-element groups per row
+    T* arow = a + ((int64_t)b * H + h) * W * kp;
+    for (int i = threadIdx.x; i < W * vpr; i += blockDim.x) {
+        const int w = i / vpr, k0 = (i % vpr) * 4;
+        float v[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            int k = k0 + j;
+            const bool low = k >= KH;
+            if (low) k -= KH;
+            float val = 0.f;
+            if (k < K) {
+                const float xv = xs[koff[k] + w];
+                const float hi = (float)to_operand(xv, T());
+                val = low ? xv - hi : hi;
+            }
+            v[j] = val;
+        }
+        store_operand4(arow + (int64_t)w * kp + k0, make_float4(v[0], v[1], v[2], v[3]));
+    }
+}
+
 // ---------------------------------------------------------------------------------------------- GroupNorm(1)+FiLM+SiLU
 __device__ __forceinline__ float silu(float v) { return v / (1.0f + expf(-v)); }
 // fast variant for the bandwidth-bound apply kernel: MUFU.EX2 + MUFU.RCP (relative error ~1e-6, far below the 2^-11 of the
@@ -239,21 +283,22 @@ constexpr int LA_CTX = LA_D * LA_D + 2 * LA_D;
 // 4 pixel groups x 64 threads; each thread owns a 4x4 block of the 32x32 context in registers (16 FMA per two
 // 16-byte shared loads).  k is read twice (column max, then exp-weighted accumulation), v once.
 constexpr int LA_CHUNK = 128;
-__global__ void __launch_bounds__(256) linattn_context_kernel(const float* __restrict__ qkv, float* __restrict__ ctx, int n) {
+// k / v rows: kbase / vbase + pixel * ld (+ head * 32); ld = 384 for a packed qkv tensor, 256 for the kv tensor of the fused path
+__global__ void __launch_bounds__(256) linattn_context_kernel(const float* __restrict__ kbase, const float* __restrict__ vbase, int ld,
+                                                              float* __restrict__ ctx, int n) {
     __shared__ __align__(16) float ek[LA_CHUNK][LA_D];
     __shared__ __align__(16) float vs[LA_CHUNK][LA_D];
     __shared__ float red[8][LA_D];
     __shared__ float kmax[LA_D];
     const int b = blockIdx.x / LA_HEADS, h = blockIdx.x % LA_HEADS;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const float* base = qkv + (int64_t)b * n * LA_QKV;
-    const float* kp = base + LA_HID + h * LA_D;
-    const float* vp = base + 2 * LA_HID + h * LA_D;
+    const float* kp = kbase + (int64_t)b * n * ld + h * LA_D;
+    const float* vp = vbase + (int64_t)b * n * ld + h * LA_D;
     {   // column max of k over the n pixels: 8 pixels x 4 channels per thread and iteration (16-byte loads)
         const int c4 = (tid & 7) * 4, r = tid >> 3;  // 32 pixel rows per pass
         float4 m = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
         for (int i = r; i < n; i += 32) {
-            const float4 kv = *reinterpret_cast<const float4*>(kp + (int64_t)i * LA_QKV + c4);
+            const float4 kv = *reinterpret_cast<const float4*>(kp + (int64_t)i * ld + c4);
             m.x = fmaxf(m.x, kv.x); m.y = fmaxf(m.y, kv.y); m.z = fmaxf(m.z, kv.z); m.w = fmaxf(m.w, kv.w);
         }
         // reduce over the 4 pixel rows held by one warp (lanes with equal lane&7), then across the 8 warps
@@ -287,8 +332,8 @@ __global__ void __launch_bounds__(256) linattn_context_kernel(const float* __res
             const int r = rr + lr;
             float4 kv = make_float4(0.f, 0.f, 0.f, 0.f), vv = kv;
             if (r < cnt) {
-                kv = *reinterpret_cast<const float4*>(kp + (int64_t)(n0 + r) * LA_QKV + lc4);
-                vv = *reinterpret_cast<const float4*>(vp + (int64_t)(n0 + r) * LA_QKV + lc4);
+                kv = *reinterpret_cast<const float4*>(kp + (int64_t)(n0 + r) * ld + lc4);
+                vv = *reinterpret_cast<const float4*>(vp + (int64_t)(n0 + r) * ld + lc4);
                 kv = make_float4(expf(kv.x - km.x), expf(kv.y - km.y), expf(kv.z - km.z), expf(kv.w - km.w));
             }
             *reinterpret_cast<float4*>(&ek[r][lc4]) = kv;   // rows >= cnt hold zeros: they add nothing
@@ -337,46 +382,153 @@ __global__ void __launch_bounds__(256) linattn_context_kernel(const float* __res
     }
 }
 
-// out[n, h*32+e] = 32^-0.5 * sum_d ctx[d,e] * softmax_d(q[n,:])[d]      grid = (B*heads, ceil(n/256)), thread per pixel
-template <typename T>
+// out[n, h*32+e] = 32^-0.5 * sum_d ctx[d,e] * softmax_d(q[n,:])[d]
+// One CTA = P consecutive pixels of one sample x all 4 heads, 256 threads = 8 warps, warp w -> head w & 3, pixel tiles of 16.
+// The q rows (512 bytes per pixel) are staged through shared memory with coalesced 16-byte loads; the per-head
+// [16 px x 32] x [32 x 32] products run on mma.sync.m16n8k8 TF32 (operands rounded to nearest first, fp32 accumulate) --
+// a K = N = 32 contraction is far too small for a tcgen05 tile, and the scalar-FMA version of this kernel was bound by
+// shared-memory operand reads (3.3 ms per step at B = 1024).  In the A-fragment layout a pixel's 32 logits sit in the
+// 4 lanes of a quad, so softmax_d costs two shuffles.  Results leave through the same staging tile (256 / 512 bytes
+// per pixel, coalesced).  Strides: q tile 132 floats, context 40 floats per d-row (both conflict free for the fragments).
+constexpr int LA_QLD = LA_HID + 4;
+constexpr int LA_CLD = 40;
+__device__ __forceinline__ void mma_tf32_16x8x8(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3]) : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+template <int P, typename T>
 __global__ void __launch_bounds__(256) linattn_apply_kernel(const float* __restrict__ qkv, const float* __restrict__ ctx,
                                                             T* __restrict__ out, int n) {
-    __shared__ __align__(16) float cs[LA_D][LA_D];
-    const int b = blockIdx.x / LA_HEADS, h = blockIdx.x % LA_HEADS;
-    for (int i = threadIdx.x; i < LA_D * LA_D; i += blockDim.x) cs[i >> 5][i & 31] = ctx[(int64_t)blockIdx.x * LA_CTX + i];
-    __syncthreads();
-    const int i = blockIdx.y * 256 + threadIdx.x;
-    if (i >= n) return;
-    const float* qp = qkv + ((int64_t)b * n + i) * LA_QKV + h * LA_D;
-    float q[LA_D];
-#pragma unroll
-    for (int j = 0; j < LA_D; j += 4) {
-        const float4 t = *reinterpret_cast<const float4*>(qp + j);
-        q[j] = t.x; q[j + 1] = t.y; q[j + 2] = t.z; q[j + 3] = t.w;
+    extern __shared__ __align__(16) float sm_apply[];
+    float* cs = sm_apply;                                  // [4][32][LA_CLD] contexts of this sample (TF32-rounded)
+    float* qs = sm_apply + LA_HEADS * LA_D * LA_CLD;       // [P][LA_QLD] q rows, later the output rows
+    const int tiles = n / P;
+    const int b = blockIdx.x / tiles, p0 = (blockIdx.x % tiles) * P;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (int i = tid; i < LA_HEADS * LA_D * LA_D; i += 256) {
+        const int hh = i >> 10, d = (i >> 5) & 31, e = i & 31;
+        cs[(hh * LA_D + d) * LA_CLD + e] = to_tf32(ctx[((int64_t)b * LA_HEADS + hh) * LA_CTX + (i & 1023)]);
     }
-    float mx = q[0];
+    const float* qbase = qkv + ((int64_t)b * n + p0) * LA_QKV;
+    for (int idx = tid; idx < P * 32; idx += 256) {        // P pixels x 32 float4
+        const int px = idx >> 5, c4 = (idx & 31) * 4;
+        *reinterpret_cast<float4*>(qs + px * LA_QLD + c4) = __ldcs(reinterpret_cast<const float4*>(qbase + (int64_t)px * LA_QKV + c4));
+    }
+    __syncthreads();
+    const int h = warp & 3, g = lane >> 2, t = lane & 3;
+    // B fragments of this head's context: b0 = ctx[8k + t][8j + g], b1 = ctx[8k + t + 4][8j + g]
+    uint32_t bf[4][4][2];
+    const float* ch = cs + h * LA_D * LA_CLD;
 #pragma unroll
-    for (int j = 1; j < LA_D; ++j) mx = fmaxf(mx, q[j]);
-    float den = 0.f;
+    for (int k = 0; k < 4; ++k)
 #pragma unroll
-    for (int j = 0; j < LA_D; ++j) { q[j] = expf(q[j] - mx); den += q[j]; }
-    const float sc = 0.17677669529663687f / den;  // 32^-0.5 / sum
-    float o[LA_D];
+        for (int j = 0; j < 4; ++j) {
+            bf[k][j][0] = __float_as_uint(ch[(8 * k + t) * LA_CLD + 8 * j + g]);
+            bf[k][j][1] = __float_as_uint(ch[(8 * k + t + 4) * LA_CLD + 8 * j + g]);
+        }
+    float acc[P / 32][4][4];   // this warp's pixel tiles (tile = (warp >> 2) + 2 * i) x 4 n-tiles x C fragment
 #pragma unroll
-    for (int e = 0; e < LA_D; ++e) o[e] = 0.f;
+    for (int i = 0; i < P / 32; ++i) {
+        const int r0 = ((warp >> 2) + 2 * i) * 16;
+        // A fragment source: rows r0 + g and r0 + g + 8, logits d = 8k + t and 8k + t + 4
+        float qa[2][8];
 #pragma unroll
-    for (int d = 0; d < LA_D; ++d) {
-        const float w = q[d] * sc;
+        for (int rr = 0; rr < 2; ++rr)
 #pragma unroll
-        for (int e = 0; e < LA_D; e += 4) {
-            const float4 c4 = *reinterpret_cast<const float4*>(&cs[d][e]);
-            o[e] = fmaf(w, c4.x, o[e]); o[e + 1] = fmaf(w, c4.y, o[e + 1]);
-            o[e + 2] = fmaf(w, c4.z, o[e + 2]); o[e + 3] = fmaf(w, c4.w, o[e + 3]);
+            for (int k = 0; k < 4; ++k) {
+                qa[rr][2 * k] = qs[(r0 + g + 8 * rr) * LA_QLD + h * LA_D + 8 * k + t];
+                qa[rr][2 * k + 1] = qs[(r0 + g + 8 * rr) * LA_QLD + h * LA_D + 8 * k + t + 4];
+            }
+#pragma unroll
+        for (int rr = 0; rr < 2; ++rr) {
+            float mx = qa[rr][0];
+#pragma unroll
+            for (int k = 1; k < 8; ++k) mx = fmaxf(mx, qa[rr][k]);
+            mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
+            mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
+            float den = 0.f;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) { qa[rr][k] = expf(qa[rr][k] - mx); den += qa[rr][k]; }
+            den += __shfl_xor_sync(0xffffffffu, den, 1);
+            den += __shfl_xor_sync(0xffffffffu, den, 2);
+            const float sc = 0.17677669529663687f / den;  // 32^-0.5 / sum
+#pragma unroll
+            for (int k = 0; k < 8; ++k) qa[rr][k] = to_tf32(qa[rr][k] * sc);
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+#pragma unroll
+            for (int v = 0; v < 4; ++v) acc[i][j][v] = 0.f;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const uint32_t a[4] = {__float_as_uint(qa[0][2 * k]), __float_as_uint(qa[1][2 * k]), __float_as_uint(qa[0][2 * k + 1]),
+                                   __float_as_uint(qa[1][2 * k + 1])};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) mma_tf32_16x8x8(acc[i][j], a, bf[k][j][0], bf[k][j][1]);
         }
     }
-    T* op = out + ((int64_t)b * n + i) * LA_HID + h * LA_D;
+    __syncthreads();   // all q reads done: the tile becomes the output staging
+    T* os = reinterpret_cast<T*>(qs);
+    constexpr int OLD = LA_QLD * (int)(sizeof(float) / sizeof(T));   // same 528-byte row pitch in elements of T
 #pragma unroll
-    for (int e = 0; e < LA_D; e += 4) store_operand4(op + e, make_float4(o[e], o[e + 1], o[e + 2], o[e + 3]));
+    for (int i = 0; i < P / 32; ++i) {
+        const int r0 = ((warp >> 2) + 2 * i) * 16;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            // C fragment: (row g, cols 2t, 2t+1), (row g + 8, cols 2t, 2t+1) of n-tile j
+            T* o0 = os + (r0 + g) * OLD + h * LA_D + 8 * j + 2 * t;
+            T* o1 = os + (r0 + g + 8) * OLD + h * LA_D + 8 * j + 2 * t;
+            o0[0] = to_operand(acc[i][j][0], T()); o0[1] = to_operand(acc[i][j][1], T());
+            o1[0] = to_operand(acc[i][j][2], T()); o1[1] = to_operand(acc[i][j][3], T());
+        }
+    }
+    __syncthreads();
+    // coalesced copy-out: P rows of 128 * sizeof(T) bytes
+    constexpr int V = 16 / (int)sizeof(T);          // elements per 16-byte vector
+    constexpr int VPR = LA_HID / V;                 // vectors per row
+    T* obase = out + ((int64_t)b * n + p0) * LA_HID;
+    for (int idx = tid; idx < P * VPR; idx += 256) {
+        const int r = idx / VPR, c = (idx % VPR) * V;
+        *reinterpret_cast<uint4*>(obase + (int64_t)r * LA_HID + c) = *reinterpret_cast<const uint4*>(os + r * OLD + c);
+    }
+}
+
+// Folded output projection of LinearAttention: out_proj[n, co] = sum_{h,e} W[co, 32h + e] * sum_d ctx_h[d, e] qs_h[n, d]
+//                                                            = sum_{h,d} qs_h[n, d] * Wf_b[co, 32h + d],
+// Wf_b[co, 32h + d] = sum_e W[co, 32h + e] ctx_{b,h}[d, e]: a per-sample [Cout, 128] weight.  The context apply then IS the 1x1
+// output projection (one tcgen05 GEMM with per-sample weights) and the [B*n, 128] attention tensor is never materialised.
+// grid = B, 256 threads: the sample's four contexts are loaded once, then 32 output channels per iteration; thread -> column
+// hd = tid & 127 (its 32 context values live in registers) and 16 of the block's 32 output channels.
+template <typename T>
+__global__ void __launch_bounds__(256) linattn_fold_kernel(const float* __restrict__ ws, const float* __restrict__ w_out,
+                                                           T* __restrict__ wf, int Cout) {
+    __shared__ float cs[LA_HEADS * LA_D][LA_D + 1];   // ctx[h*32 + d][e], padded: lanes walk d
+    __shared__ __align__(16) float wsm[32][LA_HID];
+    const int b = blockIdx.x;
+    for (int i = threadIdx.x; i < LA_HEADS * LA_D * LA_D; i += 256)
+        cs[i >> 5][i & 31] = ws[((int64_t)b * LA_HEADS + (i >> 10)) * LA_CTX + (i & 1023)];
+    __syncthreads();
+    const int hd = threadIdx.x & 127, h = hd >> 5, half_id = threadIdx.x >> 7;
+    float c[LA_D];
+#pragma unroll
+    for (int e = 0; e < LA_D; ++e) c[e] = cs[hd][e];
+    for (int co0 = 0; co0 < Cout; co0 += 32) {
+        __syncthreads();
+        for (int i = threadIdx.x; i < 32 * LA_HID / 4; i += 256)
+            reinterpret_cast<float4*>(&wsm[0][0])[i] = __ldg(reinterpret_cast<const float4*>(w_out + (int64_t)co0 * LA_HID) + i);
+        __syncthreads();
+#pragma unroll 4
+        for (int r = 0; r < 16; ++r) {
+            const int co = half_id * 16 + r;
+            float acc = 0.f;
+#pragma unroll
+            for (int e = 0; e < LA_D; e += 4) {
+                const float4 wv = *reinterpret_cast<const float4*>(&wsm[co][h * LA_D + e]);   // same address across a warp: broadcast
+                acc = fmaf(wv.x, c[e], acc); acc = fmaf(wv.y, c[e + 1], acc); acc = fmaf(wv.z, c[e + 2], acc); acc = fmaf(wv.w, c[e + 3], acc);
+            }
+            wf[((int64_t)b * Cout + co0 + co) * LA_HID + hd] = to_operand(acc, T());
+        }
+    }
 }
 
 // full softmax attention for n <= 32 tokens: one warp per (b, head), lane = query token
@@ -540,6 +692,20 @@ extern "C" int sdc_stem_conv7(int prec, const float* x, const float* w, const fl
     return SDC_OK;
 }
 
+extern "C" int sdc_stem_im2col(int prec, const float* x, void* a, int B, int Cin, int H, int W, int kp, void* stream) {
+    SDC_CHECK_PREC("stem_im2col");
+    SDC_REQUIRE(x && a && B > 0 && Cin > 0 && H > 0 && W > 0, "stem_im2col: bad arguments");
+    SDC_REQUIRE(kp % 8 == 0 && kp / 2 >= Cin * 49, "stem_im2col: kp=%d must be a multiple of 8 and >= 2*Cin*49", kp);
+    const size_t sm = ((size_t)Cin * 7 * (W + 6) + (size_t)Cin * 49) * sizeof(float);
+    SDC_REQUIRE(sm <= 48 * 1024, "stem_im2col: row window does not fit shared memory");
+    if (prec == SDC_PREC_F16)
+        stem_im2col_kernel<__half><<<(unsigned)(B * H), 256, sm, as_stream(stream)>>>(x, (__half*)a, Cin, H, W, kp);
+    else
+        stem_im2col_kernel<float><<<(unsigned)(B * H), 256, sm, as_stream(stream)>>>(x, (float*)a, Cin, H, W, kp);
+    SDC_LAUNCHED();
+    return SDC_OK;
+}
+
 extern "C" int sdc_gn_silu(int prec, const float* x, const double* stats, const float* gamma, const float* beta,
                            const float* scale_shift, const int32_t* t_index, int64_t ss_stride, const void* residual,
                            int residual_operand, void* y, int B, int HW, int C, void* stream) {
@@ -604,11 +770,46 @@ extern "C" int sdc_linear_attention(int prec, const float* qkv, void* out, void*
     SDC_CHECK_PREC("linear_attention");
     SDC_REQUIRE(qkv && out && workspace && B > 0 && n > 0, "linear_attention: bad arguments");
     float* ctx = reinterpret_cast<float*>(workspace);
-    linattn_context_kernel<<<(unsigned)(B * LA_HEADS), 256, 0, as_stream(stream)>>>(qkv, ctx, n);
+    linattn_context_kernel<<<(unsigned)(B * LA_HEADS), 256, 0, as_stream(stream)>>>(qkv + LA_HID, qkv + 2 * LA_HID, LA_QKV, ctx, n);
     SDC_LAUNCHED();
-    dim3 grid((unsigned)(B * LA_HEADS), (unsigned)((n + 255) / 256));
-    if (prec == SDC_PREC_F16) linattn_apply_kernel<__half><<<grid, 256, 0, as_stream(stream)>>>(qkv, ctx, (__half*)out, n);
-    else linattn_apply_kernel<float><<<grid, 256, 0, as_stream(stream)>>>(qkv, ctx, (float*)out, n);
+    SDC_REQUIRE(n % 32 == 0, "linear_attention: n=%d must be a multiple of 32", n);
+    const size_t sm128 = (LA_HEADS * LA_D * LA_CLD + 128 * LA_QLD) * sizeof(float), sm32 = (LA_HEADS * LA_D * LA_CLD + 32 * LA_QLD) * sizeof(float);
+    static bool attr_set = false;
+    if (!attr_set) {
+        SDC_CUDA(cudaFuncSetAttribute(linattn_apply_kernel<128, __half>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm128));
+        SDC_CUDA(cudaFuncSetAttribute(linattn_apply_kernel<128, float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm128));
+        attr_set = true;
+    }
+    cudaStream_t st = as_stream(stream);
+    if (n % 128 == 0) {
+        const unsigned grid = (unsigned)(B * (n / 128));
+        if (prec == SDC_PREC_F16) linattn_apply_kernel<128, __half><<<grid, 256, sm128, st>>>(qkv, ctx, (__half*)out, n);
+        else linattn_apply_kernel<128, float><<<grid, 256, sm128, st>>>(qkv, ctx, (float*)out, n);
+    } else {
+        const unsigned grid = (unsigned)(B * (n / 32));
+        if (prec == SDC_PREC_F16) linattn_apply_kernel<32, __half><<<grid, 256, sm32, st>>>(qkv, ctx, (__half*)out, n);
+        else linattn_apply_kernel<32, float><<<grid, 256, sm32, st>>>(qkv, ctx, (float*)out, n);
+    }
+    SDC_LAUNCHED();
+    return SDC_OK;
+}
+
+extern "C" int sdc_linear_attention_context(const float* k, const float* v, int ld, void* workspace, int B, int n, void* stream) {
+    SDC_REQUIRE(k && v && workspace && B > 0 && n > 0 && ld % 4 == 0, "linear_attention_context: bad arguments");
+    linattn_context_kernel<<<(unsigned)(B * LA_HEADS), 256, 0, as_stream(stream)>>>(k, v, ld, reinterpret_cast<float*>(workspace), n);
+    SDC_LAUNCHED();
+    return SDC_OK;
+}
+
+extern "C" int sdc_linear_attention_fold(int prec, const void* workspace, const float* w_out, void* w_folded, int B, int Cout,
+                                         void* stream) {
+    SDC_CHECK_PREC("linear_attention_fold");
+    SDC_REQUIRE(workspace && w_out && w_folded && B > 0 && Cout > 0 && Cout % 32 == 0, "linear_attention_fold: Cout %% 32 != 0 or null pointer");
+    const unsigned grid = (unsigned)B;
+    if (prec == SDC_PREC_F16)
+        linattn_fold_kernel<__half><<<grid, 256, 0, as_stream(stream)>>>(reinterpret_cast<const float*>(workspace), w_out, (__half*)w_folded, Cout);
+    else
+        linattn_fold_kernel<float><<<grid, 256, 0, as_stream(stream)>>>(reinterpret_cast<const float*>(workspace), w_out, (float*)w_folded, Cout);
     SDC_LAUNCHED();
     return SDC_OK;
 }

@@ -8,6 +8,7 @@ implicit-GEMM convolutions) and csrc/unet_ops.cu (fused GroupNorm/SiLU, LayerNor
 activations.  Packed TF32 weights and the per-timestep FiLM table are cached and rebuilt whenever a parameter's
 version counter or storage changes (optimiser / EMA updates between chains).
 """
+import ctypes
 import math
 import os
 
@@ -22,11 +23,16 @@ L.register({
     "sdc_conv_gemm": (c_i, [c_i, c_i, c_p, c_i, c_p, c_i, c_p, c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_p]),
     "sdc_conv3x3_row": (c_i, [c_i, c_p, c_i, c_p, c_i, c_p, c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_p]),
     "sdc_stem_conv7": (c_i, [c_i, c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_p]),
+    "sdc_stem_im2col": (c_i, [c_i, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_p]),
     "sdc_gn_silu": (c_i, [c_i, c_p, c_p, c_p, c_p, c_p, c_p, c_i64, c_p, c_i, c_p, c_i, c_i, c_i, c_p]),
     "sdc_channel_layernorm": (c_i, [c_i, c_p, c_i, c_p, c_p, c_p, c_i64, c_i, c_i, c_p]),
     "sdc_linear_attention_workspace": (c_i64, [c_i]),
     "sdc_linear_attention": (c_i, [c_i, c_p, c_p, c_p, c_i, c_i, c_p]),
     "sdc_attention": (c_i, [c_i, c_p, c_p, c_i, c_i, c_p]),
+    "sdc_conv1x1_qkv": (c_i, [c_i, c_p, c_i, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_p]),
+    "sdc_linear_attention_context": (c_i, [c_p, c_p, c_i, c_p, c_i, c_i, c_p]),
+    "sdc_linear_attention_fold": (c_i, [c_i, c_p, c_p, c_p, c_i, c_i, c_p]),
+    "sdc_conv1x1_per_sample": (c_i, [c_i, c_p, c_i, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_p]),
     "sdc_upsample2x": (c_i, [c_i, c_p, c_p, c_i, c_i, c_i, c_i, c_p]),
     "sdc_head_conv1": (c_i, [c_i, c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_p]),
     "sdc_linear_rows": (c_i, [c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_p]),
@@ -123,6 +129,37 @@ def _st():
 
 USE_ROW_KERNEL = os.environ.get("SDC_NO_ROW_KERNEL", "0") != "1"  # halo-reuse kernel for the 16x128 level
 PROFILE = None  # bench.py sets this to a list: every conv launch is then bracketed by CUDA events on its stream
+
+
+class _Timed:
+    """Brackets one conv launch with CUDA events on its stream when bench.py has set PROFILE."""
+
+    def __init__(self, flops, shape):
+        self.flops, self.shape = flops, shape
+
+    def __enter__(self):
+        self.prof = PROFILE
+        if self.prof is not None:
+            self.e0, self.e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            self.e0.record()
+
+    def __exit__(self, *exc):
+        if self.prof is not None and exc[0] is None:
+            self.e1.record()
+            self.prof.append((self.e0, self.e1, self.flops, self.shape))
+
+
+def conv1x1_qkv(a, c, wp, q_out, kv_out, B, H, W, prec):
+    """qkv projection of LinearAttention with the q-softmax epilogue (see include/safediffcon_b200_unet.h)."""
+    hid = HEADS * DIM_HEAD
+    with _Timed(2.0 * B * H * W * 3 * hid * c, (KIND_1x1, B, H, W, c, 3 * hid)):
+        L.check(L.lib().sdc_conv1x1_qkv(prec, L.ptr(a), c, L.ptr(wp), L.ptr(q_out), L.ptr(kv_out), B, H, W, hid, _st()))
+
+
+def conv1x1_per_sample(a, c, w_folded, bias, out, B, H, W, Cout, prec):
+    """1x1 convolution whose [Cout, c] weight differs per sample (folded LinearAttention output projection)."""
+    with _Timed(2.0 * B * H * W * Cout * c, (KIND_1x1, B, H, W, c, Cout)):
+        L.check(L.lib().sdc_conv1x1_per_sample(prec, L.ptr(a), c, L.ptr(w_folded), L.ptr(bias), L.ptr(out), 0, B, H, W, Cout, _st()))
 
 
 def conv_gemm(kind, a0, c0, a1, c1, wp, bias, residual, out, stats, operand_out, B, H, W, Cout, prec=PREC_TF32):
@@ -307,7 +344,8 @@ class Unet2D(nn.Module):
                 inner = m.fn.fn
                 d = dict(g_in=m.fn.norm.g.detach().float().reshape(-1).contiguous(), qkv=conv(inner.to_qkv, KIND_1x1))
                 if isinstance(inner, _LinearAttention):
-                    d.update(out=conv(inner.to_out[0], KIND_1x1), g_out=inner.to_out[1].g.detach().float().reshape(-1).contiguous(), full=False)
+                    d.update(out=conv(inner.to_out[0], KIND_1x1), g_out=inner.to_out[1].g.detach().float().reshape(-1).contiguous(), full=False,
+                             out_w32=inner.to_out[0].weight.detach().float().reshape(inner.to_out[0].weight.shape[0], -1).contiguous())
                 else:
                     d.update(out=conv(inner.to_out, KIND_1x1), g_out=None, full=True)
                 return d
@@ -324,7 +362,17 @@ class Unet2D(nn.Module):
                 pk["ups"].append(dict(b1=rb(lvl[0]), b2=rb(lvl[1]), attn=at(lvl[2]), upsample=is_up,
                                       up=conv(lvl[3][1] if is_up else lvl[3], KIND_3x3)))
             pk["final"] = rb(self.final_res_block)
-            pk["stem"] = (self.init_conv.weight.detach().float().contiguous(), self.init_conv.bias.detach().float().contiguous())
+            # stem 7x7 as a tcgen05 GEMM over an im2col operand whose K axis holds the input's high and low parts (see
+            # sdc_stem_im2col): W[c, Cin*49] repeated at columns 0 and kp/2 of a [c, kp] matrix
+            ws = self.init_conv.weight.detach().float()
+            c_stem, k_stem = ws.shape[0], ws[0].numel()
+            kh = (k_stem + 31) // 32 * 32
+            kp = 2 * kh if (2 * kh) % 64 == 0 else 2 * (kh + 32)
+            wrep = torch.zeros(c_stem, kp, device=dev, dtype=torch.float32)
+            wrep[:, :k_stem] = ws.reshape(c_stem, k_stem)
+            wrep[:, kp // 2:kp // 2 + k_stem] = ws.reshape(c_stem, k_stem)
+            pk["stem"] = dict(w=pack_conv_weight(KIND_1x1, wrep.reshape(c_stem, kp, 1, 1), prec),
+                              b=self.init_conv.bias.detach().float().contiguous(), cout=c_stem, kp=kp)
             pk["head"] = (self.final_conv.weight.detach().float().reshape(self.out_dim, -1).contiguous(),
                           self.final_conv.bias.detach().float().contiguous())
             # all ResnetBlock FiLM projections stacked: one [E_total, time_dim] matrix, block i owns rows [off, off+2*Cout)
@@ -456,6 +504,20 @@ class Unet2D(nn.Module):
             M, n = B * h * w, h * w
             xn = opd(M, c)
             L.check(lib.sdc_channel_layernorm(prec, L.ptr(xin), 1, L.ptr(p["g_in"]), None, L.ptr(xn), M, c, 1, _st()))
+            hid = HEADS * DIM_HEAD
+            if not p["full"] and not keep and n % 128 == 0:
+                # fused inference path: q-softmax in the qkv epilogue, context folded into a per-sample output projection
+                qs, kv = opd(M, hid), f32(M, 2 * hid)
+                conv1x1_qkv(xn, c, p["qkv"]["w"], qs, kv, B, h, w, prec)
+                ws = torch.empty(lib.sdc_linear_attention_workspace(B), device=dev, dtype=torch.uint8)
+                L.check(lib.sdc_linear_attention_context(L.ptr(kv), ctypes.c_void_p(kv.data_ptr() + 4 * hid), 2 * hid, L.ptr(ws), B, n, _st()))
+                wf = opd(B * c, hid)
+                L.check(lib.sdc_linear_attention_fold(prec, L.ptr(ws), L.ptr(p["out_w32"]), L.ptr(wf), B, c, _st()))
+                proj = f32(M, c)
+                conv1x1_per_sample(qs, hid, wf, p["out"]["b"], proj, B, h, w, c, prec)
+                out = xn  # reuse: LN1's output is dead once q / kv exist
+                L.check(lib.sdc_channel_layernorm(prec, L.ptr(proj), 0, L.ptr(p["g_out"]), L.ptr(xin), L.ptr(out), M, c, 1, _st()))
+                return out
             qkv = f32(M, 3 * HEADS * DIM_HEAD)
             conv(KIND_1x1, xn, c, None, 0, p["qkv"], None, qkv, None, False, h, w)
             att = opd(M, HEADS * DIM_HEAD)
@@ -478,7 +540,10 @@ class Unet2D(nn.Module):
 
         c = self.init_conv.weight.shape[0]
         cur = opd(B * H * W, c)
-        L.check(lib.sdc_stem_conv7(prec, L.ptr(x), L.ptr(pk["stem"][0]), L.ptr(pk["stem"][1]), L.ptr(cur), B, Cin, H, W, c, _st()))
+        patches = opd(B * H * W, pk["stem"]["kp"])
+        L.check(lib.sdc_stem_im2col(prec, L.ptr(x), L.ptr(patches), B, Cin, H, W, pk["stem"]["kp"], _st()))
+        conv(KIND_1x1, patches, pk["stem"]["kp"], None, 0, pk["stem"], None, cur, None, True, H, W)
+        del patches
         r, r_c = cur, c
         h, w = H, W
         skips = []
