@@ -10,10 +10,11 @@ Public surface mirrors the reference modules it replaces:
 All compute runs in hand-written CUDA kernels behind the C ABI of include/safediffcon_b200.h; there is no CPU
 fallback (calls raise when the library or a CUDA device is missing).
 """
-from .solver import burgers_numeric_solve, burgers_numeric_solve_free  # noqa: F401
+from .solver import burgers_numeric_solve, burgers_numeric_solve_free, burgers_score, control_and_score  # noqa: F401
 from .metrics import control_trajectories, evaluate_samples, calculate_safety_metrics, calculate_safety_score  # noqa: F401
 from .guidance import (calculate_guidance, get_finetune_guidance, get_weight, normalize_weights, safety_guidance,  # noqa: F401
                        SafetyGuidance, SCALER)
+from . import conformal, runner  # noqa: F401
 from .conformal import ConformalCalculator, kth_select  # noqa: F401
 from .diffusion import GaussianDiffusion, ModelPrediction  # noqa: F401
 from .unet import Unet2D  # noqa: F401
