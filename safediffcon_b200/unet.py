@@ -162,7 +162,7 @@ def conv1x1_per_sample(a, c, w_folded, bias, out, B, H, W, Cout, prec):
         L.check(L.lib().sdc_conv1x1_per_sample(prec, L.ptr(a), c, L.ptr(w_folded), L.ptr(bias), L.ptr(out), 0, B, H, W, Cout, _st()))
 
 
-def conv_gemm(kind, a0, c0, a1, c1, wp, bias, residual, out, stats, operand_out, B, H, W, Cout, prec=PREC_TF32):
+def conv_gemm(kind, a0, c0, a1, c1, wp, bias, residual, out, stats, operand_out, B, H, W, Cout, prec=PREC_TF32, algo_k=None):
     """out[B*H*W, Cout] = conv(a0 | a1) + bias (+ residual).  a0/a1/wp/residual are operand-precision tensors; `out` is an
     operand-precision tensor when operand_out else fp32."""
     od = operand_dtype(prec)
@@ -184,7 +184,9 @@ def conv_gemm(kind, a0, c0, a1, c1, wp, bias, residual, out, stats, operand_out,
     if prof is not None:
         e1.record()
         taps = {KIND_1x1: 1, KIND_3x3: 9, KIND_UNSHUFFLE: 4}[kind]
-        prof.append((e0, e1, 2.0 * B * H * W * Cout * taps * (c0 + c1), (kind, B, H, W, c0 + c1, Cout)))
+        # algorithmic FLOPs: algo_k overrides the GEMM K when the operand carries padding / split columns (tensor-core stem)
+        k_alg = taps * (c0 + c1) if algo_k is None else algo_k
+        prof.append((e0, e1, 2.0 * B * H * W * Cout * k_alg, (kind, B, H, W, c0 + c1, Cout)))
 
 
 def pack_conv_weight(kind, w, prec=PREC_TF32):
@@ -468,8 +470,8 @@ class Unet2D(nn.Module):
         f32 = lambda rows, c: torch.empty(rows, c, device=dev, dtype=torch.float32)  # noqa: E731  (conv outputs ahead of a norm)
         opd = lambda rows, c: torch.empty(rows, c, device=dev, dtype=od)  # noqa: E731  (tensor-core operands)
 
-        def conv(kind, a0, c0, a1, c1, cw, residual, out, st, operand_out, h, w):
-            conv_gemm(kind, a0, c0, a1, c1, cw["w"], cw["b"], residual, out, st, operand_out, B, h, w, cw["cout"], prec)
+        def conv(kind, a0, c0, a1, c1, cw, residual, out, st, operand_out, h, w, algo_k=None):
+            conv_gemm(kind, a0, c0, a1, c1, cw["w"], cw["b"], residual, out, st, operand_out, B, h, w, cw["cout"], prec, algo_k)
 
         def resnet(p, m, a0, c0, a1, c1, h, w):
             """ResnetBlock (unet.py:166-180) on one or two concatenated NHWC inputs -> operand [B*h*w, Cout]."""
@@ -542,7 +544,7 @@ class Unet2D(nn.Module):
         cur = opd(B * H * W, c)
         patches = opd(B * H * W, pk["stem"]["kp"])
         L.check(lib.sdc_stem_im2col(prec, L.ptr(x), L.ptr(patches), B, Cin, H, W, pk["stem"]["kp"], _st()))
-        conv(KIND_1x1, patches, pk["stem"]["kp"], None, 0, pk["stem"], None, cur, None, True, H, W)
+        conv(KIND_1x1, patches, pk["stem"]["kp"], None, 0, pk["stem"], None, cur, None, True, H, W, algo_k=Cin * 49)
         del patches
         r, r_c = cur, c
         h, w = H, W
