@@ -115,6 +115,33 @@ int sdc_fill_normal(float* x, int64_t B, int64_t per_sample, uint64_t seed, int6
 /* *counter += 1 on the stream (advances the captured-graph step). */
 int sdc_advance_counter(int32_t* counter, void* stream);
 
+/* Device-resident state of one reverse chain.  A whole reverse step (denoiser + sdc_reverse_step_state +
+ * sdc_chain_state_advance) captured ONCE in a CUDA graph then serves every step of every chain of that shape: the
+ * step index, the Philox seed and the global sample offset are read from device memory instead of kernel arguments
+ * (the reference's python loop, 1D/model/diffusion.py:380-449,470-523, re-issues ~600 launches per step). */
+typedef struct {
+    int32_t step;          /* row of the sdc_step_coef table used by the next reverse step */
+    int32_t reserved;
+    uint64_t seed;         /* Philox key */
+    int64_t sample_offset; /* global index of sample 0 of this shard */
+} sdc_chain_state;
+
+/* state (device) <- (step, seed, sample_offset); t_index[0..B) (device int32, may be NULL) <- coef[step].t, the
+ * per-sample diffusion-time index the denoiser's FiLM lookup reads. */
+int sdc_chain_state_set(sdc_chain_state* state, int32_t step, uint64_t seed, int64_t sample_offset,
+                        const sdc_step_coef* coef, int n_steps, int32_t* t_index, int64_t B, void* stream);
+/* state->step += 1; t_index[0..B) <- coef[min(step, n_steps-1)].t */
+int sdc_chain_state_advance(sdc_chain_state* state, const sdc_step_coef* coef, int n_steps, int32_t* t_index, int64_t B,
+                            void* stream);
+/* sdc_reverse_step with (step, seed, sample_offset) taken from *state on the device. */
+int sdc_reverse_step_state(int sampler, const float* x, const float* eps, const float* noise, float* out,
+                           float* x0_out, float* eps_out, const sdc_step_coef* coef, const sdc_chain_state* state,
+                           const sdc_guidance* guidance /* host */, const float* grad,
+                           const float* u_init, const float* u_final, const float* w_gt, int cond_idx, int pad_writes,
+                           int clip_denoised, int64_t B, int H, int W, void* stream);
+/* adds n to sdc_launch_count(): kernels replayed from a captured graph are accounted by the host layer */
+void sdc_count_launches(int64_t n);
+
 /* ------------------------------------------------------------------------------------------------
  * Conformal calibration.  Replaces calculate_guidance/get_weight (1D/inference/guidance.py:9-46), the
  * nonconformity score of ConformalCalculator.get_conformal_scores (1D/inference/conformal.py:74-85),

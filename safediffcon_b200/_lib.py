@@ -30,6 +30,10 @@ class Guidance(ctypes.Structure):
                 ("nt", ctypes.c_int32)]
 
 
+class ChainState(ctypes.Structure):
+    _fields_ = [("step", ctypes.c_int32), ("reserved", ctypes.c_int32), ("seed", c_u64), ("sample_offset", c_i64)]
+
+
 _SIGS = {
     "sdc_version": (c_i, []),
     "sdc_last_error": (ctypes.c_char_p, []),
@@ -43,6 +47,11 @@ _SIGS = {
     "sdc_write_conditions": (c_i, [c_p, c_p, c_p, c_p, c_i, c_i, c_i64, c_i, c_i, c_p]),
     "sdc_fill_normal": (c_i, [c_p, c_i64, c_i64, c_u64, c_i64, ctypes.c_int32, c_p]),
     "sdc_advance_counter": (c_i, [c_p, c_p]),
+    "sdc_chain_state_set": (c_i, [c_p, ctypes.c_int32, c_u64, c_i64, c_p, c_i, c_p, c_i64, c_p]),
+    "sdc_chain_state_advance": (c_i, [c_p, c_p, c_i, c_p, c_i64, c_p]),
+    "sdc_reverse_step_state": (c_i, [c_i, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, ctypes.POINTER(Guidance), c_p, c_p, c_p, c_p,
+                                     c_i, c_i, c_i, c_i64, c_i, c_i, c_p]),
+    "sdc_count_launches": (None, [c_i64]),
     "sdc_safety_stat": (c_i, [c_p, c_p, c_i, c_f, c_i, c_i64, c_i, c_i, c_p]),
     "sdc_conformal_scores": (c_i, [c_p, c_p, c_p, c_p, ctypes.POINTER(Guidance), c_f, c_i64, c_i, c_i, c_p]),
     "sdc_normalize_weights": (c_i, [c_p, c_p, c_p, c_i64, c_p]),

@@ -17,3 +17,5 @@ void set_error(const char* fmt, ...) {
 extern "C" int sdc_version(void) { return 100; }
 extern "C" const char* sdc_last_error(void) { return sdc::g_err; }
 extern "C" int64_t sdc_launch_count(void) { return sdc::g_launches.load(); }
+/* launches replayed from a captured CUDA graph are counted by the host layer (one call per replay) */
+extern "C" void sdc_count_launches(int64_t n) { sdc::g_launches.fetch_add(n); }

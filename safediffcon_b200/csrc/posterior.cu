@@ -17,6 +17,7 @@ namespace sdc {
 struct StepArgs {
     const float* x; const float* eps; const float* noise; float* out; float* x0_out; float* eps_out;
     const sdc_step_coef* coef; int step; const int32_t* counter;
+    const sdc_chain_state* state;  // device-resident (step, seed, sample_offset): captured-graph replays
     sdc_guidance g; float g_unit;  // g_unit = fp32(w_score*scaler/(nt*W)) for mode 1
     const float* grad; const float* u_init; const float* u_final; const float* w_gt;
     int cond_idx; int pad_writes; int clip_denoised; int sampler;
@@ -45,7 +46,7 @@ __global__ void __launch_bounds__(256) reverse_step_kernel(StepArgs p) {
     const int64_t b = blockIdx.x;
     const int HW = p.H * p.W;
     const int n4 = 3 * HW / 4;
-    const sdc_step_coef cf = p.coef[p.counter ? *p.counter : p.step];
+    const sdc_step_coef cf = p.coef[p.state ? p.state->step : (p.counter ? *p.counter : p.step)];
     const bool ddim = p.sampler == SDC_SAMPLER_DDIM;
     const bool clip = ddim;  // clip_x_start is set by ddim_sample only
     const float4* x4 = reinterpret_cast<const float4*>(p.x) + b * n4;
@@ -112,8 +113,8 @@ __global__ void __launch_bounds__(256) reverse_step_kernel(StepArgs p) {
     }
 
     // ---- pass 2: elementwise update ----
-    const Philox ph(p.seed);
-    const int64_t gs = p.sample_offset + b;
+    const Philox ph(p.state ? p.state->seed : p.seed);
+    const int64_t gs = (p.state ? p.state->sample_offset : p.sample_offset) + b;
     const float4* z4 = p.noise ? reinterpret_cast<const float4*>(p.noise) + b * n4 : nullptr;
     const float4* g4 = (p.g.mode == 3 && p.grad) ? reinterpret_cast<const float4*>(p.grad) + b * n4 : nullptr;
     float4* o4 = reinterpret_cast<float4*>(p.out) + b * n4;
@@ -191,16 +192,31 @@ __global__ void __launch_bounds__(256) fill_normal_kernel(float* x, int64_t per4
 
 __global__ void advance_counter_kernel(int32_t* c) { *c += 1; }
 
+// state <- (step, seed, offset) when `set`, else state->step += 1; then t_index[0..B) <- coef[min(step, n_steps-1)].t
+__global__ void __launch_bounds__(256) chain_state_kernel(sdc_chain_state* state, int set, int32_t step, uint64_t seed,
+                                                          int64_t sample_offset, const sdc_step_coef* coef, int n_steps,
+                                                          int32_t* t_index, int64_t B) {
+    __shared__ int32_t s_t;
+    if (threadIdx.x == 0) {
+        int32_t st = set ? step : state->step + 1;
+        if (set) { state->seed = seed; state->sample_offset = sample_offset; state->reserved = 0; }
+        state->step = st;
+        s_t = coef[st < n_steps ? st : n_steps - 1].t;
+    }
+    __syncthreads();
+    if (t_index) for (int64_t i = threadIdx.x; i < B; i += blockDim.x) t_index[i] = s_t;
+}
+
 }  // namespace sdc
 
 using namespace sdc;
 
-extern "C" int sdc_reverse_step(int sampler, const float* x, const float* eps, const float* noise, float* out,
-                                float* x0_out, float* eps_out, const sdc_step_coef* coef, int step,
-                                const int32_t* step_counter, const sdc_guidance* guidance, const float* grad,
-                                const float* u_init, const float* u_final, const float* w_gt, int cond_idx, int pad_writes,
-                                int clip_denoised, uint64_t seed, int64_t sample_offset, int64_t B, int H, int W,
-                                void* stream) {
+static int reverse_step_launch(int sampler, const float* x, const float* eps, const float* noise, float* out,
+                               float* x0_out, float* eps_out, const sdc_step_coef* coef, int step,
+                               const int32_t* step_counter, const sdc_chain_state* state, const sdc_guidance* guidance,
+                               const float* grad, const float* u_init, const float* u_final, const float* w_gt, int cond_idx,
+                               int pad_writes, int clip_denoised, uint64_t seed, int64_t sample_offset, int64_t B, int H, int W,
+                               void* stream) {
     SDC_REQUIRE(sampler == SDC_SAMPLER_DDIM || sampler == SDC_SAMPLER_DDPM, "reverse_step: unknown sampler %d", sampler);
     SDC_REQUIRE(B >= 0 && H > 0 && W > 0 && W % 4 == 0, "reverse_step: need W %% 4 == 0 (got H=%d W=%d)", H, W);
     SDC_REQUIRE(B < (1LL << 31), "reverse_step: batch too large");
@@ -208,7 +224,7 @@ extern "C" int sdc_reverse_step(int sampler, const float* x, const float* eps, c
     SDC_REQUIRE(x && eps && out && coef, "reverse_step: null pointer");
     StepArgs p{};
     p.x = x; p.eps = eps; p.noise = noise; p.out = out; p.x0_out = x0_out; p.eps_out = eps_out;
-    p.coef = coef; p.step = step; p.counter = step_counter;
+    p.coef = coef; p.step = step; p.counter = step_counter; p.state = state;
     if (guidance) p.g = *guidance; else { p.g.mode = 0; p.g.nt = 0; p.g.scaler = 1.f; }
     SDC_REQUIRE(p.g.mode >= 0 && p.g.mode <= 3, "reverse_step: bad guidance mode %d", p.g.mode);
     if (p.g.mode == 1 || p.g.mode == 2) {
@@ -220,6 +236,42 @@ extern "C" int sdc_reverse_step(int sampler, const float* x, const float* eps, c
     p.cond_idx = cond_idx; p.pad_writes = pad_writes; p.clip_denoised = clip_denoised; p.sampler = sampler;
     p.seed = seed; p.sample_offset = sample_offset; p.H = H; p.W = W;
     reverse_step_kernel<<<(unsigned)B, 256, 0, as_stream(stream)>>>(p);
+    SDC_LAUNCHED();
+    return SDC_OK;
+}
+
+extern "C" int sdc_reverse_step(int sampler, const float* x, const float* eps, const float* noise, float* out,
+                                float* x0_out, float* eps_out, const sdc_step_coef* coef, int step,
+                                const int32_t* step_counter, const sdc_guidance* guidance, const float* grad,
+                                const float* u_init, const float* u_final, const float* w_gt, int cond_idx, int pad_writes,
+                                int clip_denoised, uint64_t seed, int64_t sample_offset, int64_t B, int H, int W,
+                                void* stream) {
+    return reverse_step_launch(sampler, x, eps, noise, out, x0_out, eps_out, coef, step, step_counter, nullptr, guidance, grad,
+                               u_init, u_final, w_gt, cond_idx, pad_writes, clip_denoised, seed, sample_offset, B, H, W, stream);
+}
+
+extern "C" int sdc_reverse_step_state(int sampler, const float* x, const float* eps, const float* noise, float* out,
+                                      float* x0_out, float* eps_out, const sdc_step_coef* coef, const sdc_chain_state* state,
+                                      const sdc_guidance* guidance, const float* grad, const float* u_init,
+                                      const float* u_final, const float* w_gt, int cond_idx, int pad_writes, int clip_denoised,
+                                      int64_t B, int H, int W, void* stream) {
+    SDC_REQUIRE(state != nullptr, "reverse_step_state: null chain state");
+    return reverse_step_launch(sampler, x, eps, noise, out, x0_out, eps_out, coef, 0, nullptr, state, guidance, grad, u_init,
+                               u_final, w_gt, cond_idx, pad_writes, clip_denoised, 0, 0, B, H, W, stream);
+}
+
+extern "C" int sdc_chain_state_set(sdc_chain_state* state, int32_t step, uint64_t seed, int64_t sample_offset,
+                                   const sdc_step_coef* coef, int n_steps, int32_t* t_index, int64_t B, void* stream) {
+    SDC_REQUIRE(state && coef && n_steps > 0 && step >= 0 && B >= 0, "chain_state_set: bad arguments");
+    chain_state_kernel<<<1, 256, 0, as_stream(stream)>>>(state, 1, step, seed, sample_offset, coef, n_steps, t_index, B);
+    SDC_LAUNCHED();
+    return SDC_OK;
+}
+
+extern "C" int sdc_chain_state_advance(sdc_chain_state* state, const sdc_step_coef* coef, int n_steps, int32_t* t_index,
+                                       int64_t B, void* stream) {
+    SDC_REQUIRE(state && coef && n_steps > 0 && B >= 0, "chain_state_advance: bad arguments");
+    chain_state_kernel<<<1, 256, 0, as_stream(stream)>>>(state, 0, 0, 0, 0, coef, n_steps, t_index, B);
     SDC_LAUNCHED();
     return SDC_OK;
 }

@@ -10,7 +10,9 @@ Training (``forward`` = p_losses) is a "next" row and raises as well.
 """
 import ctypes
 import math
-from collections import namedtuple
+import os
+import types
+from collections import OrderedDict, namedtuple
 
 import torch
 import torch.nn as nn
@@ -22,6 +24,21 @@ ModelPrediction = namedtuple('ModelPrediction', ['pred_noise', 'pred_x_start'])
 
 SAMPLER_DDIM, SAMPLER_DDPM = 0, 1
 _INIT_TAG = 0x7FFFFFFF  # RNG tag of the initial x_T draw
+# Chains of at most this many samples replay ONE captured CUDA graph per reverse step (below ~256 samples the ~150 launches
+# of a step cost more host time than device time; above it the chain is device-bound and eager launches keep the
+# activation pool shared).  SDC_GRAPH_MAX_BATCH=0 disables graphs.
+GRAPH_MAX_BATCH = int(os.environ.get("SDC_GRAPH_MAX_BATCH", "256"))
+GRAPH_CACHE_ENTRIES = 4
+
+
+class _GraphCache:
+    """Captured reverse-step graphs of one GaussianDiffusion; never deep-copied (EMA wrappers copy the module)."""
+
+    def __init__(self):
+        self.entries = OrderedDict()
+
+    def __deepcopy__(self, memo):
+        return _GraphCache()
 
 
 def linear_beta_schedule(timesteps):
@@ -115,6 +132,7 @@ class GaussianDiffusion(nn.Module):
         self.condition_idx = condition_idx
         self.prior_beta = prior_beta
         self._tables = {}
+        self._graphs = _GraphCache()
 
     # ------------------------------------------------------------------ helpers
     def predict_start_from_noise(self, x_t, t, noise):
@@ -257,6 +275,77 @@ class GaussianDiffusion(nn.Module):
         g = g * sched
         return (eps + g) if proj is None else proj(eps, g)
 
+    # ------------------------------------------------------------------ captured-graph chain (small batches)
+    def _graph_entry(self, sampler, shape, table, rows, gstruct, conds, has_noise, clip_denoised):
+        """One reverse step (denoiser + fused posterior update in place + chain-state advance) captured in a CUDA graph
+        over static buffers.  Step index / diffusion time, Philox seed and sample offset live in device memory
+        (sdc_chain_state), and the denoiser's packed weights are refreshed in place when parameters change, so one graph
+        serves every step of every chain with this shape, sampler and guidance."""
+        B, C, H, W = shape
+        device = self.betas.device
+        pk = self.model._packed()
+        self.model._film_table(pk)
+        gkey = None if gstruct is None else tuple(getattr(gstruct, f) for f, _ in gstruct._fields_)
+        key = (id(self.model), id(pk), pk["prec"], shape, sampler, tuple(rows), gkey, tuple(c is not None for c in conds), has_noise,
+               self.condition_idx, bool(self.train_on_padded_locations), bool(clip_denoised))
+        cache = self._graphs.entries
+        if key in cache:
+            cache.move_to_end(key)
+            return cache[key]
+        lib = L.lib()
+        e = types.SimpleNamespace(pk=pk, table=table, n_steps=len(rows))
+        e.img = torch.zeros(shape, device=device)
+        e.t_index = torch.zeros(B, dtype=torch.int32, device=device)
+        e.state = torch.zeros(ctypes.sizeof(L.ChainState), dtype=torch.uint8, device=device)
+        e.u0 = torch.zeros(B, W, device=device) if conds[0] is not None else None
+        e.uT = torch.zeros(B, W, device=device) if conds[1] is not None else None
+        e.wg = torch.zeros(B, H, W, device=device) if conds[2] is not None else None
+        e.noise = torch.zeros(shape, device=device) if has_noise else None
+        pad = int(not self.train_on_padded_locations)
+
+        def one_step():
+            eps = self.model.denoise_indexed(e.img, e.t_index)
+            L.check(lib.sdc_reverse_step_state(
+                sampler, L.ptr(e.img), L.ptr(eps), L.ptr(e.noise), L.ptr(e.img), None, None, L.ptr(table), L.ptr(e.state),
+                ctypes.byref(gstruct) if gstruct is not None else None, None, L.ptr(e.u0), L.ptr(e.uT), L.ptr(e.wg),
+                self.condition_idx, pad, int(bool(clip_denoised)), B, H, W, L.stream_ptr()))
+            L.check(lib.sdc_chain_state_advance(L.ptr(e.state), L.ptr(table), e.n_steps, L.ptr(e.t_index), B, L.stream_ptr()))
+
+        L.check(lib.sdc_chain_state_set(L.ptr(e.state), 0, 0, 0, L.ptr(table), e.n_steps, L.ptr(e.t_index), B, L.stream_ptr()))
+        one_step()   # eager warm-up on the static buffers: lazy initialisation happens outside the capture
+        n0 = L.launch_count()
+        e.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(e.graph):
+            one_step()
+        e.n_launch = L.launch_count() - n0
+        cache[key] = e
+        while len(cache) > GRAPH_CACHE_ENTRIES:
+            cache.popitem(last=False)
+        return e
+
+    def _graph_chain(self, sampler, shape, table, times, rows, gstruct, conds, noise_iter, seed, offset, clip_denoised):
+        B, C, H, W = shape
+        lib = L.lib()
+        e = self._graph_entry(sampler, tuple(shape), table, rows, gstruct, conds, noise_iter is not None, clip_denoised)
+        table = e.table   # the captured launches read the entry's own copy (equal rows => equal contents)
+        for dst, src in zip((e.u0, e.uT, e.wg), conds):
+            if dst is not None:
+                dst.copy_(src.reshape(dst.shape))
+        if noise_iter is not None:
+            e.img.copy_(next(noise_iter))
+        else:
+            L.check(lib.sdc_fill_normal(L.ptr(e.img), B, e.img[0].numel(), seed, offset, _INIT_TAG, L.stream_ptr()))
+        L.check(lib.sdc_write_conditions(L.ptr(e.img), L.ptr(e.u0), L.ptr(e.uT), L.ptr(e.wg), self.condition_idx,
+                                         int(not self.train_on_padded_locations), B, H, W, L.stream_ptr()))
+        L.check(lib.sdc_chain_state_set(L.ptr(e.state), 0, seed & 0xFFFFFFFFFFFFFFFF, offset, L.ptr(table), e.n_steps,
+                                        L.ptr(e.t_index), B, L.stream_ptr()))
+        for step in range(len(times)):
+            if noise_iter is not None and step != len(times) - 1:
+                e.noise.copy_(next(noise_iter))
+            e.graph.replay()
+            lib.sdc_count_launches(e.n_launch)
+        return e.img.clone()
+
     # ------------------------------------------------------------------ reference API
     def model_predictions(self, x, t, x_self_cond=None, residual=None, clip_x_start=False, rederive_pred_noise=False, **kwargs):
         """(pred_noise, pred_x_start) for per-sample times t (reference diffusion.py:226-286), torch ops on the device."""
@@ -328,12 +417,15 @@ class GaussianDiffusion(nn.Module):
         ddim = sampler == SAMPLER_DDIM
         B, C, H, W = shape
 
+        second_call = (not ddim) and (not self.guidance_u0)  # DDPM calibration-style path: two p_sample calls per step
+        if (0 < B <= GRAPH_MAX_BATCH and hasattr(self.model, "denoise_indexed") and nablaJ is None and not second_call
+                and not return_all and max(times) < getattr(self.model, "table_timesteps", 0)):
+            return self._graph_chain(sampler, shape, table, times, rows, gstruct, conds, noise_iter, seed, offset, clip_denoised)
         img = self._initial(shape, device, noise_iter, seed, offset)
         L.check(L.lib().sdc_write_conditions(L.ptr(img), L.ptr(conds[0]), L.ptr(conds[1]), L.ptr(conds[2]), self.condition_idx,
                                              int(not self.train_on_padded_locations), B, H, W, L.stream_ptr()))
         imgs = [img.clone()] if return_all else None
         nxt = torch.empty_like(img)
-        second_call = (not ddim) and (not self.guidance_u0)  # DDPM calibration-style path: two p_sample calls per step
         for step, t in enumerate(times):
             last = step == len(times) - 1
             eps = L.dev_f32(self._eps(img, t), 'eps')

@@ -225,6 +225,33 @@ class _InputVJP(torch.autograd.Function):
         return gx, None, None, None
 
 
+def _same_layout(a, b):
+    """Two packed-weight trees hold tensors of identical shape / dtype / device at identical places."""
+    if isinstance(a, torch.Tensor) or isinstance(b, torch.Tensor):
+        return (isinstance(a, torch.Tensor) and isinstance(b, torch.Tensor) and a.shape == b.shape and a.dtype == b.dtype
+                and a.device == b.device)
+    if isinstance(a, dict) and isinstance(b, dict):
+        ka = [k for k in a if k not in ("table", "dgrad")]
+        kb = [k for k in b if k not in ("table", "dgrad")]
+        return ka == kb and all(_same_layout(a[k], b[k]) for k in ka)
+    if isinstance(a, (list, tuple)) and isinstance(b, (list, tuple)):
+        return len(a) == len(b) and all(_same_layout(x, y) for x, y in zip(a, b))
+    return a == b
+
+
+def _copy_into(dst, src):
+    """dst <- src leaf by leaf, keeping dst's storage (captured CUDA graphs hold these pointers)."""
+    if isinstance(dst, torch.Tensor):
+        dst.copy_(src)
+    elif isinstance(dst, dict):
+        for k in dst:
+            if k not in ("table", "dgrad"):
+                _copy_into(dst[k], src[k])
+    elif isinstance(dst, (list, tuple)):
+        for x, y in zip(dst, src):
+            _copy_into(x, y)
+
+
 class _PackCache:
     """Packed-weight cache that is never deep-copied (EMA wrappers deepcopy the module; the copy repacks lazily)."""
 
@@ -388,6 +415,17 @@ class Unet2D(nn.Module):
             pk["time"] = tuple(t.detach().float().contiguous() for t in (self.time_mlp[1].weight, self.time_mlp[1].bias,
                                                                             self.time_mlp[3].weight, self.time_mlp[3].bias))
             pk["table"] = None
+            old = self._cache.pack
+            if old is not None and _same_layout(old, pk):
+                # parameters changed (optimiser / EMA step) but not their layout: refresh the existing buffers in place so
+                # that captured reverse-step graphs (GaussianDiffusion._graph_entry) stay valid
+                _copy_into(old, pk)
+                old.pop("dgrad", None)
+                if old["table"] is not None:
+                    tab, old["table"] = old["table"], None
+                    tab.copy_(self._film_table(old))
+                    old["table"] = tab
+                pk = old
         self._cache.pack, self._cache.key = pk, key
         return pk
 
@@ -444,7 +482,14 @@ class Unet2D(nn.Module):
                 eps = self._run(x, time, None, tape)
             return eps, self._vjp(tape, L.dev_f32(grad_eps, "grad_eps"))
 
-    def _run(self, x, time, table_row, tape=None):
+    def denoise_indexed(self, x, t_index):
+        """eps with the integer diffusion times read from a device int32 tensor [B] that the caller updates in place
+        (captured-graph chains: the same launches serve every step; see GaussianDiffusion._graph_chain)."""
+        assert t_index.dtype == torch.int32 and t_index.is_cuda and t_index.numel() == x.shape[0]
+        with torch.no_grad(), torch.cuda.device(x.device):
+            return self._run(L.dev_f32(x, "x"), None, None, t_index=t_index)
+
+    def _run(self, x, time, table_row, tape=None, t_index=None):
         """tape: None for inference (buffers are reused); a list to record what the backward-data pass needs (every
         normalisation input is then kept in its own buffer)."""
         pk = self._packed()
@@ -456,7 +501,9 @@ class Unet2D(nn.Module):
         B, Cin, H, W = x.shape
         assert Cin == self.channels
         # FiLM rows: integer times index the cached 1000-row table; anything else is evaluated per sample
-        if table_row is not None:
+        if t_index is not None:
+            film = self._film_table(pk)
+        elif table_row is not None:
             film, t_index = self._film_table(pk)[table_row:table_row + 1], None
         elif not torch.is_floating_point(time):
             film, t_index = self._film_table(pk), time.to(device=dev, dtype=torch.int32).clamp(0, self.table_timesteps - 1).contiguous()

@@ -35,6 +35,7 @@ def test_struct_layouts():
     from safediffcon_b200 import _lib
     assert ctypes.sizeof(_lib.StepCoef) == 32
     assert ctypes.sizeof(_lib.Guidance) == 24
+    assert ctypes.sizeof(_lib.ChainState) == 24
 
 
 def test_version_and_error_string():
