@@ -160,6 +160,38 @@ int sdc_head_conv1_bwd(const float* g, const float* w, float* dx, int B, int HW,
  * (computed by a 1x1 sdc_conv_gemm); column index ci*49 + ky*7 + kx. */
 int sdc_stem_col2im(const float* t, float* dx, int B, int Cin, int H, int W, int ld, void* stream);
 
+/* ---------------------------------------------------------------------------------------------------------------
+ * Parameter gradients (what autograd accumulates into the U-Net parameters when the reference back-propagates the
+ * inference-time fine-tuning loss through the last DDIM step, 1D/model/diffusion.py:524-551 and
+ * 1D/inference/inference_ft.py:189-226, or the post-training loss, 1D/posttrain/post_train.py:206-260).  The activation
+ * gradients dY come from the backward-data pass above; every output below is ACCUMULATED (+=) into a caller-zeroed
+ * fp32 buffer with atomics.
+ * ------------------------------------------------------------------------------------------------------------- */
+
+/* Weight gradient of a convolution in the torch OIHW layout: dw[co, ci, ky, kx] += sum_p dy[p, co] * a[p + (ky,kx), ci].
+ * kind as in sdc_conv_gemm (0 = 1x1, 1 = 3x3 pad 1, 2 = pixel-unshuffle + 1x1: dw[co, c*4 + 2 p1 + p2], input 2H x 2W);
+ * a0 | a1: the NHWC input segments of the forward call (fp16 if a_half else fp32), dy: [B*H*W, Cout] fp32.
+ * mma.sync TF32 with operands rounded to nearest, fp32 accumulation. */
+int sdc_conv_wgrad(int kind, int a_half, const void* a0, int c0, const void* a1, int c1, const float* dy, float* dw,
+                   int B, int H, int W, int Cout, void* stream);
+
+/* out[c] += sum over the M rows of x[M, C] (conv bias gradient from dY). */
+int sdc_colsum(const float* x, float* out, int64_t M, int C, void* stream);
+
+/* Per (sample, channel) sums of the GroupNorm+FiLM+SiLU backward: P[b, 0, c] += sum_p dz, P[b, 1, c] += sum_p dz * xhat with
+ * dz = dy * silu'(z); arguments as sdc_gn_silu_bwd.  From these: d gamma_c = sum_b (1+sc_bc) P1, d beta_c = sum_b (1+sc_bc) P0,
+ * d scale_bc = gamma_c P1 + beta_c P0, d shift_bc = P0. */
+int sdc_gn_param_grad(const float* dy, const float* x, const double* stats, const float* gamma, const float* beta,
+                      const float* scale_shift, const int32_t* t_index, int64_t ss_stride, float* P, int B, int HW, int C,
+                      void* stream);
+
+/* dg[c] += sum_rows dy[row, c] * xhat[row, c] for the channel LayerNorm (x: its forward input, fp16 if x_half). */
+int sdc_channel_layernorm_gain_grad(const float* dy, const void* x, int x_half, float* dg, int64_t M, int C, void* stream);
+
+/* Head 1x1 conv: dw[o, c] += sum g[b, o, p] x[(b,p), c], db[o] += sum g[b, o, p]  (g: NCHW fp32 gradient of the output). */
+int sdc_head_conv1_wgrad(const float* g, const void* x, int x_half, float* dw, float* db, int B, int HW, int Cin, int Cout,
+                         void* stream);
+
 #ifdef __cplusplus
 }
 #endif

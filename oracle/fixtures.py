@@ -125,3 +125,35 @@ def config1_conditions(B, seed=0):
     u0_t = torch.from_numpy(u0) / 10.0
     uT_t = torch.from_numpy(traj[:, -1, :].copy()) / 10.0
     return u0_t, uT_t, torch.from_numpy(traj)
+
+
+PGRAD_SAMPLES = 256
+
+
+def grad_digest(named_grads):
+    """Compact fingerprint of a set of parameter gradients (full tensors would be ~100 MB): per parameter the L2 norm,
+    the sum, and PGRAD_SAMPLES evenly spaced entries of the flattened tensor."""
+    import numpy as np
+    out = {}
+    for name, g in named_grads:
+        flat = g.detach().double().flatten().cpu()
+        idx = torch.linspace(0, flat.numel() - 1, PGRAD_SAMPLES).round().long()
+        out[name + "|norm"] = np.float64(flat.norm().item())
+        out[name + "|sum"] = np.float64(flat.sum().item())
+        out[name + "|samples"] = flat[idx].numpy()
+    return out
+
+
+def finetune_loss(sample, Q=0.0, u_bound=0.8, scaler=10.0):
+    """InferenceFT.finetune_step's objective (/root/reference/1D/inference/inference_ft.py:189-203) on a sample() output."""
+    pred = sample * scaler
+    s = pred[:, 2, :11, :].amax(dim=(-1, -2))
+    obj = torch.maximum(s + Q - u_bound ** 2, torch.zeros_like(s))
+    return torch.nn.functional.mse_loss(obj, torch.zeros_like(s))
+
+
+def last_step_state(B, seed=71):
+    """x_t entering the last DDIM-200 pair (t = 4): a dataset-like state plus a little noise, so that the predicted x0
+    stays inside the clamp and the fine-tuning hinge is active."""
+    g = torch.Generator().manual_seed(seed)
+    return calibration_states(B) + 0.01 * torch.randn(B, 3, 16, 128, generator=g)

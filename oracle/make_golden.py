@@ -188,6 +188,45 @@ def gen_unet_vjp():
         save(f"unet_dim{dim}_vjp", eps=eps.detach(), grad_x=gx)
 
 
+def gen_unet_pgrad():
+    """Parameter gradients of the unmodified reference, stored as digests (fixtures.grad_digest):
+    (a) dense cotangent: d<eps, g>/d(theta) for the dim-64 denoiser, per-sample times;
+    (b) the inference-time fine-tuning loss back-propagated through sample(enable_grad=True) (DDIM, last step under
+        autograd, diffusion.py:524-551 + inference_ft.py:189-203), Q chosen so that the hinge is active."""
+    dim, B = 64, 2
+    net = _unet(dim).train()
+    x, t = fx.unet_inputs(B)
+    g = fx.unet_cotangent(B)
+    eps = net(x, t)
+    net.zero_grad()
+    eps.backward(g)
+    save(f"unet_dim{dim}_pgrad", eps=eps.detach(), **fx.grad_digest([(n, p.grad) for n, p in net.named_parameters()]))
+    # (b) the reference's last-step code path (diffusion.py:524-531): model_predictions under autograd at the last time of
+    # the DDIM-200 grid, then finetune_step's loss.  (A free-running chain of a random-init model saturates the clamp of
+    # x0, which zeroes every gradient -- hence a dataset-like x_t.)
+    net = _unet(dim).train()
+    gd = _diffusion(1000, 200, model=net)
+    t_last, Q = 4, 0.0
+    assert gd_time_pairs(gd)[-1] == (t_last, -1)
+    img = fx.last_step_state(B)
+    with torch.enable_grad():
+        time_cond = torch.full((B,), t_last, dtype=torch.long)
+        pred_noise, x_start, *_ = gd.model_predictions(img, time_cond, None, clip_x_start=True, rederive_pred_noise=True,
+                                                       nablaJ=_guidance_fn(Q), J_scheduler=None)
+    loss = fx.finetune_loss(x_start, Q=Q)
+    assert float(loss) > 0 and float(x_start.abs().max()) < 1.0
+    net.zero_grad()
+    loss.backward()
+    save(f"unet_dim{dim}_ft_pgrad", x_start=x_start.detach(), loss=loss.detach(),
+         **fx.grad_digest([(n, p.grad) for n, p in net.named_parameters()]))
+
+
+def gd_time_pairs(gd):
+    times = torch.linspace(-1, gd.num_timesteps - 1, steps=gd.sampling_timesteps + 1)
+    times = list(reversed(times.int().tolist()))
+    return list(zip(times[:-1], times[1:]))
+
+
 def gen_config1():
     """BASELINE config 1: real U-Net (seed 42), B=8, DDIM-200 eta=1 guided (w_score 500, Q 0), then solver+metrics."""
     from data.generate_burgers import burgers_numeric_solve_free
@@ -229,7 +268,7 @@ def gen_config1():
 
 
 ALL = {"schedule": gen_schedule, "solver": gen_solver, "chains": gen_chains, "guidance": gen_guidance,
-       "conformal": gen_conformal, "unet": gen_unet, "unet_vjp": gen_unet_vjp, "config1": gen_config1}
+       "conformal": gen_conformal, "unet": gen_unet, "unet_vjp": gen_unet_vjp, "unet_pgrad": gen_unet_pgrad, "config1": gen_config1}
 
 if __name__ == "__main__":
     names = sys.argv[1:] or [k for k in ALL if k != "config1"]

@@ -323,7 +323,24 @@ class GaussianDiffusion(nn.Module):
             cache.popitem(last=False)
         return e
 
-    def _graph_chain(self, sampler, shape, table, times, rows, gstruct, conds, noise_iter, seed, offset, clip_denoised):
+    def _last_step_with_grad(self, img, t, coef_row, kwargs):
+        """Final DDIM pair (t, -1) under autograd: x0 = clamp(c1 x - c2 eps'), eps' = eps + nablaJ(x0.detach()) * sched,
+        the same fp32 mul / sub / clamp sequence as the fused kernel, on a denoiser output that carries parameter
+        gradients (reference diffusion.py:524-531 with model_predictions :226-286)."""
+        c1, c2, sched = coef_row[0], coef_row[1], coef_row[5]
+        nablaJ, proj = kwargs.get('nablaJ'), kwargs.get('proj_guidance')
+        with torch.enable_grad():
+            tb = torch.full((img.shape[0],), t, device=img.device, dtype=torch.long)
+            eps = self.model(img, tb)
+            x0 = (c1 * img - c2 * eps).clamp(-1., 1.)
+            if self.guidance_u0 and nablaJ is not None:
+                g = nablaJ(x0.clone().detach().requires_grad_()) * sched
+                eps = (eps + g) if proj is None else proj(eps, g)
+                x0 = (c1 * img - c2 * eps).clamp(-1., 1.)
+            return x0
+
+    def _graph_chain(self, sampler, shape, table, times, rows, gstruct, conds, noise_iter, seed, offset, clip_denoised,
+                     n_steps=None):
         B, C, H, W = shape
         lib = L.lib()
         e = self._graph_entry(sampler, tuple(shape), table, rows, gstruct, conds, noise_iter is not None, clip_denoised)
@@ -339,7 +356,7 @@ class GaussianDiffusion(nn.Module):
                                          int(not self.train_on_padded_locations), B, H, W, L.stream_ptr()))
         L.check(lib.sdc_chain_state_set(L.ptr(e.state), 0, seed & 0xFFFFFFFFFFFFFFFF, offset, L.ptr(table), e.n_steps,
                                         L.ptr(e.t_index), B, L.stream_ptr()))
-        for step in range(len(times)):
+        for step in range(len(times) if n_steps is None else n_steps):
             if noise_iter is not None and step != len(times) - 1:
                 e.noise.copy_(next(noise_iter))
             e.graph.replay()
@@ -418,9 +435,17 @@ class GaussianDiffusion(nn.Module):
         B, C, H, W = shape
 
         second_call = (not ddim) and (not self.guidance_u0)  # DDPM calibration-style path: two p_sample calls per step
+        # the reference runs the LAST DDIM step under torch.enable_grad() (diffusion.py:524-551): when the denoiser has
+        # trainable parameters the returned x0 then carries the autograd graph InferenceFT.finetune_step back-propagates
+        with torch.enable_grad():
+            grad_last = bool(ddim and enable_grad and not return_all and hasattr(self.model, "wants_param_grad")
+                             and self.model.wants_param_grad())
+        n_plain = len(times) - (1 if grad_last else 0)
         if (0 < B <= GRAPH_MAX_BATCH and hasattr(self.model, "denoise_indexed") and nablaJ is None and not second_call
                 and not return_all and max(times) < getattr(self.model, "table_timesteps", 0)):
-            return self._graph_chain(sampler, shape, table, times, rows, gstruct, conds, noise_iter, seed, offset, clip_denoised)
+            img = self._graph_chain(sampler, shape, table, times, rows, gstruct, conds, noise_iter, seed, offset, clip_denoised,
+                                    n_plain)
+            return self._last_step_with_grad(img, times[-1], rows[-1], kwargs) if grad_last else img
         img = self._initial(shape, device, noise_iter, seed, offset)
         L.check(L.lib().sdc_write_conditions(L.ptr(img), L.ptr(conds[0]), L.ptr(conds[1]), L.ptr(conds[2]), self.condition_idx,
                                              int(not self.train_on_padded_locations), B, H, W, L.stream_ptr()))
@@ -428,6 +453,8 @@ class GaussianDiffusion(nn.Module):
         nxt = torch.empty_like(img)
         for step, t in enumerate(times):
             last = step == len(times) - 1
+            if last and grad_last:
+                return self._last_step_with_grad(img, t, rows[step], kwargs)
             eps = L.dev_f32(self._eps(img, t), 'eps')
             z = None
             if noise_iter is not None and not last:

@@ -49,6 +49,11 @@ L.register({
     "sdc_add_inplace": (c_i, [c_p, c_p, c_i64, c_i, c_p]),
     "sdc_head_conv1_bwd": (c_i, [c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_p]),
     "sdc_stem_col2im": (c_i, [c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_p]),
+    "sdc_conv_wgrad": (c_i, [c_i, c_i, c_p, c_i, c_p, c_i, c_p, c_p, c_i, c_i, c_i, c_i, c_p]),
+    "sdc_colsum": (c_i, [c_p, c_p, c_i64, c_i, c_p]),
+    "sdc_gn_param_grad": (c_i, [c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_i64, c_p, c_i, c_i, c_i, c_p]),
+    "sdc_channel_layernorm_gain_grad": (c_i, [c_p, c_p, c_i, c_p, c_i64, c_i, c_p]),
+    "sdc_head_conv1_wgrad": (c_i, [c_p, c_p, c_i, c_p, c_p, c_i, c_i, c_i, c_i, c_p]),
 })
 
 HEADS, DIM_HEAD = 4, 32
@@ -252,6 +257,28 @@ def _copy_into(dst, src):
             _copy_into(x, y)
 
 
+class _TrainFn(torch.autograd.Function):
+    """eps = Unet2D(x, t) with the full backward: d/dx, d/d(FiLM rows) and every convolution / norm parameter gradient
+    (csrc/unet_bwd.cu, csrc/unet_wgrad.cu, tcgen05 dgrad convolutions).  The time-MLP parameters receive their gradients
+    through `film`, which the caller computes with differentiable torch ops on [B, 4*dim] matrices."""
+
+    @staticmethod
+    def forward(ctx, x, film, net, *params):
+        tape = []
+        with torch.cuda.device(x.device):
+            out = net._run(x.detach(), None, None, tape, film_rows=film.detach().float().contiguous())
+        ctx.net, ctx.tape, ctx.params = net, tape, params
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        pg = {}
+        with torch.cuda.device(g.device):
+            gx = ctx.net._vjp(ctx.tape, L.dev_f32(g, "grad_eps"), pgrads=pg, need_gx=ctx.needs_input_grad[0])
+        ctx.tape = None
+        return (gx, pg["film"], None) + tuple(pg.get(id(p)) for p in ctx.params)
+
+
 class _PackCache:
     """Packed-weight cache that is never deep-copied (EMA wrappers deepcopy the module; the copy repacks lazily)."""
 
@@ -361,17 +388,17 @@ class Unet2D(nn.Module):
         with torch.no_grad(), torch.cuda.device(dev):
             def conv(m, kind):
                 return dict(w=pack_conv_weight(kind, m.weight, prec), b=None if m.bias is None else m.bias.detach().float().contiguous(),
-                            cout=m.weight.shape[0])
+                            cout=m.weight.shape[0], mod=m)
 
             def rb(m):
                 return dict(c1=conv(m.block1.proj, KIND_3x3), c2=conv(m.block2.proj, KIND_3x3),
                             g1=(m.block1.norm.weight.detach().float().contiguous(), m.block1.norm.bias.detach().float().contiguous()),
                             g2=(m.block2.norm.weight.detach().float().contiguous(), m.block2.norm.bias.detach().float().contiguous()),
-                            res=conv(m.res_conv, KIND_1x1) if isinstance(m.res_conv, nn.Conv2d) else None, cout=m.dim_out)
+                            res=conv(m.res_conv, KIND_1x1) if isinstance(m.res_conv, nn.Conv2d) else None, cout=m.dim_out, mod=m)
 
             def at(m):
                 inner = m.fn.fn
-                d = dict(g_in=m.fn.norm.g.detach().float().reshape(-1).contiguous(), qkv=conv(inner.to_qkv, KIND_1x1))
+                d = dict(g_in=m.fn.norm.g.detach().float().reshape(-1).contiguous(), qkv=conv(inner.to_qkv, KIND_1x1), mod=m)
                 if isinstance(inner, _LinearAttention):
                     d.update(out=conv(inner.to_out[0], KIND_1x1), g_out=inner.to_out[1].g.detach().float().reshape(-1).contiguous(), full=False,
                              out_w32=inner.to_out[0].weight.detach().float().reshape(inner.to_out[0].weight.shape[0], -1).contiguous())
@@ -462,8 +489,33 @@ class Unet2D(nn.Module):
             raise NotImplementedError("self-conditioning / residual conditioning are outside the 1D hot path")
         return self._forward(x, time=time)
 
+    def _conv_norm_params(self):
+        """Parameters whose gradients the CUDA backward produces directly (everything except the time-embedding MLPs)."""
+        return [p for n, p in self.named_parameters() if not n.startswith("time_mlp.") and ".mlp." not in n]
+
+    def wants_param_grad(self):
+        return torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters())
+
+    def _film_rows_autograd(self, B, time, table_row, device):
+        """FiLM (scale | shift) rows [B, E_total] with torch ops, differentiable w.r.t. the time-MLP parameters
+        (reference unet.py:81-95,152-155,310-315); column layout = the packed FiLM table's."""
+        if table_row is not None:
+            t = torch.full((B,), float(table_row), device=device)
+        else:
+            t = time.to(device=device, dtype=torch.float32)
+        half = self.dim // 2
+        freq = torch.exp(torch.arange(half, device=device) * -(math.log(self.theta) / (half - 1)))
+        emb = t[:, None] * freq[None, :]
+        h = self.time_mlp(torch.cat((emb.sin(), emb.cos()), dim=-1))
+        return torch.cat([m.mlp(h) for m in self._resnet_blocks()], dim=1)
+
     def _forward(self, x, time=None, table_row=None):
         x = L.dev_f32(x, "x")
+        if self.wants_param_grad():
+            # training forward: activations are recorded, backward yields parameter gradients (SURVEY.md section 8f row 1)
+            self._packed()   # fixes the FiLM column offsets
+            film = self._film_rows_autograd(x.shape[0], time, table_row, x.device)
+            return _TrainFn.apply(x, film, self, *self._conv_norm_params())
         if torch.is_grad_enabled() and x.requires_grad:
             # autograd w.r.t. the INPUT (guidance callables that differentiate through the denoiser); parameters get no
             # gradient from this path (fine-tuning is SURVEY.md section 8f)
@@ -489,7 +541,7 @@ class Unet2D(nn.Module):
         with torch.no_grad(), torch.cuda.device(x.device):
             return self._run(L.dev_f32(x, "x"), None, None, t_index=t_index)
 
-    def _run(self, x, time, table_row, tape=None, t_index=None):
+    def _run(self, x, time, table_row, tape=None, t_index=None, film_rows=None):
         """tape: None for inference (buffers are reused); a list to record what the backward-data pass needs (every
         normalisation input is then kept in its own buffer)."""
         pk = self._packed()
@@ -501,7 +553,9 @@ class Unet2D(nn.Module):
         B, Cin, H, W = x.shape
         assert Cin == self.channels
         # FiLM rows: integer times index the cached 1000-row table; anything else is evaluated per sample
-        if t_index is not None:
+        if film_rows is not None:
+            film, t_index = film_rows, torch.arange(B, device=dev, dtype=torch.int32)
+        elif t_index is not None:
             film = self._film_table(pk)
         elif table_row is not None:
             film, t_index = self._film_table(pk)[table_row:table_row + 1], None
@@ -543,7 +597,8 @@ class Unet2D(nn.Module):
             # TF32 mode: in place; F16 mode: h1's buffer is dead after conv2
             out = opd(M, cout) if keep else (raw2 if od == torch.float32 else h1)
             if keep:
-                tape.append(("resnet", dict(p=p, c0=c0, c1=c1, h=h, w=w, raw1=raw, s1=s1, raw2=raw2, s2=s2, ss=ss)))
+                tape.append(("resnet", dict(p=p, c0=c0, c1=c1, h=h, w=w, raw1=raw, s1=s1, raw2=raw2, s2=s2, ss=ss, a0=a0, a1=a1, h1=h1,
+                                            film_off=m._film_off)))
             L.check(lib.sdc_gn_silu(prec, L.ptr(raw2), L.ptr(s2), L.ptr(p["g2"][0]), L.ptr(p["g2"][1]), None, None, 0, L.ptr(res),
                                     res_operand, L.ptr(out), B, h * w, cout, _st()))
             return out
@@ -572,19 +627,19 @@ class Unet2D(nn.Module):
             att = opd(M, HEADS * DIM_HEAD)
             if p["full"]:
                 L.check(lib.sdc_attention(prec, L.ptr(qkv), L.ptr(att), B, n, _st()))
-                out = xn  # reuse
+                out = opd(M, c) if keep else xn  # inference: reuse LN1's buffer
                 conv(KIND_1x1, att, HEADS * DIM_HEAD, None, 0, p["out"], xin, out, None, True, h, w)
                 if keep:
-                    tape.append(("attn", dict(p=p, c=c, h=h, w=w, xin=xin, qkv=qkv)))
+                    tape.append(("attn", dict(p=p, c=c, h=h, w=w, xin=xin, qkv=qkv, xn=xn, att=att)))
                 return out
             ws = torch.empty(lib.sdc_linear_attention_workspace(B), device=dev, dtype=torch.uint8)
             L.check(lib.sdc_linear_attention(prec, L.ptr(qkv), L.ptr(att), L.ptr(ws), B, n, _st()))
             proj = f32(M, c)
             conv(KIND_1x1, att, HEADS * DIM_HEAD, None, 0, p["out"], None, proj, None, False, h, w)
-            out = xn  # reuse: LN1's output is dead once qkv exists
+            out = opd(M, c) if keep else xn  # inference: LN1's output is dead once qkv exists
             L.check(lib.sdc_channel_layernorm(prec, L.ptr(proj), 0, L.ptr(p["g_out"]), L.ptr(xin), L.ptr(out), M, c, 1, _st()))
             if keep:
-                tape.append(("attn", dict(p=p, c=c, h=h, w=w, xin=xin, qkv=qkv, proj=proj, ws=ws)))
+                tape.append(("attn", dict(p=p, c=c, h=h, w=w, xin=xin, qkv=qkv, proj=proj, ws=ws, xn=xn, att=att)))
             return out
 
         c = self.init_conv.weight.shape[0]
@@ -597,7 +652,7 @@ class Unet2D(nn.Module):
         h, w = H, W
         skips = []
         rec = tape.append if keep else (lambda item: None)
-        rec(("stem", dict(B=B, Cin=Cin, H=H, W=W, c=c, t_index=t_index, E=E)))
+        rec(("stem", dict(B=B, Cin=Cin, H=H, W=W, c=c, t_index=t_index, E=E, x=x, film=film)))
         for lvl_m, lvl in zip(self.downs, pk["downs"]):
             cur = resnet(lvl["b1"], lvl_m[0], cur, c, None, 0, h, w)
             skips.append((cur, c))
@@ -614,7 +669,7 @@ class Unet2D(nn.Module):
             else:
                 nxt = opd(B * h * w, cout)
                 conv(KIND_3x3, cur, c, None, 0, lvl["down"], None, nxt, None, True, h, w)
-            rec(("down", dict(p=lvl["down"], unshuffle=lvl["unshuffle"], c=c, h=h, w=w)))
+            rec(("down", dict(p=lvl["down"], unshuffle=lvl["unshuffle"], c=c, h=h, w=w, inp=cur)))
             cur, c = nxt, cout
         cur = resnet(pk["mid1"], self.mid_block1, cur, c, None, 0, h, w)
         cur = attention(pk["mid_attn"], cur, c, h, w)
@@ -634,9 +689,10 @@ class Unet2D(nn.Module):
                 cur = up
             nxt = opd(B * h * w, cout)
             conv(KIND_3x3, cur, c, None, 0, lvl["up"], None, nxt, None, True, h, w)
-            rec(("up", dict(p=lvl["up"], upsample=lvl["upsample"], c=c, h=h, w=w)))
+            rec(("up", dict(p=lvl["up"], upsample=lvl["upsample"], c=c, h=h, w=w, inp=cur)))
             cur, c = nxt, cout
         cur = resnet(pk["final"], self.final_res_block, cur, c, r, r_c, h, w)
+        rec(("head", dict(inp=cur)))
         out = torch.empty(B, self.out_dim, H, W, device=dev, dtype=torch.float32)
         L.check(lib.sdc_head_conv1(prec, L.ptr(cur), L.ptr(pk["head"][0]), L.ptr(pk["head"][1]), L.ptr(out), B, H * W,
                                    self.final_res_block.dim_out, self.out_dim, _st()))
@@ -685,8 +741,12 @@ class Unet2D(nn.Module):
         pk["dgrad"] = d
         return d
 
-    def _vjp(self, tape, g_eps):
-        """d<eps, g_eps>/dx for the forward recorded on `tape` (reverse walk)."""
+    def _vjp(self, tape, g_eps, pgrads=None, need_gx=True):
+        """d<eps, g_eps>/dx for the forward recorded on `tape` (reverse walk).
+
+        pgrads: None, or a dict that receives {id(parameter): fp32 gradient} for every convolution / norm parameter of
+        the network (csrc/unet_wgrad.cu) plus "film" -> d/d(FiLM rows) [B, E_total], from which autograd reaches the
+        time-MLP parameters."""
         pk = self._packed()
         dg = self._dgrad_pack(pk)
         lib = L.lib()
@@ -695,6 +755,49 @@ class Unet2D(nn.Module):
         B, t_index, E = st0["B"], st0["t_index"], st0["E"]
         f32 = lambda rows, c: torch.empty(rows, c, device=dev, dtype=torch.float32)  # noqa: E731
         sums = torch.empty(B, 2, device=dev, dtype=torch.float64)
+        want_p = pgrads is not None
+        if want_p:
+            film = st0["film"]   # per-sample FiLM rows [B, E] (the training forward never uses the per-timestep table)
+            assert film.shape[0] == B and t_index is not None
+            pgrads["film"] = torch.zeros(B, E, device=dev, dtype=torch.float32)
+            rows_of = t_index.long()
+
+        def acc_grad(param, grad):
+            key = id(param)
+            pgrads[key] = grad if key not in pgrads else pgrads[key] + grad
+
+        def conv_wgrad(kind, cw, a0, c0, a1, c1, dy, h, w):
+            """weight (+ bias) gradient of convolution `cw` from its forward inputs and the gradient of its output"""
+            m = cw["mod"]
+            dw = torch.zeros(m.weight.shape, device=dev, dtype=torch.float32)
+            L.check(lib.sdc_conv_wgrad(kind, int(a0.dtype == torch.float16), L.ptr(a0), c0, L.ptr(a1), c1, L.ptr(dy), L.ptr(dw),
+                                       B, h, w, cw["cout"], _st()))
+            acc_grad(m.weight, dw)
+            if m.bias is not None:
+                db = torch.zeros(cw["cout"], device=dev, dtype=torch.float32)
+                L.check(lib.sdc_colsum(L.ptr(dy), L.ptr(db), B * h * w, cw["cout"], _st()))
+                acc_grad(m.bias, db)
+
+        def gn_pgrad(norm, dy, raw, stats, gb, ss, film_off, hw, c):
+            """GroupNorm affine gradients and, for block1, the FiLM (scale, shift) gradients"""
+            P = torch.zeros(B, 2, c, device=dev, dtype=torch.float32)
+            L.check(lib.sdc_gn_param_grad(L.ptr(dy), L.ptr(raw), L.ptr(stats), L.ptr(gb[0]), L.ptr(gb[1]), L.ptr(ss),
+                                          L.ptr(t_index) if ss is not None else None, E if ss is not None else 0, L.ptr(P),
+                                          B, hw, c, _st()))
+            p0, p1 = P[:, 0], P[:, 1]
+            if ss is not None:
+                sc1 = film[rows_of, film_off:film_off + c] + 1.0
+                acc_grad(norm.weight, (sc1 * p1).sum(0))
+                acc_grad(norm.bias, (sc1 * p0).sum(0))
+                pgrads["film"][:, film_off:film_off + 2 * c] += torch.cat([gb[0] * p1 + gb[1] * p0, p0], dim=1)
+            else:
+                acc_grad(norm.weight, p1.sum(0))
+                acc_grad(norm.bias, p0.sum(0))
+
+        def ln_pgrad(gain, dy, x, M, c):
+            d = torch.zeros(c, device=dev, dtype=torch.float32)
+            L.check(lib.sdc_channel_layernorm_gain_grad(L.ptr(dy), L.ptr(x), int(x.dtype == torch.float16), L.ptr(d), M, c, _st()))
+            acc_grad(gain.g, d.reshape(gain.g.shape))
 
         def dgrad(kind, g, cin_g, cw, rows, residual, out_c, operand_out, h, w):
             """Data gradient of conv `cw` restricted to input channels `rows` = (lo, hi): conv of g with Wt[lo:hi]."""
@@ -717,6 +820,14 @@ class Unet2D(nn.Module):
             d_raw2 = gn_bwd(g, r["raw2"], r["s2"], p["g2"], None, h * w, cout)
             d_h1 = dgrad(KIND_3x3, d_raw2, cout, p["c2"], (0, cout), None, cout, False, h, w)
             d_raw1 = gn_bwd(d_h1, r["raw1"], r["s1"], p["g1"], r["ss"], h * w, cout)
+            if want_p:
+                m = p["mod"]
+                gn_pgrad(m.block2.norm, g, r["raw2"], r["s2"], p["g2"], None, 0, h * w, cout)
+                conv_wgrad(KIND_3x3, p["c2"], r["h1"], cout, None, 0, d_raw2, h, w)
+                gn_pgrad(m.block1.norm, d_h1, r["raw1"], r["s1"], p["g1"], r["ss"], r["film_off"], h * w, cout)
+                conv_wgrad(KIND_3x3, p["c1"], r["a0"], c0, r["a1"], c1, d_raw1, h, w)
+                if p["res"] is not None:
+                    conv_wgrad(KIND_1x1, p["res"], r["a0"], c0, r["a1"], c1, g, h, w)
             outs = []
             for lo, hi in ((0, c0), (c0, c0 + c1)):
                 if hi == lo:
@@ -734,16 +845,26 @@ class Unet2D(nn.Module):
             M, n, hid = B * h * w, h * w, HEADS * DIM_HEAD
             xin = r["xin"]
             d_qkv = f32(M, 3 * hid)
+            inner = p["mod"].fn.fn if want_p else None
             if p["full"]:
                 d_att = dgrad(KIND_1x1, g, c, p["out"], (0, hid), None, hid, False, h, w)
                 L.check(lib.sdc_attention_bwd(L.ptr(r["qkv"]), L.ptr(d_att), L.ptr(d_qkv), B, n, _st()))
+                if want_p:
+                    conv_wgrad(KIND_1x1, p["out"], r["att"], hid, None, 0, g, h, w)
             else:
                 d_proj = f32(M, c)
                 L.check(lib.sdc_channel_layernorm_bwd(L.ptr(g), L.ptr(r["proj"]), 0, L.ptr(p["g_out"]), None, L.ptr(d_proj), M, c, 1, _st()))
                 d_att = dgrad(KIND_1x1, d_proj, c, p["out"], (0, hid), None, hid, False, h, w)
                 wsb = torch.empty(lib.sdc_linear_attention_bwd_workspace(B), device=dev, dtype=torch.uint8)
                 L.check(lib.sdc_linear_attention_bwd(L.ptr(r["qkv"]), L.ptr(d_att), L.ptr(r["ws"]), L.ptr(wsb), L.ptr(d_qkv), B, n, _st()))
+                if want_p:
+                    ln_pgrad(inner.to_out[1], g, r["proj"], M, c)
+                    conv_wgrad(KIND_1x1, p["out"], r["att"], hid, None, 0, d_proj, h, w)
+            if want_p:
+                conv_wgrad(KIND_1x1, p["qkv"], r["xn"], c, None, 0, d_qkv, h, w)
             d_xn = dgrad(KIND_1x1, d_qkv, 3 * hid, p["qkv"], (0, c), None, c, False, h, w)
+            if want_p:
+                ln_pgrad(p["mod"].fn.norm, d_xn, xin, M, c)
             d_x = f32(M, c)
             L.check(lib.sdc_channel_layernorm_bwd(L.ptr(d_xn), L.ptr(xin), int(xin.dtype == torch.float16), L.ptr(p["g_in"]), L.ptr(g),
                                                   L.ptr(d_x), M, c, 1, _st()))
@@ -756,9 +877,19 @@ class Unet2D(nn.Module):
         # ---- reverse walk ----
         i = len(tape) - 1
         kind, r = tape[i]
-        assert kind == "resnet"   # final_res_block; the head is not on the tape (no saved state)
+        assert kind == "head"
         Hh, Ww = st0["H"], st0["W"]
         cfin = self.final_res_block.dim_out
+        if want_p:
+            dwh = torch.zeros(self.out_dim, cfin, device=dev, dtype=torch.float32)
+            dbh = torch.zeros(self.out_dim, device=dev, dtype=torch.float32)
+            L.check(lib.sdc_head_conv1_wgrad(L.ptr(g_eps), L.ptr(r["inp"]), int(r["inp"].dtype == torch.float16), L.ptr(dwh), L.ptr(dbh),
+                                             B, Hh * Ww, cfin, self.out_dim, _st()))
+            acc_grad(self.final_conv.weight, dwh.reshape(self.final_conv.weight.shape))
+            acc_grad(self.final_conv.bias, dbh)
+        i -= 1
+        kind, r = tape[i]
+        assert kind == "resnet"   # final_res_block
         g = f32(B * Hh * Ww, cfin)
         L.check(lib.sdc_head_conv1_bwd(L.ptr(g_eps), L.ptr(pk["head"][0]), L.ptr(g), B, Hh * Ww, cfin, self.out_dim, 1, _st()))
         g, g_r = resnet_bwd(r, g)
@@ -768,6 +899,8 @@ class Unet2D(nn.Module):
             kind, r = tape[i]
             if kind == "up":
                 c, h, w = r["c"], r["h"], r["w"]
+                if want_p:
+                    conv_wgrad(KIND_3x3, r["p"], r["inp"], c, None, 0, g, h, w)
                 if r["upsample"]:
                     g_hi = dgrad(KIND_3x3, g, r["p"]["cout"], r["p"], (0, c), None, c, False, h, w)
                     g = f32(B * (h // 2) * (w // 2), c)
@@ -784,6 +917,8 @@ class Unet2D(nn.Module):
                 # the tensor entering the downsample was also pushed as a skip: its up-path gradient is the last entry
                 c, h, w = r["c"], r["h"], r["w"]
                 sg = skip_grads.pop()
+                if want_p:
+                    conv_wgrad(KIND_UNSHUFFLE if r["unshuffle"] else KIND_3x3, r["p"], r["inp"], c, None, 0, g, h, w)
                 if r["unshuffle"]:
                     t = dgrad(KIND_1x1, g, r["p"]["cout"], r["p"], (0, 4 * c), None, 4 * c, False, h, w)
                     g = f32(B * 4 * h * w, c)
@@ -798,8 +933,24 @@ class Unet2D(nn.Module):
             i -= 1
         assert not skip_grads
         g = add_(g, g_r)   # the stem output also feeds final_res_block (r = x.clone(), unet.py:393)
-        wt, kp = dg["stem"]
         c = st0["c"]
+        if want_p:
+            # stem 7x7: weight gradient of the GEMM over the (high | low) im2col operand, the two halves folded back
+            prec, kps = pk["prec"], pk["stem"]["kp"]
+            patches = torch.empty(B * Hh * Ww, kps, device=dev, dtype=operand_dtype(prec))
+            L.check(lib.sdc_stem_im2col(prec, L.ptr(st0["x"]), L.ptr(patches), B, st0["Cin"], Hh, Ww, kps, _st()))
+            dwp = torch.zeros(c, kps, device=dev, dtype=torch.float32)
+            L.check(lib.sdc_conv_wgrad(KIND_1x1, int(patches.dtype == torch.float16), L.ptr(patches), kps, None, 0, L.ptr(g), L.ptr(dwp),
+                                       B, Hh, Ww, c, _st()))
+            k = st0["Cin"] * 49
+            acc_grad(self.init_conv.weight, (dwp[:, :k] + dwp[:, kps // 2:kps // 2 + k]).reshape(self.init_conv.weight.shape))
+            dbs = torch.zeros(c, device=dev, dtype=torch.float32)
+            L.check(lib.sdc_colsum(L.ptr(g), L.ptr(dbs), B * Hh * Ww, c, _st()))
+            acc_grad(self.init_conv.bias, dbs)
+            del patches
+        if not need_gx:
+            return None
+        wt, kp = dg["stem"]
         t = f32(B * Hh * Ww, kp)
         conv_gemm(KIND_1x1, g, c, None, 0, wt, None, None, t, None, False, B, Hh, Ww, kp, PREC_TF32)
         gx = torch.empty(B, st0["Cin"], Hh, Ww, device=dev, dtype=torch.float32)
