@@ -221,6 +221,23 @@ def gen_unet_pgrad():
          **fx.grad_digest([(n, p.grad) for n, p in net.named_parameters()]))
 
 
+def gen_ploss():
+    """Training loss of the unmodified reference (GaussianDiffusion.p_losses, diffusion.py:638-733) and its parameter
+    gradients (digest), on dataset-like states with fixed t and noise."""
+    dim, B = 64, 2
+    net = _unet(dim).train()
+    gd = _diffusion(1000, 200, model=net)
+    x0 = fx.calibration_states(B)
+    t = torch.tensor([417, 3])
+    noise = fx.chain_noise(B, 1, seed=9)[0]
+    per_sample = gd.p_losses(x0.clone(), t, noise=noise.clone(), mean=False)
+    loss = gd.p_losses(x0.clone(), t, noise=noise.clone(), mean=True)
+    net.zero_grad()
+    loss.backward()
+    save(f"unet_dim{dim}_ploss", per_sample=per_sample.detach(), loss=loss.detach(),
+         **fx.grad_digest([(n, p.grad) for n, p in net.named_parameters()]))
+
+
 def gd_time_pairs(gd):
     times = torch.linspace(-1, gd.num_timesteps - 1, steps=gd.sampling_timesteps + 1)
     times = list(reversed(times.int().tolist()))
@@ -268,7 +285,7 @@ def gen_config1():
 
 
 ALL = {"schedule": gen_schedule, "solver": gen_solver, "chains": gen_chains, "guidance": gen_guidance,
-       "conformal": gen_conformal, "unet": gen_unet, "unet_vjp": gen_unet_vjp, "unet_pgrad": gen_unet_pgrad, "config1": gen_config1}
+       "conformal": gen_conformal, "unet": gen_unet, "unet_vjp": gen_unet_vjp, "unet_pgrad": gen_unet_pgrad, "ploss": gen_ploss, "config1": gen_config1}
 
 if __name__ == "__main__":
     names = sys.argv[1:] or [k for k in ALL if k != "config1"]

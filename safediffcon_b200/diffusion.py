@@ -6,7 +6,8 @@ to the denoiser evaluation, with no host synchronisation inside the chain.
 Scope: objective 'pred_noise', temporal 2-D layout [B, C, Nt, Nx], u0/uT/w conditioning,
 pad writes, safety guidance.  Options that no shipped 1D config enables (self-conditioning, residual
 conditioning, two-model evaluation, recurrence, expand_condition, pred_x0/pred_v) raise NotImplementedError.
-Training (``forward`` = p_losses) is a "next" row and raises as well.
+``forward`` / ``p_losses`` (training loss) and the ``enable_grad`` last DDIM step run the denoiser's CUDA forward with its
+full CUDA backward (parameter gradients), so the reference's InferenceFT / PostTrainPipeline optimiser loops work on it.
 """
 import ctypes
 import math
@@ -502,5 +503,45 @@ class GaussianDiffusion(nn.Module):
         sample_fn = self.p_sample_loop if not self.is_ddim_sampling else self.ddim_sample
         return sample_fn(sample_size, clip_denoised=clip_denoised, w_groundtruth=w_groundtruth, enable_grad=enable_grad, **kwargs)
 
+    # ------------------------------------------------------------------ training loss
+    def q_sample(self, x_start, t, noise=None):
+        """x_t ~ q(x_t | x_0) (reference diffusion.py:629-636)."""
+        noise = torch.randn_like(x_start) if noise is None else noise
+        return extract(self.sqrt_alphas_cumprod, t, x_start.shape) * x_start + \
+            extract(self.sqrt_one_minus_alphas_cumprod, t, x_start.shape) * noise
+
+    def p_losses(self, x_start, t, noise=None, mean=True):
+        """Diffusion training loss of the reference (diffusion.py:638-733) for the options this implementation covers
+        (pred_noise, u0/uT conditioning, pad masking).  The denoiser call is the CUDA forward whose backward yields the
+        parameter gradients (unet.py: _TrainFn); the surrounding [B,3,16,128] algebra is plain torch, as in the reference.
+        The reference zeroes the conditioned rows of the caller's `noise` tensor in place; so does this."""
+        noise = torch.randn_like(x_start) if noise is None else noise
+        x = self.q_sample(x_start=x_start, t=t, noise=noise)
+        if self.is_condition_u0:
+            self.set_condition(x, x_start[:, 0, 0, :], x.shape, 'u0')
+        if self.is_condition_uT:
+            self.set_condition(x, x_start[:, 0, self.condition_idx, :], x.shape, 'uT')
+        if not self.train_on_padded_locations:
+            self.set_pad_condition(x)
+        model_out = self.model(x, t, None, residual=None)
+        target = noise
+        if self.train_on_partially_observed is not None:
+            raise NotImplementedError("train_on_partially_observed is outside the 1D hot path")
+        if self.is_condition_u0 and self.is_condition_u0_zero_pred_noise:
+            self.set_condition(noise, torch.zeros_like(x[:, 0, 0, :]), x.shape, 'u0')
+        if self.is_condition_uT and self.is_condition_uT_zero_pred_noise:
+            self.set_condition(noise, torch.zeros_like(x[:, 0, 0, :]), x.shape, 'uT')
+        if not self.train_on_padded_locations:
+            model_out = model_out.clone()
+            self.set_pad_condition(model_out, origin_img=target)
+        loss = torch.nn.functional.mse_loss(model_out, target, reduction='none')
+        loss = loss.reshape(loss.shape[0], -1).mean(dim=1)
+        loss = loss * extract(self.loss_weight, t, loss.shape)
+        return loss.mean() if mean else loss
+
     def forward(self, img, *args, **kwargs):
-        raise NotImplementedError("training loss (p_losses) is outside the accelerated hot path (SURVEY.md section 8f)")
+        """loss = p_losses(img, t ~ U{0..T-1}) (reference diffusion.py:735-746)."""
+        b, c, nt, nx = img.shape
+        assert (nt, nx) == tuple(self.traj_size), f'traj size must be (nt, nx) of ({nt, nx}), but got {self.traj_size}'
+        t = torch.randint(0, self.num_timesteps, (b,), device=img.device).long()
+        return self.p_losses(img, t, *args, **kwargs)

@@ -1,2 +1,3 @@
 set -x
-python -m pytest tests/test_unet_pgrad_gpu.py -q -s > gpurun_out/pgrad_tests.log 2>&1; echo "pgrad tests rc=$?"; tail -40 gpurun_out/pgrad_tests.log
+python -m pytest tests -m gpu -q -s > gpurun_out/r01f_tests.log 2>&1; echo "tests rc=$?"; tail -15 gpurun_out/r01f_tests.log
+

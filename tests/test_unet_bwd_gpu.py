@@ -233,9 +233,17 @@ def test_unet_input_gradient_vs_reference_golden(dim, precision, golden):
     r = rel(gx.cpu(), ref_gx)
     per = [rel(gx[i].cpu(), ref_gx[i]) for i in range(2)]
     assert r < 3e-3 and max(per) < 3e-3, (r, per)
-    # explicit API gives the same numbers; the no-grad path is untouched by the tape
+    # trainable parameters route autograd through the full backward (FiLM rows by torch); frozen parameters (an EMA copy) through
+    # the input-only VJP, which must be bit-identical to the explicit API
     eps2, gx2 = net.vjp(x.cuda(), t.cuda(), gct.cuda())
-    assert torch.equal(gx2, gx) and torch.equal(eps2, eps.detach())
+    # (the two paths evaluate exp/sin of the time embedding with different libm's: 1-ulp frequency differences times t <= 999)
+    assert rel(gx2, gx) < 2e-3 and rel(eps2, eps.detach()) < 1e-3
+    for p in net.parameters():
+        p.requires_grad_(False)
+    xf = x.cuda().requires_grad_()
+    eps_f = net(xf, t.cuda())
+    (gx_f,) = torch.autograd.grad(eps_f, xf, gct.cuda())
+    assert torch.equal(gx2, gx_f) and torch.equal(eps2, eps_f.detach())
     with torch.no_grad():   # the inference path (fused attention, reused buffers) agrees with the recording path to rounding
         assert rel(net(x.cuda(), t.cuda()), eps.detach()) < 1e-3
     # linearity of the VJP in the cotangent (size-independent property)

@@ -245,3 +245,26 @@ def test_sample_enable_grad_feeds_an_optimizer_step(monkeypatch):
     for p in net.parameters():
         p.requires_grad_(False)
     assert not gd.sample(enable_grad=True, **kw).requires_grad
+
+
+def test_training_loss_and_gradients_vs_reference(golden):
+    """GaussianDiffusion.p_losses (the loss PostTrainPipeline re-weights, post_train.py:206-260) and its parameter gradients."""
+    import safediffcon_b200 as s
+    gold = golden("unet_dim64_ploss")
+    net = _net("f16")
+    gd = s.GaussianDiffusion(net, seq_length=(16, 128), timesteps=1000, sampling_timesteps=200, ddim_sampling_eta=1.0, temporal=True,
+                             use_conv2d=True, is_condition_u0=True, is_condition_uT=True, condition_idx=10).cuda()
+    x0 = fx.calibration_states(2).cuda()
+    t = torch.tensor([417, 3]).cuda()
+    noise = fx.chain_noise(2, 1, seed=9)[0].cuda()
+    per_sample = gd.p_losses(x0.clone(), t, noise=noise.clone(), mean=False)
+    assert rel(per_sample.detach().cpu(), torch.from_numpy(gold["per_sample"])) < 1e-3
+    loss = gd.p_losses(x0.clone(), t, noise=noise.clone(), mean=True)
+    assert abs(loss.item() / float(gold["loss"]) - 1) < 1e-3
+    net.zero_grad()
+    loss.backward()
+    worst = _check_digest(net, gold, tol_samples=1e-2, tol_norm=5e-3)
+    print("worst training-loss gradient error", worst)
+    # forward(img) draws t itself and returns a scalar with a graph
+    out = gd(x0)
+    assert out.ndim == 0 and out.requires_grad
