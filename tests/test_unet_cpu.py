@@ -56,3 +56,23 @@ def test_oracle_input_gradient_matches_reference_golden(golden):
         g = golden(f"unet_dim{dim}_vjp")
         assert np.allclose(eps.detach().numpy(), g["eps"], rtol=0, atol=1e-5 * np.abs(g["eps"]).max())
         assert np.allclose(gx.numpy(), g["grad_x"], rtol=0, atol=1e-5 * np.abs(g["grad_x"]).max())
+
+
+def test_oracle_parameter_gradients_match_reference_golden(golden):
+    """Oracle restatement under autograd reproduces the reference's parameter-gradient digests: the
+    dense-cotangent set and the drop-in module's key layout (all 276 parameters)."""
+    import safediffcon_b200 as s
+    from oracle import fixtures as fx, unet_ref
+    torch.manual_seed(42)
+    net = s.Unet2D(dim=64, dim_mults=(1, 2, 4, 8), channels=3, resnet_block_groups=1)
+    sd = {k: v.detach().clone().requires_grad_() for k, v in net.state_dict().items()}
+    x, t = fx.unet_inputs(2)
+    eps = unet_ref.unet_forward(sd, x, t)
+    grads = torch.autograd.grad(eps, list(sd.values()), fx.unet_cotangent(2))
+    got = fx.grad_digest(zip(sd.keys(), grads))
+    g = golden("unet_dim64_pgrad")
+    assert {k[:-5] for k in g.files if k.endswith("|norm")} == set(sd)
+    for k in sd:
+        assert abs(got[k + "|norm"] / float(g[k + "|norm"]) - 1) < 1e-4, k
+        scale = float(g[k + "|norm"]) / np.sqrt(sd[k].numel())
+        assert np.abs(got[k + "|samples"] - g[k + "|samples"]).max() < 2e-3 * scale + 1e-12, k
