@@ -23,7 +23,10 @@ extern "C" {
 /* Repack an OIHW fp32 conv weight [Cout, Cin, kh, kw] into the K-major GEMM operand Wp[Cout, taps*Cin]
  * (K index = tap*Cin + cin, tap = ky*kw_ + kx), rounded to the operand precision.
  * kind 0: 1x1, 1: 3x3, 2: the 1x1 conv that follows the pixel-unshuffle of Downsample2d (unet.py:39-43):
- * Cin = 4*C with channel index c*4 + p1*2 + p2  ->  K index = (p1*2+p2)*C + c. */
+ * Cin = 4*C with channel index c*4 + p1*2 + p2  ->  K index = (p1*2+p2)*C + c.
+ * kind 3: the 3x3 conv that follows the nearest x2 upsample of Upsample2d (unet.py:33-37), packed for the fused
+ * upsample convolution: Wp[4*Cout, 4*Cin], row = phase*Cout + co (phase = 2a + b = parity of the output pixel), K index =
+ * (2r + s)*Cin + ci over the 2x2 low-resolution window; each entry is the sum of the 3x3 taps that read that input pixel. */
 int sdc_pack_conv_weight(int prec, int kind, const float* w_oihw, void* w_packed, int Cout, int Cin, void* stream);
 
 /* Implicit-GEMM convolution on tcgen05 (replaces nn.Conv2d 3x3 pad 1 / 1x1, unet.py:132,161,189-192,232-233,345,370,
@@ -32,6 +35,9 @@ int sdc_pack_conv_weight(int prec, int kind, const float* w_oihw, void* w_packed
  * out[B*H*W, Cout] = conv + bias (+ residual[B*H*W, Cout], an operand-precision tensor).
  * stats (optional): double[B][2], += (sum, sum of squares) of the fp32 results per sample (GroupNorm(1, C)).
  * operand_out: 1 = store `out` in the operand precision (it feeds another convolution), 0 = plain fp32.
+ * kind 3 (nearest-upsample x2 followed by 3x3 pad 1, Upsample2d): H x W is the INPUT size, out is [B*2H*2W, Cout]; the
+ * upsampled tensor is never materialised -- output pixel (2i+a, 2j+b) is a 2x2 convolution of the input with the phase-(a, b)
+ * weights of sdc_pack_conv_weight(kind 3), i.e. 4/9 of the multiply-adds; single input, no residual / stats, W = 16 or W % 32 == 0.
  * Requirements: W | 128, (H*W) % 32 == 0, input channels % 32 (TF32) / % 64 (F16) == 0, Cout % 32 == 0. */
 int sdc_conv_gemm(int prec, int kind, const void* a0, int c0, const void* a1, int c1, const void* w_packed, const float* bias,
                   const void* residual, void* out, double* stats, int operand_out, int B, int H, int W, int Cout,

@@ -3,7 +3,9 @@
 // Replaces every nn.Conv2d of Unet2D except the 3-channel stem (/root/reference/1D/model/unet.py:132,161,
 // 189-192,232-233,33-43,345,370,378):   out[M, Cout] = im2col(A)[M, K] * Wp[Cout, K]^T + bias
 //   M = B*H*W output pixels (NHWC activations: fp16, or fp32 containers holding TF32-rounded values)
-//   K = taps * Cin   (3x3 pad 1: 9 taps; 1x1: 1 tap; pixel-unshuffle 2x2/stride 2: 4 taps),
+//   K = taps * Cin   (3x3 pad 1: 9 taps; 1x1: 1 tap; pixel-unshuffle 2x2/stride 2: 4 taps; nearest-upsample x2 + 3x3: four
+//       2x2 phase convolutions of 4 taps on the LOW-resolution input -- the upsampled tensor never exists and the
+//       contraction is 2.25x shorter, see kind 3 below),
 //       Cin may be the concatenation of two tensors (U-Net skip connections) -> two K segments, no torch.cat.
 //
 // Mapping (persistent: one CTA per SM walks a contiguous range of 128 x BN output tiles, 192 threads):
@@ -35,7 +37,13 @@ constexpr int STG_BUF = 4096;  // one epilogue staging buffer: 32 rows x 128 byt
 constexpr int STG_BYTES = 4 * 2 * STG_BUF;   // 4 epilogue warps x double buffer
 
 struct GemmParams {
-    int kind;            // 0: 1x1, 1: 3x3 pad 1, 2: 2x2 stride-2 (pixel-unshuffle + 1x1)
+    int kind;            // 0: 1x1, 1: 3x3 pad 1, 2: 2x2 stride-2 (pixel-unshuffle + 1x1), 3: nearest-upsample x2 + 3x3 pad 1
+                         //    (Upsample2d, unet.py:33-37).  Kind 3: output pixel (2i+a, 2j+b) only sees the 2x2 input window
+                         //    rows {i+a-1, i+a}, cols {j+b-1, j+b}: per phase (a, b) a 4-tap convolution whose weights are sums
+                         //    of the 3x3 taps that land on the same input pixel (packed by sdc_pack_conv_weight kind 3 as
+                         //    Wp[phase*Cout + co, tap*Cin + ci]); zero padding of the upsampled image == out-of-range input rows.
+                         //    M, H, W describe the INPUT (low) resolution; every phase writes a strided quarter of the output.
+    int phases;          // 4 for kind 3, else 1; tile id = (m * phases + phase) * tiles_n + n
     int M;               // valid output rows
     int Cout;
     int bn;              // N tile (multiple of 32, <= 256)
@@ -86,9 +94,10 @@ __device__ __forceinline__ void conv_gemm_body(const CUtensorMap& map_a0, const 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t rank = PAIR ? cluster_ctarank() : 0u;
     const bool leader = rank == 0;
-    const int taps = p.kind == 1 ? 9 : (p.kind == 2 ? 4 : 1);
+    const int taps = p.kind == 1 ? 9 : (p.kind >= 2 ? 4 : 1);
     const int ctot = p.c0 + p.c1;
     const int chunks = ctot / BK;
+    const int tiles_pn = p.phases * p.tiles_n;
     const int num_kb = taps * chunks;
     uint32_t acc_cols = 32;                      // TMEM columns per accumulator buffer (power of two >= bn)
     while ((int)acc_cols < p.bn) acc_cols <<= 1;
@@ -117,7 +126,8 @@ __device__ __forceinline__ void conv_gemm_body(const CUtensorMap& map_a0, const 
         if (lane == 0) {
             int g = 0;  // running K-block counter across tiles (smem ring position)
             for (int tile = tile_lo; tile < tile_hi; ++tile) {
-                const int mq = tile / p.tiles_n, nt = tile - mq * p.tiles_n;
+                const int mq = tile / tiles_pn, pn = tile - mq * tiles_pn;
+                const int phase = pn / p.tiles_n, nt = pn - phase * p.tiles_n;
                 const int mt = PAIR ? 2 * mq + (int)rank : mq;
                 // tile origin in (image, row); tiles always span full rows (bw == W)
                 const int pix0 = mt * BM;
@@ -142,12 +152,14 @@ __device__ __forceinline__ void conv_gemm_body(const CUtensorMap& map_a0, const 
                         if constexpr (PAIR) tma_load_5d_2sm(sa, ma, &full_bar[s], (tap & 1) * cin + cseg, 0, tap >> 1, h0, b0);
                         else tma_load_5d(sa, ma, &full_bar[s], (tap & 1) * cin + cseg, 0, tap >> 1, h0, b0);
                     } else {
-                        const int dy = p.kind == 1 ? tap / 3 - 1 : 0;
-                        const int dx = p.kind == 1 ? tap % 3 - 1 : 0;
+                        int dy = 0, dx = 0;
+                        if (p.kind == 1) { dy = tap / 3 - 1; dx = tap % 3 - 1; }
+                        else if (p.kind == 3) { dy = (phase >> 1) - 1 + (tap >> 1); dx = (phase & 1) - 1 + (tap & 1); }
                         if constexpr (PAIR) tma_load_4d_2sm(sa, ma, &full_bar[s], cseg, dx, h0 + dy, b0);
                         else tma_load_4d(sa, ma, &full_bar[s], cseg, dx, h0 + dy, b0);
                     }
-                    const int wrow = nt * p.bn + b0 * p.w_sample_rows;   // per-sample weights: tiles never straddle samples (host check)
+                    // per-sample weights: tiles never straddle samples (host check); kind 3: one weight block per phase
+                    const int wrow = nt * p.bn + b0 * p.w_sample_rows + phase * p.Cout;
                     if constexpr (PAIR) tma_load_2d_2sm(sb, &map_w, &full_bar[s], tap * ctot + cc, wrow + (int)rank * b_rows);
                     else tma_load_2d(sb, &map_w, &full_bar[s], tap * ctot + cc, wrow);
                 }
@@ -192,7 +204,9 @@ __device__ __forceinline__ void conv_gemm_body(const CUtensorMap& map_a0, const 
         int it = 0;
         uint32_t nchunk = 0;
         for (int tile = tile_lo; tile < tile_hi; ++tile, ++it) {
-            const int mq = tile / p.tiles_n, nt = tile - mq * p.tiles_n;
+            const int mq = tile / tiles_pn, pn = tile - mq * tiles_pn;
+            const int phase = pn / p.tiles_n, nt = pn - phase * p.tiles_n;
+            const int up = p.kind == 3 ? phase : -1;
             const int mt = PAIR ? 2 * mq + (int)rank : mq;
             const int buf = it & 1;
             mbar_wait(&acc_full[buf], (uint32_t)(it >> 1) & 1u);
@@ -211,8 +225,8 @@ __device__ __forceinline__ void conv_gemm_body(const CUtensorMap& map_a0, const 
                 const act_t* rrow = resid ? resid + (size_t)m * p.Cout + col : nullptr;
                 if (m_w < p.M) {
                     if (col < p.q_cols) epilogue_chunk_qsoftmax<HALF>(taddr, sb, &map_q, col, m_w, lane);
-                    else if (out_half) epilogue_chunk<true, act_t>(taddr, sb, &map_out, col - p.q_cols, m_w, row_ok, p.bias, rrow, false, s1, s2, lane);
-                    else epilogue_chunk<false, act_t>(taddr, sb, &map_out, col - p.q_cols, m_w, row_ok, p.bias, rrow, p.operand_out != 0, s1, s2, lane);
+                    else if (out_half) epilogue_chunk<true, act_t>(taddr, sb, &map_out, col - p.q_cols, m_w, row_ok, p.bias, rrow, false, s1, s2, lane, up, p.W);
+                    else epilogue_chunk<false, act_t>(taddr, sb, &map_out, col - p.q_cols, m_w, row_ok, p.bias, rrow, p.operand_out != 0, s1, s2, lane, up, p.W);
                 }
             }
             // accumulator buffer fully read -> hand it back to the MMA warp
@@ -286,7 +300,9 @@ static int conv_gemm_launch(int prec, int kind, const void* a0, int c0, const vo
     SDC_REQUIRE(prec == SDC_PREC_TF32 || prec == SDC_PREC_F16, "conv_gemm: precision %d", prec);
     const bool half = prec == SDC_PREC_F16;
     const int BK = half ? 64 : 32;
-    SDC_REQUIRE(kind >= 0 && kind <= 2, "conv_gemm: kind %d", kind);
+    SDC_REQUIRE(kind >= 0 && kind <= 3, "conv_gemm: kind %d", kind);
+    SDC_REQUIRE(kind != 3 || (c1 == 0 && !residual && !stats && !q_cols && !per_sample_weights && (W == 16 || W % 32 == 0)),
+                "conv_gemm: the fused upsample convolution takes one input, no residual / statistics, input W of 16 or a multiple of 32");
     SDC_REQUIRE(B > 0 && H > 0 && W > 0, "conv_gemm: empty problem");
     SDC_REQUIRE(a0 && w_packed && out, "conv_gemm: null pointer");
     SDC_REQUIRE(c0 > 0 && c0 % BK == 0 && c1 >= 0 && c1 % BK == 0 && (c1 == 0 || a1), "conv_gemm: channels must be multiples of %d", BK);
@@ -304,6 +320,7 @@ static int conv_gemm_launch(int prec, int kind, const void* a0, int c0, const vo
     GemmParams p{};
     p.q_cols = q_cols;
     p.w_sample_rows = per_sample_weights ? Cout : 0;
+    p.phases = kind == 3 ? 4 : 1;
     p.kind = kind; p.M = B * H * W; p.Cout = Cout; p.bn = bn; p.H = H; p.W = W; p.bh = bh; p.bb = bb;
     p.c0 = c0; p.c1 = c1; p.operand_out = operand_out; p.hw_per_sample = H * W;
     p.bias = bias; p.residual = residual; p.out = out; p.stats = stats;
@@ -318,14 +335,14 @@ static int conv_gemm_launch(int prec, int kind, const void* a0, int c0, const vo
     // CTA pairs (cta_group::2) whenever there are at least as many 256-row pair tiles as SM pairs
     // per-sample weights: every (pair) tile must lie inside one sample
     SDC_REQUIRE(!per_sample_weights || (H * W) % BM == 0, "conv_gemm: per-sample weights need H*W %% 128 == 0");
-    const bool pair = allow_pair && ((tiles_m + 1) / 2) * (Cout / bn) >= n_sm / 2 && (!per_sample_weights || (H * W) % (2 * BM) == 0);
+    const bool pair = allow_pair && ((tiles_m + 1) / 2) * (Cout / bn) * p.phases >= n_sm / 2 && (!per_sample_weights || (H * W) % (2 * BM) == 0);
     const int stage_bytes = A_BYTES + (pair ? bn / 2 : bn) * 128;
     int stages = (190 * 1024) / stage_bytes;
     if (stages > 8) stages = 8;
     p.stages = stages;
     const int smem_bytes = stages * stage_bytes + STG_BYTES + (2 * stages + 4) * 8 + 16 + 1024;
     p.tiles_n = Cout / bn;
-    p.tiles_total = (pair ? (tiles_m + 1) / 2 : tiles_m) * p.tiles_n;
+    p.tiles_total = (pair ? (tiles_m + 1) / 2 : tiles_m) * p.tiles_n * p.phases;
     const int workers = pair ? n_sm / 2 : n_sm;
     const int ctas = p.tiles_total < workers ? p.tiles_total : workers;
     p.tiles_per_cta = (p.tiles_total + ctas - 1) / ctas;
@@ -335,15 +352,27 @@ static int conv_gemm_launch(int prec, int kind, const void* a0, int c0, const vo
     int rc = encode_act(&ma0, a0, kind, B, H, W, c0, bh, bb, half);
     if (rc) return rc;
     if (c1) { rc = encode_act(&ma1, a1, kind, B, H, W, c1, bh, bb, half); if (rc) return rc; } else ma1 = ma0;
-    const int taps = kind == 1 ? 9 : (kind == 2 ? 4 : 1);
+    const int taps = kind == 1 ? 9 : (kind >= 2 ? 4 : 1);
     const cuuint64_t ktot = (cuuint64_t)taps * (c0 + c1);
-    cuuint64_t wd[2] = {ktot, (cuuint64_t)Cout * (cuuint64_t)(per_sample_weights ? B : 1)};
+    cuuint64_t wd[2] = {ktot, (cuuint64_t)Cout * (cuuint64_t)(per_sample_weights ? B : p.phases)};
     cuuint64_t ws[1] = {ktot * (half ? 2 : 4)};
     cuuint32_t wb[2] = {(cuuint32_t)BK, (cuuint32_t)(pair ? bn / 2 : bn)};
     rc = encode_tmap(&mw, w_packed, 2, wd, ws, wb, half);
     if (rc) return rc;
     CUtensorMap mo, mq;
-    rc = encode_out_tmap(&mo, out, p.M, Cout - q_cols, half && operand_out);
+    if (kind == 3) {
+        // high-resolution output [B, 2H, 2W, Cout] viewed as {Cout, 2 (b), W, 2 (a), B*H}; a 32-row chunk = 32 consecutive
+        // low-resolution pixels = box {32 cols, 1, min(W, 32), 1, 32 / min(W, 32)}
+        const bool oh = half && operand_out;
+        const cuuint64_t eb = oh ? 2 : 4;
+        const cuuint32_t bw = W < 32 ? W : 32;
+        cuuint64_t od[5] = {(cuuint64_t)Cout, 2, (cuuint64_t)W, 2, (cuuint64_t)B * H};
+        cuuint64_t os[4] = {(cuuint64_t)Cout * eb, (cuuint64_t)2 * Cout * eb, (cuuint64_t)2 * W * Cout * eb, (cuuint64_t)4 * W * Cout * eb};
+        cuuint32_t ob[5] = {32, 1, bw, 1, 32 / bw};
+        rc = encode_tmap(&mo, out, 5, od, os, ob, oh, oh ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B);
+    } else {
+        rc = encode_out_tmap(&mo, out, p.M, Cout - q_cols, half && operand_out);
+    }
     if (rc) return rc;
     if (q_cols) { rc = encode_out_tmap(&mq, q_out, p.M, q_cols, half); if (rc) return rc; } else mq = mo;
 

@@ -128,6 +128,10 @@ __device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t sr
     asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
                  ::"l"(map), "r"(src_smem), "r"(c0), "r"(c1) : "memory");
 }
+__device__ __forceinline__ void tma_store_5d(const CUtensorMap* map, uint32_t src_smem, int c0, int c1, int c2, int c3, int c4) {
+    asm volatile("cp.async.bulk.tensor.5d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5, %6}], [%1];"
+                 ::"l"(map), "r"(src_smem), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4) : "memory");
+}
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
@@ -147,7 +151,7 @@ __device__ __forceinline__ void bulk_wait() { asm volatile("cp.async.bulk.wait_g
 template <bool OUT_HALF, typename res_t>
 __device__ __forceinline__ void epilogue_chunk(uint32_t taddr, uint32_t stg, const CUtensorMap* map_out, int col, int row0,
                                                bool row_ok, const float* __restrict__ bias, const res_t* __restrict__ res_row,
-                                               bool round, float& s1, float& s2, int lane) {
+                                               bool round, float& s1, float& s2, int lane, int up_phase = -1, int up_w = 0) {
     uint32_t r[32];
     tmem_ld32(taddr, r);
     float v[32];
@@ -199,7 +203,10 @@ __device__ __forceinline__ void epilogue_chunk(uint32_t taddr, uint32_t stg, con
     fence_proxy_async();   // generic-proxy writes above -> visible to the async proxy (TMA) below
     __syncwarp();
     if (lane == 0) {
-        tma_store_2d(map_out, stg, col, row0);
+        // up_phase >= 0: rows are low-resolution pixels of one phase (a, b) of a fused nearest-upsample convolution; the output
+        // map is the 5-D view {Cout, 2 (b), W, 2 (a), B*H} of the high-resolution tensor (see conv_gemm.cu, kind 3)
+        if (up_phase >= 0) tma_store_5d(map_out, stg, col, up_phase & 1, row0 % up_w, up_phase >> 1, row0 / up_w);
+        else tma_store_2d(map_out, stg, col, row0);
         bulk_commit();
     }
 }

@@ -9,6 +9,27 @@
 namespace sdc {
 
 // ---------------------------------------------------------------------------------------------- weight packing
+// kind 3 (nearest-upsample x2 + 3x3): Wp[(phase*Cout + co), tap*Cin + ci] with phase = 2a + b (output pixel parity), tap = 2r + s
+// (position in the 2x2 low-resolution window): the sum of the 3x3 taps (ky, kx) whose upsampled pixel (2i+a+ky-1, 2j+b+kx-1)
+// falls on low-resolution pixel (i+a-1+r, j+b-1+s): a = 0: r = 0 <- ky 0, r = 1 <- ky 1,2;  a = 1: r = 0 <- ky 0,1, r = 1 <- ky 2.
+template <typename T>
+__global__ void pack_upconv_weight_kernel(const float* __restrict__ w, T* __restrict__ wp, int Cout, int Cin) {
+    const int64_t total = (int64_t)16 * Cout * Cin;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int K = 4 * Cin;
+        const int row = (int)(i / K), k = (int)(i % K);
+        const int phase = row / Cout, co = row % Cout, tap = k / Cin, ci = k % Cin;
+        const int a = phase >> 1, b = phase & 1, r = tap >> 1, s2 = tap & 1;
+        const int ky0 = a == 0 ? (r == 0 ? 0 : 1) : (r == 0 ? 0 : 2), ky1 = a == 0 ? (r == 0 ? 0 : 2) : (r == 0 ? 1 : 2);
+        const int kx0 = b == 0 ? (s2 == 0 ? 0 : 1) : (s2 == 0 ? 0 : 2), kx1 = b == 0 ? (s2 == 0 ? 0 : 2) : (s2 == 0 ? 1 : 2);
+        const float* wk = w + ((int64_t)co * Cin + ci) * 9;
+        float v = 0.f;
+        for (int ky = ky0; ky <= ky1; ++ky)
+            for (int kx = kx0; kx <= kx1; ++kx) v += wk[ky * 3 + kx];
+        wp[i] = to_operand(v, T());
+    }
+}
+
 template <typename T>
 __global__ void pack_conv_weight_kernel(int kind, const float* __restrict__ w, T* __restrict__ wp, int Cout, int Cin) {
     const int taps = kind == 1 ? 9 : 1;
@@ -660,8 +681,17 @@ static inline unsigned blocks_for(int64_t n, int per) { int64_t b = (n + per - 1
 
 extern "C" int sdc_pack_conv_weight(int prec, int kind, const float* w, void* wp, int Cout, int Cin, void* stream) {
     SDC_CHECK_PREC("pack_conv_weight");
-    SDC_REQUIRE(kind >= 0 && kind <= 2 && w && wp && Cout > 0 && Cin > 0, "pack_conv_weight: bad arguments");
+    SDC_REQUIRE(kind >= 0 && kind <= 3 && w && wp && Cout > 0 && Cin > 0, "pack_conv_weight: bad arguments");
     SDC_REQUIRE(kind != 2 || Cin % 4 == 0, "pack_conv_weight: unshuffle conv needs Cin %% 4 == 0");
+    if (kind == 3) {
+        const int64_t tot = (int64_t)16 * Cout * Cin;
+        if (prec == SDC_PREC_F16)
+            pack_upconv_weight_kernel<__half><<<blocks_for(tot, 256), 256, 0, as_stream(stream)>>>(w, (__half*)wp, Cout, Cin);
+        else
+            pack_upconv_weight_kernel<float><<<blocks_for(tot, 256), 256, 0, as_stream(stream)>>>(w, (float*)wp, Cout, Cin);
+        SDC_LAUNCHED();
+        return SDC_OK;
+    }
     const int64_t total = (int64_t)Cout * Cin * (kind == 1 ? 9 : 1);
     if (prec == SDC_PREC_F16)
         pack_conv_weight_kernel<__half><<<blocks_for(total, 256), 256, 0, as_stream(stream)>>>(kind, w, (__half*)wp, Cout, Cin);

@@ -57,7 +57,7 @@ L.register({
 })
 
 HEADS, DIM_HEAD = 4, 32
-KIND_1x1, KIND_3x3, KIND_UNSHUFFLE = 0, 1, 2
+KIND_1x1, KIND_3x3, KIND_UNSHUFFLE, KIND_UP2X = 0, 1, 2, 3
 PREC_TF32, PREC_F16 = 0, 1   # operand precision of the tensor-core convolutions (include/safediffcon_b200_unet.h)
 PREC_NAMES = {"tf32": PREC_TF32, "f16": PREC_F16}
 
@@ -133,6 +133,7 @@ def _st():
 
 
 USE_ROW_KERNEL = os.environ.get("SDC_NO_ROW_KERNEL", "0") != "1"  # halo-reuse kernel for the 16x128 level
+FUSE_UPSAMPLE = os.environ.get("SDC_NO_FUSED_UPSAMPLE", "0") != "1"  # Upsample2d as four 2x2 phase convolutions (inference path)
 PROFILE = None  # bench.py sets this to a list: every conv launch is then bracketed by CUDA events on its stream
 
 
@@ -188,16 +189,20 @@ def conv_gemm(kind, a0, c0, a1, c1, wp, bias, residual, out, stats, operand_out,
                                       L.ptr(out), L.ptr(stats), int(operand_out), B, H, W, Cout, _st()))
     if prof is not None:
         e1.record()
-        taps = {KIND_1x1: 1, KIND_3x3: 9, KIND_UNSHUFFLE: 4}[kind]
-        # algorithmic FLOPs: algo_k overrides the GEMM K when the operand carries padding / split columns (tensor-core stem)
+        taps = {KIND_1x1: 1, KIND_3x3: 9, KIND_UNSHUFFLE: 4, KIND_UP2X: 4}[kind]
+        # algorithmic FLOPs: algo_k overrides the GEMM K when the operand carries padding / split columns (tensor-core stem);
+        # the fused upsample convolution is counted with the multiply-adds it EXECUTES (4 phases x 4 taps on H x W input pixels),
+        # not the 9 taps x 4HW of the reference formulation
         k_alg = taps * (c0 + c1) if algo_k is None else algo_k
-        prof.append((e0, e1, 2.0 * B * H * W * Cout * k_alg, (kind, B, H, W, c0 + c1, Cout)))
+        rows = B * H * W * (4 if kind == KIND_UP2X else 1)
+        prof.append((e0, e1, 2.0 * rows * Cout * k_alg, (kind, B, H, W, c0 + c1, Cout)))
 
 
 def pack_conv_weight(kind, w, prec=PREC_TF32):
     w = w.detach().to(torch.float32).contiguous()
     cout, cin = w.shape[0], w.shape[1]
-    wp = torch.empty(cout, w[0].numel(), device=w.device, dtype=operand_dtype(prec))
+    shape = (4 * cout, 4 * cin) if kind == KIND_UP2X else (cout, w[0].numel())
+    wp = torch.empty(shape, device=w.device, dtype=operand_dtype(prec))
     L.check(L.lib().sdc_pack_conv_weight(prec, kind, L.ptr(w), L.ptr(wp), cout, cin, _st()))
     return wp
 
@@ -415,8 +420,10 @@ class Unet2D(nn.Module):
             pk["ups"] = []
             for lvl in self.ups:
                 is_up = isinstance(lvl[3], nn.Sequential)
-                pk["ups"].append(dict(b1=rb(lvl[0]), b2=rb(lvl[1]), attn=at(lvl[2]), upsample=is_up,
-                                      up=conv(lvl[3][1] if is_up else lvl[3], KIND_3x3)))
+                up = conv(lvl[3][1] if is_up else lvl[3], KIND_3x3)
+                if is_up:   # inference: nearest-upsample folded into four 2x2 phase convolutions (conv_gemm.cu kind 3)
+                    up["w_up"] = pack_conv_weight(KIND_UP2X, lvl[3][1].weight, prec)
+                pk["ups"].append(dict(b1=rb(lvl[0]), b2=rb(lvl[1]), attn=at(lvl[2]), upsample=is_up, up=up))
             pk["final"] = rb(self.final_res_block)
             # stem 7x7 as a tcgen05 GEMM over an im2col operand whose K axis holds the input's high and low parts (see
             # sdc_stem_im2col): W[c, Cin*49] repeated at columns 0 and kp/2 of a [c, kp] matrix
@@ -481,8 +488,9 @@ class Unet2D(nn.Module):
 
     # ------------------------------------------------------------------ forward
     def denoise_uniform(self, x, t_int):
-        """eps for a batch-uniform integer diffusion time (sampler fast path: no per-sample index tensor)."""
-        return self._forward(x, table_row=int(t_int))
+        """eps for a batch-uniform integer diffusion time (sampler fast path: no per-sample index tensor).  Inference only:
+        never records parameter gradients (`forward` does, like the reference module under autograd)."""
+        return self._forward(x, table_row=int(t_int), param_grad=False)
 
     def forward(self, x, time, x_self_cond=None, residual=None):
         if x_self_cond is not None or residual is not None:
@@ -509,9 +517,9 @@ class Unet2D(nn.Module):
         h = self.time_mlp(torch.cat((emb.sin(), emb.cos()), dim=-1))
         return torch.cat([m.mlp(h) for m in self._resnet_blocks()], dim=1)
 
-    def _forward(self, x, time=None, table_row=None):
+    def _forward(self, x, time=None, table_row=None, param_grad=True):
         x = L.dev_f32(x, "x")
-        if self.wants_param_grad():
+        if param_grad and self.wants_param_grad():
             # training forward: activations are recorded, backward yields parameter gradients
             self._packed()   # fixes the FiLM column offsets
             film = self._film_rows_autograd(x.shape[0], time, table_row, x.device)
@@ -682,6 +690,12 @@ class Unet2D(nn.Module):
             cur = resnet(lvl["b2"], lvl_m[1], cur, c, s, sc, h, w)
             cur = attention(lvl["attn"], cur, c, h, w)
             cout = lvl["up"]["cout"]
+            if lvl["upsample"] and not keep and FUSE_UPSAMPLE and (w == 16 or w % 32 == 0):
+                nxt = opd(B * 4 * h * w, cout)
+                conv_gemm(KIND_UP2X, cur, c, None, 0, lvl["up"]["w_up"], lvl["up"]["b"], None, nxt, None, True, B, h, w, cout, prec)
+                h, w = 2 * h, 2 * w
+                cur, c = nxt, cout
+                continue
             if lvl["upsample"]:
                 up = opd(B * 4 * h * w, c)
                 L.check(lib.sdc_upsample2x(prec, L.ptr(cur), L.ptr(up), B, h, w, c, _st()))

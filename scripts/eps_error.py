@@ -5,6 +5,8 @@ import numpy as np
 import torch
 import safediffcon_b200 as s
 
+torch.set_grad_enabled(False)   # the inference path (fused attention, fused upsample convolutions)
+
 G = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
 torch.manual_seed(42)
 net = s.Unet2D(dim=128, dim_mults=(1, 2, 4, 8), channels=3, resnet_block_groups=1).cuda()

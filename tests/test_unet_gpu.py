@@ -372,3 +372,40 @@ def test_weight_cache_follows_parameter_updates():
     with torch.no_grad():
         ref = unet_ref.unet_forward({k: v.cpu() for k, v in net.state_dict().items()}, x, t)
     assert rel(b.cpu(), ref) < 1e-3
+
+
+UPCONV_CASES = [
+    # B, h, w (INPUT size), cin, cout, operand_out
+    (2, 2, 16, 64, 64, True),       # 2x16 -> 4x32: a 32-row chunk spans two image rows
+    (3, 4, 32, 128, 64, True),
+    (2, 8, 64, 64, 128, False),     # 8x64 -> 16x128, fp32 output
+    (5, 2, 16, 64, 32, True),       # ragged batch (4 images per tile)
+    (70, 4, 32, 64, 128, True),     # CTA pairs
+    (37, 8, 64, 64, 256, True),     # CTA pairs, odd tile count, N tile 256
+]
+UPCONV_PARAMS = [(c, p) for c in UPCONV_CASES for p in (TF32, F16)]
+
+
+@pytest.mark.parametrize("case,prec", UPCONV_PARAMS, ids=[f"{'f16' if pr else 'tf32'}_B{c[0]}_{c[1]}x{c[2]}_c{c[3]}_o{c[4]}" for c, pr in UPCONV_PARAMS])
+def test_fused_upsample_conv_vs_torch(case, prec):
+    """Upsample2d (nearest x2 + 3x3 pad 1, reference unet.py:33-37) as four 2x2 phase convolutions on the low-resolution input."""
+    from safediffcon_b200 import unet as U
+    B, h, w_, cin, cout, rnd = case
+    g = torch.Generator().manual_seed(h * w_ + cin + cout)
+    x = quant(torch.randn(B, cin, h, w_, generator=g), prec).cuda()
+    w = (torch.randn(cout, cin, 3, 3, generator=g) / np.sqrt(cin * 9)).cuda()
+    bias = torch.randn(cout, generator=g).cuda()
+    a0 = as_operand(nhwc(x), prec)
+    wp = U.pack_conv_weight(U.KIND_UP2X, w, prec)
+    assert wp.shape == (4 * cout, 4 * cin)
+    out = torch.full((B * 4 * h * w_, cout), float("nan"), dtype=U.operand_dtype(prec) if rnd else torch.float32).cuda()
+    U.conv_gemm(U.KIND_UP2X, a0, cin, None, 0, wp, bias, None, out, None, rnd, B, h, w_, cout, prec)
+    torch.cuda.synchronize()
+    ref = F.conv2d(F.interpolate(x.double(), scale_factor=2, mode="nearest"), w.double(), bias.double(), padding=1)
+    ref = ref.permute(0, 2, 3, 1).reshape(B * 4 * h * w_, cout)
+    out = out.double()
+    assert torch.isfinite(out).all()
+    # the phase weights are sums of up to four taps rounded once to the operand precision (2^-11 relative)
+    err = (out - ref).abs().max().item()
+    assert err < 3e-3 * max(1.0, ref.abs().max().item()), err
+    assert ((out - ref).norm() / ref.norm()).item() < 6e-4
