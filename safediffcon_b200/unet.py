@@ -390,23 +390,25 @@ class Unet2D(nn.Module):
                                "(there is no CPU fallback)")
         prec = self._prec()
         pk = {"prec": prec}
+        # every tensor of the pack owns its storage (.clone()): the in-place refresh below must never write through an alias of
+        # a parameter (it would bump the parameter's version counter -- invalidating this very cache and autograd's saved tensors)
         with torch.no_grad(), torch.cuda.device(dev):
             def conv(m, kind):
-                return dict(w=pack_conv_weight(kind, m.weight, prec), b=None if m.bias is None else m.bias.detach().float().contiguous(),
+                return dict(w=pack_conv_weight(kind, m.weight, prec), b=None if m.bias is None else m.bias.detach().float().clone(),
                             cout=m.weight.shape[0], mod=m)
 
             def rb(m):
                 return dict(c1=conv(m.block1.proj, KIND_3x3), c2=conv(m.block2.proj, KIND_3x3),
-                            g1=(m.block1.norm.weight.detach().float().contiguous(), m.block1.norm.bias.detach().float().contiguous()),
-                            g2=(m.block2.norm.weight.detach().float().contiguous(), m.block2.norm.bias.detach().float().contiguous()),
+                            g1=(m.block1.norm.weight.detach().float().clone(), m.block1.norm.bias.detach().float().clone()),
+                            g2=(m.block2.norm.weight.detach().float().clone(), m.block2.norm.bias.detach().float().clone()),
                             res=conv(m.res_conv, KIND_1x1) if isinstance(m.res_conv, nn.Conv2d) else None, cout=m.dim_out, mod=m)
 
             def at(m):
                 inner = m.fn.fn
-                d = dict(g_in=m.fn.norm.g.detach().float().reshape(-1).contiguous(), qkv=conv(inner.to_qkv, KIND_1x1), mod=m)
+                d = dict(g_in=m.fn.norm.g.detach().float().reshape(-1).clone(), qkv=conv(inner.to_qkv, KIND_1x1), mod=m)
                 if isinstance(inner, _LinearAttention):
-                    d.update(out=conv(inner.to_out[0], KIND_1x1), g_out=inner.to_out[1].g.detach().float().reshape(-1).contiguous(), full=False,
-                             out_w32=inner.to_out[0].weight.detach().float().reshape(inner.to_out[0].weight.shape[0], -1).contiguous())
+                    d.update(out=conv(inner.to_out[0], KIND_1x1), g_out=inner.to_out[1].g.detach().float().reshape(-1).clone(), full=False,
+                             out_w32=inner.to_out[0].weight.detach().float().reshape(inner.to_out[0].weight.shape[0], -1).clone())
                 else:
                     d.update(out=conv(inner.to_out, KIND_1x1), g_out=None, full=True)
                 return d
@@ -435,9 +437,9 @@ class Unet2D(nn.Module):
             wrep[:, :k_stem] = ws.reshape(c_stem, k_stem)
             wrep[:, kp // 2:kp // 2 + k_stem] = ws.reshape(c_stem, k_stem)
             pk["stem"] = dict(w=pack_conv_weight(KIND_1x1, wrep.reshape(c_stem, kp, 1, 1), prec),
-                              b=self.init_conv.bias.detach().float().contiguous(), cout=c_stem, kp=kp)
-            pk["head"] = (self.final_conv.weight.detach().float().reshape(self.out_dim, -1).contiguous(),
-                          self.final_conv.bias.detach().float().contiguous())
+                              b=self.init_conv.bias.detach().float().clone(), cout=c_stem, kp=kp)
+            pk["head"] = (self.final_conv.weight.detach().float().reshape(self.out_dim, -1).clone(),
+                          self.final_conv.bias.detach().float().clone())
             # all ResnetBlock FiLM projections stacked: one [E_total, time_dim] matrix, block i owns rows [off, off+2*Cout)
             ws, bs, off = [], [], 0
             for i, m in enumerate(self._resnet_blocks()):
@@ -446,7 +448,7 @@ class Unet2D(nn.Module):
                 m._film_off = off
                 off += m.mlp[1].weight.shape[0]
             pk["film_w"], pk["film_b"], pk["film_total"] = torch.cat(ws).contiguous(), torch.cat(bs).contiguous(), off
-            pk["time"] = tuple(t.detach().float().contiguous() for t in (self.time_mlp[1].weight, self.time_mlp[1].bias,
+            pk["time"] = tuple(t.detach().float().clone() for t in (self.time_mlp[1].weight, self.time_mlp[1].bias,
                                                                             self.time_mlp[3].weight, self.time_mlp[3].bias))
             pk["table"] = None
             old = self._cache.pack

@@ -1,4 +1,4 @@
 set -x
-python scripts/eps_error.py > gpurun_out/eps_error.txt 2>&1; cat gpurun_out/eps_error.txt | tail -12
-python scripts/time_unet.py 1024 > gpurun_out/time_unet.txt 2>&1; SDC_NO_FUSED_UPSAMPLE=1 python scripts/time_unet.py 1024 >> gpurun_out/time_unet.txt 2>&1; cat gpurun_out/time_unet.txt
-python bench.py > gpurun_out/r01g_bench.json 2> gpurun_out/r01g_bench.err; echo "bench rc=$?"; cut -c1-300 gpurun_out/r01g_bench.json
+python -m pytest tests/test_graph_chain_gpu.py tests/test_unet_pgrad_gpu.py -q -x > gpurun_out/t.log 2>&1; echo "tests rc=$?"; tail -5 gpurun_out/t.log
+python scripts/time_finetune.py 50 > gpurun_out/time_finetune.txt 2>&1; tail -3 gpurun_out/time_finetune.txt
+ncu --set full --import-source on --clock-control none --profile-from-start off -k regex:conv_gemm2 --launch-skip 1 --launch-count 1 -o gpurun_out/r01_qkv_conv_v2 python scripts/one_step.py 1024 > gpurun_out/ncu_qkv.log 2>&1; tail -2 gpurun_out/ncu_qkv.log

@@ -80,6 +80,12 @@ def test_graph_follows_parameter_updates(monkeypatch):
     assert new == 0, "parameter update must not force a re-capture"
     assert torch.equal(eager, graph)
     assert not torch.equal(first, graph)
+    # the in-place refresh writes into buffers the pack owns: sampling never touches a parameter's version counter (an alias
+    # would invalidate the cache key on every call and autograd's saved tensors of a recorded last step)
+    versions = [p._version for p in gd.model.parameters()]
+    key = gd.model._key()
+    gd.sample(**kw)
+    assert versions == [p._version for p in gd.model.parameters()] and key == gd.model._key()
 
 
 def test_graph_cache_is_not_deep_copied():
