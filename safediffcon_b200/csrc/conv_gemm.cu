@@ -14,7 +14,9 @@
 //            weight slab, both SWIZZLE_128B, completing on an mbarrier;
 //   warp 1   allocates TMEM, then one thread issues tcgen05.mma.kind::f16|tf32 (M=128|256, N=BN, 32 bytes of K) x4 per K block,
 //            accumulating in TMEM, and releases smem stages with tcgen05.commit;
-//   warps 2-5 epilogue: tcgen05.ld the accumulator (each warp owns its 32-lane TMEM quarter, lane = output row), add
+//   warps 2-9 epilogue (two per 32-lane TMEM quarter, alternating 32-column chunks: the per-chunk chain TMEM load -> registers
+//            -> shared -> TMA store is latency bound, ncu showed 31% issue utilisation and 62% of HBM on the qkv projection with
+//            four warps): tcgen05.ld the accumulator (lane = output row), add
 //            bias / residual in registers, accumulate per-sample GroupNorm statistics (sum, sum of squares -> fp64
 //            atomics), round to the operand precision if the output feeds another convolution, write the 32x32
 //            chunk into a swizzled shared staging buffer and hand it to ONE TMA store (tc_ptx.cuh: epilogue_chunk).
@@ -32,9 +34,10 @@ namespace sdc {
 // ------------------------------------------------------------------------------------------ kernel
 constexpr int BM = 128;        // output pixels per tile (= UMMA M)
 constexpr int A_BYTES = BM * 128;   // one K block of activations: 128 rows of 128 bytes (32 TF32 or 64 FP16 channels)
-constexpr int GEMM_THREADS = 192;
+constexpr int EPI_WARPS = 8;   // two warps per TMEM lane quarter, alternating 32-column chunks
+constexpr int GEMM_THREADS = 64 + 32 * EPI_WARPS;
 constexpr int STG_BUF = 4096;  // one epilogue staging buffer: 32 rows x 128 bytes (TMA-store box)
-constexpr int STG_BYTES = 4 * 2 * STG_BUF;   // 4 epilogue warps x double buffer
+constexpr int STG_BYTES = EPI_WARPS * STG_BUF;   // one buffer per epilogue warp
 
 struct GemmParams {
     int kind;            // 0: 1x1, 1: 3x3 pad 1, 2: 2x2 stride-2 (pixel-unshuffle + 1x1), 3: nearest-upsample x2 + 3x3 pad 1
@@ -112,7 +115,7 @@ __device__ __forceinline__ void conv_gemm_body(const CUtensorMap& map_a0, const 
         tma_prefetch_desc(&map_out);
         if (p.q_cols) tma_prefetch_desc(&map_q);
         for (int s = 0; s < p.stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-        for (int b = 0; b < 2; ++b) { mbar_init(&acc_full[b], 1); mbar_init(&acc_empty[b], PAIR ? 8 : 4); }
+        for (int b = 0; b < 2; ++b) { mbar_init(&acc_full[b], 1); mbar_init(&acc_empty[b], PAIR ? 2 * EPI_WARPS : EPI_WARPS); }
         fence_barrier_init();
     }
     if (warp == 1) { if constexpr (PAIR) tmem_alloc_2sm(tmem_slot, 2 * acc_cols); else tmem_alloc(tmem_slot, 2 * acc_cols); }
@@ -197,12 +200,11 @@ __device__ __forceinline__ void conv_gemm_body(const CUtensorMap& map_a0, const 
         }
     } else {
         // ---- epilogue: warp w may only touch TMEM lanes [32*(w%4), 32*(w%4)+32); lane = accumulator row ----
-        const int q = warp & 3;
-        const uint32_t stg = smem_u32(staging + q * 2 * STG_BUF);
+        const int q = warp & 3, half_id = (warp - 2) >> 2;   // TMEM lane quarter; which of the two column-chunk parities
+        const uint32_t stg = smem_u32(staging + (warp - 2) * STG_BUF);
         const act_t* resid = reinterpret_cast<const act_t*>(p.residual);
         const bool out_half = HALF && p.operand_out;
         int it = 0;
-        uint32_t nchunk = 0;
         for (int tile = tile_lo; tile < tile_hi; ++tile, ++it) {
             const int mq = tile / tiles_pn, pn = tile - mq * tiles_pn;
             const int phase = pn / p.tiles_n, nt = pn - phase * p.tiles_n;
@@ -215,18 +217,14 @@ __device__ __forceinline__ void conv_gemm_body(const CUtensorMap& map_a0, const 
             const int m = m_w + lane;
             const bool row_ok = m < p.M;
             float s1 = 0.f, s2 = 0.f;
-            for (int c = 0; c < p.bn; c += 32, ++nchunk) {
-                // the bulk store that last read this staging buffer (two chunks ago) must have finished reading it
-                if (lane == 0) bulk_wait_read<1>();
-                __syncwarp();
+            for (int c = 32 * half_id; c < p.bn; c += 64) {
                 const int col = nt * p.bn + c;
                 const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)buf * acc_cols + (uint32_t)c;
-                const uint32_t sb = stg + (nchunk & 1u) * STG_BUF;
                 const act_t* rrow = resid ? resid + (size_t)m * p.Cout + col : nullptr;
                 if (m_w < p.M) {
-                    if (col < p.q_cols) epilogue_chunk_qsoftmax<HALF>(taddr, sb, &map_q, col, m_w, lane);
-                    else if (out_half) epilogue_chunk<true, act_t>(taddr, sb, &map_out, col - p.q_cols, m_w, row_ok, p.bias, rrow, false, s1, s2, lane, up, p.W);
-                    else epilogue_chunk<false, act_t>(taddr, sb, &map_out, col - p.q_cols, m_w, row_ok, p.bias, rrow, p.operand_out != 0, s1, s2, lane, up, p.W);
+                    if (col < p.q_cols) epilogue_chunk_qsoftmax<HALF>(taddr, stg, &map_q, col, m_w, lane, true);
+                    else if (out_half) epilogue_chunk<true, act_t>(taddr, stg, &map_out, col - p.q_cols, m_w, row_ok, p.bias, rrow, false, s1, s2, lane, up, p.W, true, p.stats != nullptr);
+                    else epilogue_chunk<false, act_t>(taddr, stg, &map_out, col - p.q_cols, m_w, row_ok, p.bias, rrow, p.operand_out != 0, s1, s2, lane, up, p.W, true, p.stats != nullptr);
                 }
             }
             // accumulator buffer fully read -> hand it back to the MMA warp

@@ -151,7 +151,8 @@ __device__ __forceinline__ void bulk_wait() { asm volatile("cp.async.bulk.wait_g
 template <bool OUT_HALF, typename res_t>
 __device__ __forceinline__ void epilogue_chunk(uint32_t taddr, uint32_t stg, const CUtensorMap* map_out, int col, int row0,
                                                bool row_ok, const float* __restrict__ bias, const res_t* __restrict__ res_row,
-                                               bool round, float& s1, float& s2, int lane, int up_phase = -1, int up_w = 0) {
+                                               bool round, float& s1, float& s2, int lane, int up_phase = -1, int up_w = 0,
+                                               bool wait_stg = false, bool want_stats = true) {
     uint32_t r[32];
     tmem_ld32(taddr, r);
     float v[32];
@@ -171,12 +172,18 @@ __device__ __forceinline__ void epilogue_chunk(uint32_t taddr, uint32_t stg, con
             v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
         }
     }
-    if (row_ok) {
+    if (row_ok && want_stats) {
         float a1 = 0.f, a2 = 0.f;
 #pragma unroll
         for (int j = 0; j < 32; ++j) { a1 += v[j]; a2 = fmaf(v[j], v[j], a2); }
         s1 += a1;
         s2 += a2;
+    }
+    if (wait_stg) {
+        // single staging buffer per warp: the bulk store of this warp's previous chunk must have finished READING it (the TMEM
+        // load and the arithmetic above already overlapped that read)
+        if (lane == 0) bulk_wait_read<0>();
+        __syncwarp();
     }
     if constexpr (OUT_HALF) {
         const uint32_t rowa = stg + (uint32_t)lane * 64u, sw = ((uint32_t)lane >> 1) & 3u;
@@ -216,7 +223,7 @@ __device__ __forceinline__ void epilogue_chunk(uint32_t taddr, uint32_t stg, con
 // registers and stored in the operand precision (it is the A operand of the folded output projection).
 template <bool OUT_HALF>
 __device__ __forceinline__ void epilogue_chunk_qsoftmax(uint32_t taddr, uint32_t stg, const CUtensorMap* map_q, int col, int row0,
-                                                        int lane) {
+                                                        int lane, bool wait_stg = false) {
     uint32_t r[32];
     tmem_ld32(taddr, r);
     float v[32];
@@ -224,11 +231,16 @@ __device__ __forceinline__ void epilogue_chunk_qsoftmax(uint32_t taddr, uint32_t
 #pragma unroll
     for (int j = 0; j < 32; ++j) { v[j] = __uint_as_float(r[j]); mx = fmaxf(mx, v[j]); }
     float den = 0.f;
+    // ex2.approx (2 ulp) on arguments <= 0: far inside the 2^-11 rounding of the fp16 / tf32 store below
 #pragma unroll
-    for (int j = 0; j < 32; ++j) { v[j] = expf(v[j] - mx); den += v[j]; }
+    for (int j = 0; j < 32; ++j) { v[j] = __expf(v[j] - mx); den += v[j]; }
     const float sc = 0.17677669529663687f / den;
 #pragma unroll
     for (int j = 0; j < 32; ++j) v[j] *= sc;
+    if (wait_stg) {
+        if (lane == 0) bulk_wait_read<0>();
+        __syncwarp();
+    }
     if constexpr (OUT_HALF) {
         const uint32_t rowa = stg + (uint32_t)lane * 64u, sw = ((uint32_t)lane >> 1) & 3u;
 #pragma unroll

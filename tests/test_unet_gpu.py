@@ -40,6 +40,7 @@ def rel(a, b):
 
 @pytest.fixture(autouse=True)
 def _fp32_reference():
+    torch.set_grad_enabled(True)
     torch.backends.cudnn.allow_tf32 = False
     torch.backends.cuda.matmul.allow_tf32 = False
 
@@ -329,6 +330,7 @@ def test_unet_eps_vs_reference_golden(dim, B, precision, golden):
     assert net.precision == ("f16" if dim % 64 == 0 else "tf32")   # default: FP16 operands whenever the channel counts allow
     net.precision = precision
     x, t = fx.unet_inputs(B)
+    torch.set_grad_enabled(False)   # the inference path (the recording path is covered by tests/test_unet_pgrad_gpu.py)
     eps = net(x.cuda(), t.cuda())
     ref = torch.from_numpy(golden(f"unet_dim{dim}")["eps"])
     assert eps.shape == ref.shape
@@ -341,6 +343,7 @@ def test_unet_eps_vs_reference_golden(dim, B, precision, golden):
     # float times take the per-sample FiLM evaluation
     e1 = net(x.cuda(), t.cuda().float())
     assert rel(e1.cpu(), ref) < 1e-3
+    torch.set_grad_enabled(True)
 
 
 def test_unet_intermediates_localise_errors(golden):
