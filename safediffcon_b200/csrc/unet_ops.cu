@@ -302,7 +302,9 @@ constexpr int LA_CTX = LA_D * LA_D + 2 * LA_D;
 
 // ctx[b,h,d,e] = sum_n softmax_n(k)[d,n] * v[e,n]          grid = B*heads, 256 threads
 // 4 pixel groups x 64 threads; each thread owns a 4x4 block of the 32x32 context in registers (16 FMA per two
-// 16-byte shared loads).  k is read twice (column max, then exp-weighted accumulation), v once.
+// 16-byte shared loads).  SINGLE pass over k and v (each read once from HBM): the column maximum of k is tracked online --
+// per 128-pixel chunk the running maximum m_d is raised to the chunk's and the accumulators of row d are rescaled by
+// exp(m_old - m_new) (softmax is invariant under the shift; the two-pass version read k twice: 3.1 -> 2.1 GB per 16x128 call).
 constexpr int LA_CHUNK = 128;
 // k / v rows: kbase / vbase + pixel * ld (+ head * 32); ld = 384 for a packed qkv tensor, 256 for the kv tensor of the fused path
 __global__ void __launch_bounds__(256) linattn_context_kernel(const float* __restrict__ kbase, const float* __restrict__ vbase, int ld,
@@ -311,54 +313,67 @@ __global__ void __launch_bounds__(256) linattn_context_kernel(const float* __res
     __shared__ __align__(16) float vs[LA_CHUNK][LA_D];
     __shared__ float red[8][LA_D];
     __shared__ float kmax[LA_D];
+    __shared__ float rescale[LA_D];
     const int b = blockIdx.x / LA_HEADS, h = blockIdx.x % LA_HEADS;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const float* kp = kbase + (int64_t)b * n * ld + h * LA_D;
     const float* vp = vbase + (int64_t)b * n * ld + h * LA_D;
-    {   // column max of k over the n pixels: 8 pixels x 4 channels per thread and iteration (16-byte loads)
-        const int c4 = (tid & 7) * 4, r = tid >> 3;  // 32 pixel rows per pass
-        float4 m = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
-        for (int i = r; i < n; i += 32) {
-            const float4 kv = *reinterpret_cast<const float4*>(kp + (int64_t)i * ld + c4);
-            m.x = fmaxf(m.x, kv.x); m.y = fmaxf(m.y, kv.y); m.z = fmaxf(m.z, kv.z); m.w = fmaxf(m.w, kv.w);
-        }
-        // reduce over the 4 pixel rows held by one warp (lanes with equal lane&7), then across the 8 warps
-#pragma unroll
-        for (int o = 8; o < 32; o <<= 1) {
-            m.x = fmaxf(m.x, __shfl_xor_sync(0xffffffffu, m.x, o)); m.y = fmaxf(m.y, __shfl_xor_sync(0xffffffffu, m.y, o));
-            m.z = fmaxf(m.z, __shfl_xor_sync(0xffffffffu, m.z, o)); m.w = fmaxf(m.w, __shfl_xor_sync(0xffffffffu, m.w, o));
-        }
-        if (lane < 8) { red[warp][c4] = m.x; red[warp][c4 + 1] = m.y; red[warp][c4 + 2] = m.z; red[warp][c4 + 3] = m.w; }
-        __syncthreads();
-        if (tid < LA_D) {
-            float t = red[0][tid];
-#pragma unroll
-            for (int w = 1; w < 8; ++w) t = fmaxf(t, red[w][tid]);
-            kmax[tid] = t;
-        }
-        __syncthreads();
-    }
+    if (tid < LA_D) kmax[tid] = -INFINITY;
     const int ng = tid >> 6, t64 = tid & 63;
     const int d0 = (t64 >> 3) * 4, e0 = (t64 & 7) * 4;
     float acc[4][4], ksum[4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) { ksum[i] = 0.f; for (int j = 0; j < 4; ++j) acc[i][j] = 0.f; }
-    const int lc4 = (tid & 7) * 4, lr = tid >> 3;
-    const float4 km = *reinterpret_cast<const float4*>(&kmax[lc4]);
+    const int lc4 = (tid & 7) * 4, lr = tid >> 3;   // loader role: 4 channels x pixel rows lr, lr+32, lr+64, lr+96 of the chunk
     for (int n0 = 0; n0 < n; n0 += LA_CHUNK) {
         const int cnt = min(LA_CHUNK, n - n0);
-        __syncthreads();
+        float4 kraw[LA_CHUNK / 32];
+        float4 m = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+        __syncthreads();   // the previous chunk's tiles are consumed
 #pragma unroll
-        for (int rr = 0; rr < LA_CHUNK; rr += 32) {
-            const int r = rr + lr;
-            float4 kv = make_float4(0.f, 0.f, 0.f, 0.f), vv = kv;
+        for (int rr = 0; rr < LA_CHUNK / 32; ++rr) {
+            const int r = rr * 32 + lr;
+            float4 kv = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY), vv = make_float4(0.f, 0.f, 0.f, 0.f);
             if (r < cnt) {
                 kv = *reinterpret_cast<const float4*>(kp + (int64_t)(n0 + r) * ld + lc4);
                 vv = *reinterpret_cast<const float4*>(vp + (int64_t)(n0 + r) * ld + lc4);
-                kv = make_float4(expf(kv.x - km.x), expf(kv.y - km.y), expf(kv.z - km.z), expf(kv.w - km.w));
             }
-            *reinterpret_cast<float4*>(&ek[r][lc4]) = kv;   // rows >= cnt hold zeros: they add nothing
+            kraw[rr] = kv;
+            m.x = fmaxf(m.x, kv.x); m.y = fmaxf(m.y, kv.y); m.z = fmaxf(m.z, kv.z); m.w = fmaxf(m.w, kv.w);
             *reinterpret_cast<float4*>(&vs[r][lc4]) = vv;
+        }
+        // chunk column maximum: lanes with equal (lane & 7) hold the same 4 channels
+#pragma unroll
+        for (int o = 8; o < 32; o <<= 1) {
+            m.x = fmaxf(m.x, __shfl_xor_sync(0xffffffffu, m.x, o)); m.y = fmaxf(m.y, __shfl_xor_sync(0xffffffffu, m.y, o));
+            m.z = fmaxf(m.z, __shfl_xor_sync(0xffffffffu, m.z, o)); m.w = fmaxf(m.w, __shfl_xor_sync(0xffffffffu, m.w, o));
+        }
+        if (lane < 8) { red[warp][lc4] = m.x; red[warp][lc4 + 1] = m.y; red[warp][lc4 + 2] = m.z; red[warp][lc4 + 3] = m.w; }
+        __syncthreads();
+        if (tid < LA_D) {
+            float t = red[0][tid];
+#pragma unroll
+            for (int w = 1; w < 8; ++w) t = fmaxf(t, red[w][tid]);
+            const float mo = kmax[tid], mn = fmaxf(mo, t);
+            rescale[tid] = (mo == mn) ? 1.0f : expf(mo - mn);   // first chunk: exp(-inf) = 0 on zero accumulators
+            kmax[tid] = mn;
+        }
+        __syncthreads();
+        {
+            const float4 km = *reinterpret_cast<const float4*>(&kmax[lc4]);
+#pragma unroll
+            for (int rr = 0; rr < LA_CHUNK / 32; ++rr) {
+                const int r = rr * 32 + lr;
+                const float4 kv = kraw[rr];   // rows >= cnt hold -inf -> exp = 0: they add nothing
+                *reinterpret_cast<float4*>(&ek[r][lc4]) = make_float4(expf(kv.x - km.x), expf(kv.y - km.y), expf(kv.z - km.z), expf(kv.w - km.w));
+            }
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const float sc = rescale[d0 + i];
+                ksum[i] *= sc;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][j] *= sc;
+            }
         }
         __syncthreads();
 #pragma unroll 8
