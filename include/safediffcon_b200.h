@@ -143,6 +143,23 @@ int sdc_reverse_step_state(int sampler, const float* x, const float* eps, const 
 void sdc_count_launches(int64_t n);
 
 /* ------------------------------------------------------------------------------------------------
+ * Synthetic data (the step BEFORE the path).  Replaces the float64 numpy field evaluation of make_data_varying_f
+ * (1D/data/generate_burgers.py:338-418) and the per-item tensor assembly of BurgersDataset._process_data
+ * (1D/data/burgers.py:104-142).  The O(N) random scalars are drawn on the host from numpy's RNG in the reference's order.
+ */
+/* params_u0:[Nu0,6] = (loc1, amp1, sig1, loc2, amp2, sig2); params_f:[Nf,terms,5] = (amp, loc_x, sig_x, loc_t, sig_t), all
+ * DEVICE float64; x_grid:[s], t_grid:[t] device float32 (torch.linspace values).  Outputs: u0 as float64 and/or float32
+ * [Nu0,s] (either may be NULL), f:[Nf,t,s] float32 = float32(sum of terms) (* alpha, clamped to +-10 when alpha != 1).
+ * partial_control: 0 = none, 1 = 'front_rear_quarter' mask (the caller doubles amp_compensate as the reference does). */
+int sdc_burgers_fields(const double* params_u0, const double* params_f, const float* x_grid, const float* t_grid,
+                       double* u0_f64, float* u0_f32, float* f, int64_t Nu0, int64_t Nf, int s, int t, int terms,
+                       double amp_compensate, int partial_control, float alpha, void* stream);
+/* state:[N,3,pad,s] = (u, f, safety)/scaler from u_traj:[N,nt1,s], f:[N,nt,s]; safety = u^2, or its per-sample maximum
+ * broadcast when use_max_safety; rows beyond nt1 / nt are zero. */
+int sdc_dataset_states(const float* u_traj, const float* f, float* state, int64_t N, int nt1, int nt, int pad, int s,
+                       float scaler, int use_max_safety, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
  * Conformal calibration.  Replaces calculate_guidance/get_weight (1D/inference/guidance.py:9-46), the
  * nonconformity score of ConformalCalculator.get_conformal_scores (1D/inference/conformal.py:74-85),
  * normalize_weights (guidance.py:48-66) and calculate_quantile (conformal.py:95-118).

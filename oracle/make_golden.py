@@ -238,6 +238,28 @@ def gen_ploss():
          **fx.grad_digest([(n, p.grad) for n, p in net.named_parameters()]))
 
 
+def gen_datagen():
+    """Reference generator + dataset assembly: make_data_varying_f under np.random.seed(0), the
+    'front_rear_quarter' partial-control variant, and the [3,16,128] state of BurgersDataset._process_data (that method is
+    executed unbound on a stand-in object: the class itself needs h5py files)."""
+    from data.generate_burgers import make_data_varying_f, burgers_numeric_solve_free
+    import numpy as np_
+    np_.random.seed(0)
+    u0, f = make_data_varying_f(16, 12, 128, 10)
+    np_.random.seed(3)
+    u0p, fp = make_data_varying_f(3, 4, 128, 10, partial_control='front_rear_quarter', alpha=1.7)
+    save("datagen", u0=u0, f=f, u0_partial=u0p, f_partial=fp)
+    # dataset states from reference rollouts
+    import data.burgers as rb
+    traj = burgers_numeric_solve_free(torch.tensor(u0[:12], dtype=torch.float32), f, visc=0.01, T=1.0, dt=1e-4, num_t=10)
+    outs = {}
+    for use_max in (True, False):
+        ds = types.SimpleNamespace(safety_transform=lambda u: u.pow(2), use_max_safety=use_max, stack_u_and_f=True,
+                                   pad_for_2d_conv=True, pad_size=16, scaler=10.0)
+        outs[f"states_max{int(use_max)}"] = torch.stack([rb.BurgersDataset._process_data(ds, (traj[i], f[i])) for i in range(12)])
+    save("dataset_states", traj=traj, f=f, **outs)
+
+
 def gd_time_pairs(gd):
     times = torch.linspace(-1, gd.num_timesteps - 1, steps=gd.sampling_timesteps + 1)
     times = list(reversed(times.int().tolist()))
@@ -285,7 +307,7 @@ def gen_config1():
 
 
 ALL = {"schedule": gen_schedule, "solver": gen_solver, "chains": gen_chains, "guidance": gen_guidance,
-       "conformal": gen_conformal, "unet": gen_unet, "unet_vjp": gen_unet_vjp, "unet_pgrad": gen_unet_pgrad, "ploss": gen_ploss, "config1": gen_config1}
+       "conformal": gen_conformal, "unet": gen_unet, "unet_vjp": gen_unet_vjp, "unet_pgrad": gen_unet_pgrad, "ploss": gen_ploss, "datagen": gen_datagen, "config1": gen_config1}
 
 if __name__ == "__main__":
     names = sys.argv[1:] or [k for k in ALL if k != "config1"]

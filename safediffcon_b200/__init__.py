@@ -7,6 +7,7 @@ Public surface mirrors the reference modules it replaces:
   conformal ConformalCalculator                                    (1D/inference/conformal.py)
   diffusion GaussianDiffusion                                      (1D/model/diffusion.py)
   unet      Unet2D                                                 (1D/model/unet.py)
+  datagen   make_data_varying_f, dataset_states                    (1D/data/generate_burgers.py, 1D/data/burgers.py)
 All compute runs in hand-written CUDA kernels behind the C ABI of include/safediffcon_b200.h; there is no CPU
 fallback (calls raise when the library or a CUDA device is missing).
 """
@@ -18,5 +19,6 @@ from . import conformal, runner  # noqa: F401
 from .conformal import ConformalCalculator, kth_select  # noqa: F401
 from .diffusion import GaussianDiffusion, ModelPrediction  # noqa: F401
 from .unet import Unet2D  # noqa: F401
+from .datagen import make_data_varying_f, dataset_states  # noqa: F401
 
 __version__ = "0.1.0"

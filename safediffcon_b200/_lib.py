@@ -52,6 +52,8 @@ _SIGS = {
     "sdc_reverse_step_state": (c_i, [c_i, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, ctypes.POINTER(Guidance), c_p, c_p, c_p, c_p,
                                      c_i, c_i, c_i, c_i64, c_i, c_i, c_p]),
     "sdc_count_launches": (None, [c_i64]),
+    "sdc_burgers_fields": (c_i, [c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_i64, c_i64, c_i, c_i, c_i, c_d, c_i, c_f, c_p]),
+    "sdc_dataset_states": (c_i, [c_p, c_p, c_p, c_i64, c_i, c_i, c_i, c_i, c_f, c_i, c_p]),
     "sdc_safety_stat": (c_i, [c_p, c_p, c_i, c_f, c_i, c_i64, c_i, c_i, c_p]),
     "sdc_conformal_scores": (c_i, [c_p, c_p, c_p, c_p, ctypes.POINTER(Guidance), c_f, c_i64, c_i, c_i, c_p]),
     "sdc_normalize_weights": (c_i, [c_p, c_p, c_p, c_i64, c_p]),

@@ -114,3 +114,25 @@ def test_conformal_scores(golden):
     w = cr.normalize_weights(torch.cat(ws))
     assert np.array_equal(w.numpy(), g["weights"])
     assert np.array_equal((w * torch.cat(sc)).numpy(), g["scores"])
+
+
+def test_datagen_oracle_bit_exact(golden):
+    from oracle import datagen_ref as dg
+    g = golden("datagen")
+    np.random.seed(0)
+    u0, f = dg.make_data_varying_f(16, 12, 128, 10)
+    assert u0.dtype == np.float64 and np.array_equal(u0, g["u0"])
+    assert f.dtype == torch.float32 and np.array_equal(f.numpy(), g["f"])
+    np.random.seed(3)
+    u0p, fp = dg.make_data_varying_f(3, 4, 128, 10, partial_control='front_rear_quarter', alpha=1.7)
+    assert np.array_equal(u0p, g["u0_partial"]) and np.array_equal(fp.numpy(), g["f_partial"])
+    assert (fp.numpy()[:, :, 32:96] == 0).all() and np.abs(fp.numpy()).max() <= 10.0
+
+
+def test_dataset_states_oracle_bit_exact(golden):
+    from oracle import datagen_ref as dg
+    g = golden("dataset_states")
+    traj, f = torch.from_numpy(g["traj"]), torch.from_numpy(g["f"])
+    for use_max in (True, False):
+        out = dg.dataset_states(traj, f, use_max_safety=use_max)
+        assert np.array_equal(out.numpy(), g[f"states_max{int(use_max)}"])
