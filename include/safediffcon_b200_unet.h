@@ -86,13 +86,14 @@ int sdc_linear_attention(int prec, const float* qkv, void* out, void* workspace,
 /* Fused LinearAttention path (same math as sdc_conv_gemm(qkv) + sdc_linear_attention + sdc_conv_gemm(to_out), without ever
  * materialising the [B*n, 128] attention tensor):
  *   1. sdc_conv1x1_qkv: the bias-free qkv projection (unet.py:189,203) whose epilogue applies q <- softmax_d(q) * 32^-0.5 to
- *      the q columns in registers; writes qs[B*H*W, hidden] (operand precision) and kv[B*H*W, 2*hidden] (fp32: k | v).
+ *      the q columns in registers; writes qs[B*H*W, hidden] (operand precision) and kv[B*H*W, 2*hidden] (k | v; fp32, or fp16 when
+ *      kv_operand != 0, FP16 mode only -- pass the same flag to step 2).
  *   2. sdc_linear_attention_context: ctx = softmax_n(k) v^T per (sample, head) from rows k + i*ld, v + i*ld into the workspace.
  *   3. sdc_linear_attention_fold: per-sample folded projection Wf_b[Cout, 128] = W_out (x) ctx_b (operand precision).
  *   4. sdc_conv1x1_per_sample: out[B*H*W, Cout] = qs * Wf_b^T + bias (H*W must be a multiple of 128). */
-int sdc_conv1x1_qkv(int prec, const void* a, int c, const void* w_packed, void* q_out, float* kv_out, int B, int H, int W, int hidden,
-                    void* stream);
-int sdc_linear_attention_context(const float* k, const float* v, int ld, void* workspace, int B, int n, void* stream);
+int sdc_conv1x1_qkv(int prec, const void* a, int c, const void* w_packed, void* q_out, void* kv_out, int kv_operand, int B, int H, int W,
+                    int hidden, void* stream);
+int sdc_linear_attention_context(const void* k, const void* v, int ld, int kv_operand, void* workspace, int B, int n, void* stream);
 int sdc_linear_attention_fold(int prec, const void* workspace, const float* w_out, void* w_folded, int B, int Cout, void* stream);
 int sdc_conv1x1_per_sample(int prec, const void* a, int c, const void* w_per_sample, const float* bias, void* out, int operand_out,
                            int B, int H, int W, int Cout, void* stream);

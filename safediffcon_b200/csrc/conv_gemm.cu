@@ -60,7 +60,8 @@ struct GemmParams {
     int tiles_total;     // tiles_m * tiles_n, tile id = m * tiles_n + n (consecutive ids share the A window)
     int tiles_per_cta;
     int q_cols;          // > 0: LinearAttention qkv mode -- output columns [0, q_cols) get softmax_d * 32^-0.5 per 32-column head and
-                         //      go to a second tensor (map_q, operand precision); columns [q_cols, Cout) go to `out` (fp32)
+                         //      go to a second tensor (map_q, operand precision); columns [q_cols, Cout) go to `out` (fp32, or fp16
+                         //      when operand_out is set in FP16 mode: k and v are then read at half the bytes by the context pass)
     int w_sample_rows;   // > 0: per-sample weights -- sample b uses weight rows [b * w_sample_rows, (b + 1) * w_sample_rows)
     const float* bias;       // [Cout] or null
     const void* residual;    // [M, Cout] in the operand precision, or null (added after bias)
@@ -313,8 +314,8 @@ static int conv_gemm_launch(int prec, int kind, const void* a0, int c0, const vo
     SDC_REQUIRE(bb * bh * W == BM && (H * W) % 32 == 0, "conv_gemm: H*W=%d cannot be tiled into 128-pixel blocks", H * W);
     SDC_REQUIRE(bb == 1 || bh == H, "conv_gemm: tile spans images only when it holds whole images");
     int bn = Cout % 256 == 0 ? 256 : (Cout % 128 == 0 ? 128 : (Cout % 64 == 0 ? 64 : 32));
-    SDC_REQUIRE(q_cols >= 0 && q_cols % 32 == 0 && q_cols < Cout && (q_cols == 0 || (q_out && !bias && !residual && !stats && !operand_out)),
-                "conv_gemm: qkv mode needs q_out, q_cols %% 32 == 0 and a plain fp32 kv output");
+    SDC_REQUIRE(q_cols >= 0 && q_cols % 32 == 0 && q_cols < Cout && (q_cols == 0 || (q_out && !bias && !residual && !stats && (!operand_out || half))),
+                "conv_gemm: qkv mode needs q_out, q_cols %% 32 == 0 and a kv output that is plain fp32 or (FP16 mode) an operand");
     GemmParams p{};
     p.q_cols = q_cols;
     p.w_sample_rows = per_sample_weights ? Cout : 0;
@@ -402,11 +403,12 @@ extern "C" int sdc_conv_gemm(int prec, int kind, const void* a0, int c0, const v
                             stream);
 }
 
-extern "C" int sdc_conv1x1_qkv(int prec, const void* a, int c, const void* w_packed, void* q_out, float* kv_out, int B, int H, int W,
-                               int hidden, void* stream) {
+extern "C" int sdc_conv1x1_qkv(int prec, const void* a, int c, const void* w_packed, void* q_out, void* kv_out, int kv_operand, int B,
+                               int H, int W, int hidden, void* stream) {
     SDC_REQUIRE(hidden > 0 && hidden % 32 == 0 && q_out && kv_out, "conv1x1_qkv: bad arguments");
-    return conv_gemm_launch(prec, 0, a, c, nullptr, 0, w_packed, nullptr, nullptr, kv_out, nullptr, 0, B, H, W, 3 * hidden, q_out, hidden, 0,
-                            stream);
+    SDC_REQUIRE(!kv_operand || prec == SDC_PREC_F16, "conv1x1_qkv: an operand-precision kv tensor exists only in FP16 mode");
+    return conv_gemm_launch(prec, 0, a, c, nullptr, 0, w_packed, nullptr, nullptr, kv_out, nullptr, kv_operand ? 1 : 0, B, H, W, 3 * hidden,
+                            q_out, hidden, 0, stream);
 }
 
 extern "C" int sdc_conv1x1_per_sample(int prec, const void* a, int c, const void* w_per_sample, const float* bias, void* out,

@@ -307,7 +307,10 @@ constexpr int LA_CTX = LA_D * LA_D + 2 * LA_D;
 // exp(m_old - m_new) (softmax is invariant under the shift; the two-pass version read k twice: 3.1 -> 2.1 GB per 16x128 call).
 constexpr int LA_CHUNK = 128;
 // k / v rows: kbase / vbase + pixel * ld (+ head * 32); ld = 384 for a packed qkv tensor, 256 for the kv tensor of the fused path
-__global__ void __launch_bounds__(256) linattn_context_kernel(const float* __restrict__ kbase, const float* __restrict__ vbase, int ld,
+// TK = float (packed fp32 qkv / kv tensors) or __half (kv written in the operand precision by the fused qkv projection: k only
+// enters through exp(k - max) and v through a 2048-term sum, rounding them to 10 bits moves eps by < 1e-6 relative)
+template <typename TK>
+__global__ void __launch_bounds__(256) linattn_context_kernel(const TK* __restrict__ kbase, const TK* __restrict__ vbase, int ld,
                                                               float* __restrict__ ctx, int n) {
     __shared__ __align__(16) float ek[LA_CHUNK][LA_D];
     __shared__ __align__(16) float vs[LA_CHUNK][LA_D];
@@ -316,8 +319,8 @@ __global__ void __launch_bounds__(256) linattn_context_kernel(const float* __res
     __shared__ float rescale[LA_D];
     const int b = blockIdx.x / LA_HEADS, h = blockIdx.x % LA_HEADS;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const float* kp = kbase + (int64_t)b * n * ld + h * LA_D;
-    const float* vp = vbase + (int64_t)b * n * ld + h * LA_D;
+    const TK* kp = kbase + (int64_t)b * n * ld + h * LA_D;
+    const TK* vp = vbase + (int64_t)b * n * ld + h * LA_D;
     if (tid < LA_D) kmax[tid] = -INFINITY;
     const int ng = tid >> 6, t64 = tid & 63;
     const int d0 = (t64 >> 3) * 4, e0 = (t64 & 7) * 4;
@@ -335,8 +338,8 @@ __global__ void __launch_bounds__(256) linattn_context_kernel(const float* __res
             const int r = rr * 32 + lr;
             float4 kv = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY), vv = make_float4(0.f, 0.f, 0.f, 0.f);
             if (r < cnt) {
-                kv = *reinterpret_cast<const float4*>(kp + (int64_t)(n0 + r) * ld + lc4);
-                vv = *reinterpret_cast<const float4*>(vp + (int64_t)(n0 + r) * ld + lc4);
+                kv = load4(kp + (int64_t)(n0 + r) * ld + lc4);
+                vv = load4(vp + (int64_t)(n0 + r) * ld + lc4);
             }
             kraw[rr] = kv;
             m.x = fmaxf(m.x, kv.x); m.y = fmaxf(m.y, kv.y); m.z = fmaxf(m.z, kv.z); m.w = fmaxf(m.w, kv.w);
@@ -815,7 +818,7 @@ extern "C" int sdc_linear_attention(int prec, const float* qkv, void* out, void*
     SDC_CHECK_PREC("linear_attention");
     SDC_REQUIRE(qkv && out && workspace && B > 0 && n > 0, "linear_attention: bad arguments");
     float* ctx = reinterpret_cast<float*>(workspace);
-    linattn_context_kernel<<<(unsigned)(B * LA_HEADS), 256, 0, as_stream(stream)>>>(qkv + LA_HID, qkv + 2 * LA_HID, LA_QKV, ctx, n);
+    linattn_context_kernel<float><<<(unsigned)(B * LA_HEADS), 256, 0, as_stream(stream)>>>(qkv + LA_HID, qkv + 2 * LA_HID, LA_QKV, ctx, n);
     SDC_LAUNCHED();
     SDC_REQUIRE(n % 32 == 0, "linear_attention: n=%d must be a multiple of 32", n);
     const size_t sm128 = (LA_HEADS * LA_D * LA_CLD + 128 * LA_QLD) * sizeof(float), sm32 = (LA_HEADS * LA_D * LA_CLD + 32 * LA_QLD) * sizeof(float);
@@ -839,9 +842,14 @@ extern "C" int sdc_linear_attention(int prec, const float* qkv, void* out, void*
     return SDC_OK;
 }
 
-extern "C" int sdc_linear_attention_context(const float* k, const float* v, int ld, void* workspace, int B, int n, void* stream) {
+extern "C" int sdc_linear_attention_context(const void* k, const void* v, int ld, int kv_operand, void* workspace, int B, int n, void* stream) {
     SDC_REQUIRE(k && v && workspace && B > 0 && n > 0 && ld % 4 == 0, "linear_attention_context: bad arguments");
-    linattn_context_kernel<<<(unsigned)(B * LA_HEADS), 256, 0, as_stream(stream)>>>(k, v, ld, reinterpret_cast<float*>(workspace), n);
+    if (kv_operand)
+        linattn_context_kernel<__half><<<(unsigned)(B * LA_HEADS), 256, 0, as_stream(stream)>>>((const __half*)k, (const __half*)v, ld,
+                                                                                              reinterpret_cast<float*>(workspace), n);
+    else
+        linattn_context_kernel<float><<<(unsigned)(B * LA_HEADS), 256, 0, as_stream(stream)>>>((const float*)k, (const float*)v, ld,
+                                                                                             reinterpret_cast<float*>(workspace), n);
     SDC_LAUNCHED();
     return SDC_OK;
 }

@@ -29,8 +29,8 @@ L.register({
     "sdc_linear_attention_workspace": (c_i64, [c_i]),
     "sdc_linear_attention": (c_i, [c_i, c_p, c_p, c_p, c_i, c_i, c_p]),
     "sdc_attention": (c_i, [c_i, c_p, c_p, c_i, c_i, c_p]),
-    "sdc_conv1x1_qkv": (c_i, [c_i, c_p, c_i, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_p]),
-    "sdc_linear_attention_context": (c_i, [c_p, c_p, c_i, c_p, c_i, c_i, c_p]),
+    "sdc_conv1x1_qkv": (c_i, [c_i, c_p, c_i, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_p]),
+    "sdc_linear_attention_context": (c_i, [c_p, c_p, c_i, c_i, c_p, c_i, c_i, c_p]),
     "sdc_linear_attention_fold": (c_i, [c_i, c_p, c_p, c_p, c_i, c_i, c_p]),
     "sdc_conv1x1_per_sample": (c_i, [c_i, c_p, c_i, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_p]),
     "sdc_upsample2x": (c_i, [c_i, c_p, c_p, c_i, c_i, c_i, c_i, c_p]),
@@ -159,7 +159,8 @@ def conv1x1_qkv(a, c, wp, q_out, kv_out, B, H, W, prec):
     """qkv projection of LinearAttention with the q-softmax epilogue (see include/safediffcon_b200_unet.h)."""
     hid = HEADS * DIM_HEAD
     with _Timed(2.0 * B * H * W * 3 * hid * c, (KIND_1x1, B, H, W, c, 3 * hid)):
-        L.check(L.lib().sdc_conv1x1_qkv(prec, L.ptr(a), c, L.ptr(wp), L.ptr(q_out), L.ptr(kv_out), B, H, W, hid, _st()))
+        L.check(L.lib().sdc_conv1x1_qkv(prec, L.ptr(a), c, L.ptr(wp), L.ptr(q_out), L.ptr(kv_out), int(kv_out.dtype == torch.float16),
+                                        B, H, W, hid, _st()))
 
 
 def conv1x1_per_sample(a, c, w_folded, bias, out, B, H, W, Cout, prec):
@@ -621,10 +622,11 @@ class Unet2D(nn.Module):
             hid = HEADS * DIM_HEAD
             if not p["full"] and not keep and n % 128 == 0:
                 # fused inference path: q-softmax in the qkv epilogue, context folded into a per-sample output projection
-                qs, kv = opd(M, hid), f32(M, 2 * hid)
+                qs, kv = opd(M, hid), opd(M, 2 * hid)   # F16 mode: k | v in fp16 (half the bytes through the context pass)
                 conv1x1_qkv(xn, c, p["qkv"]["w"], qs, kv, B, h, w, prec)
                 ws = torch.empty(lib.sdc_linear_attention_workspace(B), device=dev, dtype=torch.uint8)
-                L.check(lib.sdc_linear_attention_context(L.ptr(kv), ctypes.c_void_p(kv.data_ptr() + 4 * hid), 2 * hid, L.ptr(ws), B, n, _st()))
+                L.check(lib.sdc_linear_attention_context(L.ptr(kv), ctypes.c_void_p(kv.data_ptr() + kv.element_size() * hid), 2 * hid,
+                                                         int(kv.dtype == torch.float16), L.ptr(ws), B, n, _st()))
                 wf = opd(B * c, hid)
                 L.check(lib.sdc_linear_attention_fold(prec, L.ptr(ws), L.ptr(p["out_w32"]), L.ptr(wf), B, c, _st()))
                 proj = f32(M, c)

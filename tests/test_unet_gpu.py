@@ -267,11 +267,12 @@ def test_fused_linear_attention_vs_torch(prec):
         bout = torch.randn(c, generator=g).cuda()
         # fused path
         a = as_operand(nhwc(x).reshape(M, c), prec)
-        qs, kv = torch.empty(M, 128, dtype=od).cuda(), torch.empty(M, 256).cuda()
+        qs, kv = torch.empty(M, 128, dtype=od).cuda(), torch.empty(M, 256, dtype=od).cuda()   # F16 mode: k | v in fp16
         U.conv1x1_qkv(a, c, U.pack_conv_weight(0, wqkv, prec), qs, kv, B, H, W, prec)
         ws = torch.empty(lib.sdc_linear_attention_workspace(B), dtype=torch.uint8).cuda()
         import ctypes
-        L.check(lib.sdc_linear_attention_context(L.ptr(kv), ctypes.c_void_p(kv.data_ptr() + 512), 256, L.ptr(ws), B, n, L.stream_ptr()))
+        L.check(lib.sdc_linear_attention_context(L.ptr(kv), ctypes.c_void_p(kv.data_ptr() + 128 * kv.element_size()), 256,
+                                                 int(kv.dtype == torch.float16), L.ptr(ws), B, n, L.stream_ptr()))
         wf = torch.empty(B * c, 128, dtype=od).cuda()
         L.check(lib.sdc_linear_attention_fold(prec, L.ptr(ws), L.ptr(wout.reshape(c, 128).contiguous()), L.ptr(wf), B, c, L.stream_ptr()))
         out = torch.empty(M, c).cuda()
@@ -286,7 +287,7 @@ def test_fused_linear_attention_vs_torch(prec):
         qref = nhwc((q.softmax(-2) * 32 ** -0.5).reshape(B, 128, H, W)).reshape(M, 128)
         assert (qs.double() - qref).abs().max().item() < 1e-3 * qref.abs().max().item()
         kvref = nhwc(qkv[:, 128:]).reshape(M, 256)
-        assert (kv.double() - kvref).abs().max().item() < 2e-5 * kvref.abs().max().item()
+        assert (kv.double() - kvref).abs().max().item() < (2e-5 if kv.dtype == torch.float32 else 6e-4) * kvref.abs().max().item()
         err = (out.double() - ref).abs().max().item()
         assert err < 2e-3 * ref.abs().max().item(), (B, H, W, c, err, ref.abs().max().item())
 
