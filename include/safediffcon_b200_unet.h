@@ -65,8 +65,10 @@ int sdc_stem_im2col(int prec, const float* x, void* a, int B, int Cin, int H, in
  * y = silu(((x - mean_b) * rstd_b * gamma_c + beta_c) * (scale_bc + 1) + shift_bc) + res ; mean/rstd from
  * stats[b] = (sum, sumsq) over C*HW elements, eps 1e-5, biased variance.  scale_shift: [n_t, 2C] rows
  * (scale | shift) indexed by t_index[b] (NULL t_index = row 0 for every sample), or NULL for none.
- * x: fp32 (a conv output).  residual: operand precision if residual_operand else fp32.  y: operand. */
-int sdc_gn_silu(int prec, const float* x, const double* stats, const float* gamma, const float* beta, const float* scale_shift,
+ * x: a conv output -- fp32, or fp16 if x_operand (FP16 mode, compact intermediates: the statistics were taken from the fp32
+ * accumulators, only the stored activations are rounded; the residual must then be fp16 too).
+ * residual: operand precision if residual_operand else fp32.  y: operand. */
+int sdc_gn_silu(int prec, const void* x, int x_operand, const double* stats, const float* gamma, const float* beta, const float* scale_shift,
                 const int32_t* t_index, int64_t ss_stride, const void* residual, int residual_operand, void* y, int B, int HW,
                 int C, void* stream);
 

@@ -240,6 +240,89 @@ __global__ void __launch_bounds__(256) gn_silu_kernel(const float* __restrict__ 
     }
 }
 
+// FP16-input variant (compact intermediates: the conv epilogue took the statistics from its fp32 accumulators and stored the
+// activations as fp16): a thread owns 8 channels (256 % (C/8) == 0), 4 independent 16-byte loads in flight, 16-byte stores.
+// Bytes per element: 2 in + 2 out (+2 residual) instead of 4 + 2 (+2|4).
+__device__ __forceinline__ void unpack8(const uint4& u, float* f) {
+    const __half2* h = reinterpret_cast<const __half2*>(&u);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { const float2 t = __half22float2(h[k]); f[2 * k] = t.x; f[2 * k + 1] = t.y; }
+}
+__device__ __forceinline__ uint4 pack8(const float* f) {
+    uint4 u;
+    __half2* h = reinterpret_cast<__half2*>(&u);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) h[k] = __floats2half2_rn(f[2 * k], f[2 * k + 1]);
+    return u;
+}
+__global__ void __launch_bounds__(256) gn_silu_h8_kernel(const __half* __restrict__ x, const double* __restrict__ stats,
+                                                         const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                         const float* __restrict__ scale_shift, const int32_t* __restrict__ t_index,
+                                                         int64_t ss_stride, const __half* __restrict__ residual, __half* __restrict__ y,
+                                                         int HW, int C, int pix_per_cta) {
+    const int b = blockIdx.x;
+    const double cnt = (double)HW * (double)C;
+    const double mean_d = stats[2 * b] / cnt;
+    double var_d = stats[2 * b + 1] / cnt - mean_d * mean_d;
+    if (var_d < 0.0) var_d = 0.0;
+    const float mean = (float)mean_d, rstd = (float)(1.0 / sqrt(var_d + 1e-5));
+    const float* ss = scale_shift ? scale_shift + (int64_t)(t_index ? t_index[b] : 0) * ss_stride : nullptr;
+    const int c8n = C / 8;
+    const int c = (threadIdx.x % c8n) * 8;
+    float A[8], Bc[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        const float g = gamma[c + k] * rstd;
+        float a = g, bb = beta[c + k] - mean * g;
+        if (ss) {
+            const float sc = ss[c + k] + 1.0f;
+            a *= sc;
+            bb = bb * sc + ss[C + c + k];
+        }
+        A[k] = a;
+        Bc[k] = bb;
+    }
+    const int64_t row0 = (int64_t)b * HW + (int64_t)blockIdx.y * pix_per_cta;
+    const int rows = min(pix_per_cta, HW - (int)blockIdx.y * pix_per_cta);
+    const uint4* x8 = reinterpret_cast<const uint4*>(x + row0 * C);
+    const uint4* r8 = residual ? reinterpret_cast<const uint4*>(residual + row0 * C) : nullptr;
+    uint4* y8 = reinterpret_cast<uint4*>(y + row0 * C);
+    const int total = rows * c8n;
+    int i = threadIdx.x;
+    for (; i + 3 * 256 < total; i += 4 * 256) {
+        uint4 v[4], r[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) v[u] = __ldcs(x8 + i + u * 256);   // streamed once: evict first
+        if (r8) {
+#pragma unroll
+            for (int u = 0; u < 4; ++u) r[u] = r8[i + u * 256];
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            float f[8], rf[8];
+            unpack8(v[u], f);
+            if (r8) unpack8(r[u], rf);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                f[k] = silu_fast(fmaf(f[k], A[k], Bc[k]));
+                if (r8) f[k] += rf[k];
+            }
+            y8[i + u * 256] = pack8(f);
+        }
+    }
+    for (; i < total; i += 256) {
+        float f[8], rf[8];
+        unpack8(x8[i], f);
+        if (r8) unpack8(r8[i], rf);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            f[k] = silu_fast(fmaf(f[k], A[k], Bc[k]));
+            if (r8) f[k] += rf[k];
+        }
+        y8[i] = pack8(f);
+    }
+}
+
 // ---------------------------------------------------------------------------------------------- channel LayerNorm
 // one warp per RPW pixel rows (RPW = 4 for C <= 256 so that 4-8 independent 16-byte loads are in flight per lane);
 // C <= 1024 kept in registers, two-pass variance like torch.var(unbiased=False)
@@ -754,18 +837,24 @@ extern "C" int sdc_stem_im2col(int prec, const float* x, void* a, int B, int Cin
     return SDC_OK;
 }
 
-extern "C" int sdc_gn_silu(int prec, const float* x, const double* stats, const float* gamma, const float* beta,
+extern "C" int sdc_gn_silu(int prec, const void* xv, int x_operand, const double* stats, const float* gamma, const float* beta,
                            const float* scale_shift, const int32_t* t_index, int64_t ss_stride, const void* residual,
                            int residual_operand, void* y, int B, int HW, int C, void* stream) {
     SDC_CHECK_PREC("gn_silu");
+    const float* x = (const float*)xv;
     SDC_REQUIRE(x && stats && gamma && beta && y && B > 0 && HW > 0, "gn_silu: bad arguments");
     SDC_REQUIRE(C % 4 == 0 && C <= 4096, "gn_silu: C=%d unsupported", C);
+    SDC_REQUIRE(!x_operand || (prec == SDC_PREC_F16 && C % 8 == 0 && 256 % (C / 8) == 0 && (!residual || residual_operand)),
+                "gn_silu: an fp16 input needs FP16 mode, C/8 dividing 256 and an fp16 residual");
     int ppc = HW;  // pixels per CTA: aim for >= 2 waves of CTAs without shrinking below 32 pixels
     while (ppc > 32 && (int64_t)B * (HW / ppc) < 2 * 148 && ppc % 2 == 0) ppc /= 2;
     dim3 grid((unsigned)B, (unsigned)((HW + ppc - 1) / ppc));
     const size_t sm = 2 * C * sizeof(float);
     cudaStream_t st = as_stream(stream);
-    if (prec == SDC_PREC_F16) {
+    if (x_operand) {
+        gn_silu_h8_kernel<<<grid, 256, 0, st>>>((const __half*)xv, stats, gamma, beta, scale_shift, t_index, ss_stride,
+                                                (const __half*)residual, (__half*)y, HW, C, ppc);
+    } else if (prec == SDC_PREC_F16) {
         if (residual_operand)
             gn_silu_kernel<__half, __half><<<grid, 256, sm, st>>>(x, stats, gamma, beta, scale_shift, t_index, ss_stride,
                                                                    (const __half*)residual, (__half*)y, HW, C, ppc);

@@ -245,7 +245,11 @@ def test_unet_input_gradient_vs_reference_golden(dim, precision, golden):
     (gx_f,) = torch.autograd.grad(eps_f, xf, gct.cuda())
     assert torch.equal(gx2, gx_f) and torch.equal(eps2, eps_f.detach())
     with torch.no_grad():   # the inference path (fused attention, reused buffers) agrees with the recording path to rounding
+        net.compact_intermediates = False
         assert rel(net(x.cuda(), t.cuda()), eps.detach()) < 1e-3
+        # fp16 norm inputs (FP16 inference default) add one independent 2^-11 rounding per normalised tensor on this path only
+        net.compact_intermediates = True
+        assert rel(net(x.cuda(), t.cuda()), eps.detach()) < (1.5e-3 if precision == "f16" else 1e-3)
     # linearity of the VJP in the cotangent (size-independent property)
     _, gx3 = net.vjp(x.cuda(), t.cuda(), -2.0 * gct.cuda())
     assert rel(gx3, -2.0 * gx) < 2e-3

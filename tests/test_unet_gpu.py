@@ -188,12 +188,19 @@ def test_gn_silu_vs_torch(prec):
         # fp32 residual (the 1x1 res_conv output) and operand-precision residual (the block input)
         for res_operand in (0, 1):
             r_in = as_operand(quant(res.cpu(), prec).cuda(), prec) if res_operand else res
-            L.check(lib.sdc_gn_silu(prec, L.ptr(xr), L.ptr(stats), L.ptr(gamma), L.ptr(beta), L.ptr(table), L.ptr(tidx), 3 * C,
+            L.check(lib.sdc_gn_silu(prec, L.ptr(xr), 0, L.ptr(stats), L.ptr(gamma), L.ptr(beta), L.ptr(table), L.ptr(tidx), 3 * C,
                                     L.ptr(r_in), res_operand, L.ptr(y), B, HW, C, L.stream_ptr()))
             ref = ref0 + r_in.float()
             assert (y.float() - ref).abs().max().item() < 2e-3 * ref.abs().max().item()
+            if prec == F16 and res_operand and C % 8 == 0 and 256 % (C // 8) == 0:
+                # compact intermediates: fp16 input (statistics from the fp32 values), also in place
+                xh = xr.half()
+                for dst in (y, xh):
+                    L.check(lib.sdc_gn_silu(prec, L.ptr(xh), 1, L.ptr(stats), L.ptr(gamma), L.ptr(beta), L.ptr(table), L.ptr(tidx), 3 * C,
+                                            L.ptr(r_in), 1, L.ptr(dst), B, HW, C, L.stream_ptr()))
+                    assert (dst.float() - ref).abs().max().item() < 3e-3 * ref.abs().max().item()
         # no FiLM, no residual, uniform row 0
-        L.check(lib.sdc_gn_silu(prec, L.ptr(xr), L.ptr(stats), L.ptr(gamma), L.ptr(beta), None, None, 0, None, 0, L.ptr(y), B, HW, C,
+        L.check(lib.sdc_gn_silu(prec, L.ptr(xr), 0, L.ptr(stats), L.ptr(gamma), L.ptr(beta), None, None, 0, None, 0, L.ptr(y), B, HW, C,
                                 L.stream_ptr()))
         ref2 = F.silu(F.group_norm(x, 1, gamma, beta, eps=1e-5)).permute(0, 2, 1).reshape(B * HW, C)
         assert (y.float() - ref2).abs().max().item() < 2e-3 * ref2.abs().max().item()
