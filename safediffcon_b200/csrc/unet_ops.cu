@@ -504,6 +504,183 @@ __global__ void __launch_bounds__(256) linattn_context_kernel(const TK* __restri
     }
 }
 
+// ---- FP16 k | v (fused inference path): the same context on mma.sync.m16n8k16 (fp16 operands, fp32 accumulate) ----
+// The scalar kernel above is bound by shared-memory operand reads (two LDS.128 per 16 FMA: 0.7 ms per 16x128-level call at
+// B = 1024 for 1 GB of fp16 k | v).  Here ctx[d, e] = sum_n ek[n, d] v[n, e] is a [32 x n] x [n x 32] product with the pixel axis as
+// K: both operands sit in shared memory pixel-major ([n][32] halves, 80-byte rows -> conflict-free ldmatrix), and
+// ldmatrix.trans delivers the A fragment (ek^T) and the B fragment (v) directly.  grid = B * heads, 128 threads; per 128-pixel
+// chunk a thread converts 4 rows x 8 channels (always the same channels: their running sums stay in registers), the four
+// warps each multiply a 32-pixel quarter, the 32 x 32 partial contexts are reduced through shared memory at the end.
+// ek = exp(k - max_d + 8 ln 2): the factor 256 keeps small weights out of the fp16 subnormal range and cancels in ctx = acc / ksum.
+constexpr int LC_CH = 128, LC_LD = 40;
+__device__ __forceinline__ void ldsm_x4_trans(uint32_t (&r)[4], uint32_t addr) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+__device__ __forceinline__ void mma_f16_16x8x16(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3]) : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ float ex2_approx(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ uint32_t hmax2_u32(uint32_t a, uint32_t b) {
+    const __half2 r = __hmax2(*reinterpret_cast<const __half2*>(&a), *reinterpret_cast<const __half2*>(&b));
+    return *reinterpret_cast<const uint32_t*>(&r);
+}
+__global__ void __launch_bounds__(128) linattn_context_mma_kernel(const __half* __restrict__ kbase, const __half* __restrict__ vbase,
+                                                                  int ld, float* __restrict__ ctx, int n) {
+    __shared__ __align__(16) __half tiles[2 * LC_CH * LC_LD];   // ek | v, 10 KB each; reused for the final reduction (16 KB)
+    __shared__ float red[4][LA_D];
+    __shared__ float kmax[LA_D];
+    __shared__ float rescale[LA_D];
+    __half* ek = tiles;
+    __half* vs = tiles + LC_CH * LC_LD;
+    const int b = blockIdx.x / LA_HEADS, h = blockIdx.x % LA_HEADS;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const __half* kp = kbase + (int64_t)b * n * ld + h * LA_D;
+    const __half* vp = vbase + (int64_t)b * n * ld + h * LA_D;
+    const int cg = tid & 3, pr = tid >> 2;   // loader role: channels 8 cg .. 8 cg + 7 of chunk rows pr, pr + 32, pr + 64, pr + 96
+    if (tid < LA_D) kmax[tid] = -INFINITY;
+    float acc[2][4][4];
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+#pragma unroll
+            for (int k = 0; k < 4; ++k) acc[i][j][k] = 0.f;
+    float ksum[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) ksum[j] = 0.f;
+    constexpr float LOG2E = 1.4426950408889634f;
+    const uint32_t ek_s = (uint32_t)__cvta_generic_to_shared(ek), vs_s = (uint32_t)__cvta_generic_to_shared(vs);
+    for (int n0 = 0; n0 < n; n0 += LC_CH) {
+        const int cnt = min(LC_CH, n - n0);
+        uint4 kr[4], vr[4];
+#pragma unroll
+        for (int rr = 0; rr < 4; ++rr) {
+            const int r = pr + 32 * rr;
+            kr[rr] = make_uint4(0xFC00FC00u, 0xFC00FC00u, 0xFC00FC00u, 0xFC00FC00u);   // -inf: exp = 0, rows past the end add nothing
+            vr[rr] = make_uint4(0u, 0u, 0u, 0u);
+            if (r < cnt) {
+                kr[rr] = __ldcs(reinterpret_cast<const uint4*>(kp + (int64_t)(n0 + r) * ld + cg * 8));
+                vr[rr] = __ldcs(reinterpret_cast<const uint4*>(vp + (int64_t)(n0 + r) * ld + cg * 8));
+            }
+        }
+        uint32_t m2[4] = {kr[0].x, kr[0].y, kr[0].z, kr[0].w};
+#pragma unroll
+        for (int rr = 1; rr < 4; ++rr) {
+            m2[0] = hmax2_u32(m2[0], kr[rr].x); m2[1] = hmax2_u32(m2[1], kr[rr].y);
+            m2[2] = hmax2_u32(m2[2], kr[rr].z); m2[3] = hmax2_u32(m2[3], kr[rr].w);
+        }
+#pragma unroll
+        for (int o = 4; o < 32; o <<= 1) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) m2[j] = hmax2_u32(m2[j], __shfl_xor_sync(0xffffffffu, m2[j], o));
+        }
+        __syncthreads();   // the previous chunk's tiles, maxima and rescale factors are consumed
+        if (lane < 4) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&m2[j]));
+                red[warp][cg * 8 + 2 * j] = f.x;
+                red[warp][cg * 8 + 2 * j + 1] = f.y;
+            }
+        }
+#pragma unroll
+        for (int rr = 0; rr < 4; ++rr) *reinterpret_cast<uint4*>(vs + (pr + 32 * rr) * LC_LD + cg * 8) = vr[rr];
+        __syncthreads();
+        if (tid < LA_D) {
+            const float t = fmaxf(fmaxf(red[0][tid], red[1][tid]), fmaxf(red[2][tid], red[3][tid]));
+            const float mo = kmax[tid], mn = fmaxf(mo, t);
+            rescale[tid] = (mo == mn) ? 1.0f : __expf(mo - mn);   // first chunk: exp(-inf) = 0 on zero accumulators
+            kmax[tid] = mn;
+        }
+        __syncthreads();
+        {
+            float off[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                off[j] = fmaf(-kmax[cg * 8 + j], LOG2E, 8.0f);
+                ksum[j] *= rescale[cg * 8 + j];
+            }
+#pragma unroll
+            for (int rr = 0; rr < 4; ++rr) {
+                float f[8];
+                unpack8(kr[rr], f);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) f[j] = ex2_approx(fmaf(f[j], LOG2E, off[j]));
+                const uint4 e8 = pack8(f);
+                unpack8(e8, f);   // the sums use the values the tensor cores see
+#pragma unroll
+                for (int j = 0; j < 8; ++j) ksum[j] += f[j];
+                *reinterpret_cast<uint4*>(ek + (pr + 32 * rr) * LC_LD + cg * 8) = e8;
+            }
+            const int g = lane >> 2;
+#pragma unroll
+            for (int mt = 0; mt < 2; ++mt) {
+                const float s0 = rescale[mt * 16 + g], s1 = rescale[mt * 16 + g + 8];
+#pragma unroll
+                for (int nt = 0; nt < 4; ++nt) { acc[mt][nt][0] *= s0; acc[mt][nt][1] *= s0; acc[mt][nt][2] *= s1; acc[mt][nt][3] *= s1; }
+            }
+        }
+        __syncthreads();
+#pragma unroll
+        for (int ks = 0; ks < 2; ++ks) {
+            const int k0 = warp * 32 + ks * 16;
+            uint32_t a[2][4], bb[2][4];
+#pragma unroll
+            for (int mt = 0; mt < 2; ++mt)
+                ldsm_x4_trans(a[mt], ek_s + 2u * (uint32_t)((k0 + (lane & 7) + ((lane >> 4) << 3)) * LC_LD + mt * 16 + (((lane >> 3) & 1) << 3)));
+#pragma unroll
+            for (int np = 0; np < 2; ++np)
+                ldsm_x4_trans(bb[np], vs_s + 2u * (uint32_t)((k0 + (lane & 7) + (((lane >> 3) & 1) << 3)) * LC_LD + np * 16 + ((lane >> 4) << 3)));
+#pragma unroll
+            for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+                for (int nt = 0; nt < 4; ++nt) mma_f16_16x8x16(acc[mt][nt], a[mt], bb[nt >> 1][(nt & 1) * 2], bb[nt >> 1][(nt & 1) * 2 + 1]);
+        }
+    }
+    // reduce the four warps' partial contexts and channel sums
+    __syncthreads();
+    float* racc = reinterpret_cast<float*>(tiles);   // [4][32][32] floats = 16 KB
+    {
+        const int g = lane >> 2, c2 = 2 * (lane & 3);
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+            for (int nt = 0; nt < 4; ++nt) {
+                float* o = racc + warp * 1024 + (mt * 16 + g) * LA_D + nt * 8 + c2;
+                *reinterpret_cast<float2*>(o) = make_float2(acc[mt][nt][0], acc[mt][nt][1]);
+                *reinterpret_cast<float2*>(o + 8 * LA_D) = make_float2(acc[mt][nt][2], acc[mt][nt][3]);
+            }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            float t = ksum[j];
+#pragma unroll
+            for (int o = 4; o < 32; o <<= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+            ksum[j] = t;
+        }
+        if (lane < 4) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) red[warp][cg * 8 + j] = ksum[j];
+        }
+    }
+    __syncthreads();
+    float* cb = ctx + (int64_t)blockIdx.x * LA_CTX;
+    for (int i = tid; i < LA_D * LA_D; i += 128) {
+        const int d = i >> 5;
+        const float ks = (red[0][d] + red[1][d]) + (red[2][d] + red[3][d]);
+        cb[i] = ((racc[i] + racc[1024 + i]) + (racc[2048 + i] + racc[3072 + i])) / ks;
+    }
+    if (tid < LA_D) {
+        cb[LA_D * LA_D + tid] = kmax[tid];
+        cb[LA_D * LA_D + LA_D + tid] = ((red[0][tid] + red[1][tid]) + (red[2][tid] + red[3][tid])) * (1.0f / 256.0f);
+    }
+}
+
 // out[n, h*32+e] = 32^-0.5 * sum_d ctx[d,e] * softmax_d(q[n,:])[d]
 // One CTA = P consecutive pixels of one sample x all 4 heads, 256 threads = 8 warps, warp w -> head w & 3, pixel tiles of 16.
 // The q rows (512 bytes per pixel) are staged through shared memory with coalesced 16-byte loads; the per-head
@@ -933,9 +1110,12 @@ extern "C" int sdc_linear_attention(int prec, const float* qkv, void* out, void*
 
 extern "C" int sdc_linear_attention_context(const void* k, const void* v, int ld, int kv_operand, void* workspace, int B, int n, void* stream) {
     SDC_REQUIRE(k && v && workspace && B > 0 && n > 0 && ld % 4 == 0, "linear_attention_context: bad arguments");
-    if (kv_operand)
-        linattn_context_kernel<__half><<<(unsigned)(B * LA_HEADS), 256, 0, as_stream(stream)>>>((const __half*)k, (const __half*)v, ld,
-                                                                                              reinterpret_cast<float*>(workspace), n);
+    if (kv_operand) {
+        SDC_REQUIRE(ld % 8 == 0 && (reinterpret_cast<uintptr_t>(k) & 15) == 0 && (reinterpret_cast<uintptr_t>(v) & 15) == 0,
+                    "linear_attention_context: fp16 k | v rows must be 16-byte aligned");
+        linattn_context_mma_kernel<<<(unsigned)(B * LA_HEADS), 128, 0, as_stream(stream)>>>((const __half*)k, (const __half*)v, ld,
+                                                                                          reinterpret_cast<float*>(workspace), n);
+    }
     else
         linattn_context_kernel<float><<<(unsigned)(B * LA_HEADS), 256, 0, as_stream(stream)>>>((const float*)k, (const float*)v, ld,
                                                                                              reinterpret_cast<float*>(workspace), n);
