@@ -117,42 +117,45 @@ __global__ void stem_conv7_kernel(const float* __restrict__ x, const float* __re
 // ci*49 + ky*7 + kx), columns [KH, KH+K) the LOW part (x - high, rounded to the operand precision), the rest zeros.
 // With the stem weights repeated in both column ranges the tcgen05 GEMM sees the fp32 input to ~2^-22 although its
 // operands are fp16 / tf32.  One CTA = one image row; the 7 input rows it needs are staged in shared memory.
+// Thread -> one group of 8 consecutive columns (one 16-byte store in FP16 mode) for pixels w = wl, wl + blockDim / groups, ...:
+// the patch offsets of its columns live in registers, the inner loop is 8 shared loads + conversions + one store (the earlier
+// version re-derived (pixel, column) by integer division per 4 elements and was issue bound at 0.29 of the copy peak).
 template <typename T>
 __global__ void __launch_bounds__(256) stem_im2col_kernel(const float* __restrict__ x, T* __restrict__ a, int Cin, int H, int W,
                                                           int kp) {
-    extern __shared__ float xs[];   // [Cin][7][W + 6], then the patch-offset table int[K]
+    extern __shared__ float xs[];   // [Cin][7][W + 6]
     const int b = blockIdx.x / H, h = blockIdx.x % H;
     const int WP = W + 6, K = Cin * 49, KH = kp / 2;
-    int* koff = reinterpret_cast<int*>(xs + Cin * 7 * WP);   // column k -> offset of (ci, ky, kx) inside the window
-    for (int k = threadIdx.x; k < K; k += blockDim.x) {
-        const int ci = k / 49, t = k - ci * 49, ky = t / 7, kx = t - ky * 7;
-        koff[k] = (ci * 7 + ky) * WP + kx;
-    }
     for (int i = threadIdx.x; i < Cin * 7 * WP; i += blockDim.x) {
         const int ci = i / (7 * WP), r = (i / WP) % 7, c = i % WP;
         const int hh = h + r - 3, ww = c - 3;
         xs[i] = (hh >= 0 && hh < H && ww >= 0 && ww < W) ? x[(((int64_t)b * Cin + ci) * H + hh) * W + ww] : 0.f;
     }
     __syncthreads();
-    const int vpr = kp / 4;   // 4-element groups per row
-    T* arow = a + ((int64_t)b * H + h) * W * kp;
-    for (int i = threadIdx.x; i < W * vpr; i += blockDim.x) {
-        const int w = i / vpr, k0 = (i % vpr) * 4;
-        float v[4];
+    const int groups = kp / 8;                       // column groups per row
+    const int wstep = blockDim.x / groups;           // pixels in flight per pass (threads beyond groups * wstep idle)
+    const int grp = threadIdx.x % groups, wl = threadIdx.x / groups;
+    if (wl >= wstep) return;
+    int off[8];       // offset of column (ci, ky, kx) inside the window, or -1 for padding columns
+    bool low = false;
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            int k = k0 + j;
-            const bool low = k >= KH;
-            if (low) k -= KH;
-            float val = 0.f;
-            if (k < K) {
-                const float xv = xs[koff[k] + w];
-                const float hi = (float)to_operand(xv, T());
-                val = low ? xv - hi : hi;
-            }
-            v[j] = val;
+    for (int j = 0; j < 8; ++j) {
+        int k = grp * 8 + j;
+        if (k >= KH) { k -= KH; low = true; }   // KH is a multiple of 8: a group is entirely high or entirely low
+        const int ci = k / 49, t = k - ci * 49, ky = t / 7, kx = t - ky * 7;
+        off[j] = k < K ? (ci * 7 + ky) * WP + kx : -1;
+    }
+    T* arow = a + ((int64_t)b * H + h) * W * kp + grp * 8;
+    for (int w = wl; w < W; w += wstep) {
+        float v[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const float xv = off[j] >= 0 ? xs[off[j] + w] : 0.f;
+            const float hi = (float)to_operand(xv, T());
+            v[j] = low ? xv - hi : hi;
         }
-        store_operand4(arow + (int64_t)w * kp + k0, make_float4(v[0], v[1], v[2], v[3]));
+        store_operand4(arow + (int64_t)w * kp, make_float4(v[0], v[1], v[2], v[3]));
+        store_operand4(arow + (int64_t)w * kp + 4, make_float4(v[4], v[5], v[6], v[7]));
     }
 }
 
@@ -373,6 +376,77 @@ __global__ void __launch_bounds__(256) channel_layernorm_kernel(const TX* __rest
                 if (r4) { const float4 rr = load4(r4 + 4 * i); o.x += rr.x; o.y += rr.y; o.z += rr.z; o.w += rr.w; }
                 if constexpr (sizeof(TY) == 2) store_operand4(y4 + 4 * i, o);
                 else { if (operand_out) store_operand4(y4 + 4 * i, o); else store4(reinterpret_cast<float*>(y4) + 4 * i, o); }
+            }
+        }
+    }
+}
+
+// FP16 in / FP16 out variant (every LayerNorm of the compact FP16 inference path).  ncu on the kernel above at C = 128: 0.59 of
+// the copy peak with 81% issue utilisation -- a 32-lane row costs 10 shuffles for 4 elements per lane.  Here a row is owned by
+// LPR lanes (8 for C = 128) holding VPL 16-byte vectors (8 channels) each: 2 log2(LPR) shuffles per 8 VPL elements, 32 / LPR rows
+// per warp pass, and RG independent row groups in flight per lane.  Lane l of a row reads vectors l, l + LPR, ... (coalesced).
+template <int LPR, int VPL, int RG>
+__global__ void __launch_bounds__(256) channel_layernorm_h_kernel(const __half* __restrict__ x, const float* __restrict__ g,
+                                                                  const __half* __restrict__ residual, __half* __restrict__ y,
+                                                                  int64_t M) {
+    constexpr int C = LPR * VPL * 8, RPP = 32 / LPR;   // rows per warp pass
+    const int lane = threadIdx.x & 31, sub = lane % LPR, rsel = lane / LPR;
+    const int64_t warp_id = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int64_t row0 = warp_id * (RPP * RG) + rsel;
+    float gv[VPL][8];
+#pragma unroll
+    for (int j = 0; j < VPL; ++j) {
+        const float4 a = __ldg(reinterpret_cast<const float4*>(g + (j * LPR + sub) * 8));
+        const float4 b = __ldg(reinterpret_cast<const float4*>(g + (j * LPR + sub) * 8 + 4));
+        gv[j][0] = a.x; gv[j][1] = a.y; gv[j][2] = a.z; gv[j][3] = a.w; gv[j][4] = b.x; gv[j][5] = b.y; gv[j][6] = b.z; gv[j][7] = b.w;
+    }
+    uint4 xv[RG][VPL], rv[RG][VPL];
+#pragma unroll
+    for (int r = 0; r < RG; ++r) {
+        const int64_t row = row0 + (int64_t)r * RPP;
+#pragma unroll
+        for (int j = 0; j < VPL; ++j) {
+            xv[r][j] = make_uint4(0u, 0u, 0u, 0u);
+            rv[r][j] = make_uint4(0u, 0u, 0u, 0u);
+            if (row < M) {
+                xv[r][j] = __ldcs(reinterpret_cast<const uint4*>(x + row * C) + j * LPR + sub);
+                if (residual) rv[r][j] = __ldg(reinterpret_cast<const uint4*>(residual + row * C) + j * LPR + sub);
+            }
+        }
+    }
+#pragma unroll
+    for (int r = 0; r < RG; ++r) {
+        const int64_t row = row0 + (int64_t)r * RPP;
+        float f[VPL][8];
+        float sm = 0.f;
+#pragma unroll
+        for (int j = 0; j < VPL; ++j) {
+            unpack8(xv[r][j], f[j]);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) sm += f[j][k];
+        }
+#pragma unroll
+        for (int o = 1; o < LPR; o <<= 1) sm += __shfl_xor_sync(0xffffffffu, sm, o);
+        const float mean = sm * (1.0f / (float)C);
+        float q = 0.f;
+#pragma unroll
+        for (int j = 0; j < VPL; ++j)
+#pragma unroll
+            for (int k = 0; k < 8; ++k) { f[j][k] -= mean; q = fmaf(f[j][k], f[j][k], q); }
+#pragma unroll
+        for (int o = 1; o < LPR; o <<= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+        const float rstd = rsqrtf(q * (1.0f / (float)C) + 1e-5f);
+        if (row < M) {
+#pragma unroll
+            for (int j = 0; j < VPL; ++j) {
+                float rf[8];
+                if (residual) unpack8(rv[r][j], rf);
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    f[j][k] = f[j][k] * rstd * gv[j][k];
+                    if (residual) f[j][k] += rf[k];
+                }
+                reinterpret_cast<uint4*>(y + row * C)[j * LPR + sub] = pack8(f[j]);
             }
         }
     }
@@ -1003,8 +1077,8 @@ extern "C" int sdc_stem_conv7(int prec, const float* x, const float* w, const fl
 extern "C" int sdc_stem_im2col(int prec, const float* x, void* a, int B, int Cin, int H, int W, int kp, void* stream) {
     SDC_CHECK_PREC("stem_im2col");
     SDC_REQUIRE(x && a && B > 0 && Cin > 0 && H > 0 && W > 0, "stem_im2col: bad arguments");
-    SDC_REQUIRE(kp % 8 == 0 && kp / 2 >= Cin * 49, "stem_im2col: kp=%d must be a multiple of 8 and >= 2*Cin*49", kp);
-    const size_t sm = ((size_t)Cin * 7 * (W + 6) + (size_t)Cin * 49) * sizeof(float);
+    SDC_REQUIRE(kp % 16 == 0 && kp / 2 >= Cin * 49 && kp / 8 <= 256, "stem_im2col: kp=%d must be a multiple of 16, >= 2*Cin*49, <= 2048", kp);
+    const size_t sm = (size_t)Cin * 7 * (W + 6) * sizeof(float);
     SDC_REQUIRE(sm <= 48 * 1024, "stem_im2col: row window does not fit shared memory");
     if (prec == SDC_PREC_F16)
         stem_im2col_kernel<__half><<<(unsigned)(B * H), 256, sm, as_stream(stream)>>>(x, (__half*)a, Cin, H, W, kp);
@@ -1069,7 +1143,15 @@ extern "C" int sdc_channel_layernorm(int prec, const void* x, int x_operand, con
     SDC_REQUIRE(C % 4 == 0 && C <= 1024, "channel_layernorm: C=%d unsupported (multiple of 4, <= 1024)", C);
     cudaStream_t st = as_stream(stream);
     if (prec == SDC_PREC_F16) {
-        if (x_operand) launch_layernorm<__half, __half>(x, g, residual, y, M, C, 1, st);
+        const __half* xh = (const __half*)x;
+        const __half* rh = (const __half*)residual;
+        __half* yh = (__half*)y;
+        // rows per CTA = 8 warps x (32 / LPR) x RG
+        if (x_operand && C == 128) channel_layernorm_h_kernel<8, 2, 2><<<(unsigned)((M + 63) / 64), 256, 0, st>>>(xh, g, rh, yh, M);
+        else if (x_operand && C == 256) channel_layernorm_h_kernel<16, 2, 2><<<(unsigned)((M + 31) / 32), 256, 0, st>>>(xh, g, rh, yh, M);
+        else if (x_operand && C == 512) channel_layernorm_h_kernel<32, 2, 2><<<(unsigned)((M + 15) / 16), 256, 0, st>>>(xh, g, rh, yh, M);
+        else if (x_operand && C == 1024) channel_layernorm_h_kernel<32, 4, 1><<<(unsigned)((M + 7) / 8), 256, 0, st>>>(xh, g, rh, yh, M);
+        else if (x_operand) launch_layernorm<__half, __half>(x, g, residual, y, M, C, 1, st);
         else launch_layernorm<float, __half>(x, g, residual, y, M, C, 1, st);
     } else {
         launch_layernorm<float, float>(x, g, residual, y, M, C, operand_out, st);
