@@ -31,20 +31,3 @@ def burgers_instances(n, seed=0, s=128, nt=10, amp_compensate=2.0):
         tm = bump(rng.uniform(0, 1, (n, 1, 1)), rng.uniform(0.05, 0.2, (n, 1, 1)), tt)
         f += amp * sp * (amp_compensate * tm)
     return u0.astype(np.float32), f.astype(np.float32)
-
-
-def dataset_states(u_traj, f, pad=16, scaler=10.0, use_max_safety=True):
-    """Assemble model-space states [n, 3, pad, s] = (u, f, s)/scaler from rollouts u_traj [n, 11, s] and f [n, 10, s]
-    following the reference dataset layout (/root/reference/1D/data/burgers.py:113-142): safety channel u^2
-    (replaced by its per-sample max when use_max_safety), zero-padded in time."""
-    u_traj = np.asarray(u_traj, dtype=np.float32)
-    f = np.asarray(f, dtype=np.float32)
-    n, nt1, s = u_traj.shape
-    st = np.zeros((n, 3, pad, s), dtype=np.float32)
-    st[:, 0, :nt1] = u_traj
-    st[:, 1, : f.shape[1]] = f
-    sc = u_traj ** 2
-    if use_max_safety:
-        sc = np.broadcast_to(sc.max(axis=(1, 2), keepdims=True), sc.shape)
-    st[:, 2, :nt1] = sc
-    return st / np.float32(scaler)

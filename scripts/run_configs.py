@@ -77,7 +77,7 @@ def main():
     rank, ws = setup()
     import safediffcon_b200 as s
     from safediffcon_b200 import runner
-    from safediffcon_b200.synthetic import burgers_instances, dataset_states
+    from safediffcon_b200.synthetic import burgers_instances
     cfg = Cfg()
     runner.all_gather_concat(torch.zeros(4, 2, device="cuda"), 4 * ws)   # NCCL communicator set-up is not part of any timed region
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -112,8 +112,9 @@ def main():
         gd = build_model(args.steps, args.ddpm)
         t_host0 = time.perf_counter()
         u0, f = burgers_instances(hi - lo, seed=400 + rank)
-        traj = s.burgers_numeric_solve_free(torch.from_numpy(u0).cuda(), torch.from_numpy(f).cuda(), 0.01, 1.0).cpu().numpy()
-        states = torch.from_numpy(dataset_states(traj, f)).pin_memory()   # (u, f, s) / 10, s = max u^2 broadcast
+        f_d = torch.from_numpy(f).cuda()
+        traj = s.burgers_numeric_solve_free(torch.from_numpy(u0).cuda(), f_d, 0.01, 1.0)
+        states = s.dataset_states(traj, f_d).cpu().pin_memory()   # (u, f, s) / 10, s = max u^2 broadcast; calibration states start on the host
         t_data = time.perf_counter() - t_host0
         barrier(ws)
         e0.record()

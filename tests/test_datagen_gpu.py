@@ -96,3 +96,40 @@ def test_generated_data_feeds_the_solver_full_size():
     # true division like the reference's CPU path (torch's CUDA scalar division multiplies by the reciprocal instead)
     assert torch.equal(st[:, 2, 0, 0].cpu(), (traj * traj).amax(dim=(1, 2)).cpu() / 10.0)
     assert torch.equal(st[:, 0, :11].cpu(), traj.cpu() / 10.0)
+
+
+def test_burgers_dataset_drop_in(golden):
+    """BurgersDataset over in-memory rollouts: items equal the reference's _process_data output (golden), whole split on the device."""
+    import safediffcon_b200 as s
+    g = golden("dataset_states")
+    traj, f = torch.from_numpy(g["traj"]), torch.from_numpy(g["f"])
+    for use_max in (True, False):
+        cfg = type("C", (), dict(use_max_safety=use_max))()
+        ds = s.BurgersDataset.from_tensors(traj, f, split="test", config=cfg)
+        assert len(ds) == 12 and ds.pad_size == 16 and ds.nx == 128 and ds.nt_total == 11 and ds.scaler == 10.0
+        assert ds[3].is_cuda and ds[3].shape == (3, 16, 128)
+        assert np.array_equal(torch.stack([ds[i] for i in range(12)]).cpu().numpy(), g[f"states_max{int(use_max)}"])
+        batch = next(iter(torch.utils.data.DataLoader(ds, batch_size=5, shuffle=False)))
+        assert batch.is_cuda and np.array_equal(batch.cpu().numpy(), g[f"states_max{int(use_max)}"][:5])
+    # unnormalised targets (get_target: is_normalize=False) and item indices
+    raw = s.BurgersDataset.from_tensors(traj, f, split="test", is_normalize=False, is_need_idx=True)
+    item, idx = raw[2]
+    assert idx == 2 and torch.equal(item[0, :11].cpu(), traj[2])
+    tgt = s.get_target([0, 5], dataset=s.BurgersDataset.from_tensors(traj, f, split="test", is_normalize=False))
+    assert tgt.shape == (2, 11, 128) and torch.equal(tgt.cpu(), traj[[0, 5]])
+    # flat layout (stack_u_and_f=False): cat(u, f, s) along time, burgers.py:131-134
+    flat = s.BurgersDataset.from_tensors(traj, f, split="test", stack_u_and_f=False)
+    assert flat[0].shape == (32, 128) and torch.equal(flat[0][11:21].cpu(), f[0] / 10.0)
+    # custom safety score goes through torch with the same layout rules
+    cust = s.BurgersDataset.from_tensors(traj, f, split="test", safety_transform=lambda u: u.abs())
+    assert torch.equal(cust[1][2, 0, 0].cpu(), traj[1].abs().max() / 10.0)
+
+
+def test_burgers_dataset_synthetic_feeds_the_chain():
+    import safediffcon_b200 as s
+    ds = s.BurgersDataset.synthetic(64, seed=5, split="cal")
+    st = ds.states
+    assert st.shape == (64, 3, 16, 128) and torch.isfinite(st).all() and (st[:, 2, :11] >= 0).all()
+    np.random.seed(5)
+    u0r, fr = dg.make_data_varying_f(64, 64, 128, 10)
+    assert torch.allclose(st[:, 0, 0].cpu() * 10.0, torch.from_numpy(u0r).float(), atol=1e-6)
