@@ -30,7 +30,7 @@ import torch  # noqa: E402
 CHAIN_STEPS = 1000
 CONV_GFLOP_PER_SAMPLE = 27.811 - 0.0771 - 0.0016  # tcgen05 convs only: minus the 7x7 stem and the 3-channel head
 W_SCORE, U_BOUND, Q_GUIDE = 500.0, 0.8, 0.0
-TRAFFIC_BYTES_PER_LAUNCH = 766.8e6  # mean dram read+write bytes per conv launch of one step at B=1024 (ncu, profiles/r01_conv_f16_per_launch_metrics.csv)
+TRAFFIC_BYTES_PER_LAUNCH = 540.4e6  # mean dram read+write bytes per conv launch of one step at B=1024 (ncu, 74 launches, 40.0 GB: profiles/r01_per_launch_metrics_v6_B1024.csv)
 
 
 class Cfg:
