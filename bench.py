@@ -156,6 +156,51 @@ def cpu_baseline_obj(steps=8):
             "rollouts_per_s": 1024.0 / t_solve, "torch_threads": torch.get_num_threads()}
 
 
+def torch_gpu_baseline_obj(B, dev, ms_step_ours):
+    """The incumbent library path on THIS GPU: the oracle's functional torch restatement of the
+    reference denoiser run by PyTorch eager on CUDA -- cuDNN TF32 convolutions (what the reference's sample() uses on a GPU) and
+    bf16 autocast -- one evaluation of the same batch, CUDA events.  A reported baseline like cpu_baseline: checker code, timed."""
+    import contextlib
+    from oracle import unet_ref
+    import safediffcon_b200 as s
+    torch.manual_seed(42)
+    net = s.Unet2D(dim=128, dim_mults=(1, 2, 4, 8), channels=3, resnet_block_groups=1)
+    sd = {k: v.detach().to(dev) for k, v in net.state_dict().items()}
+    del net
+    torch.backends.cudnn.allow_tf32 = True
+    torch.backends.cuda.matmul.allow_tf32 = True
+    torch.backends.cudnn.benchmark = True
+    out = {"kind": "port", "what": "oracle/unet_ref.py (functional restatement of the reference Unet2D) under PyTorch eager + cuDNN on this GPU, "
+                                   "one denoiser evaluation per step (posterior update not included)", "torch": torch.__version__}
+    while B >= 64:
+        try:
+            x = torch.randn(B, 3, 16, 128, device=dev)
+            t = torch.full((B,), 500, device=dev, dtype=torch.long)
+            for mode in ("tf32", "bf16_autocast"):
+                ctx = torch.autocast("cuda", dtype=torch.bfloat16) if mode == "bf16_autocast" else contextlib.nullcontext()
+                with torch.no_grad(), ctx:
+                    for _ in range(3):
+                        unet_ref.unet_forward(sd, x, t)
+                    torch.cuda.synchronize()
+                    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    e0.record()
+                    for _ in range(5):
+                        unet_ref.unet_forward(sd, x, t)
+                    e1.record()
+                    torch.cuda.synchronize()
+                ms = e0.elapsed_time(e1) / 5
+                out[f"ms_per_eval_{mode}"] = ms
+                out[f"samples_per_s_{mode}"] = B / (CHAIN_STEPS * ms / 1e3)
+            out["batch"] = B
+            out["ours_ms_per_step_same_batch"] = ms_step_ours if B == 1024 else None
+            break
+        except torch.cuda.OutOfMemoryError:
+            B //= 2
+            torch.cuda.empty_cache()
+    torch.cuda.empty_cache()
+    return out
+
+
 def run_reference_arm(args):
     ws, rank = int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -335,6 +380,13 @@ def main():
                                                     "d2h_bytes_per_step": 0, "skipped": True}}
         if not args.no_cpu and ws >= 1:
             line["cpu_baseline"] = cpu_baseline_obj()
+        if not args.no_cpu and ws == 1:
+            del img, nxt
+            torch.cuda.empty_cache()
+            try:
+                line["torch_gpu_baseline"] = torch_gpu_baseline_obj(B, dev, ms_step)
+            except Exception as ex:   # a reported extra: never lose the bench line over it
+                line["torch_gpu_baseline"] = {"error": repr(ex)[:200]}
         print(json.dumps(line), flush=True)
     if dist is not None:
         dist.barrier()
