@@ -117,9 +117,9 @@ __global__ void stem_conv7_kernel(const float* __restrict__ x, const float* __re
 // ci*49 + ky*7 + kx), columns [KH, KH+K) the LOW part (x - high, rounded to the operand precision), the rest zeros.
 // With the stem weights repeated in both column ranges the tcgen05 GEMM sees the fp32 input to ~2^-22 although its
 // operands are fp16 / tf32.  One CTA = one image row; the 7 input rows it needs are staged in shared memory.
-// Thread -> one group of 8 consecutive columns (one 16-byte store in FP16 mode) for pixels w = wl, wl + blockDim / groups, ...:
-// the patch offsets of its columns live in registers, the inner loop is 8 shared loads + conversions + one store (the earlier
-// version re-derived (pixel, column) by integer division per 4 elements and was issue bound at 0.29 of the copy peak).
+// Thread -> one group of 8 consecutive patch columns for pixels w = wl, wl + blockDim / groups, ...; it writes the group's high part
+// and its low part (two 16-byte stores in FP16 mode) from the same 8 shared loads.  The patch offsets of its columns live in
+// registers (the first version re-derived (pixel, column) by integer division per 4 elements: issue bound, 0.29 of the copy peak).
 template <typename T>
 __global__ void __launch_bounds__(256) stem_im2col_kernel(const float* __restrict__ x, T* __restrict__ a, int Cin, int H, int W,
                                                           int kp) {
@@ -132,16 +132,14 @@ __global__ void __launch_bounds__(256) stem_im2col_kernel(const float* __restric
         xs[i] = (hh >= 0 && hh < H && ww >= 0 && ww < W) ? x[(((int64_t)b * Cin + ci) * H + hh) * W + ww] : 0.f;
     }
     __syncthreads();
-    const int groups = kp / 8;                       // column groups per row
+    const int groups = KH / 8;                       // groups of 8 patch columns; a thread writes the group's high AND low part
     const int wstep = blockDim.x / groups;           // pixels in flight per pass (threads beyond groups * wstep idle)
     const int grp = threadIdx.x % groups, wl = threadIdx.x / groups;
     if (wl >= wstep) return;
     int off[8];       // offset of column (ci, ky, kx) inside the window, or -1 for padding columns
-    bool low = false;
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-        int k = grp * 8 + j;
-        if (k >= KH) { k -= KH; low = true; }   // KH is a multiple of 8: a group is entirely high or entirely low
+        const int k = grp * 8 + j;
         const int ci = k / 49, t = k - ci * 49, ky = t / 7, kx = t - ky * 7;
         off[j] = k < K ? (ci * 7 + ky) * WP + kx : -1;
     }
@@ -149,13 +147,30 @@ __global__ void __launch_bounds__(256) stem_im2col_kernel(const float* __restric
     for (int w = wl; w < W; w += wstep) {
         float v[8];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            const float xv = off[j] >= 0 ? xs[off[j] + w] : 0.f;
-            const float hi = (float)to_operand(xv, T());
-            v[j] = low ? xv - hi : hi;
+        for (int j = 0; j < 8; ++j) v[j] = off[j] >= 0 ? xs[off[j] + w] : 0.f;
+        if constexpr (sizeof(T) == 2) {
+            uint4 hi, lo;
+            uint32_t* hw = reinterpret_cast<uint32_t*>(&hi);
+            uint32_t* lw = reinterpret_cast<uint32_t*>(&lo);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const __half2 h2 = __floats2half2_rn(v[2 * j], v[2 * j + 1]);
+                const float2 f2 = __half22float2(h2);
+                const __half2 l2 = __floats2half2_rn(v[2 * j] - f2.x, v[2 * j + 1] - f2.y);
+                hw[j] = *reinterpret_cast<const uint32_t*>(&h2);
+                lw[j] = *reinterpret_cast<const uint32_t*>(&l2);
+            }
+            *reinterpret_cast<uint4*>(arow + (int64_t)w * kp) = hi;
+            *reinterpret_cast<uint4*>(arow + (int64_t)w * kp + KH) = lo;
+        } else {
+            float hi[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) hi[j] = (float)to_operand(v[j], T());
+            store_operand4(arow + (int64_t)w * kp, make_float4(hi[0], hi[1], hi[2], hi[3]));
+            store_operand4(arow + (int64_t)w * kp + 4, make_float4(hi[4], hi[5], hi[6], hi[7]));
+            store_operand4(arow + (int64_t)w * kp + KH, make_float4(v[0] - hi[0], v[1] - hi[1], v[2] - hi[2], v[3] - hi[3]));
+            store_operand4(arow + (int64_t)w * kp + KH + 4, make_float4(v[4] - hi[4], v[5] - hi[5], v[6] - hi[6], v[7] - hi[7]));
         }
-        store_operand4(arow + (int64_t)w * kp, make_float4(v[0], v[1], v[2], v[3]));
-        store_operand4(arow + (int64_t)w * kp + 4, make_float4(v[4], v[5], v[6], v[7]));
     }
 }
 
@@ -630,19 +645,21 @@ __global__ void __launch_bounds__(128) linattn_context_mma_kernel(const __half* 
     for (int j = 0; j < 8; ++j) ksum[j] = 0.f;
     constexpr float LOG2E = 1.4426950408889634f;
     const uint32_t ek_s = (uint32_t)__cvta_generic_to_shared(ek), vs_s = (uint32_t)__cvta_generic_to_shared(vs);
-    for (int n0 = 0; n0 < n; n0 += LC_CH) {
+    // Software pipeline: the k rows of chunk i+1 are requested (into the registers chunk i has just finished with) before the
+    // MMAs of chunk i, and v goes global -> shared with cp.async (zero fill past the end) while the maxima / exponentials run.
+    uint4 kr[4];
+    auto load_k = [&](int n0) {
         const int cnt = min(LC_CH, n - n0);
-        uint4 kr[4], vr[4];
 #pragma unroll
         for (int rr = 0; rr < 4; ++rr) {
             const int r = pr + 32 * rr;
             kr[rr] = make_uint4(0xFC00FC00u, 0xFC00FC00u, 0xFC00FC00u, 0xFC00FC00u);   // -inf: exp = 0, rows past the end add nothing
-            vr[rr] = make_uint4(0u, 0u, 0u, 0u);
-            if (r < cnt) {
-                kr[rr] = __ldcs(reinterpret_cast<const uint4*>(kp + (int64_t)(n0 + r) * ld + cg * 8));
-                vr[rr] = __ldcs(reinterpret_cast<const uint4*>(vp + (int64_t)(n0 + r) * ld + cg * 8));
-            }
+            if (r < cnt) kr[rr] = __ldcs(reinterpret_cast<const uint4*>(kp + (int64_t)(n0 + r) * ld + cg * 8));
         }
+    };
+    load_k(0);
+    for (int n0 = 0; n0 < n; n0 += LC_CH) {
+        const int cnt = min(LC_CH, n - n0);
         uint32_t m2[4] = {kr[0].x, kr[0].y, kr[0].z, kr[0].w};
 #pragma unroll
         for (int rr = 1; rr < 4; ++rr) {
@@ -655,6 +672,14 @@ __global__ void __launch_bounds__(128) linattn_context_mma_kernel(const __half* 
             for (int j = 0; j < 4; ++j) m2[j] = hmax2_u32(m2[j], __shfl_xor_sync(0xffffffffu, m2[j], o));
         }
         __syncthreads();   // the previous chunk's tiles, maxima and rescale factors are consumed
+#pragma unroll
+        for (int rr = 0; rr < 4; ++rr) {
+            const int r = pr + 32 * rr;
+            const __half* src = vp + (int64_t)(n0 + min(r, cnt - 1)) * ld + cg * 8;   // clamped address, 0 source bytes past the end
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(vs_s + 2u * (uint32_t)(r * LC_LD + cg * 8)), "l"(src),
+                         "r"(r < cnt ? 16 : 0) : "memory");
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
         if (lane < 4) {
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
@@ -663,8 +688,6 @@ __global__ void __launch_bounds__(128) linattn_context_mma_kernel(const __half* 
                 red[warp][cg * 8 + 2 * j + 1] = f.y;
             }
         }
-#pragma unroll
-        for (int rr = 0; rr < 4; ++rr) *reinterpret_cast<uint4*>(vs + (pr + 32 * rr) * LC_LD + cg * 8) = vr[rr];
         __syncthreads();
         if (tid < LA_D) {
             const float t = fmaxf(fmaxf(red[0][tid], red[1][tid]), fmaxf(red[2][tid], red[3][tid]));
@@ -700,6 +723,8 @@ __global__ void __launch_bounds__(128) linattn_context_mma_kernel(const __half* 
                 for (int nt = 0; nt < 4; ++nt) { acc[mt][nt][0] *= s0; acc[mt][nt][1] *= s0; acc[mt][nt][2] *= s1; acc[mt][nt][3] *= s1; }
             }
         }
+        if (n0 + LC_CH < n) load_k(n0 + LC_CH);   // prefetch: in flight across the barrier and the MMAs below
+        asm volatile("cp.async.wait_all;" ::: "memory");
         __syncthreads();
 #pragma unroll
         for (int ks = 0; ks < 2; ++ks) {
@@ -995,6 +1020,61 @@ __global__ void __launch_bounds__(256) head_conv1_kernel(const T* __restrict__ x
     }
 }
 
+// Fast path of the head for the dim-128 model in FP16 mode (Cin = 128, Cout = 3): 4 lanes per pixel, a lane owns the four
+// 8-channel vectors j, j + 4, j + 8, j + 12 of the pixel row (a warp's load instruction covers 8 pixels x 64 contiguous bytes) and
+// keeps its 3 x 32 weights in registers; 6 shuffles per 32 elements (the generic kernel above: 9 per 16 and one shared load per
+// 4 FMAs -- 0.36 of the copy peak).  Two pixels per lane in flight.
+__global__ void __launch_bounds__(128) head_conv1_h128_kernel(const __half* __restrict__ x, const float* __restrict__ w,
+                                                              const float* __restrict__ bias, float* __restrict__ out, int64_t M,
+                                                              int HW) {
+    const int lane = threadIdx.x & 31, j = lane & 3;
+    float wr[3][32];
+#pragma unroll
+    for (int o = 0; o < 3; ++o)
+#pragma unroll
+        for (int v = 0; v < 4; ++v)
+#pragma unroll
+            for (int k = 0; k < 8; ++k) wr[o][v * 8 + k] = __ldg(w + o * 128 + (v * 4 + j) * 8 + k);
+    const float b0 = bias ? bias[0] : 0.f, b1 = bias ? bias[1] : 0.f, b2 = bias ? bias[2] : 0.f;
+    const int64_t gw = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), nw = (int64_t)gridDim.x * (blockDim.x >> 5);
+    for (int64_t p0 = gw * 16; p0 < M; p0 += nw * 16) {   // a warp: 2 x 8 pixels per iteration
+        uint4 xv[2][4];
+        int64_t row[2];
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            row[u] = p0 + u * 8 + (lane >> 2);
+#pragma unroll
+            for (int v = 0; v < 4; ++v)
+                xv[u][v] = row[u] < M ? __ldcs(reinterpret_cast<const uint4*>(x + row[u] * 128) + v * 4 + j) : make_uint4(0u, 0u, 0u, 0u);
+        }
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            float a0 = 0.f, a1 = 0.f, a2 = 0.f;
+#pragma unroll
+            for (int v = 0; v < 4; ++v) {
+                float f[8];
+                unpack8(xv[u][v], f);
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    a0 = fmaf(f[k], wr[0][v * 8 + k], a0);
+                    a1 = fmaf(f[k], wr[1][v * 8 + k], a1);
+                    a2 = fmaf(f[k], wr[2][v * 8 + k], a2);
+                }
+            }
+#pragma unroll
+            for (int o = 1; o < 4; o <<= 1) {
+                a0 += __shfl_xor_sync(0xffffffffu, a0, o);
+                a1 += __shfl_xor_sync(0xffffffffu, a1, o);
+                a2 += __shfl_xor_sync(0xffffffffu, a2, o);
+            }
+            if (row[u] < M && j < 3) {   // lane j of the quad writes output channel j
+                const int64_t b = row[u] / HW, p = row[u] % HW;
+                out[(b * 3 + j) * HW + p] = j == 0 ? a0 + b0 : (j == 1 ? a1 + b1 : a2 + b2);
+            }
+        }
+    }
+}
+
 __device__ __forceinline__ float act_in(float v, int act) {
     if (act == 1) return silu(v);
     if (act == 2) return 0.5f * v * (1.0f + erff(v * 0.7071067811865476f));
@@ -1248,7 +1328,9 @@ extern "C" int sdc_head_conv1(int prec, const void* x, const float* w, const flo
     SDC_REQUIRE(M % 4 == 0, "head_conv1: B*HW must be a multiple of 4");   // a warp's 4 pixels are all valid or all absent
     const unsigned grid = blocks_for(M * 8, 256);
     const size_t sm = (size_t)Cout * Cin * sizeof(float);
-    if (prec == SDC_PREC_F16)
+    if (prec == SDC_PREC_F16 && Cin == 128 && Cout == 3)
+        head_conv1_h128_kernel<<<blocks_for(M, 64), 128, 0, as_stream(stream)>>>((const __half*)x, w, bias, out, M, HW);
+    else if (prec == SDC_PREC_F16)
         head_conv1_kernel<__half><<<grid, 256, sm, as_stream(stream)>>>((const __half*)x, w, bias, out, M, HW, Cin, Cout);
     else
         head_conv1_kernel<float><<<grid, 256, sm, as_stream(stream)>>>((const float*)x, w, bias, out, M, HW, Cin, Cout);
