@@ -895,13 +895,15 @@ __global__ void __launch_bounds__(256) linattn_apply_kernel(const float* __restr
 //                                                            = sum_{h,d} qs_h[n, d] * Wf_b[co, 32h + d],
 // Wf_b[co, 32h + d] = sum_e W[co, 32h + e] ctx_{b,h}[d, e]: a per-sample [Cout, 128] weight.  The context apply then IS the 1x1
 // output projection (one tcgen05 GEMM with per-sample weights) and the [B*n, 128] attention tensor is never materialised.
-// grid = B, 256 threads: the sample's four contexts are loaded once, then 32 output channels per iteration; thread -> column
-// hd = tid & 127 (its 32 context values live in registers) and 16 of the block's 32 output channels.
+// grid = B, 256 threads: the sample's four contexts are loaded once, then 16 output channels per iteration; thread -> column
+// hd = tid & 127 (its 32 context values live in registers) and 8 of the slab's 16 output channels.  Shared memory is kept at
+// 25 KB so that all B = 1024 CTAs are resident in one wave (with 32-channel slabs, 33 KB, 6 CTAs per SM fitted and a second,
+// nearly empty wave doubled the time of this latency-bound kernel).
 template <typename T>
 __global__ void __launch_bounds__(256) linattn_fold_kernel(const float* __restrict__ ws, const float* __restrict__ w_out,
                                                            T* __restrict__ wf, int Cout) {
     __shared__ float cs[LA_HEADS * LA_D][LA_D + 1];   // ctx[h*32 + d][e], padded: lanes walk d
-    __shared__ __align__(16) float wsm[32][LA_HID];
+    __shared__ __align__(16) float wsm[16][LA_HID];
     const int b = blockIdx.x;
     for (int i = threadIdx.x; i < LA_HEADS * LA_D * LA_D; i += 256)
         cs[i >> 5][i & 31] = ws[((int64_t)b * LA_HEADS + (i >> 10)) * LA_CTX + (i & 1023)];
@@ -910,14 +912,14 @@ __global__ void __launch_bounds__(256) linattn_fold_kernel(const float* __restri
     float c[LA_D];
 #pragma unroll
     for (int e = 0; e < LA_D; ++e) c[e] = cs[hd][e];
-    for (int co0 = 0; co0 < Cout; co0 += 32) {
+    for (int co0 = 0; co0 < Cout; co0 += 16) {
         __syncthreads();
-        for (int i = threadIdx.x; i < 32 * LA_HID / 4; i += 256)
+        for (int i = threadIdx.x; i < 16 * LA_HID / 4; i += 256)
             reinterpret_cast<float4*>(&wsm[0][0])[i] = __ldg(reinterpret_cast<const float4*>(w_out + (int64_t)co0 * LA_HID) + i);
         __syncthreads();
 #pragma unroll 4
-        for (int r = 0; r < 16; ++r) {
-            const int co = half_id * 16 + r;
+        for (int r = 0; r < 8; ++r) {
+            const int co = half_id * 8 + r;
             float acc = 0.f;
 #pragma unroll
             for (int e = 0; e < LA_D; e += 4) {
@@ -1288,7 +1290,7 @@ extern "C" int sdc_linear_attention_context(const void* k, const void* v, int ld
 extern "C" int sdc_linear_attention_fold(int prec, const void* workspace, const float* w_out, void* w_folded, int B, int Cout,
                                          void* stream) {
     SDC_CHECK_PREC("linear_attention_fold");
-    SDC_REQUIRE(workspace && w_out && w_folded && B > 0 && Cout > 0 && Cout % 32 == 0, "linear_attention_fold: Cout %% 32 != 0 or null pointer");
+    SDC_REQUIRE(workspace && w_out && w_folded && B > 0 && Cout > 0 && Cout % 16 == 0, "linear_attention_fold: Cout %% 16 != 0 or null pointer");
     const unsigned grid = (unsigned)B;
     if (prec == SDC_PREC_F16)
         linattn_fold_kernel<__half><<<grid, 256, 0, as_stream(stream)>>>(reinterpret_cast<const float*>(workspace), w_out, (__half*)w_folded, Cout);
