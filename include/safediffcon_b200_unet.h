@@ -50,6 +50,17 @@ int sdc_conv3x3_row(int prec, const void* a0, int c0, const void* a1, int c1, co
                     const void* residual, void* out, double* stats, int operand_out, int B, int H, int W, int Cout,
                     void* stream);
 
+/* sdc_conv3x3_row (FP16 mode, fp16 output, no bias-side residual) with the GroupNorm(1, C) + FiLM + SiLU (+ residual) of the
+ * following sdc_gn_silu call applied IN PLACE by the same kernel: every cluster owns whole samples, so after the last rows of a sample
+ * it re-reads its rows (L2 resident), normalises them with the statistics the epilogues accumulated in stats[b] and overwrites them.
+ * Arguments gamma .. gn_residual as in sdc_gn_silu (gn_residual: fp16 or NULL).  Returns -1 (nothing done) when the shape or batch
+ * is not eligible (needs the CTA-pair kernel: B * H / 4 >= SM pairs, H % 4 == 0, W == 128, Cout <= 128); the caller then issues
+ * sdc_conv3x3_row / sdc_conv_gemm followed by sdc_gn_silu.  Experimental: numerically equivalent to the two-kernel sequence (tests) but
+ * not faster on B200 yet (see csrc/conv_row.cu); the Python layer keeps it off unless Unet2D.fuse_groupnorm is set. */
+int sdc_conv3x3_row_gn(const void* a0, int c0, const void* a1, int c1, const void* w_packed, const float* bias, void* out,
+                       double* stats, const float* gamma, const float* beta, const float* scale_shift, const int32_t* t_index,
+                       int64_t ss_stride, const void* gn_residual, int B, int H, int W, int Cout, void* stream);
+
 /* Stem: 7x7 pad 3 convolution of the NCHW model input (unet.py:326,392).  x:[B,Cin,H,W] NCHW fp32, w:[Cout,Cin,7,7] OIHW
  * (unpacked, fp32), out: NHWC operand [B*H*W, Cout].  FP32 CUDA-core kernel (0.3% of the FLOPs). */
 int sdc_stem_conv7(int prec, const float* x, const float* w, const float* bias, void* out, int B, int Cin, int H, int W,

@@ -22,6 +22,7 @@ L.register({
     "sdc_pack_conv_weight": (c_i, [c_i, c_i, c_p, c_p, c_i, c_i, c_p]),
     "sdc_conv_gemm": (c_i, [c_i, c_i, c_p, c_i, c_p, c_i, c_p, c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_p]),
     "sdc_conv3x3_row": (c_i, [c_i, c_p, c_i, c_p, c_i, c_p, c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_p]),
+    "sdc_conv3x3_row_gn": (c_i, [c_p, c_i, c_p, c_i, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_i64, c_p, c_i, c_i, c_i, c_i, c_p]),
     "sdc_stem_conv7": (c_i, [c_i, c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_p]),
     "sdc_stem_im2col": (c_i, [c_i, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_p]),
     "sdc_gn_silu": (c_i, [c_i, c_p, c_i, c_p, c_p, c_p, c_p, c_p, c_i64, c_p, c_i, c_p, c_i, c_i, c_i, c_p]),
@@ -153,6 +154,17 @@ class _Timed:
         if self.prof is not None and exc[0] is None:
             self.e1.record()
             self.prof.append((self.e0, self.e1, self.flops, self.shape))
+
+
+def conv_row_gn(a0, c0, a1, c1, cw, out, stats, gn, ss, t_index, ss_stride, residual, B, H, W, Cout):
+    """3x3 convolution of the full-resolution level with the following GroupNorm + FiLM + SiLU (+ residual) applied in place by the
+    same kernel (FP16, include/safediffcon_b200_unet.h: sdc_conv3x3_row_gn).  Returns 0, or -1 when not eligible (nothing launched)."""
+    with _Timed(2.0 * B * H * W * Cout * 9 * (c0 + c1), (KIND_3x3, B, H, W, c0 + c1, Cout)):
+        rc = L.lib().sdc_conv3x3_row_gn(L.ptr(a0), c0, L.ptr(a1), c1, L.ptr(cw["w"]), L.ptr(cw["b"]), L.ptr(out), L.ptr(stats),
+                                        L.ptr(gn[0]), L.ptr(gn[1]), L.ptr(ss), L.ptr(t_index), ss_stride, L.ptr(residual), B, H, W, Cout, _st())
+    if rc > 0:
+        L.check(rc)
+    return rc
 
 
 def conv1x1_qkv(a, c, wp, q_out, kv_out, B, H, W, prec):
@@ -365,6 +377,10 @@ class Unet2D(nn.Module):
         # HBM-bound norm kernels move 4 instead of 6 bytes per element.  `net.compact_intermediates = False` (or SDC_COMPACT=0)
         # keeps fp32.  The recording (backward) path always keeps fp32.
         self.compact_intermediates = os.environ.get("SDC_COMPACT", "1") != "0"
+        # EXPERIMENTAL (off): with compact intermediates and batches >= 256 the 3x3 convolutions of the 16x128 level can normalise
+        # their own output in place (sdc_conv3x3_row_gn) instead of a separate GroupNorm pass.  Correct (tests) but currently
+        # 5 % slower than the separate kernels (csrc/conv_row.cu explains why); SDC_FUSE_GN=1 enables it.
+        self.fuse_groupnorm = os.environ.get("SDC_FUSE_GN", "0") == "1"
 
     # ------------------------------------------------------------------ weight packing / FiLM table
     def _resnet_blocks(self):
@@ -598,6 +614,24 @@ class Unet2D(nn.Module):
             M, cout = B * h * w, p["cout"]
             s1, s2 = stats[stat_i[0]], stats[stat_i[0] + 1]
             stat_i[0] += 2
+            if cmp and self.fuse_groupnorm and w == 128 and cout <= 128 and B >= 256 and USE_ROW_KERNEL:
+                # full-resolution level, large batch: GroupNorm + FiLM + SiLU (+ residual) applied in place by the conv kernel
+                # itself (sdc_conv3x3_row_gn): no separate normalisation pass over HBM
+                ss = film[:, m._film_off:]
+                raw = opd(M, cout)
+                rc = conv_row_gn(a0, c0, a1, c1, p["c1"], raw, s1, p["g1"], ss, t_index, E, None, B, h, w, cout)
+                if rc == 0:
+                    if p["res"] is not None:
+                        res = opd(M, cout)
+                        conv(KIND_1x1, a0, c0, a1, c1, p["res"], None, res, None, True, h, w)
+                    else:
+                        assert a1 is None
+                        res = a0
+                    raw2 = opd(M, cout)
+                    rc = conv_row_gn(raw, cout, None, 0, p["c2"], raw2, s2, p["g2"], None, None, 0, res, B, h, w, cout)
+                    assert rc == 0
+                    return raw2
+                s1.zero_()   # not eligible after all: fall through to the unfused sequence
             if cmp:
                 # compact intermediates (FP16 inference): the conv epilogue takes the GroupNorm sums from its fp32 accumulators and
                 # stores fp16; normalisation runs in place; the 1x1 res_conv output lands in conv1's dead buffer, also fp16
