@@ -83,6 +83,14 @@ int sdc_gn_silu(int prec, const void* x, int x_operand, const double* stats, con
                 const int32_t* t_index, int64_t ss_stride, const void* residual, int residual_operand, void* y, int B, int HW,
                 int C, void* stream);
 
+/* The network's LAST GroupNorm + SiLU + residual fused with the 1x1 head convolution (final_res_block.block2 + final_conv,
+ * unet.py:178-180,378,426): out[b, o, p] = sum_c head_w[o, c] * (silu(GN(x)[b, p, c]) + residual[b, p, c]) + head_b[o], NCHW fp32.
+ * x: fp32 [B*HW, C] (C = 128), stats as in sdc_gn_silu, residual fp16 if residual_operand else fp32, Cout <= 4.  The activation
+ * stays fp32 in registers (never stored, never rounded). */
+int sdc_gn_silu_head(const float* x, const double* stats, const float* gamma, const float* beta, const void* residual,
+                     int residual_operand, const float* head_w, const float* head_b, float* out, int B, int HW, int C, int Cout,
+                     void* stream);
+
 /* Channel LayerNorm (unet.py:53-63): y = (x - mean_c) * rsqrt(var_c + 1e-5) * g (+ residual), per pixel row.
  * x: operand precision if x_operand else fp32; residual and y: operand precision (TF32 mode: y is rounded to TF32
  * only when operand_out is set; F16 mode: y is always fp16). */

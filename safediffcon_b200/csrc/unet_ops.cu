@@ -341,6 +341,76 @@ __global__ void __launch_bounds__(256) gn_silu_h8_kernel(const __half* __restric
     }
 }
 
+// Last GroupNorm of the network fused with the 1x1 head convolution (final_res_block.block2's norm + SiLU + residual, then
+// final_conv, unet.py:178-180,378,426): eps[b, o, p] = sum_c w[o, c] * (silu(GN(x)[p, c]) + res[p, c]) + bias[o].  The activation
+// never exists in memory: it stays fp32 in registers, so the head sees it unrounded (the last rounding site in front of the
+// output carried 13% of the eps error variance) and one write + one read of a [B*HW, C] tensor disappear.
+// x: fp32 conv output (C = 128); residual: fp16 or fp32.  16 lanes per pixel (8 channels each), a warp covers 2 pixels; the
+// (<= 4) dot products are reduced with a transposing butterfly: 5 shuffles instead of 16.
+template <typename TR>
+__global__ void __launch_bounds__(256) gn_silu_head_kernel(const float* __restrict__ x, const double* __restrict__ stats,
+                                                           const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                           const TR* __restrict__ residual, const float* __restrict__ hw,
+                                                           const float* __restrict__ hb, float* __restrict__ out, int HW, int Cout,
+                                                           int pix_per_cta) {
+    constexpr int C = 128;
+    const int b = blockIdx.x;
+    const double cnt = (double)HW * (double)C;
+    const double mean_d = stats[2 * b] / cnt;
+    double var_d = stats[2 * b + 1] / cnt - mean_d * mean_d;
+    if (var_d < 0.0) var_d = 0.0;
+    const float mean = (float)mean_d, rstd = (float)(1.0 / sqrt(var_d + 1e-5));
+    const int lane = threadIdx.x & 31, sub = lane & 15;
+    const int c = sub * 8;
+    float A[8], Bc[8], w[4][8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        const float g = gamma[c + k] * rstd;
+        A[k] = g;
+        Bc[k] = beta[c + k] - mean * g;
+#pragma unroll
+        for (int o = 0; o < 4; ++o) w[o][k] = o < Cout ? hw[o * C + c + k] : 0.f;
+    }
+    const int o_mine = ((sub & 1) << 1) | ((sub >> 1) & 1);   // output channel this lane ends up holding (lanes 0-3 of a half warp)
+    const float bias = (o_mine < Cout && hb) ? hb[o_mine] : 0.f;
+    const int p0 = blockIdx.y * pix_per_cta, p1 = min(HW, p0 + pix_per_cta);
+    const int pl = threadIdx.x >> 4;   // 16 pixels per pass
+    for (int pp = p0 + pl; pp < p1; pp += 32) {   // two pixels per lane in flight; pix_per_cta % 32 == 0: uniform trip count (shuffles below)
+        float d[2][4];
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            const int px = pp + 16 * u;
+            const bool ok = px < p1;
+            const int64_t off = ((int64_t)b * HW + (ok ? px : p0)) * C + c;
+            const float4 x0 = __ldcs(reinterpret_cast<const float4*>(x + off)), x1 = __ldcs(reinterpret_cast<const float4*>(x + off + 4));
+            const float4 r0 = load4(residual + off), r1 = load4(residual + off + 4);
+            const float xv[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
+            const float rv[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+            d[u][0] = d[u][1] = d[u][2] = d[u][3] = 0.f;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                const float y = silu_fast(fmaf(xv[k], A[k], Bc[k])) + rv[k];
+#pragma unroll
+                for (int o = 0; o < 4; ++o) d[u][o] = fmaf(y, w[o][k], d[u][o]);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            // step 1 (xor 1): even lanes keep (d0, d1), odd lanes keep (d2, d3); step 2 (xor 2): bit 1 clear keeps the first
+            const bool odd = sub & 1, hi = sub & 2;
+            float k0 = odd ? d[u][2] : d[u][0], k1 = odd ? d[u][3] : d[u][1];
+            k0 += __shfl_xor_sync(0xffffffffu, odd ? d[u][0] : d[u][2], 1);
+            k1 += __shfl_xor_sync(0xffffffffu, odd ? d[u][1] : d[u][3], 1);
+            float kk = hi ? k1 : k0;
+            kk += __shfl_xor_sync(0xffffffffu, hi ? k0 : k1, 2);
+            kk += __shfl_xor_sync(0xffffffffu, kk, 4);
+            kk += __shfl_xor_sync(0xffffffffu, kk, 8);
+            const int px = pp + 16 * u;
+            if (sub < 4 && o_mine < Cout && px < p1) out[((int64_t)b * Cout + o_mine) * HW + px] = kk + bias;
+        }
+    }
+}
+
 // ---------------------------------------------------------------------------------------------- channel LayerNorm
 // one warp per RPW pixel rows (RPW = 4 for C <= 256 so that 4-8 independent 16-byte loads are in flight per lane);
 // C <= 1024 kept in registers, two-pass variance like torch.var(unbiased=False)
@@ -1198,6 +1268,23 @@ extern "C" int sdc_gn_silu(int prec, const void* xv, int x_operand, const double
         gn_silu_kernel<float, float><<<grid, 256, sm, st>>>(x, stats, gamma, beta, scale_shift, t_index, ss_stride,
                                                              (const float*)residual, (float*)y, HW, C, ppc);
     }
+    SDC_LAUNCHED();
+    return SDC_OK;
+}
+
+extern "C" int sdc_gn_silu_head(const float* x, const double* stats, const float* gamma, const float* beta, const void* residual,
+                                int residual_operand, const float* head_w, const float* head_b, float* out, int B, int HW, int C,
+                                int Cout, void* stream) {
+    SDC_REQUIRE(x && stats && gamma && beta && residual && head_w && out && B > 0 && HW > 0, "gn_silu_head: bad arguments");
+    SDC_REQUIRE(C == 128 && Cout >= 1 && Cout <= 4 && HW % 32 == 0, "gn_silu_head: C=%d Cout=%d HW=%d unsupported (C = 128, Cout <= 4, HW %% 32 == 0)", C, Cout, HW);
+    int ppc = HW;
+    while (ppc > 32 && (int64_t)B * (HW / ppc) < 2 * 148 && ppc % 2 == 0) ppc /= 2;
+    dim3 grid((unsigned)B, (unsigned)((HW + ppc - 1) / ppc));
+    cudaStream_t st = as_stream(stream);
+    if (residual_operand)
+        gn_silu_head_kernel<__half><<<grid, 256, 0, st>>>(x, stats, gamma, beta, (const __half*)residual, head_w, head_b, out, HW, Cout, ppc);
+    else
+        gn_silu_head_kernel<float><<<grid, 256, 0, st>>>(x, stats, gamma, beta, (const float*)residual, head_w, head_b, out, HW, Cout, ppc);
     SDC_LAUNCHED();
     return SDC_OK;
 }

@@ -26,6 +26,7 @@ L.register({
     "sdc_stem_conv7": (c_i, [c_i, c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_p]),
     "sdc_stem_im2col": (c_i, [c_i, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_p]),
     "sdc_gn_silu": (c_i, [c_i, c_p, c_i, c_p, c_p, c_p, c_p, c_p, c_i64, c_p, c_i, c_p, c_i, c_i, c_i, c_p]),
+    "sdc_gn_silu_head": (c_i, [c_p, c_p, c_p, c_p, c_p, c_i, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_p]),
     "sdc_channel_layernorm": (c_i, [c_i, c_p, c_i, c_p, c_p, c_p, c_i64, c_i, c_i, c_p]),
     "sdc_linear_attention_workspace": (c_i64, [c_i]),
     "sdc_linear_attention": (c_i, [c_i, c_p, c_p, c_p, c_i, c_i, c_p]),
@@ -373,7 +374,7 @@ class Unet2D(nn.Module):
         self.precision = os.environ.get("SDC_PRECISION", default)
         # FP16 inference only: convolution outputs that feed a GroupNorm / LayerNorm (and the 1x1 res_conv output) are stored as
         # fp16 instead of fp32.  The norm statistics still come from the fp32 accumulators; only the stored activations carry one
-        # more 2^-11 rounding (eps error 6.3e-4 -> 7.5e-4 relative on the dim-128 model, inside the 1e-3 contract), and the
+        # more 2^-11 rounding (eps error 6.3e-4 -> 6.6e-4 relative on the dim-128 model with the last block kept in fp32), and the
         # HBM-bound norm kernels move 4 instead of 6 bytes per element.  `net.compact_intermediates = False` (or SDC_COMPACT=0)
         # keeps fp32.  The recording (backward) path always keeps fp32.
         self.compact_intermediates = os.environ.get("SDC_COMPACT", "1") != "0"
@@ -609,11 +610,31 @@ class Unet2D(nn.Module):
         def conv(kind, a0, c0, a1, c1, cw, residual, out, st, operand_out, h, w, algo_k=None):
             conv_gemm(kind, a0, c0, a1, c1, cw["w"], cw["b"], residual, out, st, operand_out, B, h, w, cw["cout"], prec, algo_k)
 
-        def resnet(p, m, a0, c0, a1, c1, h, w):
-            """ResnetBlock (unet.py:166-180) on one or two concatenated NHWC inputs -> operand [B*h*w, Cout]."""
+        def resnet(p, m, a0, c0, a1, c1, h, w, head=None):
+            """ResnetBlock (unet.py:166-180) on one or two concatenated NHWC inputs -> operand [B*h*w, Cout].
+            head = (w, b, out): the block is the last one; its second normalisation is fused with the 1x1 head convolution and the
+            block keeps fp32 norm inputs (the last rounding sites in front of the output dominate the eps error: with them exact the
+            compact path is as accurate as fp32 intermediates everywhere, 6.3-7.0e-4 instead of 7.4-8.3e-4)."""
             M, cout = B * h * w, p["cout"]
             s1, s2 = stats[stat_i[0]], stats[stat_i[0] + 1]
             stat_i[0] += 2
+            if head is not None:
+                raw = f32(M, cout)
+                conv(KIND_3x3, a0, c0, a1, c1, p["c1"], None, raw, s1, False, h, w)
+                ss = film[:, m._film_off:]
+                h1 = opd(M, cout)
+                L.check(lib.sdc_gn_silu(prec, L.ptr(raw), 0, L.ptr(s1), L.ptr(p["g1"][0]), L.ptr(p["g1"][1]), L.ptr(ss), L.ptr(t_index), E,
+                                        None, 0, L.ptr(h1), B, h * w, cout, _st()))
+                conv(KIND_3x3, h1, cout, None, 0, p["c2"], None, raw, s2, False, h, w)   # conv1's output is dead: reuse its buffer
+                if p["res"] is not None:
+                    res = h1   # dead after conv2
+                    conv(KIND_1x1, a0, c0, a1, c1, p["res"], None, res, None, True, h, w)
+                else:
+                    assert a1 is None
+                    res = a0
+                L.check(lib.sdc_gn_silu_head(L.ptr(raw), L.ptr(s2), L.ptr(p["g2"][0]), L.ptr(p["g2"][1]), L.ptr(res), 1, L.ptr(head[0]),
+                                             L.ptr(head[1]), L.ptr(head[2]), B, h * w, cout, head[2].shape[1], _st()))
+                return None
             if cmp and self.fuse_groupnorm and w == 128 and cout <= 128 and B >= 256 and USE_ROW_KERNEL:
                 # full-resolution level, large batch: GroupNorm + FiLM + SiLU (+ residual) applied in place by the conv kernel
                 # itself (sdc_conv3x3_row_gn): no separate normalisation pass over HBM
@@ -770,9 +791,12 @@ class Unet2D(nn.Module):
             conv(KIND_3x3, cur, c, None, 0, lvl["up"], None, nxt, None, True, h, w)
             rec(("up", dict(p=lvl["up"], upsample=lvl["upsample"], c=c, h=h, w=w, inp=cur)))
             cur, c = nxt, cout
+        out = torch.empty(B, self.out_dim, H, W, device=dev, dtype=torch.float32)
+        if cmp and pk["final"]["cout"] == 128 and self.out_dim <= 4:
+            resnet(pk["final"], self.final_res_block, cur, c, r, r_c, h, w, head=(pk["head"][0], pk["head"][1], out))
+            return out
         cur = resnet(pk["final"], self.final_res_block, cur, c, r, r_c, h, w)
         rec(("head", dict(inp=cur)))
-        out = torch.empty(B, self.out_dim, H, W, device=dev, dtype=torch.float32)
         L.check(lib.sdc_head_conv1(prec, L.ptr(cur), L.ptr(pk["head"][0]), L.ptr(pk["head"][1]), L.ptr(out), B, H * W,
                                    self.final_res_block.dim_out, self.out_dim, _st()))
         return out

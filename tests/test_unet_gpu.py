@@ -487,3 +487,28 @@ def test_fused_groupnorm_path_matches_unfused_network():
         b = net(x, t)
     assert torch.isfinite(a).all()
     assert rel(a, b) < 3e-4, rel(a, b)
+
+
+@pytest.mark.parametrize("res_half", [True, False])
+def test_gn_silu_head_vs_torch(res_half):
+    """Last GroupNorm + SiLU + residual fused with the 1x1 head convolution == torch (fp32), NCHW output."""
+    L, lib = _L()
+    import safediffcon_b200.unet  # noqa: F401
+    for B, HW in ((3, 2048), (300, 2048), (2, 64)):
+        C, Cout = 128, 3
+        g = torch.Generator().manual_seed(B + HW)
+        x = (torch.randn(B, C, HW, generator=g) * 1.7 + 0.3).cuda()
+        gamma, beta = (1 + 0.3 * torch.randn(C, generator=g)).cuda(), (0.2 * torch.randn(C, generator=g)).cuda()
+        res = torch.randn(B * HW, C, generator=g).cuda()
+        if res_half:
+            res = res.half()
+        hw_, hb_ = (torch.randn(Cout, C, generator=g) / np.sqrt(C)).cuda(), torch.randn(Cout, generator=g).cuda()
+        xr = x.permute(0, 2, 1).reshape(B * HW, C).contiguous()
+        stats = torch.stack([xr.double().reshape(B, -1).sum(1), (xr.double() ** 2).reshape(B, -1).sum(1)], 1).contiguous()
+        out = torch.full((B, Cout, HW), float("nan")).cuda()
+        L.check(lib.sdc_gn_silu_head(L.ptr(xr), L.ptr(stats), L.ptr(gamma), L.ptr(beta), L.ptr(res), int(res_half), L.ptr(hw_), L.ptr(hb_),
+                                     L.ptr(out), B, HW, C, Cout, L.stream_ptr()))
+        y = F.silu(F.group_norm(x, 1, gamma, beta, eps=1e-5)).permute(0, 2, 1).reshape(B * HW, C) + res.float()
+        ref = (y.double() @ hw_.double().t() + hb_.double()).reshape(B, HW, Cout).permute(0, 2, 1)
+        assert torch.isfinite(out).all()
+        assert (out.double() - ref).abs().max().item() < 2e-5 * ref.abs().max().item()
