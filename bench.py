@@ -24,6 +24,16 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
+# The contract is ONE JSON line on stdout.  Libraries write there too (NCCL prints its version banner to stdout under
+# NCCL_DEBUG=VERSION/INFO), so file descriptor 1 is pointed at stderr for the whole run and the line goes to the saved descriptor.
+_JSON_FD = os.dup(1)
+sys.stdout.flush()
+os.dup2(2, 1)
+
+
+def emit(line):
+    os.write(_JSON_FD, (json.dumps(line) + "\n").encode())
+
 import numpy as np  # noqa: E402
 import torch  # noqa: E402
 
@@ -221,7 +231,7 @@ def run_reference_arm(args):
                              "sample": "each step = 2 guided DDPM reverse steps at B=8 on the host cores (oracle port of the reference's "
                                        "PyTorch-CPU path: /root/reference is absent on the GPU box) + 1/10 of a 1024-trajectory rollout"},
             "e2e": {"value": v, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def workload_config(args, B_ref=None):
@@ -387,7 +397,7 @@ def main():
                 line["torch_gpu_baseline"] = torch_gpu_baseline_obj(B, dev, ms_step)
             except Exception as ex:   # a reported extra: never lose the bench line over it
                 line["torch_gpu_baseline"] = {"error": repr(ex)[:200]}
-        print(json.dumps(line), flush=True)
+        emit(line)
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
