@@ -309,8 +309,18 @@ def main():
         one_step(args.warmup + i)
     e1.record()
     barrier(dist)
-    clocks = sampler.stop()
     launches = L.launch_count() - launches0
+    # short timed regions (a few steps) end before nvidia-smi has produced a sample: keep the same load running, untimed, until a few
+    # samples exist (at most 3 s) so that the clocks line always describes the GPU under this workload
+    in_region = len(sampler.rows)
+    t_extra = time.perf_counter()
+    extra = 0
+    while len(sampler.rows) < 4 and time.perf_counter() - t_extra < 3.0 and sampler.proc is not None:
+        one_step((args.warmup + args.steps + extra) % 900)
+        extra += 1
+        torch.cuda.synchronize()
+    clocks = sampler.stop()
+    clocks["samples_in_timed_region"] = in_region
     ms_step = max_over_ranks(dist, e0.elapsed_time(e1) / args.steps)
 
     # ---- rollout + scoring of this batch (device-timed) and the rollout-only measurement (config 3) ----
