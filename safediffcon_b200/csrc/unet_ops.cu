@@ -1277,8 +1277,10 @@ extern "C" int sdc_gn_silu_head(const float* x, const double* stats, const float
                                 int Cout, void* stream) {
     SDC_REQUIRE(x && stats && gamma && beta && residual && head_w && out && B > 0 && HW > 0, "gn_silu_head: bad arguments");
     SDC_REQUIRE(C == 128 && Cout >= 1 && Cout <= 4 && HW % 32 == 0, "gn_silu_head: C=%d Cout=%d HW=%d unsupported (C = 128, Cout <= 4, HW %% 32 == 0)", C, Cout, HW);
+    // pixels per CTA: at least ~8 waves of CTAs (3 resident per SM) so that the last, partial wave costs little -- one CTA per sample
+    // at B = 1024 is 2.3 waves, 77% efficient, and this kernel is not purely bandwidth bound (0.65 of the copy peak, ncu)
     int ppc = HW;
-    while (ppc > 32 && (int64_t)B * (HW / ppc) < 2 * 148 && ppc % 2 == 0) ppc /= 2;
+    while (ppc > 32 && (int64_t)B * (HW / ppc) < 8 * 3 * 148 && ppc % 64 == 0) ppc /= 2;
     dim3 grid((unsigned)B, (unsigned)((HW + ppc - 1) / ppc));
     cudaStream_t st = as_stream(stream);
     if (residual_operand)
