@@ -1251,6 +1251,10 @@ extern "C" int sdc_gn_silu(int prec, const void* xv, int x_operand, const double
                 "gn_silu: an fp16 input needs FP16 mode, C/8 dividing 256 and an fp16 residual");
     int ppc = HW;  // pixels per CTA: aim for >= 2 waves of CTAs without shrinking below 32 pixels
     while (ppc > 32 && (int64_t)B * (HW / ppc) < 2 * 148 && ppc % 2 == 0) ppc /= 2;
+    // large batches: one CTA per sample is 2.3 waves at B = 1024 (3 CTAs per SM); split while a CTA keeps >= 64K elements so that the
+    // partial last wave weighs less (SDC_GN_SPLIT=0 disables, for A/B timing)
+    static const bool split_waves = []() { const char* e = getenv("SDC_GN_SPLIT"); return !(e && e[0] == '0'); }();
+    while (split_waves && (int64_t)B * (HW / ppc) < 8 * 3 * 148 && ppc % 64 == 0 && (int64_t)(ppc / 2) * C >= 65536) ppc /= 2;
     dim3 grid((unsigned)B, (unsigned)((HW + ppc - 1) / ppc));
     const size_t sm = 2 * C * sizeof(float);
     cudaStream_t st = as_stream(stream);
