@@ -239,7 +239,7 @@ def workload_config(args, B_ref=None):
                         "safety guidance w_score=500 Q=0, + burgers rollout/J/safety scoring",
             "batch_per_gpu": args.batch if B_ref is None else B_ref, "chain_steps": CHAIN_STEPS,
             "step": "one reverse-diffusion step (U-Net eval + fused guided posterior update) over the whole batch",
-            "l2": "per-step working set (activations ~10 GB at B=1024) exceeds the 126 MB L2; no flush needed",
+            "l2": "per-step working set (activations ~5.5 GB at B=1024, 72 GB of DRAM traffic per step) exceeds the 126 MB L2; no flush needed",
             "parallelism": f"dp{args.gpus} (independent shards, all-gather of J/violation vectors only)"}
 
 
