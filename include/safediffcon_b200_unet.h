@@ -50,16 +50,28 @@ int sdc_conv3x3_row(int prec, const void* a0, int c0, const void* a1, int c1, co
                     const void* residual, void* out, double* stats, int operand_out, int B, int H, int W, int Cout,
                     void* stream);
 
-/* sdc_conv3x3_row (FP16 mode, fp16 output, no bias-side residual) with the GroupNorm(1, C) + FiLM + SiLU (+ residual) of the
- * following sdc_gn_silu call applied IN PLACE by the same kernel: every cluster owns whole samples, so after the last rows of a sample
- * it re-reads its rows (L2 resident), normalises them with the statistics the epilogues accumulated in stats[b] and overwrites them.
- * Arguments gamma .. gn_residual as in sdc_gn_silu (gn_residual: fp16 or NULL).  Returns -1 (nothing done) when the shape or batch
- * is not eligible (needs the CTA-pair kernel: B * H / 4 >= SM pairs, H % 4 == 0, W == 128, Cout <= 128); the caller then issues
- * sdc_conv3x3_row / sdc_conv_gemm followed by sdc_gn_silu.  Experimental: numerically equivalent to the two-kernel sequence (tests) but
- * not faster on B200 yet (see csrc/conv_row.cu); the Python layer keeps it off unless Unet2D.fuse_groupnorm is set. */
+/* sdc_conv3x3_row (FP16 mode, fp16 output) FUSED with the GroupNorm(1, C) + FiLM + SiLU (+ residual) that follows it in
+ * Block.forward / ResnetBlock.forward (unet.py:138-147,177-180) -- the separate sdc_gn_silu pass over HBM disappears.
+ * Deferred epilogue on the CTA-pair kernel: work items are dealt round-robin, an epilogue warp first reduces its accumulators to
+ * a partial (sum, sum of squares) of conv + bias and publishes it in its own 8-byte slot of the sample, waits until all 128 slots
+ * of the sample are filled while the tensor pipe computes the next item, then normalises the fp32 accumulators straight from
+ * TMEM and stores fp16.  sync_slots: B * SDC_GN_SLOT_BYTES bytes, EVERY BYTE 0xFF on entry (cudaMemsetAsync); stats: double[B][2],
+ * receives the per-sample totals (fixed summation order: deterministic); gamma .. gn_residual as in sdc_gn_silu (gn_residual: fp16
+ * or NULL).  Returns -1 (nothing done) when the shape is not eligible (needs FP16, H % 4 == 0, H <= 16, W == 128, Cout <= 128,
+ * Cout % 32 == 0); the caller then issues sdc_conv3x3_row / sdc_conv_gemm followed by sdc_gn_silu. */
+#define SDC_GN_SLOT_BYTES 1024
 int sdc_conv3x3_row_gn(const void* a0, int c0, const void* a1, int c1, const void* w_packed, const float* bias, void* out,
-                       double* stats, const float* gamma, const float* beta, const float* scale_shift, const int32_t* t_index,
-                       int64_t ss_stride, const void* gn_residual, int B, int H, int W, int Cout, void* stream);
+                       double* stats, void* sync_slots, const float* gamma, const float* beta, const float* scale_shift,
+                       const int32_t* t_index, int64_t ss_stride, const void* gn_residual, int B, int H, int W, int Cout, void* stream);
+
+/* The network's last convolution fused with everything behind it (final_res_block.block2 + residual + final_conv,
+ * unet.py:138-147,178-180,378,426): out[b, o, p] = sum_c head_w[o, c] * (silu(GN(conv)[b, p, c]) + gn_residual[b, p, c]) + head_b[o],
+ * NCHW fp32.  Same kernel as sdc_conv3x3_row_gn; in pass 2 a lane owns a pixel, so the 1x1 head convolution is a per-lane dot
+ * product over the normalised accumulator columns -- the activation is never stored or rounded.  head_cout <= 4.  out_nchw must
+ * be ZEROED by the caller: the two warps that own the channel halves of a pixel add their partial dot products to it. */
+int sdc_conv3x3_row_gn_head(const void* a0, int c0, const void* a1, int c1, const void* w_packed, const float* bias, double* stats,
+                            void* sync_slots, const float* gamma, const float* beta, const void* gn_residual, const float* head_w,
+                            const float* head_b, float* out_nchw, int head_cout, int B, int H, int W, int Cout, void* stream);
 
 /* Stem: 7x7 pad 3 convolution of the NCHW model input (unet.py:326,392).  x:[B,Cin,H,W] NCHW fp32, w:[Cout,Cin,7,7] OIHW
  * (unpacked, fp32), out: NHWC operand [B*H*W, Cout].  FP32 CUDA-core kernel (0.3% of the FLOPs). */

@@ -266,17 +266,18 @@ def gd_time_pairs(gd):
     return list(zip(times[:-1], times[1:]))
 
 
-def gen_config1():
-    """BASELINE config 1: real U-Net (seed 42), B=8, DDIM-200 eta=1 guided (w_score 500, Q 0), then solver+metrics."""
-    from data.generate_burgers import burgers_numeric_solve_free
+def _config1_run(sampler, Q, steps):
+    """One reference run of BASELINE config 1: real dim-128 U-Net (seed 42), B=8, guided (w_score 500),
+    `sampler` = 'ddim' (S=200, eta=1: the repo default) or 'ddpm' (the north star's 1000-step p_sample_loop), then the
+    reference solver + metrics.  Records (x_t, t, eps) at `steps` (indices of U-Net evaluations) and the state after step 0."""
     from utils.metrics import control_trajectories, evaluate_samples
     B = 8
+    S = 200 if sampler == "ddim" else 1000
     net = _unet(128)
-    gd = _diffusion(1000, 200, model=net)
+    gd = _diffusion(1000, S, model=net)
     u0, uT, tgt = fx.config1_conditions(B)
-    noises = fx.chain_noise(B, fx.n_draws(1000, 200, True), seed=1234)
+    noises = fx.chain_noise(B, fx.n_draws(1000, S, True), seed=1234)
     keep = {}
-    steps = (0, 1, 60, 120, 199)
     cnt = {"k": 0}
     orig = net.forward
 
@@ -294,22 +295,37 @@ def gen_config1():
     t0 = _time.time()
     with NoisePatch(noises):
         res = gd.sample(batch_size=B, clip_denoised=True, u_init=u0, u_final=uT, guidance_u0=True,
-                        nablaJ=_guidance_fn(0.0), J_scheduler=None, w_scheduler=None, enable_grad=False, device="cpu")
+                        nablaJ=_guidance_fn(Q), J_scheduler=None, w_scheduler=None, enable_grad=False, device="cpu")
     t_chain = _time.time() - t0
+    assert cnt["k"] == S
     pred = res * 10.0
     t0 = _time.time()
     uc = control_trajectories(pred, 11)
     t_solve = _time.time() - t0
     m = evaluate_samples(pred, uc, tgt, nt=11, u_bound=0.8)
-    save("config1_ddim", sample=res, u_controlled=uc, J=m["control_mse_mean (J)"], Rp=m["point_exceed_ratio (R_p)"],
-         Rt=m["time_exceed_ratio (R_t)"], Rs=m["sample_exceed_ratio (R_s)"], t_chain=t_chain, t_solve=t_solve,
-         threads=torch.get_num_threads(), **keep)
+    return dict(sample=res, u_controlled=uc, J=m["control_mse_mean (J)"], Rp=m["point_exceed_ratio (R_p)"],
+                Rt=m["time_exceed_ratio (R_t)"], Rs=m["sample_exceed_ratio (R_s)"], t_chain=t_chain, t_solve=t_solve,
+                threads=torch.get_num_threads(), Q=Q, **keep)
+
+
+def gen_config1():
+    """BASELINE config 1, DDIM-200 eta=1 guided, Q 0 (file name kept from round 1) and Q 0.05."""
+    save("config1_ddim", **_config1_run("ddim", 0.0, (0, 1, 60, 120, 199)))
+    save("config1_ddim_Q005", **_config1_run("ddim", 0.05, (0, 120, 199)))
+
+
+def gen_config1_ddpm():
+    """BASELINE config 1 with the north star's sampler: the 1000-step DDPM p_sample_loop (diffusion.py:368-449), Q 0 and 0.05.
+    ~10 min of CPU per run on 8 cores."""
+    save("config1_ddpm", **_config1_run("ddpm", 0.0, (0, 1, 250, 500, 750, 900, 999)))
+    save("config1_ddpm_Q005", **_config1_run("ddpm", 0.05, (0, 500, 999)))
 
 
 ALL = {"schedule": gen_schedule, "solver": gen_solver, "chains": gen_chains, "guidance": gen_guidance,
-       "conformal": gen_conformal, "unet": gen_unet, "unet_vjp": gen_unet_vjp, "unet_pgrad": gen_unet_pgrad, "ploss": gen_ploss, "datagen": gen_datagen, "config1": gen_config1}
+       "conformal": gen_conformal, "unet": gen_unet, "unet_vjp": gen_unet_vjp, "unet_pgrad": gen_unet_pgrad, "ploss": gen_ploss, "datagen": gen_datagen, "config1": gen_config1,
+       "config1_ddpm": gen_config1_ddpm}
 
 if __name__ == "__main__":
-    names = sys.argv[1:] or [k for k in ALL if k != "config1"]
+    names = sys.argv[1:] or [k for k in ALL if not k.startswith("config1")]
     for n in names:
         ALL[n]()

@@ -5,7 +5,8 @@
 
 B200-first difference: the reference assembles one [3, 16, 128] state per ``__getitem__`` on the host; here the whole split is
 assembled ONCE on the device by ``sdc_dataset_states`` (one launch) and ``__getitem__`` is a view into that tensor, so a
-``DataLoader`` over it (num_workers=0) yields device batches with no host work and no H2D copy.
+``DataLoader`` over it (num_workers=0, pin_memory=False) yields device batches with no host work and no H2D copy.  For the
+reference's multi-worker / pinned loaders pass ``host_resident=True`` (items are then CPU tensors, assembled by the same kernel).
 """
 import os
 from typing import Callable, List, Optional, Union
@@ -41,7 +42,7 @@ class BurgersDataset(Dataset):
     def __init__(self, dataset: str = "free_u_f_1e5", split: str = "train", root_path: str = None, nt_total: int = 11, nx: int = 128,
                  is_normalize: bool = True, stack_u_and_f: bool = True, pad_for_2d_conv: bool = True, pad_size: int = 16,
                  safety_transform: Optional[Callable] = None, is_need_idx: bool = False, is_subset: bool = False, config=None,
-                 device="cuda", _tensors=None):
+                 device="cuda", host_resident: bool = False, _tensors=None):
         self.root = root_path or "./datasets"
         self.split = split
         self.nt_total = nt_total
@@ -70,6 +71,12 @@ class BurgersDataset(Dataset):
         else:
             self.indices = None
         self._states = self._assemble(u, f)
+        # host_resident=True: the split is still assembled once by the CUDA kernel, then kept as a CPU tensor (shared memory),
+        # so the reference's DataLoader(num_workers=4/16, pin_memory=True) call sites (inference_ft.py:129-130,148-149,
+        # post_train.py:133-134) work unchanged: forked workers must not touch CUDA tensors and pinning needs host memory.
+        self.host_resident = bool(host_resident)
+        if self.host_resident:
+            self._states = self._states.cpu().share_memory_()
 
     # ---- alternative constructors (no HDF5 needed)
     @classmethod
@@ -115,6 +122,9 @@ class BurgersDataset(Dataset):
         return self._assemble(data[0][None], data[1][None])[0]
 
     def __getitem__(self, idx):
+        if self._states.is_cuda and torch.utils.data.get_worker_info() is not None:
+            raise RuntimeError("safediffcon_b200.BurgersDataset: items are views of a CUDA tensor, which DataLoader worker processes "
+                               "cannot read; use num_workers=0 and pin_memory=False, or construct the dataset with host_resident=True")
         i = self.indices[idx] if self.indices is not None else idx
         data = self._states[i]
         return (data, idx) if self.is_need_idx else data

@@ -218,6 +218,30 @@ __device__ __forceinline__ void epilogue_chunk(uint32_t taddr, uint32_t stg, con
     }
 }
 
+// Tail of the fp16 epilogue on its own: 32 fp32 values of this lane's row -> fp16 -> SWIZZLE_64B staging tile -> ONE TMA store
+// of the 32 x 32 chunk at (col, row0).  The caller guarantees that no in-flight bulk store still reads `stg`.
+__device__ __forceinline__ void stage_store_half(const float (&v)[32], uint32_t stg, const CUtensorMap* map_out, int col, int row0,
+                                                 int lane) {
+    const uint32_t rowa = stg + (uint32_t)lane * 64u, sw = ((uint32_t)lane >> 1) & 3u;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        uint32_t w[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const __half2 h = __floats2half2_rn(v[8 * j + 2 * k], v[8 * j + 2 * k + 1]);
+            w[k] = *reinterpret_cast<const uint32_t*>(&h);
+        }
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(rowa + (((uint32_t)j ^ sw) << 4)), "r"(w[0]), "r"(w[1]),
+                     "r"(w[2]), "r"(w[3]) : "memory");
+    }
+    fence_proxy_async();
+    __syncwarp();
+    if (lane == 0) {
+        tma_store_2d(map_out, stg, col, row0);
+        bulk_commit();
+    }
+}
+
 // Variant for the q columns of a LinearAttention qkv projection: the 32 accumulator columns of a chunk are exactly one head's
 // logits of this lane's pixel, so q <- softmax_d(q) * 32^-0.5 (/root/reference/1D/model/unet.py:206,209) is applied in
 // registers and stored in the operand precision (it is the A operand of the folded output projection).

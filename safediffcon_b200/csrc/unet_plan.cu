@@ -1,0 +1,817 @@
+// Whole-network executor behind include/safediffcon_b200_plan.h: the inference schedule of Unet2D.forward
+// (/root/reference/1D/model/unet.py:382-426) as ONE C entry point.  The handle owns the packed tcgen05 weights, the FiLM table
+// for all integer diffusion times and a first-fit layout of every activation inside the caller's workspace; a forward is
+// ~120 launches of the kernels declared in safediffcon_b200_unet.h, no allocation, no synchronisation (graph capturable).
+//
+// Dataflow per level (FP16 mode):
+//   ResnetBlock  conv3x3 (+GroupNorm+FiLM+SiLU in its epilogue on the 16x128 level, else a separate in-place sdc_gn_silu)
+//                -> conv3x3 (+GroupNorm+SiLU+residual likewise); 1x1 res_conv when the channel count changes
+//   LinearAttention  LayerNorm -> qkv 1x1 conv with the q-softmax in its epilogue -> context (softmax_n(k) v^T) -> context folded
+//                into a per-sample output projection -> per-sample 1x1 conv -> LayerNorm + residual
+//   Downsample2d as a 5-D TMA view (pixel unshuffle) feeding a 1x1 conv; Upsample2d as four 2x2 phase convolutions
+//   last block: conv + GroupNorm + SiLU + residual + 1x1 head conv in ONE kernel, NCHW fp32 out.
+#include "common.cuh"
+#include "../../include/safediffcon_b200_unet.h"
+#include "../../include/safediffcon_b200_plan.h"
+#include <nvtx3/nvToolsExt.h>
+#include <stdlib.h>
+#include <map>
+#include <string>
+#include <vector>
+
+using namespace sdc;
+
+namespace {
+
+constexpr int HID = 128;   // 4 heads x 32
+enum { K1 = 0, K3 = 1, KUN = 2, KUP = 3 };
+
+struct ParamDesc { std::string name; int64_t numel; };
+
+struct ConvP {
+    int w = -1, b = -1;          // parameter indices (b = -1: no bias)
+    int cout = 0, cin = 0, kind = K1;
+    bool up = false;             // additionally packed as a fused-upsample (kind 3) weight
+    void* packed = nullptr;      // Wp[cout, taps*cin] operand precision
+    void* packed_up = nullptr;   // Wp[4*cout, 4*cin]
+    float* bias = nullptr;
+};
+struct BlockP {
+    int mlp_w, mlp_b, g1w, g1b, g2w, g2b;
+    ConvP c1, c2, res;
+    bool has_res = false;
+    int cin = 0, cout = 0, film_off = 0;
+    float *g1[2] = {nullptr, nullptr}, *g2[2] = {nullptr, nullptr};
+    std::string name;
+};
+struct AttnP {
+    ConvP qkv, out;
+    int g_in_i = -1, g_out_i = -1, dim = 0;
+    bool full = false;
+    float *g_in = nullptr, *g_out = nullptr, *out_w32 = nullptr;
+    std::string name;
+};
+struct LevelP { BlockP b1, b2; AttnP attn; ConvP resample; bool resamples = false; };
+
+struct ProfEntry { const char* name; cudaEvent_t e0, e1; double bytes, flops; float ms; };
+
+// first-fit allocator over the caller's workspace; deterministic for a given schedule, so a dry run yields the exact size
+struct Arena {
+    uint8_t* base = nullptr;
+    int64_t cap = 0, high = 0;
+    bool dry = false;
+    std::map<int64_t, int64_t> free_;   // offset -> size
+    std::map<int64_t, int64_t> live_;
+    void reset(void* b, int64_t c, bool d) {
+        base = (uint8_t*)b; cap = c; dry = d; high = 0;
+        free_.clear(); live_.clear();
+        free_[0] = d ? (int64_t)1 << 60 : c;
+    }
+    void* alloc(int64_t bytes) {
+        bytes = (bytes + 1023) / 1024 * 1024;   // TMA store / swizzle friendly, keeps every buffer 1 KB aligned
+        for (auto it = free_.begin(); it != free_.end(); ++it) {
+            if (it->second >= bytes) {
+                const int64_t off = it->first, rest = it->second - bytes;
+                free_.erase(it);
+                if (rest > 0) free_[off + bytes] = rest;
+                live_[off] = bytes;
+                if (off + bytes > high) high = off + bytes;
+                return base + off;
+            }
+        }
+        return nullptr;
+    }
+    void release(void* p) {
+        if (!p) return;
+        const int64_t off = (uint8_t*)p - base;
+        auto it = live_.find(off);
+        if (it == live_.end()) return;
+        int64_t size = it->second, o = off;
+        live_.erase(it);
+        auto nx = free_.lower_bound(o);
+        if (nx != free_.end() && nx->first == o + size) { size += nx->second; nx = free_.erase(nx); }
+        if (nx != free_.begin()) {
+            auto pv = std::prev(nx);
+            if (pv->first + pv->second == o) { o = pv->first; size += pv->second; free_.erase(pv); }
+        }
+        free_[o] = size;
+    }
+};
+
+}  // namespace
+
+struct sdc_unet {
+    int dim = 0, channels = 0, out_dim = 0, prec = 0, table_T = 0, init_dim = 0;
+    float theta = 10000.f;
+    std::vector<int> mults;
+    std::vector<ParamDesc> params;
+    // architecture
+    ConvP stem;            // 7x7 as a 1x1 GEMM over the (high | low) im2col operand
+    int stem_kp = 0;
+    int time_w1 = -1, time_b1 = -1, time_w2 = -1, time_b2 = -1;
+    std::vector<LevelP> downs, ups;
+    BlockP mid1, mid2, fin;
+    AttnP mid_attn;
+    int head_w_i = -1, head_b_i = -1;
+    float *head_w = nullptr, *head_b = nullptr;
+    int film_total = 0;
+    // device storage (one cudaMalloc on the first pack)
+    uint8_t* slab = nullptr;
+    int64_t slab_bytes = 0;
+    std::vector<std::pair<void**, int64_t>> slab_items;   // (where to put the pointer, bytes)
+    float *film_w = nullptr, *film_b = nullptr, *table = nullptr, *t_arange = nullptr, *emb = nullptr, *th1 = nullptr, *th2 = nullptr;
+    float *tw1 = nullptr, *tb1 = nullptr, *tw2 = nullptr, *tb2 = nullptr, *stem_rep = nullptr;
+    bool packed = false;
+    // profile
+    bool prof_on = false;
+    std::vector<ProfEntry> prof;
+    size_t prof_used = 0;
+    mutable std::map<int64_t, int64_t> ws_cache;   // (B, H, W) -> workspace bytes
+};
+
+namespace {
+
+int add_param(sdc_unet* n, const std::string& name, int64_t numel) {
+    n->params.push_back({name, numel});
+    return (int)n->params.size() - 1;
+}
+void want(sdc_unet* n, void** where, int64_t bytes) { n->slab_items.push_back({where, bytes}); }
+
+ConvP make_conv(sdc_unet* n, const std::string& name, int cout, int cin, int kind, bool bias, bool up = false) {
+    ConvP c;
+    c.cout = cout; c.cin = cin; c.kind = kind; c.up = up;
+    const int taps = kind == K3 ? 9 : 1;
+    c.w = add_param(n, name + ".weight", (int64_t)cout * cin * taps);
+    if (bias) c.b = add_param(n, name + ".bias", cout);
+    const int64_t esz = n->prec == SDC_PREC_F16 ? 2 : 4;
+    want(n, &c.packed, (int64_t)cout * cin * taps * esz);
+    if (up) want(n, &c.packed_up, (int64_t)16 * cout * cin * esz);
+    if (bias) want(n, (void**)&c.bias, (int64_t)cout * 4);
+    return c;
+}
+// NOTE: make_conv registers `&c.packed` of a LOCAL; the callers below re-register after the struct has reached its final
+// address (fix_conv), so the slab pointers land in the handle's own members.
+void fix_conv(sdc_unet* n, ConvP& c, size_t& cursor) {
+    n->slab_items[cursor++].first = &c.packed;
+    if (c.up) n->slab_items[cursor++].first = &c.packed_up;
+    if (c.b >= 0) n->slab_items[cursor++].first = (void**)&c.bias;
+}
+
+void build_block(sdc_unet* n, BlockP& b, const std::string& name, int cin, int cout) {
+    const int td = 4 * n->dim;
+    b.name = name; b.cin = cin; b.cout = cout;
+    b.mlp_w = add_param(n, name + ".mlp.1.weight", (int64_t)2 * cout * td);
+    b.mlp_b = add_param(n, name + ".mlp.1.bias", 2 * cout);
+    size_t cur = n->slab_items.size();
+    b.c1 = make_conv(n, name + ".block1.proj", cout, cin, K3, true);
+    fix_conv(n, b.c1, cur);
+    b.g1w = add_param(n, name + ".block1.norm.weight", cout);
+    b.g1b = add_param(n, name + ".block1.norm.bias", cout);
+    cur = n->slab_items.size();
+    b.c2 = make_conv(n, name + ".block2.proj", cout, cout, K3, true);
+    fix_conv(n, b.c2, cur);
+    b.g2w = add_param(n, name + ".block2.norm.weight", cout);
+    b.g2b = add_param(n, name + ".block2.norm.bias", cout);
+    b.has_res = cin != cout;
+    if (b.has_res) {
+        cur = n->slab_items.size();
+        b.res = make_conv(n, name + ".res_conv", cout, cin, K1, true);
+        fix_conv(n, b.res, cur);
+    }
+    for (int k = 0; k < 2; ++k) { want(n, (void**)&b.g1[k], cout * 4); want(n, (void**)&b.g2[k], cout * 4); }
+    b.film_off = n->film_total;
+    n->film_total += 2 * cout;
+}
+
+void build_attn(sdc_unet* n, AttnP& a, const std::string& name, int dim, bool full) {
+    a.name = name; a.dim = dim; a.full = full;
+    size_t cur = n->slab_items.size();
+    a.qkv = make_conv(n, name + ".fn.fn.to_qkv", 3 * HID, dim, K1, false);
+    fix_conv(n, a.qkv, cur);
+    cur = n->slab_items.size();
+    a.out = make_conv(n, name + (full ? ".fn.fn.to_out" : ".fn.fn.to_out.0"), dim, HID, K1, true);
+    fix_conv(n, a.out, cur);
+    if (!full) {
+        a.g_out_i = add_param(n, name + ".fn.fn.to_out.1.g", dim);
+        want(n, (void**)&a.g_out, dim * 4);
+        want(n, (void**)&a.out_w32, (int64_t)dim * HID * 4);
+    }
+    a.g_in_i = add_param(n, name + ".fn.norm.g", dim);
+    want(n, (void**)&a.g_in, dim * 4);
+}
+
+#define PLAN_CUDA(expr)                                                                      \
+    do {                                                                                     \
+        cudaError_t e_ = (expr);                                                             \
+        if (e_ != cudaSuccess) {                                                             \
+            set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e_), __FILE__, __LINE__); \
+            return SDC_ERR_CUDA;                                                             \
+        }                                                                                    \
+    } while (0)
+
+__global__ void count_nonfinite_kernel(const float* __restrict__ x, int64_t n, uint32_t* __restrict__ counter) {
+    int bad = 0;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        bad += !isfinite(x[i]);
+    bad = warp_sum_i(bad);
+    if ((threadIdx.x & 31) == 0 && bad) atomicAdd(counter, (uint32_t)bad);
+}
+
+// ------------------------------------------------------------------------------------------------ forward context
+struct Fwd {
+    sdc_unet* n;
+    Arena ar;
+    bool dry;
+    void* stream;
+    int B, prec, rc = 0;
+    bool f16;
+    int64_t esz;
+    const float* film = nullptr;   // row 0 of the FiLM rows in use
+    int64_t E = 0;
+    const int32_t* t_index = nullptr;
+    double* stats = nullptr;
+    uint8_t* slots = nullptr;
+    int stat_i = 0;
+
+    void* alloc(int64_t bytes) {
+        void* p = ar.alloc(bytes);
+        if (!p && !rc) { set_error("sdc_unet_forward: workspace too small (need more than %lld bytes)", (long long)ar.cap); rc = SDC_ERR_STATE; }
+        return p;
+    }
+    void* opd(int64_t rows, int64_t c) { return alloc(rows * c * esz); }
+    void* f32(int64_t rows, int64_t c) { return alloc(rows * c * 4); }
+    void release(void* p) { ar.release(p); }
+
+    void begin(const char* name, double bytes, double flops) {
+        if (dry || !n->prof_on) return;
+        if (n->prof_used == n->prof.size()) {
+            ProfEntry e{};
+            cudaEventCreate(&e.e0);
+            cudaEventCreate(&e.e1);
+            n->prof.push_back(e);
+        }
+        ProfEntry& e = n->prof[n->prof_used];
+        e.name = name; e.bytes = bytes; e.flops = flops; e.ms = -1.f;
+        cudaEventRecord(e.e0, as_stream(stream));
+    }
+    void end() {
+        if (dry || !n->prof_on) return;
+        cudaEventRecord(n->prof[n->prof_used].e1, as_stream(stream));
+        ++n->prof_used;
+    }
+};
+
+#define RUN(name, bytes, flops, call)       \
+    do {                                    \
+        if (!f.dry && !f.rc) {              \
+            f.begin(name, bytes, flops);    \
+            const int rc__ = (call);        \
+            f.end();                        \
+            if (rc__ > 0) f.rc = rc__;      \
+        }                                   \
+    } while (0)
+
+struct Range {   // NVTX range per network block (visible in nsys / ncu --nvtx)
+    bool on;
+    Range(const Fwd& f, const std::string& name) : on(!f.dry) { if (on) nvtxRangePushA(name.c_str()); }
+    ~Range() { if (on) nvtxRangePop(); }
+};
+
+void conv(Fwd& f, int kind, const void* a0, int c0, const void* a1, int c1, const ConvP& cw, const void* wp, const void* residual, void* out,
+          double* st, int operand_out, int h, int w, double algo_k = -1.0) {
+    const int taps = kind == K3 ? 9 : (kind == K1 ? 1 : 4);
+    const double rows = (double)f.B * h * w * (kind == KUP ? 4 : 1);
+    const double k = algo_k > 0 ? algo_k : (double)taps * (c0 + c1);
+    const double oesz = operand_out ? (double)f.esz : 4.0;
+    const double bytes = (double)f.B * h * w * (kind == KUN ? 4 : 1) * (c0 + c1) * f.esz + rows * cw.cout * oesz + (double)cw.cout * k * f.esz +
+                         (residual ? rows * cw.cout * f.esz : 0.0);
+    const char* nm = kind == K3 ? "conv3x3" : (kind == K1 ? "conv1x1" : (kind == KUN ? "conv_unshuffle" : "conv_upsample"));
+    int rc = -1;
+    if (!f.dry && !f.rc) {
+        f.begin(nm, bytes, 2.0 * rows * cw.cout * k);
+        if (kind == K3 && w == 128 && cw.cout <= 128)
+            rc = sdc_conv3x3_row(f.prec, a0, c0, a1, c1, wp, cw.bias, residual, out, st, operand_out, f.B, h, w, cw.cout, f.stream);
+        if (rc != 0)
+            rc = sdc_conv_gemm(f.prec, kind, a0, c0, a1, c1, wp, cw.bias, residual, out, st, operand_out, f.B, h, w, cw.cout, f.stream);
+        f.end();
+        if (rc > 0) f.rc = rc;
+    }
+}
+
+// EXPERIMENTAL (SDC_FUSE_GN=1): conv + GroupNorm in one kernel on the 16x128 level -- correct but slower on B200 (see conv_row.cu)
+bool gn_fusable(const Fwd& f, const BlockP& p, int c0, int c1, int h, int w) {
+    static const bool on = []() { const char* e = getenv("SDC_FUSE_GN"); return e && e[0] == '1'; }();
+    return on && f.f16 && w == 128 && h % 4 == 0 && h <= 16 && p.cout <= 128 && p.cout % 32 == 0 && c0 % 64 == 0 && c1 % 64 == 0;
+}
+
+// ResnetBlock (unet.py:166-180) on one or two concatenated NHWC inputs -> operand [B*h*w, cout] (nullptr when `head_out`
+// is given: the block is the network's last one and writes eps[B, out_dim, H, W] directly)
+void* resnet(Fwd& f, const BlockP& p, const void* a0, int c0, const void* a1, int c1, int h, int w, float* head_out = nullptr) {
+    sdc_unet* n = f.n;
+    Range r(f, p.name);
+    const int64_t M = (int64_t)f.B * h * w, HW = (int64_t)h * w;
+    const int cout = p.cout;
+    double* s1 = f.stats ? f.stats + (int64_t)f.stat_i * f.B * 2 : nullptr;
+    double* s2 = f.stats ? f.stats + (int64_t)(f.stat_i + 1) * f.B * 2 : nullptr;
+    uint8_t* n1 = f.slots ? f.slots + (int64_t)f.stat_i * f.B * SDC_GN_SLOT_BYTES : nullptr;
+    uint8_t* n2 = f.slots ? f.slots + (int64_t)(f.stat_i + 1) * f.B * SDC_GN_SLOT_BYTES : nullptr;
+    f.stat_i += 2;
+    const float* ss = f.film + p.film_off;
+    const double e = (double)f.esz;
+    if (gn_fusable(f, p, c0, c1, h, w) && (!head_out || n->out_dim <= 4)) {
+        void* h1 = f.opd(M, cout);
+        RUN("conv3x3_gn", (double)M * (c0 + c1) * e + (double)M * cout * e, 2.0 * M * cout * 9.0 * (c0 + c1),
+            sdc_conv3x3_row_gn(a0, c0, a1, c1, p.c1.packed, p.c1.bias, h1, s1, n1, p.g1[0], p.g1[1], ss, f.t_index, f.E, nullptr, f.B, h, w,
+                               cout, f.stream));
+        const void* res = a0;
+        void* resbuf = nullptr;
+        if (p.has_res) {
+            resbuf = f.opd(M, cout);
+            conv(f, K1, a0, c0, a1, c1, p.res, p.res.packed, nullptr, resbuf, nullptr, 1, h, w);
+            res = resbuf;
+        }
+        void* out2 = nullptr;
+        if (head_out) {
+            if (!f.dry && !f.rc && cudaMemsetAsync(head_out, 0, (size_t)M * n->out_dim * 4, as_stream(f.stream)) != cudaSuccess) f.rc = SDC_ERR_CUDA;
+            RUN("conv3x3_gn_head", (double)M * cout * 2.0 * e + (double)M * n->out_dim * 4.0, 2.0 * M * cout * (9.0 * cout + n->out_dim),
+                sdc_conv3x3_row_gn_head(h1, cout, nullptr, 0, p.c2.packed, p.c2.bias, s2, n2, p.g2[0], p.g2[1], res, n->head_w, n->head_b,
+                                        head_out, n->out_dim, f.B, h, w, cout, f.stream));
+        } else {
+            out2 = f.opd(M, cout);
+            RUN("conv3x3_gn", (double)M * cout * 3.0 * e, 2.0 * M * cout * 9.0 * cout,
+                sdc_conv3x3_row_gn(h1, cout, nullptr, 0, p.c2.packed, p.c2.bias, out2, s2, n2, p.g2[0], p.g2[1], nullptr, nullptr, 0, res, f.B,
+                                   h, w, cout, f.stream));
+        }
+        f.release(h1);
+        f.release(resbuf);
+        return out2;
+    }
+    if (f.f16) {
+        // compact intermediates: fp16 conv outputs (statistics from the fp32 accumulators), GroupNorm in place
+        void* raw = f.opd(M, cout);
+        conv(f, K3, a0, c0, a1, c1, p.c1, p.c1.packed, nullptr, raw, s1, 1, h, w);
+        RUN("gn_silu", (double)M * cout * 2.0 * e, 0.0,
+            sdc_gn_silu(f.prec, raw, 1, s1, p.g1[0], p.g1[1], ss, f.t_index, f.E, nullptr, 0, raw, f.B, (int)HW, cout, f.stream));
+        void* raw2 = f.opd(M, cout);
+        conv(f, K3, raw, cout, nullptr, 0, p.c2, p.c2.packed, nullptr, raw2, s2, 1, h, w);
+        const void* res = a0;
+        if (p.has_res) {
+            conv(f, K1, a0, c0, a1, c1, p.res, p.res.packed, nullptr, raw, nullptr, 1, h, w);   // conv1's buffer is dead after conv2
+            res = raw;
+        }
+        if (head_out) {
+            // last block outside the fused path (other image sizes): GroupNorm apply, then the plain head convolution
+            RUN("gn_silu", (double)M * cout * 3.0 * e, 0.0,
+                sdc_gn_silu(f.prec, raw2, 1, s2, p.g2[0], p.g2[1], nullptr, nullptr, 0, res, 1, raw2, f.B, (int)HW, cout, f.stream));
+            RUN("head_conv1", (double)M * cout * e + (double)M * n->out_dim * 4.0, 2.0 * M * cout * n->out_dim,
+                sdc_head_conv1(f.prec, raw2, n->head_w, n->head_b, head_out, f.B, (int)HW, cout, n->out_dim, f.stream));
+            f.release(raw);
+            f.release(raw2);
+            return nullptr;
+        }
+        RUN("gn_silu", (double)M * cout * 3.0 * e, 0.0,
+            sdc_gn_silu(f.prec, raw2, 1, s2, p.g2[0], p.g2[1], nullptr, nullptr, 0, res, 1, raw2, f.B, (int)HW, cout, f.stream));
+        f.release(raw);
+        return raw2;
+    }
+    // TF32: fp32 conv outputs, GroupNorm in place (the normalised tensor is TF32-rounded by the kernel)
+    void* raw = f.f32(M, cout);
+    conv(f, K3, a0, c0, a1, c1, p.c1, p.c1.packed, nullptr, raw, s1, 0, h, w);
+    RUN("gn_silu", (double)M * cout * 8.0, 0.0,
+        sdc_gn_silu(f.prec, raw, 0, s1, p.g1[0], p.g1[1], ss, f.t_index, f.E, nullptr, 0, raw, f.B, (int)HW, cout, f.stream));
+    void* raw2 = f.f32(M, cout);
+    conv(f, K3, raw, cout, nullptr, 0, p.c2, p.c2.packed, nullptr, raw2, s2, 0, h, w);
+    const void* res = a0;
+    int res_operand = 1;
+    if (p.has_res) {
+        conv(f, K1, a0, c0, a1, c1, p.res, p.res.packed, nullptr, raw, nullptr, 0, h, w);
+        res = raw;
+        res_operand = 0;
+    }
+    RUN("gn_silu", (double)M * cout * 12.0, 0.0,
+        sdc_gn_silu(f.prec, raw2, 0, s2, p.g2[0], p.g2[1], nullptr, nullptr, 0, res, res_operand, raw2, f.B, (int)HW, cout, f.stream));
+    f.release(raw);
+    if (head_out) {
+        RUN("head_conv1", (double)M * cout * 4.0 + (double)M * n->out_dim * 4.0, 2.0 * M * cout * n->out_dim,
+            sdc_head_conv1(f.prec, raw2, n->head_w, n->head_b, head_out, f.B, (int)HW, cout, n->out_dim, f.stream));
+        f.release(raw2);
+        return nullptr;
+    }
+    return raw2;
+}
+
+// Residual(PreNorm(LinearAttention | Attention)) (unet.py:16-22,65-76,182-258); returns a new operand [B*h*w, c]
+void* attention(Fwd& f, const AttnP& p, const void* xin, int c, int h, int w) {
+    Range r(f, p.name);
+    const int64_t M = (int64_t)f.B * h * w;
+    const int n = h * w;
+    const double e = (double)f.esz;
+    void* xn = f.opd(M, c);
+    RUN("layernorm", (double)M * c * 2.0 * e, 0.0, sdc_channel_layernorm(f.prec, xin, 1, p.g_in, nullptr, xn, M, c, 1, f.stream));
+    if (!p.full && n % 128 == 0) {
+        void* qs = f.opd(M, HID);
+        void* kv = f.opd(M, 2 * HID);
+        RUN("conv1x1_qkv", (double)M * (c + 3.0 * HID) * e, 2.0 * M * 3.0 * HID * c,
+            sdc_conv1x1_qkv(f.prec, xn, c, p.qkv.packed, qs, kv, f.f16 ? 1 : 0, f.B, h, w, HID, f.stream));
+        void* ws = f.alloc(sdc_linear_attention_workspace(f.B));
+        RUN("linattn_context", (double)M * 2.0 * HID * e, 2.0 * M * HID * 32.0,
+            sdc_linear_attention_context(kv, (const uint8_t*)kv + HID * f.esz, 2 * HID, f.f16 ? 1 : 0, ws, f.B, n, f.stream));
+        void* wf = f.opd((int64_t)f.B * c, HID);
+        RUN("linattn_fold", (double)f.B * c * HID * e, 2.0 * f.B * c * HID * 32.0,
+            sdc_linear_attention_fold(f.prec, ws, p.out_w32, wf, f.B, c, f.stream));
+        void* proj = f.f16 ? f.opd(M, c) : f.f32(M, c);
+        RUN("conv1x1_per_sample", (double)M * HID * e + (double)M * c * (f.f16 ? 2.0 : 4.0) + (double)f.B * c * HID * e, 2.0 * M * c * HID,
+            sdc_conv1x1_per_sample(f.prec, qs, HID, wf, p.out.bias, proj, f.f16 ? 1 : 0, f.B, h, w, c, f.stream));
+        RUN("layernorm", (double)M * c * ((f.f16 ? 2.0 : 4.0) + 2.0 * e), 0.0,
+            sdc_channel_layernorm(f.prec, proj, f.f16 ? 1 : 0, p.g_out, xin, xn, M, c, 1, f.stream));
+        f.release(qs); f.release(kv); f.release(ws); f.release(wf); f.release(proj);
+        return xn;
+    }
+    void* qkv = f.f32(M, 3 * HID);
+    ConvP nb = p.qkv;
+    conv(f, K1, xn, c, nullptr, 0, nb, p.qkv.packed, nullptr, qkv, nullptr, 0, h, w);
+    void* att = f.opd(M, HID);
+    if (p.full) {
+        RUN("attention", (double)M * (3.0 * HID * 4.0 + HID * e), 4.0 * M * n * HID, sdc_attention(f.prec, (const float*)qkv, att, f.B, n, f.stream));
+        conv(f, K1, att, HID, nullptr, 0, p.out, p.out.packed, xin, xn, nullptr, 1, h, w);
+    } else {
+        void* ws = f.alloc(sdc_linear_attention_workspace(f.B));
+        RUN("linear_attention", (double)M * (3.0 * HID * 4.0 + HID * e), 4.0 * M * HID * 32.0,
+            sdc_linear_attention(f.prec, (const float*)qkv, att, ws, f.B, n, f.stream));
+        void* proj = f.f32(M, c);
+        conv(f, K1, att, HID, nullptr, 0, p.out, p.out.packed, nullptr, proj, nullptr, 0, h, w);
+        RUN("layernorm", (double)M * c * (4.0 + 2.0 * e), 0.0, sdc_channel_layernorm(f.prec, proj, 0, p.g_out, xin, xn, M, c, 1, f.stream));
+        f.release(ws);
+        f.release(proj);
+    }
+    f.release(qkv);
+    f.release(att);
+    return xn;
+}
+
+int run_forward(sdc_unet* n, Fwd& f, const float* x, float* eps, int H, int W, uint32_t* nonfinite) {
+    const int B = f.B;
+    const int n_gn = 2 * (int)(2 * n->downs.size() + 2 + 2 * n->ups.size() + 1);
+    f.stats = (double*)f.alloc((int64_t)n_gn * B * 2 * sizeof(double));
+    f.slots = f.f16 ? (uint8_t*)f.alloc((int64_t)n_gn * B * SDC_GN_SLOT_BYTES) : nullptr;
+    if (f.rc) return f.rc;
+    if (!f.dry) {
+        PLAN_CUDA(cudaMemsetAsync(f.stats, 0, (size_t)n_gn * B * 2 * sizeof(double), as_stream(f.stream)));
+        if (f.slots) PLAN_CUDA(cudaMemsetAsync(f.slots, 0xFF, (size_t)n_gn * B * SDC_GN_SLOT_BYTES, as_stream(f.stream)));
+    }
+    int c = n->init_dim, h = H, w = W;
+    void* cur = f.opd((int64_t)B * H * W, c);
+    {
+        Range r(f, "init_conv");
+        void* patches = f.opd((int64_t)B * H * W, n->stem_kp);
+        RUN("stem_im2col", (double)B * H * W * (n->channels * 4.0 + n->stem_kp * (double)f.esz), 0.0,
+            sdc_stem_im2col(f.prec, x, patches, B, n->channels, H, W, n->stem_kp, f.stream));
+        conv(f, K1, patches, n->stem_kp, nullptr, 0, n->stem, n->stem.packed, nullptr, cur, nullptr, 1, H, W, n->channels * 49.0);
+        f.release(patches);
+    }
+    void* r0 = cur;
+    const int r_c = c;
+    std::vector<std::pair<void*, int>> skips;
+    for (size_t li = 0; li < n->downs.size(); ++li) {
+        const LevelP& L = n->downs[li];
+        void* a = resnet(f, L.b1, cur, c, nullptr, 0, h, w);
+        if (cur != r0) f.release(cur);
+        skips.push_back({a, c});
+        void* b = resnet(f, L.b2, a, c, nullptr, 0, h, w);
+        void* at = attention(f, L.attn, b, c, h, w);
+        f.release(b);
+        skips.push_back({at, c});
+        const int cout = L.resample.cout;
+        Range r(f, "downs." + std::to_string(li) + ".3");
+        if (L.resamples) { h /= 2; w /= 2; }
+        void* nxt = f.opd((int64_t)B * h * w, cout);
+        conv(f, L.resamples ? KUN : K3, at, c, nullptr, 0, L.resample, L.resample.packed, nullptr, nxt, nullptr, 1, h, w);
+        cur = nxt;
+        c = cout;
+    }
+    {
+        void* a = resnet(f, n->mid1, cur, c, nullptr, 0, h, w);
+        f.release(cur);
+        void* at = attention(f, n->mid_attn, a, c, h, w);
+        f.release(a);
+        cur = resnet(f, n->mid2, at, c, nullptr, 0, h, w);
+        f.release(at);
+    }
+    for (size_t li = 0; li < n->ups.size(); ++li) {
+        const LevelP& L = n->ups[li];
+        auto s = skips.back(); skips.pop_back();
+        void* a = resnet(f, L.b1, cur, c, s.first, s.second, h, w);
+        f.release(cur);
+        f.release(s.first);
+        c = L.b1.cout;
+        s = skips.back(); skips.pop_back();
+        void* b = resnet(f, L.b2, a, c, s.first, s.second, h, w);
+        f.release(a);
+        f.release(s.first);
+        void* at = attention(f, L.attn, b, c, h, w);
+        f.release(b);
+        const int cout = L.resample.cout;
+        Range r(f, "ups." + std::to_string(li) + ".3");
+        void* nxt;
+        if (L.resamples && (w == 16 || w % 32 == 0)) {
+            nxt = f.opd((int64_t)B * 4 * h * w, cout);
+            conv(f, KUP, at, c, nullptr, 0, L.resample, L.resample.packed_up, nullptr, nxt, nullptr, 1, h, w);
+            h *= 2; w *= 2;
+        } else {
+            void* in = at;
+            void* upb = nullptr;
+            if (L.resamples) {
+                upb = f.opd((int64_t)B * 4 * h * w, c);
+                RUN("upsample2x", (double)B * 5.0 * h * w * c * f.esz, 0.0, sdc_upsample2x(f.prec, at, upb, B, h, w, c, f.stream));
+                h *= 2; w *= 2;
+                in = upb;
+            }
+            nxt = f.opd((int64_t)B * h * w, cout);
+            conv(f, K3, in, c, nullptr, 0, L.resample, L.resample.packed, nullptr, nxt, nullptr, 1, h, w);
+            f.release(upb);
+        }
+        f.release(at);
+        cur = nxt;
+        c = cout;
+    }
+    if (h != H || w != W) { set_error("sdc_unet_forward: internal size mismatch"); return SDC_ERR_STATE; }
+    resnet(f, n->fin, cur, c, r0, r_c, h, w, eps);
+    f.release(cur);
+    f.release(r0);
+    if (nonfinite && !f.dry && !f.rc) {
+        const int64_t ne = (int64_t)B * n->out_dim * H * W;
+        f.begin("count_nonfinite", ne * 4.0, 0.0);
+        count_nonfinite_kernel<<<296, 256, 0, as_stream(f.stream)>>>(eps, ne, nonfinite);
+        g_launches.fetch_add(1);
+        f.end();
+        PLAN_CUDA(cudaGetLastError());
+    }
+    return f.rc;
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------ C ABI
+extern "C" int sdc_unet_create(sdc_unet** out, int dim, const int* dim_mults, int n_mults, int channels, int out_dim, int prec,
+                               float theta, int table_timesteps) {
+    SDC_REQUIRE(out && dim_mults && n_mults >= 1 && n_mults <= 8, "sdc_unet_create: bad arguments");
+    SDC_REQUIRE(prec == SDC_PREC_F16 || prec == SDC_PREC_TF32, "sdc_unet_create: precision %d", prec);
+    SDC_REQUIRE(dim > 0 && dim % (prec == SDC_PREC_F16 ? 64 : 32) == 0, "sdc_unet_create: dim %d must be a multiple of %d", dim,
+                prec == SDC_PREC_F16 ? 64 : 32);
+    SDC_REQUIRE(channels >= 1 && channels <= 8 && out_dim >= 1 && out_dim <= 8 && table_timesteps >= 1, "sdc_unet_create: channels / out_dim / table");
+    sdc_unet* n = new sdc_unet();
+    n->dim = dim; n->init_dim = dim; n->channels = channels; n->out_dim = out_dim; n->prec = prec; n->theta = theta; n->table_T = table_timesteps;
+    n->mults.assign(dim_mults, dim_mults + n_mults);
+    const int td = 4 * dim;
+    // parameter order = Unet2D.named_parameters() (safediffcon_b200/unet.py; keys = the reference's state_dict keys)
+    n->time_w1 = add_param(n, "time_mlp.1.weight", (int64_t)td * dim);
+    n->time_b1 = add_param(n, "time_mlp.1.bias", td);
+    n->time_w2 = add_param(n, "time_mlp.3.weight", (int64_t)td * td);
+    n->time_b2 = add_param(n, "time_mlp.3.bias", td);
+    // stem: W[c, Cin*49] repeated at columns 0 and kp/2 of a [c, kp] matrix (sdc_stem_im2col's high | low operand)
+    const int k_stem = channels * 49, kh = (k_stem + 31) / 32 * 32;
+    n->stem_kp = (2 * kh) % 64 == 0 ? 2 * kh : 2 * (kh + 32);
+    n->stem.cout = dim; n->stem.cin = n->stem_kp; n->stem.kind = K1;
+    n->stem.w = add_param(n, "init_conv.weight", (int64_t)dim * channels * 49);
+    n->stem.b = add_param(n, "init_conv.bias", dim);
+    const int64_t esz = prec == SDC_PREC_F16 ? 2 : 4;
+    want(n, &n->stem.packed, (int64_t)dim * n->stem_kp * esz);
+    want(n, (void**)&n->stem.bias, dim * 4);
+    want(n, (void**)&n->stem_rep, (int64_t)dim * n->stem_kp * 4);
+    std::vector<int> dims{dim};
+    for (int m : n->mults) dims.push_back(dim * m);
+    const int nl = n_mults;
+    n->downs.resize(nl);
+    n->ups.resize(nl);
+    for (int i = 0; i < nl; ++i) {
+        const int d_in = dims[i], d_out = dims[i + 1];
+        const bool last = i == nl - 1;
+        LevelP& L = n->downs[i];
+        const std::string base = "downs." + std::to_string(i);
+        build_block(n, L.b1, base + ".0", d_in, d_in);
+        build_block(n, L.b2, base + ".1", d_in, d_in);
+        build_attn(n, L.attn, base + ".2", d_in, false);
+        size_t cur = n->slab_items.size();
+        L.resamples = !last;
+        L.resample = last ? make_conv(n, base + ".3", d_out, d_in, K3, true) : make_conv(n, base + ".3.1", d_out, 4 * d_in, KUN, true);
+        fix_conv(n, L.resample, cur);
+    }
+    const int mid = dims.back();
+    build_block(n, n->mid1, "mid_block1", mid, mid);
+    build_attn(n, n->mid_attn, "mid_attn", mid, true);
+    build_block(n, n->mid2, "mid_block2", mid, mid);
+    for (int i = 0; i < nl; ++i) {
+        const int d_in = dims[nl - 1 - i], d_out = dims[nl - i];
+        const bool last = i == nl - 1;
+        LevelP& L = n->ups[i];
+        const std::string base = "ups." + std::to_string(i);
+        build_block(n, L.b1, base + ".0", d_out + d_in, d_out);
+        build_block(n, L.b2, base + ".1", d_out + d_in, d_out);
+        build_attn(n, L.attn, base + ".2", d_out, false);
+        size_t cur = n->slab_items.size();
+        L.resamples = !last;
+        L.resample = make_conv(n, base + (last ? ".3" : ".3.1"), d_in, d_out, K3, true, !last);
+        fix_conv(n, L.resample, cur);
+    }
+    build_block(n, n->fin, "final_res_block", 2 * dim, dim);
+    n->head_w_i = add_param(n, "final_conv.weight", (int64_t)out_dim * dim);
+    n->head_b_i = add_param(n, "final_conv.bias", out_dim);
+    want(n, (void**)&n->head_w, (int64_t)out_dim * dim * 4);
+    want(n, (void**)&n->head_b, out_dim * 4);
+    // time MLP + FiLM projections + table
+    want(n, (void**)&n->tw1, (int64_t)td * dim * 4);
+    want(n, (void**)&n->tb1, td * 4);
+    want(n, (void**)&n->tw2, (int64_t)td * td * 4);
+    want(n, (void**)&n->tb2, td * 4);
+    want(n, (void**)&n->film_w, (int64_t)n->film_total * td * 4);
+    want(n, (void**)&n->film_b, (int64_t)n->film_total * 4);
+    want(n, (void**)&n->table, (int64_t)table_timesteps * n->film_total * 4);
+    want(n, (void**)&n->t_arange, (int64_t)table_timesteps * 4);
+    want(n, (void**)&n->emb, (int64_t)table_timesteps * dim * 4);
+    want(n, (void**)&n->th1, (int64_t)table_timesteps * td * 4);
+    want(n, (void**)&n->th2, (int64_t)table_timesteps * td * 4);
+    int64_t total = 0;
+    for (auto& it : n->slab_items) total += (it.second + 255) / 256 * 256;
+    n->slab_bytes = total;
+    *out = n;
+    return SDC_OK;
+}
+
+extern "C" void sdc_unet_destroy(sdc_unet* n) {
+    if (!n) return;
+    if (n->slab) cudaFree(n->slab);
+    for (auto& e : n->prof) { cudaEventDestroy(e.e0); cudaEventDestroy(e.e1); }
+    delete n;
+}
+
+extern "C" int sdc_unet_param_count(const sdc_unet* n) { return n ? (int)n->params.size() : 0; }
+extern "C" const char* sdc_unet_param_name(const sdc_unet* n, int i) {
+    return (n && i >= 0 && i < (int)n->params.size()) ? n->params[i].name.c_str() : nullptr;
+}
+extern "C" int64_t sdc_unet_param_numel(const sdc_unet* n, int i) {
+    return (n && i >= 0 && i < (int)n->params.size()) ? n->params[i].numel : -1;
+}
+
+namespace {
+__global__ void arange_kernel(float* t, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) t[i] = (float)i;
+}
+
+int copy_param(sdc_unet* n, float* dst, const float* const* params, int idx, cudaStream_t st) {
+    PLAN_CUDA(cudaMemcpyAsync(dst, params[idx], (size_t)n->params[idx].numel * 4, cudaMemcpyDeviceToDevice, st));
+    return SDC_OK;
+}
+int pack_conv(sdc_unet* n, ConvP& c, const float* const* params, void* stream) {
+    int rc = sdc_pack_conv_weight(n->prec, c.kind == KUN ? KUN : c.kind, params[c.w], c.packed, c.cout, c.cin, stream);
+    if (rc) return rc;
+    if (c.up) { rc = sdc_pack_conv_weight(n->prec, KUP, params[c.w], c.packed_up, c.cout, c.cin, stream); if (rc) return rc; }
+    if (c.b >= 0) return copy_param(n, c.bias, params, c.b, as_stream(stream));
+    return SDC_OK;
+}
+int pack_block(sdc_unet* n, BlockP& b, const float* const* params, void* stream) {
+    cudaStream_t st = as_stream(stream);
+    int rc;
+    if ((rc = pack_conv(n, b.c1, params, stream))) return rc;
+    if ((rc = pack_conv(n, b.c2, params, stream))) return rc;
+    if (b.has_res && (rc = pack_conv(n, b.res, params, stream))) return rc;
+    if ((rc = copy_param(n, b.g1[0], params, b.g1w, st))) return rc;
+    if ((rc = copy_param(n, b.g1[1], params, b.g1b, st))) return rc;
+    if ((rc = copy_param(n, b.g2[0], params, b.g2w, st))) return rc;
+    if ((rc = copy_param(n, b.g2[1], params, b.g2b, st))) return rc;
+    const int td = 4 * n->dim;
+    if ((rc = copy_param(n, n->film_w + (int64_t)b.film_off * td, params, b.mlp_w, st))) return rc;
+    return copy_param(n, n->film_b + b.film_off, params, b.mlp_b, st);
+}
+int pack_attn(sdc_unet* n, AttnP& a, const float* const* params, void* stream) {
+    cudaStream_t st = as_stream(stream);
+    int rc;
+    if ((rc = pack_conv(n, a.qkv, params, stream))) return rc;
+    if ((rc = pack_conv(n, a.out, params, stream))) return rc;
+    if ((rc = copy_param(n, a.g_in, params, a.g_in_i, st))) return rc;
+    if (!a.full) {
+        if ((rc = copy_param(n, a.g_out, params, a.g_out_i, st))) return rc;
+        if ((rc = copy_param(n, a.out_w32, params, a.out.w, st))) return rc;
+    }
+    return SDC_OK;
+}
+}  // namespace
+
+extern "C" int sdc_unet_pack_weights(sdc_unet* n, const float* const* params, int n_params, void* stream) {
+    SDC_REQUIRE(n && params, "sdc_unet_pack_weights: null arguments");
+    SDC_REQUIRE(n_params == (int)n->params.size(), "sdc_unet_pack_weights: expected %d parameter pointers, got %d", (int)n->params.size(), n_params);
+    for (int i = 0; i < n_params; ++i) SDC_REQUIRE(params[i], "sdc_unet_pack_weights: parameter %s is null", n->params[i].name.c_str());
+    cudaStream_t st = as_stream(stream);
+    if (!n->slab) {
+        PLAN_CUDA(cudaMalloc((void**)&n->slab, (size_t)n->slab_bytes));
+        int64_t off = 0;
+        for (auto& it : n->slab_items) { *it.first = n->slab + off; off += (it.second + 255) / 256 * 256; }
+    }
+    int rc;
+    // stem: replicate the 7x7 weight into the (high | low) column ranges, then pack as a 1x1 GEMM operand
+    {
+        const int c = n->dim, k = n->channels * 49, kp = n->stem_kp;
+        PLAN_CUDA(cudaMemsetAsync(n->stem_rep, 0, (size_t)c * kp * 4, st));
+        PLAN_CUDA(cudaMemcpy2DAsync(n->stem_rep, (size_t)kp * 4, params[n->stem.w], (size_t)k * 4, (size_t)k * 4, c, cudaMemcpyDeviceToDevice, st));
+        PLAN_CUDA(cudaMemcpy2DAsync(n->stem_rep + kp / 2, (size_t)kp * 4, params[n->stem.w], (size_t)k * 4, (size_t)k * 4, c, cudaMemcpyDeviceToDevice, st));
+        if ((rc = sdc_pack_conv_weight(n->prec, K1, n->stem_rep, n->stem.packed, c, kp, stream))) return rc;
+        if ((rc = copy_param(n, n->stem.bias, params, n->stem.b, st))) return rc;
+    }
+    for (auto& L : n->downs) {
+        if ((rc = pack_block(n, L.b1, params, stream))) return rc;
+        if ((rc = pack_block(n, L.b2, params, stream))) return rc;
+        if ((rc = pack_attn(n, L.attn, params, stream))) return rc;
+        if ((rc = pack_conv(n, L.resample, params, stream))) return rc;
+    }
+    if ((rc = pack_block(n, n->mid1, params, stream))) return rc;
+    if ((rc = pack_attn(n, n->mid_attn, params, stream))) return rc;
+    if ((rc = pack_block(n, n->mid2, params, stream))) return rc;
+    for (auto& L : n->ups) {
+        if ((rc = pack_block(n, L.b1, params, stream))) return rc;
+        if ((rc = pack_block(n, L.b2, params, stream))) return rc;
+        if ((rc = pack_attn(n, L.attn, params, stream))) return rc;
+        if ((rc = pack_conv(n, L.resample, params, stream))) return rc;
+    }
+    if ((rc = pack_block(n, n->fin, params, stream))) return rc;
+    if ((rc = copy_param(n, n->head_w, params, n->head_w_i, st))) return rc;
+    if ((rc = copy_param(n, n->head_b, params, n->head_b_i, st))) return rc;
+    if ((rc = copy_param(n, n->tw1, params, n->time_w1, st))) return rc;
+    if ((rc = copy_param(n, n->tb1, params, n->time_b1, st))) return rc;
+    if ((rc = copy_param(n, n->tw2, params, n->time_w2, st))) return rc;
+    if ((rc = copy_param(n, n->tb2, params, n->time_b2, st))) return rc;
+    // FiLM table for every integer time: sinusoid -> Linear -> GELU -> Linear (time_mlp), then every block's SiLU -> Linear
+    const int T = n->table_T, td = 4 * n->dim;
+    arange_kernel<<<(T + 255) / 256, 256, 0, st>>>(n->t_arange, T);
+    g_launches.fetch_add(1);
+    PLAN_CUDA(cudaGetLastError());
+    if ((rc = sdc_sinusoidal_embedding(n->t_arange, n->emb, T, n->dim, n->theta, stream))) return rc;
+    if ((rc = sdc_linear_rows(n->emb, n->tw1, n->tb1, n->th1, T, n->dim, td, 0, stream))) return rc;
+    if ((rc = sdc_linear_rows(n->th1, n->tw2, n->tb2, n->th2, T, td, td, 2, stream))) return rc;
+    if ((rc = sdc_linear_rows(n->th2, n->film_w, n->film_b, n->table, T, td, n->film_total, 1, stream))) return rc;
+    n->packed = true;
+    return SDC_OK;
+}
+
+extern "C" int64_t sdc_unet_workspace_bytes(const sdc_unet* n, int B, int H, int W) {
+    if (!n || B <= 0 || H <= 0 || W <= 0) return 0;
+    const int64_t key = ((int64_t)B << 32) | ((int64_t)H << 16) | W;
+    auto it = n->ws_cache.find(key);
+    if (it != n->ws_cache.end()) return it->second;
+    Fwd f{};
+    f.n = const_cast<sdc_unet*>(n); f.dry = true; f.stream = nullptr; f.B = B; f.prec = n->prec; f.f16 = n->prec == SDC_PREC_F16;
+    f.esz = f.f16 ? 2 : 4;
+    f.ar.reset((void*)(uintptr_t)4096, 0, true);
+    float dummy_film = 0.f;
+    f.film = &dummy_film;
+    if (run_forward(f.n, f, nullptr, (float*)(uintptr_t)4096, H, W, nullptr)) return 0;
+    n->ws_cache[key] = f.ar.high;
+    return f.ar.high;
+}
+
+extern "C" int sdc_unet_forward(sdc_unet* n, const float* x, const int32_t* t_index, int t_uniform, float* eps, int B, int H, int W,
+                                void* workspace, int64_t workspace_bytes, uint32_t* nonfinite, void* stream) {
+    SDC_REQUIRE(n && x && eps && workspace, "sdc_unet_forward: null arguments");
+    if (!n->packed) { set_error("sdc_unet_forward: sdc_unet_pack_weights has not been called"); return SDC_ERR_STATE; }
+    const int down = 1 << ((int)n->mults.size() - 1);
+    SDC_REQUIRE(B > 0 && H % down == 0 && W % down == 0 && 128 % W == 0 && (H / down) * (W / down) % 32 == 0,
+                "sdc_unet_forward: unsupported image size %d x %d (need W | 128 and %d | H, W)", H, W, down);
+    SDC_REQUIRE(t_index || (t_uniform >= 0 && t_uniform < n->table_T), "sdc_unet_forward: diffusion time %d outside the FiLM table [0, %d)",
+                t_uniform, n->table_T);
+    SDC_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 1023) == 0, "sdc_unet_forward: workspace must be 1024-byte aligned");
+    const int64_t need = sdc_unet_workspace_bytes(n, B, H, W);
+    if (workspace_bytes < need) {
+        set_error("sdc_unet_forward: workspace of %lld bytes, need %lld", (long long)workspace_bytes, (long long)need);
+        return SDC_ERR_STATE;
+    }
+    Fwd f{};
+    f.n = n; f.dry = false; f.stream = stream; f.B = B; f.prec = n->prec; f.f16 = n->prec == SDC_PREC_F16;
+    f.esz = f.f16 ? 2 : 4;
+    f.ar.reset(workspace, workspace_bytes, false);
+    f.E = n->film_total;
+    f.t_index = t_index;
+    f.film = t_index ? n->table : n->table + (int64_t)t_uniform * n->film_total;
+    if (n->prof_on) n->prof_used = 0;
+    nvtxRangePushA("sdc_unet_forward");
+    const int rc = run_forward(n, f, x, eps, H, W, nonfinite);
+    nvtxRangePop();
+    return rc;
+}
+
+extern "C" int sdc_unet_profile_enable(sdc_unet* n, int enable) {
+    SDC_REQUIRE(n, "sdc_unet_profile_enable: null handle");
+    n->prof_on = enable != 0;
+    n->prof_used = 0;
+    return SDC_OK;
+}
+extern "C" int sdc_unet_profile_count(const sdc_unet* n) { return n ? (int)n->prof_used : 0; }
+extern "C" int sdc_unet_profile_entry(const sdc_unet* n, int i, const char** name, float* ms, double* bytes, double* flops) {
+    SDC_REQUIRE(n && i >= 0 && i < (int)n->prof_used, "sdc_unet_profile_entry: index %d out of range", i);
+    const ProfEntry& e = n->prof[i];
+    float t = 0.f;
+    PLAN_CUDA(cudaEventElapsedTime(&t, e.e0, e.e1));
+    if (name) *name = e.name;
+    if (ms) *ms = t;
+    if (bytes) *bytes = e.bytes;
+    if (flops) *flops = e.flops;
+    return SDC_OK;
+}

@@ -134,6 +134,15 @@ class GaussianDiffusion(nn.Module):
         self.prior_beta = prior_beta
         self._tables = {}
         self._graphs = _GraphCache()
+        # the denoiser's cached FiLM table covers integer times [0, table_timesteps): size it for this process
+        if hasattr(self.model, "table_timesteps"):
+            self.model.table_timesteps = max(int(self.model.table_timesteps), self.num_timesteps)
+
+    def _load_from_state_dict(self, *args, **kwargs):
+        # schedule buffers may change under a cached per-step table / captured graph: drop both
+        self._tables = {}
+        self._graphs = _GraphCache()
+        return super()._load_from_state_dict(*args, **kwargs)
 
     # ------------------------------------------------------------------ helpers
     def predict_start_from_noise(self, x_t, t, noise):
@@ -170,7 +179,12 @@ class GaussianDiffusion(nn.Module):
 
     def _coef_table(self, sampler, J_scheduler):
         """Per-step scalars, computed with the same fp32 torch-CPU ops the reference applies to its buffers."""
-        key = (sampler, self.sampling_timesteps, float(self.ddim_sampling_eta), id(J_scheduler), str(self.betas.device))
+        # the schedule buffers are state-dict entries: load_state_dict / .to() may replace their contents, so their storage
+        # address and version counter are part of the key (the reference always reads the live buffers)
+        used = (self.sqrt_recip_alphas_cumprod, self.sqrt_recipm1_alphas_cumprod, self.alphas_cumprod, self.posterior_mean_coef1,
+                self.posterior_mean_coef2, self.posterior_log_variance_clipped)
+        key = (sampler, self.sampling_timesteps, float(self.ddim_sampling_eta), id(J_scheduler), str(self.betas.device),
+               tuple((b.data_ptr(), b._version) for b in used))
         if J_scheduler is None and key in self._tables:
             return self._tables[key]
         c1b = self.sqrt_recip_alphas_cumprod.cpu()
@@ -287,7 +301,7 @@ class GaussianDiffusion(nn.Module):
         pk = self.model._packed()
         self.model._film_table(pk)
         gkey = None if gstruct is None else tuple(getattr(gstruct, f) for f, _ in gstruct._fields_)
-        key = (id(self.model), id(pk), pk["prec"], shape, sampler, tuple(rows), gkey, tuple(c is not None for c in conds), has_noise,
+        key = (id(self.model), id(pk), pk.get("table_gen", 0), pk["prec"], shape, sampler, tuple(rows), gkey, tuple(c is not None for c in conds), has_noise,
                self.condition_idx, bool(self.train_on_padded_locations), bool(clip_denoised))
         cache = self._graphs.entries
         if key in cache:
@@ -383,6 +397,17 @@ class GaussianDiffusion(nn.Module):
             pred_noise = self.predict_noise_from_start(x, t, x_start)
         return ModelPrediction(pred_noise, x_start)
 
+    def p_mean_variance(self, x, t, x_self_cond=None, residual=None, **kwargs):
+        """(model_mean, posterior_variance, posterior_log_variance, x_start, pred_noise) for per-sample times t (reference
+        diffusion.py:288-297): model_predictions without inner clamps, in-place clamp of x_start, q_posterior.  Torch ops on
+        the device around the CUDA denoiser (the chains use the fused sdc_reverse_step instead; parity: tests/test_chain_gpu.py)."""
+        preds = self.model_predictions(x, t, x_self_cond, residual=residual, **kwargs)
+        x_start = preds.pred_x_start
+        if kwargs['clip_denoised']:   # a required key, as in the reference (KeyError when absent)
+            x_start.clamp_(-1., 1.)
+        model_mean, posterior_variance, posterior_log_variance = self.q_posterior(x_start=x_start, x_t=x, t=t)
+        return model_mean, posterior_variance, posterior_log_variance, x_start, preds.pred_noise
+
     @torch.no_grad()
     def p_sample(self, x, t: int, x_self_cond=None, residual=None, **kwargs):
         """One DDPM step at integer time t -> (pred_img, x_start, pred_noise) (reference diffusion.py:299-306)."""
@@ -427,6 +452,10 @@ class GaussianDiffusion(nn.Module):
 
     def _run_chain(self, sampler, shape, w_groundtruth, enable_grad, return_all, kwargs):
         device = self._require_cuda()
+        if hasattr(self.model, "revalidate_packed"):
+            # EMA / optimiser updates written through p.data do not bump version counters: compare the parameter digest once
+            # per chain (one small sync next to 200-1000 denoiser evaluations) and repack when it moved
+            self.model.revalidate_packed()
         table, times, rows = self._coef_table(sampler, kwargs.get('J_scheduler'))
         noise_iter, seed, offset = self._rng(kwargs, device)
         conds = self._conditions(kwargs, w_groundtruth, device)

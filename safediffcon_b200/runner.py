@@ -62,11 +62,43 @@ def metrics_from_vectors(J: Optional[torch.Tensor], pts: torch.Tensor, tms: torc
     return m
 
 
-def sample_controls(model, u_init, u_final, config=None, Q=None, n_total=None, sample_offset=0, seed=None, noise=None,
+def shared_seed(seed, device):
+    """One Philox seed for the whole job: an explicit seed is used as is; otherwise rank 0 draws one from torch's CPU RNG and
+    broadcasts it, so ranks that all called torch.manual_seed(s) do not each re-derive the SAME stream with offset 0."""
+    rank, ws = world()
+    if seed is not None:
+        return int(seed)
+    if ws == 1:
+        return int(torch.randint(0, 2 ** 62, (1,)).item())
+    t = torch.randint(0, 2 ** 62, (1,), dtype=torch.int64)
+    t = t.to(device) if dist.get_backend() == "nccl" else t
+    dist.broadcast(t, src=0)
+    return int(t.item())
+
+
+def default_offset(sample_offset, n_local, n_total):
+    """Global index of this rank's first unit: explicit value, else the start of its contiguous shard of n_total (when the
+    shard sizes follow shard_range), else rank * n_local.  The in-kernel noise is keyed by (seed, global index, t), which
+    makes the samples independent of the number of ranks."""
+    if sample_offset is not None:
+        return int(sample_offset)
+    rank, ws = world()
+    if ws == 1:
+        return 0
+    if n_total is not None:
+        lo, hi = shard_range(n_total, rank, ws)
+        if hi - lo == n_local:
+            return lo
+    return rank * n_local
+
+
+def sample_controls(model, u_init, u_final, config=None, Q=None, n_total=None, sample_offset=None, seed=None, noise=None,
                     w_groundtruth=None, guidance_u0=True):
     """Guided reverse chain for the local shard; returns the UNSCALED prediction (what InferenceFT.inference returns).
     u_init / u_final may be host (pinned) or device tensors in model units."""
     dev = model.betas.device
+    seed = shared_seed(seed, dev) if noise is None else 0
+    sample_offset = default_offset(sample_offset, u_init.shape[0], n_total)
     u0 = u_init.to(dev, non_blocking=True)
     uT = u_final.to(dev, non_blocking=True)
     nabla = safety_guidance(config, Q) if (config is not None and Q is not None and guidance_u0) else None
@@ -88,11 +120,13 @@ def evaluate_controls(pred_unscaled, target_final, u_bound, n_total=None, nt=11,
     return m, traj
 
 
-def calibrate_quantile(model, states, config, Q, alpha, n_total=None, sample_offset=0, seed=None, noise=None):
+def calibrate_quantile(model, states, config, Q, alpha, n_total=None, sample_offset=None, seed=None, noise=None):
     """Nonconformity scores of the local calibration shard (unguided chain clamped to the ground-truth control,
     inference/conformal.py:53-85) -> all-gather of (score, raw weight) -> weights normalised over the FULL
     vector in index order -> rank-th order statistic on the device.  Returns (quantile 0-d tensor, scores, weights)."""
     dev = model.betas.device
+    seed = shared_seed(seed, dev) if noise is None else 0
+    sample_offset = default_offset(sample_offset, states.shape[0], n_total)
     st = states.to(dev, non_blocking=True)
     pred = model.sample(batch_size=st.shape[0], clip_denoised=True, guidance_u0=False, u_init=st[:, 0, 0, :],
                         u_final=st[:, 0, config.nt - 1, :], w_groundtruth=st[:, 1, :, :], nablaJ=None, J_scheduler=None,

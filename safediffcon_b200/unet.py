@@ -22,7 +22,8 @@ L.register({
     "sdc_pack_conv_weight": (c_i, [c_i, c_i, c_p, c_p, c_i, c_i, c_p]),
     "sdc_conv_gemm": (c_i, [c_i, c_i, c_p, c_i, c_p, c_i, c_p, c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_p]),
     "sdc_conv3x3_row": (c_i, [c_i, c_p, c_i, c_p, c_i, c_p, c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_p]),
-    "sdc_conv3x3_row_gn": (c_i, [c_p, c_i, c_p, c_i, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_i64, c_p, c_i, c_i, c_i, c_i, c_p]),
+    "sdc_conv3x3_row_gn": (c_i, [c_p, c_i, c_p, c_i, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_i64, c_p, c_i, c_i, c_i, c_i, c_p]),
+    "sdc_conv3x3_row_gn_head": (c_i, [c_p, c_i, c_p, c_i, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_p]),
     "sdc_stem_conv7": (c_i, [c_i, c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_p]),
     "sdc_stem_im2col": (c_i, [c_i, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_p]),
     "sdc_gn_silu": (c_i, [c_i, c_p, c_i, c_p, c_p, c_p, c_p, c_p, c_i64, c_p, c_i, c_p, c_i, c_i, c_i, c_p]),
@@ -56,6 +57,21 @@ L.register({
     "sdc_gn_param_grad": (c_i, [c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_i64, c_p, c_i, c_i, c_i, c_p]),
     "sdc_channel_layernorm_gain_grad": (c_i, [c_p, c_p, c_i, c_p, c_i64, c_i, c_p]),
     "sdc_head_conv1_wgrad": (c_i, [c_p, c_p, c_i, c_p, c_p, c_i, c_i, c_i, c_i, c_p]),
+})
+
+L.register({
+    "sdc_unet_create": (c_i, [ctypes.POINTER(c_p), c_i, ctypes.POINTER(c_i), c_i, c_i, c_i, c_i, c_f, c_i]),
+    "sdc_unet_destroy": (None, [c_p]),
+    "sdc_unet_param_count": (c_i, [c_p]),
+    "sdc_unet_param_name": (ctypes.c_char_p, [c_p, c_i]),
+    "sdc_unet_param_numel": (c_i64, [c_p, c_i]),
+    "sdc_unet_pack_weights": (c_i, [c_p, ctypes.POINTER(c_p), c_i, c_p]),
+    "sdc_unet_workspace_bytes": (c_i64, [c_p, c_i, c_i, c_i]),
+    "sdc_unet_forward": (c_i, [c_p, c_p, c_p, c_i, c_p, c_i, c_i, c_i, c_p, c_i64, c_p, c_p]),
+    "sdc_unet_profile_enable": (c_i, [c_p, c_i]),
+    "sdc_unet_profile_count": (c_i, [c_p]),
+    "sdc_unet_profile_entry": (c_i, [c_p, c_i, ctypes.POINTER(ctypes.c_char_p), ctypes.POINTER(c_f), ctypes.POINTER(ctypes.c_double),
+                                    ctypes.POINTER(ctypes.c_double)]),
 })
 
 HEADS, DIM_HEAD = 4, 32
@@ -157,12 +173,20 @@ class _Timed:
             self.prof.append((self.e0, self.e1, self.flops, self.shape))
 
 
-def conv_row_gn(a0, c0, a1, c1, cw, out, stats, gn, ss, t_index, ss_stride, residual, B, H, W, Cout):
-    """3x3 convolution of the full-resolution level with the following GroupNorm + FiLM + SiLU (+ residual) applied in place by the
-    same kernel (FP16, include/safediffcon_b200_unet.h: sdc_conv3x3_row_gn).  Returns 0, or -1 when not eligible (nothing launched)."""
+def conv_row_gn(a0, c0, a1, c1, cw, out, stats, counters, gn, ss, t_index, ss_stride, residual, B, H, W, Cout, head=None):
+    """3x3 convolution of the full-resolution level FUSED with the following GroupNorm + FiLM + SiLU (+ residual) (FP16, deferred
+    epilogue; include/safediffcon_b200_unet.h: sdc_conv3x3_row_gn).  head = (w [o, Cout], b [o], out [B, o, H, W]): the network's
+    last block -- the 1x1 head convolution is applied in the same epilogue and `out` (the activation) is not written.
+    Returns 0, or -1 when not eligible (nothing launched)."""
     with _Timed(2.0 * B * H * W * Cout * 9 * (c0 + c1), (KIND_3x3, B, H, W, c0 + c1, Cout)):
-        rc = L.lib().sdc_conv3x3_row_gn(L.ptr(a0), c0, L.ptr(a1), c1, L.ptr(cw["w"]), L.ptr(cw["b"]), L.ptr(out), L.ptr(stats),
-                                        L.ptr(gn[0]), L.ptr(gn[1]), L.ptr(ss), L.ptr(t_index), ss_stride, L.ptr(residual), B, H, W, Cout, _st())
+        if head is None:
+            rc = L.lib().sdc_conv3x3_row_gn(L.ptr(a0), c0, L.ptr(a1), c1, L.ptr(cw["w"]), L.ptr(cw["b"]), L.ptr(out), L.ptr(stats),
+                                            L.ptr(counters), L.ptr(gn[0]), L.ptr(gn[1]), L.ptr(ss), L.ptr(t_index), ss_stride,
+                                            L.ptr(residual), B, H, W, Cout, _st())
+        else:
+            rc = L.lib().sdc_conv3x3_row_gn_head(L.ptr(a0), c0, L.ptr(a1), c1, L.ptr(cw["w"]), L.ptr(cw["b"]), L.ptr(stats),
+                                                 L.ptr(counters), L.ptr(gn[0]), L.ptr(gn[1]), L.ptr(residual), L.ptr(head[0]),
+                                                 L.ptr(head[1]), L.ptr(head[2]), head[2].shape[1], B, H, W, Cout, _st())
     if rc > 0:
         L.check(rc)
     return rc
@@ -299,11 +323,93 @@ class _TrainFn(torch.autograd.Function):
         return (gx, pg["film"], None) + tuple(pg.get(id(p)) for p in ctx.params)
 
 
+USE_PLAN = os.environ.get("SDC_NO_PLAN", "0") != "1"   # inference through the C++ executor (sdc_unet_forward)
+WORKSPACE_ENTRIES = 3
+
+
+class UnetPlan:
+    """Handle of the C++ whole-network executor (include/safediffcon_b200_plan.h): owns the packed weights, the FiLM table and
+    the launch schedule; `forward` is ONE C call.  Workspaces are torch uint8 tensors, one per problem size (captured graphs keep
+    a reference to theirs)."""
+
+    def __init__(self, dim, dim_mults, channels, out_dim, prec, theta, table_timesteps):
+        lib = L.lib()
+        h = c_p()
+        mults = (c_i * len(dim_mults))(*[int(m) for m in dim_mults])
+        L.check(lib.sdc_unet_create(ctypes.byref(h), int(dim), mults, len(dim_mults), int(channels), int(out_dim), int(prec),
+                                    float(theta), int(table_timesteps)))
+        self.handle, self.prec, self.out_dim, self.table_timesteps = h, prec, out_dim, table_timesteps
+        self.names = [lib.sdc_unet_param_name(h, i).decode() for i in range(lib.sdc_unet_param_count(h))]
+        self.numels = [int(lib.sdc_unet_param_numel(h, i)) for i in range(len(self.names))]
+        self.workspaces = {}
+        self.nonfinite = None
+        self.key = None
+
+    def __del__(self):
+        try:
+            if self.handle:
+                L.lib().sdc_unet_destroy(self.handle)
+                self.handle = None
+        except Exception:
+            pass
+
+    def pack(self, named_params):
+        """named_params: {state_dict key: fp32 CUDA tensor}.  Packs / refreshes IN PLACE (captured graphs stay valid)."""
+        keep, ptrs = [], (c_p * len(self.names))()
+        for i, (nm, ne) in enumerate(zip(self.names, self.numels)):
+            t = named_params[nm].detach()
+            if not t.is_cuda:
+                raise RuntimeError("safediffcon_b200.Unet2D: parameters are on the CPU; move the module to a CUDA device "
+                                   "(there is no CPU fallback)")
+            t = t.to(torch.float32).contiguous()
+            if t.numel() != ne:
+                raise ValueError(f"safediffcon_b200: parameter {nm} has {t.numel()} elements, the executor expects {ne}")
+            keep.append(t)
+            ptrs[i] = t.data_ptr()
+        L.check(L.lib().sdc_unet_pack_weights(self.handle, ptrs, len(self.names), _st()))
+        if self.prec == PREC_F16 and self.nonfinite is None:
+            self.nonfinite = torch.zeros(1, dtype=torch.int32, device=keep[0].device)
+
+    def workspace(self, B, H, W, device):
+        key = (B, H, W)
+        ws = self.workspaces.pop(key, None)
+        if ws is None:
+            need = int(L.lib().sdc_unet_workspace_bytes(self.handle, B, H, W))
+            if need <= 0:
+                L.check(1)
+            ws = torch.empty(need, dtype=torch.uint8, device=device)
+        self.workspaces[key] = ws   # most recently used last
+        while len(self.workspaces) > WORKSPACE_ENTRIES:
+            self.workspaces.pop(next(iter(self.workspaces)))
+        return ws
+
+    def forward(self, x, t_index=None, t_uniform=0, workspace=None):
+        B, _, H, W = x.shape
+        ws = workspace if workspace is not None else self.workspace(B, H, W, x.device)
+        out = torch.empty(B, self.out_dim, H, W, device=x.device, dtype=torch.float32)
+        L.check(L.lib().sdc_unet_forward(self.handle, L.ptr(x), L.ptr(t_index), int(t_uniform), L.ptr(out), B, H, W, L.ptr(ws), ws.numel(),
+                                         L.ptr(self.nonfinite), _st()))
+        return out
+
+    def profile(self, enable):
+        L.check(L.lib().sdc_unet_profile_enable(self.handle, int(enable)))
+
+    def profile_entries(self):
+        """[(kernel family, ms, algorithmic bytes, flops)] of the forwards since profile(True); synchronise first."""
+        lib, out = L.lib(), []
+        nm, ms, by, fl = ctypes.c_char_p(), c_f(), ctypes.c_double(), ctypes.c_double()
+        for i in range(lib.sdc_unet_profile_count(self.handle)):
+            L.check(lib.sdc_unet_profile_entry(self.handle, i, ctypes.byref(nm), ctypes.byref(ms), ctypes.byref(by), ctypes.byref(fl)))
+            out.append((nm.value.decode(), ms.value, by.value, fl.value))
+        return out
+
+
 class _PackCache:
     """Packed-weight cache that is never deep-copied (EMA wrappers deepcopy the module; the copy repacks lazily)."""
 
     def __init__(self):
-        self.pack, self.key = None, None
+        self.pack, self.key, self.fingerprint = None, None, None
+        self.plan, self.plan_gen = None, 0
 
     def __deepcopy__(self, memo):
         return _PackCache()
@@ -378,9 +484,12 @@ class Unet2D(nn.Module):
         # HBM-bound norm kernels move 4 instead of 6 bytes per element.  `net.compact_intermediates = False` (or SDC_COMPACT=0)
         # keeps fp32.  The recording (backward) path always keeps fp32.
         self.compact_intermediates = os.environ.get("SDC_COMPACT", "1") != "0"
-        # EXPERIMENTAL (off): with compact intermediates and batches >= 256 the 3x3 convolutions of the 16x128 level can normalise
-        # their own output in place (sdc_conv3x3_row_gn) instead of a separate GroupNorm pass.  Correct (tests) but currently
-        # 5 % slower than the separate kernels (csrc/conv_row.cu explains why); SDC_FUSE_GN=1 enables it.
+        # EXPERIMENTAL (off): the 3x3 convolutions of the 16x128 level can normalise their own output (sdc_conv3x3_row_gn:
+        # deferred epilogue, GroupNorm + FiLM + SiLU (+ residual, + the 1x1 head for the last block) applied to the fp32
+        # accumulators in TMEM) instead of a separate GroupNorm pass over HBM.  Correct (tests) and more accurate (one rounding
+        # site fewer per norm) but SLOWER on B200: 875 us against 417 us conv + 180 us GroupNorm at B = 1024 -- the per-item
+        # epilogue (two TMEM passes, cross-cluster exchange of the statistics, SiLU, stores) does not fit into one MMA period
+        # (profiles/r02_row_gn_*.txt).  SDC_FUSE_GN=1 enables it.
         self.fuse_groupnorm = os.environ.get("SDC_FUSE_GN", "0") == "1"
 
     # ------------------------------------------------------------------ weight packing / FiLM table
@@ -404,6 +513,72 @@ class Unet2D(nn.Module):
 
     def _key(self):
         return (self.precision,) + tuple((p.data_ptr(), p._version) for p in self.parameters())
+
+    def _fingerprint(self):
+        """Device-side digest of the parameter VALUES: (L2 norm, L1 norm) of every parameter, [2, n_params] fp32.  The version
+        counters of `_key` miss in-place writes made through `p.data` (ema_pytorch's `ema_p.data.lerp_(...)`,
+        `p.data.copy_(...)`), which is exactly how the reference's EMA copy -- the module InferenceFT samples from
+        (/root/reference/1D/inference/inference_ft.py:167-171,212-222) -- is updated."""
+        ps = [p.detach() for p in self.parameters()]
+        with torch.no_grad():
+            return torch.stack([torch.stack(torch._foreach_norm(ps, 2)), torch.stack(torch._foreach_norm(ps, 1))])
+
+    def invalidate_packed(self):
+        """Force the next evaluation to repack the weights / FiLM table (buffers are refreshed in place, so captured graphs stay valid)."""
+        self._cache.key = None
+        if self._cache.plan is not None:
+            self._cache.plan.key = None
+
+    def revalidate_packed(self):
+        """Called once per sampling chain (GaussianDiffusion._run_chain) and by anyone who has written parameters behind
+        autograd's back: compares the live parameter digest with the one taken when the pack was built (one small D2H sync) and
+        invalidates the pack if any parameter changed.  Returns True when the pack was still valid."""
+        c = self._cache
+        if c.fingerprint is None or (c.key is None and (c.plan is None or c.plan.key is None)):
+            return False
+        key = self._key()
+        stale = (c.key is not None and c.key != key) or (c.plan is not None and c.plan.key is not None and c.plan.key != key)
+        if stale or not torch.equal(c.fingerprint, self._fingerprint()):
+            self.invalidate_packed()
+            return False
+        return True
+
+    # ------------------------------------------------------------------ C++ executor (inference)
+    def _plan_ready(self):
+        """The C++ executor with weights packed for the current parameter values, or None when this configuration runs on the
+        Python schedule (SDC_NO_PLAN=1, or FP16 with fp32 intermediates)."""
+        if not USE_PLAN or (self.precision == "f16" and not self.compact_intermediates):
+            return None
+        prec = self._prec()
+        c = self._cache
+        plan = c.plan
+        if plan is None or plan.prec != prec or plan.table_timesteps != self.table_timesteps:
+            dims = [self.downs[i][0].dim_out // self.dim for i in range(1, len(self.downs))] + [self.mid_block1.dim_out // self.dim]
+            plan = UnetPlan(self.dim, dims, self.channels, self.out_dim, prec, self.theta, self.table_timesteps)
+            c.plan, c.plan_gen = plan, c.plan_gen + 1
+        key = self._key()
+        if plan.key != key:
+            dev = self.init_conv.weight.device
+            if dev.type != "cuda":
+                raise RuntimeError("safediffcon_b200.Unet2D: parameters are on the CPU; move the module to a CUDA device "
+                                   "(there is no CPU fallback)")
+            with torch.no_grad(), torch.cuda.device(dev):
+                plan.pack(dict(self.named_parameters()))
+                plan.key = key
+                c.fingerprint = self._fingerprint()
+        return plan
+
+    def take_nonfinite(self):
+        """Number of non-finite eps entries the FP16 executor has produced since the last call (one D2H sync); resets the count.
+        GaussianDiffusion checks it once per chain: fp16 activations beyond +-65504 (checkpoints with extreme pre-norm ranges)
+        surface here instead of silently turning into Inf/NaN samples."""
+        plan = self._cache.plan
+        if plan is None or plan.nonfinite is None:
+            return 0
+        n = int(plan.nonfinite.item())
+        if n:
+            plan.nonfinite.zero_()
+        return n
 
     def _packed(self):
         key = self._key()
@@ -487,7 +662,7 @@ class Unet2D(nn.Module):
                     tab.copy_(self._film_table(old))
                     old["table"] = tab
                 pk = old
-        self._cache.pack, self._cache.key = pk, key
+        self._cache.pack, self._cache.key, self._cache.fingerprint = pk, key, self._fingerprint()
         return pk
 
     def _film_rows(self, pk, t_float):
@@ -507,6 +682,9 @@ class Unet2D(nn.Module):
         return out
 
     def _film_table(self, pk):
+        if pk["table"] is not None and pk["table"].shape[0] != self.table_timesteps:
+            pk["table"] = None   # table_timesteps was raised (a GaussianDiffusion with more steps adopted this denoiser)
+            pk["table_gen"] = pk.get("table_gen", 0) + 1   # part of the captured-graph key: graphs hold the table's address
         if pk["table"] is None:
             dev = pk["film_w"].device
             t = torch.arange(self.table_timesteps, device=dev, dtype=torch.float32)
@@ -569,18 +747,44 @@ class Unet2D(nn.Module):
                 eps = self._run(x, time, None, tape)
             return eps, self._vjp(tape, L.dev_f32(grad_eps, "grad_eps"))
 
-    def denoise_indexed(self, x, t_index):
+    def denoise_indexed(self, x, t_index, workspace=None):
         """eps with the integer diffusion times read from a device int32 tensor [B] that the caller updates in place
         (captured-graph chains: the same launches serve every step; see GaussianDiffusion._graph_chain)."""
         assert t_index.dtype == torch.int32 and t_index.is_cuda and t_index.numel() == x.shape[0]
         with torch.no_grad(), torch.cuda.device(x.device):
-            return self._run(L.dev_f32(x, "x"), None, None, t_index=t_index)
+            x = L.dev_f32(x, "x")
+            if workspace is not None:
+                return self._run_plan(self._plan_ready(), x, None, None, t_index, workspace)
+            return self._run(x, None, None, t_index=t_index)
+
+    def _run_plan(self, plan, x, time, table_row, t_index, workspace=None):
+        """Inference through the C++ executor: ONE call, activations in the plan's workspace."""
+        B = x.shape[0]
+        assert x.shape[1] == self.channels
+        if table_row is not None:
+            if not 0 <= table_row < self.table_timesteps:
+                raise ValueError(f"safediffcon_b200.Unet2D: diffusion time {table_row} outside the FiLM table [0, {self.table_timesteps}); "
+                                 "set net.table_timesteps (GaussianDiffusion sizes it from its timesteps)")
+            return plan.forward(x, None, int(table_row), workspace)
+        if t_index is None:
+            if time.numel() != B:
+                raise ValueError(f"safediffcon_b200.Unet2D: time must hold one entry per sample ({B}), got {tuple(time.shape)}")
+            if bool(((time < 0) | (time >= self.table_timesteps)).any()):
+                raise ValueError(f"safediffcon_b200.Unet2D: integer diffusion times must lie in [0, {self.table_timesteps}); "
+                                 "pass float times or raise net.table_timesteps")
+            t_index = time.to(device=x.device, dtype=torch.int32).reshape(B).contiguous()
+        return plan.forward(x, t_index, 0, workspace)
 
     def _run(self, x, time, table_row, tape=None, t_index=None, film_rows=None):
         """tape: None for inference (buffers are reused); a list to record what the backward-data pass needs (every
         normalisation input is then kept in its own buffer)."""
-        pk = self._packed()
         keep = tape is not None
+        if not keep and film_rows is None and (table_row is not None or t_index is not None or
+                                               (time is not None and not torch.is_floating_point(time))):
+            plan = self._plan_ready() if self.init_conv.weight.shape[0] == self.dim else None
+            if plan is not None:
+                return self._run_plan(plan, x, time, table_row, t_index)
+        pk = self._packed()
         lib = L.lib()
         dev = x.device
         prec = pk["prec"]
@@ -593,19 +797,32 @@ class Unet2D(nn.Module):
         elif t_index is not None:
             film = self._film_table(pk)
         elif table_row is not None:
+            if not 0 <= table_row < self.table_timesteps:
+                raise ValueError(f"safediffcon_b200.Unet2D: diffusion time {table_row} outside the FiLM table [0, {self.table_timesteps}); "
+                                 "set net.table_timesteps (GaussianDiffusion sizes it from its timesteps)")
             film, t_index = self._film_table(pk)[table_row:table_row + 1], None
         elif not torch.is_floating_point(time):
-            film, t_index = self._film_table(pk), time.to(device=dev, dtype=torch.int32).clamp(0, self.table_timesteps - 1).contiguous()
+            # per-sample integer times (user-level forward / model_predictions; the chains use table_row / t_index): one small
+            # host check instead of a silent clamp -- the reference's model_predictions synchronises here too (t[0].item())
+            if time.numel() != B:
+                raise ValueError(f"safediffcon_b200.Unet2D: time must hold one entry per sample ({B}), got {tuple(time.shape)}")
+            if bool(((time < 0) | (time >= self.table_timesteps)).any()):
+                raise ValueError(f"safediffcon_b200.Unet2D: integer diffusion times must lie in [0, {self.table_timesteps}); "
+                                 "pass float times or raise net.table_timesteps")
+            film, t_index = self._film_table(pk), time.to(device=dev, dtype=torch.int32).reshape(B).contiguous()
         else:
             film, t_index = self._film_rows(pk, time.to(device=dev, dtype=torch.float32).contiguous()), \
                 torch.arange(B, device=dev, dtype=torch.int32)
         E = pk["film_total"]
         n_gn = 2 * sum(1 for _ in self._resnet_blocks())
+        cmp_early = od == torch.float16 and not keep and self.compact_intermediates
         stats = torch.zeros(n_gn, B, 2, device=dev, dtype=torch.float64)
+        # exchange slots of the fused conv + GroupNorm kernels (SDC_GN_SLOT_BYTES = 1024 per norm and sample, every byte 0xFF)
+        counters = torch.full((n_gn, B, 256), -1, device=dev, dtype=torch.int32) if (cmp_early and self.fuse_groupnorm) else None
         stat_i = [0]
         f32 = lambda rows, c: torch.empty(rows, c, device=dev, dtype=torch.float32)  # noqa: E731  (conv outputs ahead of a norm)
         opd = lambda rows, c: torch.empty(rows, c, device=dev, dtype=od)  # noqa: E731  (tensor-core operands)
-        cmp = od == torch.float16 and not keep and self.compact_intermediates
+        cmp = cmp_early
 
         def conv(kind, a0, c0, a1, c1, cw, residual, out, st, operand_out, h, w, algo_k=None):
             conv_gemm(kind, a0, c0, a1, c1, cw["w"], cw["b"], residual, out, st, operand_out, B, h, w, cw["cout"], prec, algo_k)
@@ -618,6 +835,26 @@ class Unet2D(nn.Module):
             M, cout = B * h * w, p["cout"]
             s1, s2 = stats[stat_i[0]], stats[stat_i[0] + 1]
             stat_i[0] += 2
+            if cmp and self.fuse_groupnorm and w == 128 and h % 4 == 0 and cout <= 128 and USE_ROW_KERNEL and (head is None or self.out_dim <= 4):
+                # full-resolution level: GroupNorm + FiLM + SiLU (+ residual, + 1x1 head) applied to the fp32 accumulators by the
+                # conv kernel itself (sdc_conv3x3_row_gn, deferred epilogue): no separate normalisation pass over HBM
+                si = stat_i[0] - 2
+                n1, n2 = counters[si], counters[si + 1]
+                ss = film[:, m._film_off:]
+                h1 = opd(M, cout)
+                rc = conv_row_gn(a0, c0, a1, c1, p["c1"], h1, s1, n1, p["g1"], ss, t_index, E, None, B, h, w, cout)
+                if rc == 0:
+                    if p["res"] is not None:
+                        res = opd(M, cout)
+                        conv(KIND_1x1, a0, c0, a1, c1, p["res"], None, res, None, True, h, w)
+                    else:
+                        assert a1 is None
+                        res = a0
+                    out2 = None if head is not None else opd(M, cout)
+                    rc = conv_row_gn(h1, cout, None, 0, p["c2"], out2, s2, n2, p["g2"], None, None, 0, res, B, h, w, cout, head=head)
+                    assert rc == 0
+                    return out2
+                # not eligible (nothing was launched): fall through to the unfused sequence
             if head is not None:
                 raw = f32(M, cout)
                 conv(KIND_3x3, a0, c0, a1, c1, p["c1"], None, raw, s1, False, h, w)
@@ -635,24 +872,6 @@ class Unet2D(nn.Module):
                 L.check(lib.sdc_gn_silu_head(L.ptr(raw), L.ptr(s2), L.ptr(p["g2"][0]), L.ptr(p["g2"][1]), L.ptr(res), 1, L.ptr(head[0]),
                                              L.ptr(head[1]), L.ptr(head[2]), B, h * w, cout, head[2].shape[1], _st()))
                 return None
-            if cmp and self.fuse_groupnorm and w == 128 and cout <= 128 and B >= 256 and USE_ROW_KERNEL:
-                # full-resolution level, large batch: GroupNorm + FiLM + SiLU (+ residual) applied in place by the conv kernel
-                # itself (sdc_conv3x3_row_gn): no separate normalisation pass over HBM
-                ss = film[:, m._film_off:]
-                raw = opd(M, cout)
-                rc = conv_row_gn(a0, c0, a1, c1, p["c1"], raw, s1, p["g1"], ss, t_index, E, None, B, h, w, cout)
-                if rc == 0:
-                    if p["res"] is not None:
-                        res = opd(M, cout)
-                        conv(KIND_1x1, a0, c0, a1, c1, p["res"], None, res, None, True, h, w)
-                    else:
-                        assert a1 is None
-                        res = a0
-                    raw2 = opd(M, cout)
-                    rc = conv_row_gn(raw, cout, None, 0, p["c2"], raw2, s2, p["g2"], None, None, 0, res, B, h, w, cout)
-                    assert rc == 0
-                    return raw2
-                s1.zero_()   # not eligible after all: fall through to the unfused sequence
             if cmp:
                 # compact intermediates (FP16 inference): the conv epilogue takes the GroupNorm sums from its fp32 accumulators and
                 # stores fp16; normalisation runs in place; the 1x1 res_conv output lands in conv1's dead buffer, also fp16
@@ -791,7 +1010,8 @@ class Unet2D(nn.Module):
             conv(KIND_3x3, cur, c, None, 0, lvl["up"], None, nxt, None, True, h, w)
             rec(("up", dict(p=lvl["up"], upsample=lvl["upsample"], c=c, h=h, w=w, inp=cur)))
             cur, c = nxt, cout
-        out = torch.empty(B, self.out_dim, H, W, device=dev, dtype=torch.float32)
+        # zeros: the fused conv + GroupNorm + head kernel accumulates the two channel halves of a pixel into it
+        out = torch.zeros(B, self.out_dim, H, W, device=dev, dtype=torch.float32)
         if cmp and pk["final"]["cout"] == 128 and self.out_dim <= 4:
             resnet(pk["final"], self.final_res_block, cur, c, r, r_c, h, w, head=(pk["head"][0], pk["head"][1], out))
             return out

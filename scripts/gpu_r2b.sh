@@ -1,0 +1,6 @@
+set -x
+TAG=${1:-r2b}
+timeout 600 python -m pytest tests/test_unet_gpu.py -q -x -k "fused_groupnorm or row_gn_head" > gpurun_out/t_$TAG.log 2>&1; echo "gn tests rc=$?"; tail -5 gpurun_out/t_$TAG.log
+timeout 300 python scripts/time_row_gn.py > gpurun_out/time_row_gn_$TAG.txt 2>&1; cat gpurun_out/time_row_gn_$TAG.txt
+timeout 300 python scripts/time_unet.py 1024 > gpurun_out/time_unet_$TAG.txt 2>&1; cat gpurun_out/time_unet_$TAG.txt
+SDC_FUSE_GN=0 timeout 300 python scripts/time_unet.py 1024 > gpurun_out/time_unet_${TAG}_nofuse.txt 2>&1; cat gpurun_out/time_unet_${TAG}_nofuse.txt

@@ -15,6 +15,7 @@ res = torch.randn(M // 8, cout, generator=g).half().cuda().repeat(8, 1)
 cw = dict(w=U.pack_conv_weight(1, w, 1), b=bias, cout=cout)
 y = torch.empty(M, cout, dtype=torch.float16).cuda()
 s = torch.zeros(B, 2, dtype=torch.float64).cuda()
+cnt = torch.full((B, 256), -1, dtype=torch.int32).cuda()
 lib = L.lib()
 
 
@@ -38,7 +39,8 @@ def unfused(r):
 
 def fused(r):
     s.zero_()
-    assert U.conv_row_gn(a0, c0, None, 0, cw, y, s, (gamma, beta), None, None, 0, r, B, H, W, cout) == 0
+    cnt.fill_(-1)
+    assert U.conv_row_gn(a0, c0, None, 0, cw, y, s, cnt, (gamma, beta), None, None, 0, r, B, H, W, cout) == 0
 
 
 s.zero_()
@@ -46,7 +48,7 @@ conv_only = timed(lambda: U.conv_gemm(1, a0, c0, None, 0, cw["w"], bias, None, y
 print(f"conv_row2 alone: {conv_only:.0f} us")
 for r, tag in ((None, "no residual"), (res, "residual")):
     print(f"{tag}: unfused {timed(lambda: unfused(r)):.0f} us", flush=True)
-    for dbg in ("0", "4", "8"):   # 4: GroupNorm warps synchronise only; 8: loads + arithmetic, no stores
+    for dbg in ("0", "4", "8", "12", "16", "28", "32", "60"):   # 4: no partner wait, 8: no pass 1, 16: no SiLU, 32: no stores
         os.environ["SDC_ROW_DBG"] = dbg
         print(f"{tag}: fused dbg={dbg} {timed(lambda: fused(r)):.0f} us", flush=True)
     os.environ["SDC_ROW_DBG"] = "0"

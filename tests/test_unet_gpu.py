@@ -422,10 +422,12 @@ def test_fused_upsample_conv_vs_torch(case, prec):
     assert ((out - ref).norm() / ref.norm()).item() < 6e-4
 
 
-@pytest.mark.parametrize("B,c0,c1,film,resid", [(296, 128, 0, True, False), (296, 128, 128, False, True), (300, 64, 0, True, True)])
+@pytest.mark.parametrize("B,c0,c1,film,resid", [(296, 128, 0, True, False), (296, 128, 128, False, True), (300, 64, 0, True, True),
+                                                (3, 128, 0, True, True), (19, 128, 128, True, False)])
 def test_conv3x3_row_with_fused_groupnorm(B, c0, c1, film, resid):
-    """sdc_conv3x3_row_gn (conv + in-place GroupNorm/FiLM/SiLU/residual in one kernel) == sdc_conv3x3_row followed by sdc_gn_silu,
-    and == torch on a few samples.  B = 296: 16 work items per cluster (sample aligned); B = 300: ragged last cluster."""
+    """sdc_conv3x3_row_gn (conv + GroupNorm/FiLM/SiLU/residual in one kernel, deferred epilogue) == sdc_conv3x3_row followed by
+    sdc_gn_silu, and == torch on a few samples.  B = 296 / 300: 72 clusters, 16-17 rounds, ragged last round; B = 3, 19: fewer
+    items than SM pairs / a partial second round."""
     L, lib = _L()
     from safediffcon_b200 import unet as U
     H, W, cout = 16, 128, 128
@@ -448,17 +450,20 @@ def test_conv3x3_row_with_fused_groupnorm(B, c0, c1, film, resid):
                             L.ptr(res), 1, L.ptr(y_ref), B, H * W, cout, L.stream_ptr()))
     # fused
     s = torch.zeros(B, 2, dtype=torch.float64).cuda()
+    n = torch.full((B, 256), -1, dtype=torch.int32).cuda()   # SDC_GN_SLOT_BYTES per sample, every byte 0xFF
     y = torch.full((M, cout), float("nan"), dtype=torch.float16).cuda()
-    rc = U.conv_row_gn(a0, c0, a1, c1, cw, y, s, (gamma, beta), table, tidx, 3 * cout if film else 0, res, B, H, W, cout)
+    rc = U.conv_row_gn(a0, c0, a1, c1, cw, y, s, n, (gamma, beta), table, tidx, 3 * cout if film else 0, res, B, H, W, cout)
     assert rc == 0
     torch.cuda.synchronize()
+    assert (n.view(B, 128, 2)[:, :, 0] != -1).all()   # every exchange slot of every sample was filled
     assert torch.isfinite(y.float()).all()
     assert torch.allclose(s, s_ref, rtol=1e-6, atol=1e-3)
     d = (y.float() - y_ref.float()).abs()
     scale = y_ref.float().abs().max().item()
-    assert d.max().item() < 3e-3 * scale and d.mean().item() < 1e-4 * scale, (d.max().item(), d.mean().item(), scale)
-    # torch on samples 0, 151 and the last one
-    for b in (0, 151, B - 1):
+    # the fused kernel normalises the fp32 accumulators, the unfused pair their fp16 rounding: one extra 2^-11 on the reference side
+    assert d.max().item() < 3e-3 * scale and d.mean().item() < 2e-4 * scale, (d.max().item(), d.mean().item(), scale)
+    # torch on the first, a middle and the last sample
+    for b in sorted({0, B // 2, B - 1}):
         sl = slice(b * H * W, (b + 1) * H * W)
         x = a0[sl].float() if a1 is None else torch.cat((a0[sl].float(), a1[sl].float()), dim=1)
         x = x.reshape(1, H, W, c0 + c1).permute(0, 3, 1, 2)
@@ -469,7 +474,37 @@ def test_conv3x3_row_with_fused_groupnorm(B, c0, c1, film, resid):
             z = z * (row[:cout, None, None] + 1) + row[cout:2 * cout, None, None]
         z = F.silu(z)
         ref = nhwc(z).reshape(H * W, cout) + (res[sl].float() if resid else 0)
-        assert (y[sl].float() - ref).abs().max().item() < 6e-3 * ref.abs().max().item(), b
+        assert (y[sl].float() - ref).abs().max().item() < 2e-3 * ref.abs().max().item(), b
+
+
+@pytest.mark.parametrize("B", [2, 300])
+def test_conv3x3_row_gn_head_vs_torch(B):
+    """Last convolution of the network with GroupNorm + SiLU + residual + 1x1 head convolution in its epilogue (NCHW fp32 out)."""
+    L, lib = _L()
+    from safediffcon_b200 import unet as U
+    H, W, c0, cout, co = 16, 128, 128, 128, 3
+    g = torch.Generator().manual_seed(B)
+    M = B * H * W
+    a0 = (torch.randn(M, c0, generator=g) * 0.8).half().cuda()
+    w = (torch.randn(cout, c0, 3, 3, generator=g) / np.sqrt(9 * c0)).cuda()
+    bias = torch.randn(cout, generator=g).cuda()
+    gamma, beta = (1 + 0.3 * torch.randn(cout, generator=g)).cuda(), (0.2 * torch.randn(cout, generator=g)).cuda()
+    res = torch.randn(M, cout, generator=g).half().cuda()
+    hw, hb = (torch.randn(co, cout, generator=g) / np.sqrt(cout)).cuda(), torch.randn(co, generator=g).cuda()
+    cw = dict(w=U.pack_conv_weight(1, w, F16), b=bias, cout=cout)
+    s = torch.zeros(B, 2, dtype=torch.float64).cuda()
+    n = torch.full((B, 256), -1, dtype=torch.int32).cuda()
+    out = torch.zeros(B, co, H, W).cuda()   # the kernel accumulates the two channel halves of a pixel into it
+    assert U.conv_row_gn(a0, c0, None, 0, cw, None, s, n, (gamma, beta), None, None, 0, res, B, H, W, cout, head=(hw, hb, out)) == 0
+    torch.cuda.synchronize()
+    assert torch.isfinite(out).all()
+    for b in sorted({0, B // 2, B - 1}):
+        sl = slice(b * H * W, (b + 1) * H * W)
+        x = a0[sl].float().reshape(1, H, W, c0).permute(0, 3, 1, 2)
+        z = F.silu(F.group_norm(F.conv2d(x, w.half().float(), bias, padding=1), 1, gamma, beta, eps=1e-5))
+        z = z + res[sl].float().reshape(1, H, W, cout).permute(0, 3, 1, 2)
+        ref = F.conv2d(z, hw.reshape(co, cout, 1, 1), hb)[0]
+        assert (out[b] - ref).abs().max().item() < 1e-4 * max(1.0, ref.abs().max().item()), b
 
 
 def test_fused_groupnorm_path_matches_unfused_network():
@@ -486,7 +521,9 @@ def test_fused_groupnorm_path_matches_unfused_network():
         net.fuse_groupnorm = False
         b = net(x, t)
     assert torch.isfinite(a).all()
-    assert rel(a, b) < 3e-4, rel(a, b)
+    # the fused kernels normalise fp32 accumulators where the separate ones read their fp16 rounding: the two paths differ by
+    # about one rounding site per GroupNorm of the level (both are within 7e-4 of the fp32 reference, test_unet_eps_*)
+    assert rel(a, b) < 8e-4, rel(a, b)
 
 
 @pytest.mark.parametrize("res_half", [True, False])
