@@ -25,10 +25,10 @@ ModelPrediction = namedtuple('ModelPrediction', ['pred_noise', 'pred_x_start'])
 
 SAMPLER_DDIM, SAMPLER_DDPM = 0, 1
 _INIT_TAG = 0x7FFFFFFF  # RNG tag of the initial x_T draw
-# Chains of at most this many samples replay ONE captured CUDA graph per reverse step (below ~256 samples the ~150 launches
-# of a step cost more host time than device time; above it the chain is device-bound and eager launches keep the
-# activation pool shared).  SDC_GRAPH_MAX_BATCH=0 disables graphs.
-GRAPH_MAX_BATCH = int(os.environ.get("SDC_GRAPH_MAX_BATCH", "256"))
+# Chains replay ONE captured CUDA graph per reverse step (the C++ executor keeps every activation in a workspace, so a step is
+# capturable at any batch size; below ~256 samples the ~125 launches of a step cost more host time than device time).
+# SDC_GRAPH_MAX_BATCH=0 disables graphs, a positive value restricts them to batches up to that size.
+GRAPH_MAX_BATCH = int(os.environ.get("SDC_GRAPH_MAX_BATCH", str(1 << 30)))
 GRAPH_CACHE_ENTRIES = 4
 
 
@@ -298,17 +298,24 @@ class GaussianDiffusion(nn.Module):
         serves every step of every chain with this shape, sampler and guidance."""
         B, C, H, W = shape
         device = self.betas.device
-        pk = self.model._packed()
-        self.model._film_table(pk)
+        # the denoiser's weights are (re)packed here, IN PLACE when they changed: every chain passes through this call
+        plan = self.model._plan_ready() if hasattr(self.model, "_plan_ready") else None
+        if plan is not None:
+            wkey, pk = ("plan", id(plan), plan.prec), None
+        else:
+            pk = self.model._packed()
+            self.model._film_table(pk)
+            wkey = ("pack", id(pk), pk.get("table_gen", 0), pk["prec"])
         gkey = None if gstruct is None else tuple(getattr(gstruct, f) for f, _ in gstruct._fields_)
-        key = (id(self.model), id(pk), pk.get("table_gen", 0), pk["prec"], shape, sampler, tuple(rows), gkey, tuple(c is not None for c in conds), has_noise,
+        key = (id(self.model), wkey, shape, sampler, tuple(rows), gkey, tuple(c is not None for c in conds), has_noise,
                self.condition_idx, bool(self.train_on_padded_locations), bool(clip_denoised))
         cache = self._graphs.entries
         if key in cache:
             cache.move_to_end(key)
             return cache[key]
         lib = L.lib()
-        e = types.SimpleNamespace(pk=pk, table=table, n_steps=len(rows))
+        e = types.SimpleNamespace(pk=pk, plan=plan, table=table, n_steps=len(rows))
+        e.ws = plan.workspace(B, H, W, device) if plan is not None else None   # the captured launches keep their workspace alive
         e.img = torch.zeros(shape, device=device)
         e.t_index = torch.zeros(B, dtype=torch.int32, device=device)
         e.state = torch.zeros(ctypes.sizeof(L.ChainState), dtype=torch.uint8, device=device)
@@ -319,7 +326,8 @@ class GaussianDiffusion(nn.Module):
         pad = int(not self.train_on_padded_locations)
 
         def one_step():
-            eps = self.model.denoise_indexed(e.img, e.t_index)
+            eps = self.model.denoise_indexed(e.img, e.t_index, workspace=e.ws) if e.ws is not None else \
+                self.model.denoise_indexed(e.img, e.t_index)
             L.check(lib.sdc_reverse_step_state(
                 sampler, L.ptr(e.img), L.ptr(eps), L.ptr(e.noise), L.ptr(e.img), None, None, L.ptr(table), L.ptr(e.state),
                 ctypes.byref(gstruct) if gstruct is not None else None, None, L.ptr(e.u0), L.ptr(e.uT), L.ptr(e.wg),
@@ -451,6 +459,29 @@ class GaussianDiffusion(nn.Module):
         return device
 
     def _run_chain(self, sampler, shape, w_groundtruth, enable_grad, return_all, kwargs):
+        """One sampling chain with the FP16-range guard: the FP16 executor counts non-finite eps entries on the device; the
+        count is read ONCE after the chain.  If it is non-zero the denoiser switches itself to TF32 operands (same 10-bit
+        mantissa, fp32 range), warns, and the chain is repeated with the same seed / noise -- a checkpoint whose activations
+        leave +-65504 never returns silently corrupted samples.  Non-finite values that survive TF32 are data (the reference
+        would produce them too) and are returned as they are."""
+        net = self.model
+        guard = hasattr(net, "take_nonfinite") and getattr(net, "precision", None) == "f16" and getattr(net, "overflow_fallback", True)
+        if guard:
+            if kwargs.get('noise') is not None and not isinstance(kwargs['noise'], (list, tuple)):
+                kwargs = dict(kwargs, noise=list(kwargs['noise']))   # re-iterable for the repeat
+            if kwargs.get('noise') is None and kwargs.get('seed') is None:
+                kwargs = dict(kwargs, seed=int(torch.randint(0, 2 ** 62, (1,)).item()))   # same stream for the repeat
+            net.take_nonfinite()
+        out = self._run_chain_once(sampler, shape, w_groundtruth, enable_grad, return_all, kwargs)
+        if guard and net.take_nonfinite() > 0:
+            import warnings
+            warnings.warn("safediffcon_b200: the FP16 denoiser produced non-finite values (activations beyond the fp16 range?); "
+                          "switching Unet2D.precision to 'tf32' and repeating the chain", RuntimeWarning)
+            net.precision = "tf32"
+            out = self._run_chain_once(sampler, shape, w_groundtruth, enable_grad, return_all, kwargs)
+        return out
+
+    def _run_chain_once(self, sampler, shape, w_groundtruth, enable_grad, return_all, kwargs):
         device = self._require_cuda()
         if hasattr(self.model, "revalidate_packed"):
             # EMA / optimiser updates written through p.data do not bump version counters: compare the parameter digest once

@@ -27,7 +27,7 @@ def _reduce(J, pts, tms, flg, nt1, s) -> Dict[str, float]:
     return m
 
 
-def calculate_safety_metrics(u: torch.Tensor, threshold: float, diffused_s: torch.Tensor = None,
+def calculate_safety_metrics(u: torch.Tensor, threshold: float, diffused_s: torch.Tensor,
                              use_max_safety: bool = True) -> Dict[str, float]:
     """Exceed ratios of |u| > threshold by point / time row / sample (reference utils/metrics.py:67-94)."""
     _, pts, tms, flg = burgers_score(u, None, threshold)

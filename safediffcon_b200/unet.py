@@ -491,6 +491,8 @@ class Unet2D(nn.Module):
         # epilogue (two TMEM passes, cross-cluster exchange of the statistics, SiLU, stores) does not fit into one MMA period
         # (profiles/r02_row_gn_*.txt).  SDC_FUSE_GN=1 enables it.
         self.fuse_groupnorm = os.environ.get("SDC_FUSE_GN", "0") == "1"
+        # FP16-range guard (GaussianDiffusion._run_chain): on non-finite eps the chain is repeated with TF32 operands
+        self.overflow_fallback = True
 
     # ------------------------------------------------------------------ weight packing / FiLM table
     def _resnet_blocks(self):

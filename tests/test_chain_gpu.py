@@ -208,3 +208,26 @@ def test_sample_contract():
     cpu_gd = s.GaussianDiffusion(fx.FakeEps(), seq_length=(16, 128), sampling_timesteps=4, temporal=True, use_conv2d=True)
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         cpu_gd.sample(batch_size=1)
+
+
+def test_p_mean_variance_matches_p_sample():
+    """p_mean_variance (reference diffusion.py:288-297) on the CUDA denoiser: its mean / log-variance reproduce the fused p_sample
+    step (x_{t-1} = mean + exp(0.5 logvar) z) and its x_start is the clamped prediction p_sample returns."""
+    import safediffcon_b200 as s
+    torch.manual_seed(3)
+    net = s.Unet2D(dim=32, channels=3, resnet_block_groups=1)
+    gd = s.GaussianDiffusion(net, seq_length=(16, 128), timesteps=1000, temporal=True, use_conv2d=True, is_condition_u0=True,
+                             is_condition_uT=True, condition_idx=10, guidance_u0=False).cuda()
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn(3, 3, 16, 128, generator=g).cuda()
+    z = torch.randn(3, 3, 16, 128, generator=g)
+    for t in (999, 400, 1):
+        tb = torch.full((3,), t, device="cuda", dtype=torch.long)
+        with torch.no_grad():
+            mean, var, logvar, x0, eps = gd.p_mean_variance(x, tb, clip_denoised=True)
+            img, x0_s, eps_s = gd.p_sample(x, t, noise=[z], clip_denoised=True)
+        assert var.shape == (3, 1, 1, 1) and torch.allclose(var.log().clamp(min=-46.1), logvar, atol=1e-4)
+        assert x0.abs().max() <= 1.0 and torch.allclose(x0, x0_s, atol=1e-6) and torch.allclose(eps, eps_s, atol=1e-6)
+        assert torch.allclose(img, mean + (0.5 * logvar).exp() * z.cuda(), atol=2e-6)
+    with pytest.raises(KeyError):
+        gd.p_mean_variance(x, tb)   # clip_denoised is a required key, as in the reference

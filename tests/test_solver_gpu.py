@@ -88,7 +88,7 @@ def test_metrics_match_reference_golden(golden):
                 assert list(ref.astype(int)) == m[str(k)]
             else:
                 assert abs(float(ref) - m[str(k)]) <= 2e-6 * max(1.0, abs(float(ref))), k
-    sm = s.calculate_safety_metrics(traj, 0.8)
+    sm = s.calculate_safety_metrics(traj, 0.8, None)
     assert sm['sample_exceed_ratio (R_s)'] == float(g["b08_4"])
 
 

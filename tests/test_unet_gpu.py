@@ -549,3 +549,35 @@ def test_gn_silu_head_vs_torch(res_half):
         ref = (y.double() @ hw_.double().t() + hb_.double()).reshape(B, HW, Cout).permute(0, 2, 1)
         assert torch.isfinite(out).all()
         assert (out.double() - ref).abs().max().item() < 2e-5 * ref.abs().max().item()
+
+
+def test_eps_after_adamw_steps_within_1e3():
+    """Parity away from the seed-42 initialisation: a few AdamW steps on the diffusion loss (CUDA backward) move every weight,
+    bias and norm gain; eps of the updated dim-128 model must still agree with the fp32 oracle within 1e-3, per sample, on both
+    operand precisions (north star; the oracle is pinned bit-exactly to the reference, tests/test_oracle_golden.py)."""
+    import safediffcon_b200 as s
+    torch.manual_seed(42)
+    net = s.Unet2D(dim=128, dim_mults=(1, 2, 4, 8), channels=3, resnet_block_groups=1).cuda()
+    gd = s.GaussianDiffusion(net, seq_length=(16, 128), timesteps=1000, sampling_timesteps=200, temporal=True, use_conv2d=True,
+                             is_condition_u0=True, is_condition_uT=True, condition_idx=10).cuda()
+    before = {k: v.detach().clone() for k, v in net.state_dict().items()}
+    opt = torch.optim.AdamW(net.parameters(), lr=2e-3, weight_decay=0.01)
+    x0 = fx.calibration_states(4).cuda()
+    g = torch.Generator().manual_seed(5)
+    for it in range(3):
+        t = torch.randint(0, 1000, (4,), generator=g).cuda()
+        noise = torch.randn(4, 3, 16, 128, generator=g).cuda()
+        loss = gd.p_losses(x0.clone(), t, noise=noise)
+        opt.zero_grad()
+        loss.backward()
+        opt.step()
+    moved = [((net.state_dict()[k] - v).norm() / (v.norm() + 1e-12)).item() for k, v in before.items()]
+    assert min(moved) > 1e-3 and float(np.median(moved)) > 0.02, (min(moved), float(np.median(moved)))   # every tensor changed, most by > 2 %
+    x, t = fx.unet_inputs(4)
+    with torch.no_grad():
+        ref = unet_ref.unet_forward({k: v.detach().cpu() for k, v in net.state_dict().items()}, x, t)
+        for prec in ("f16", "tf32"):
+            net.precision = prec
+            eps = net(x.cuda(), t.cuda()).cpu()
+            per = [rel(eps[i], ref[i]) for i in range(4)]
+            assert max(per) < 1e-3, (prec, per)
