@@ -55,6 +55,14 @@ int64_t sdc_unet_workspace_bytes(const sdc_unet* net, int B, int H, int W);
 int sdc_unet_forward(sdc_unet* net, const float* x, const int32_t* t_index, int t_uniform, float* eps, int B, int H, int W,
                      void* workspace, int64_t workspace_bytes, uint32_t* nonfinite, void* stream);
 
+/* Schedule switches, both EXPERIMENTAL and off by default (correct -- tests -- but measured slower than the separate kernels on
+ * B200).  SDC_UNET_FUSE_LN: FP16 mode, levels with <= 256 channels -- the PreNorm LayerNorm is folded into the
+ * qkv projection and the output LayerNorm + residual into the per-sample projection (sdc_conv1x1_qkv_ln,
+ * sdc_conv1x1_per_sample_ln).  SDC_UNET_FUSE_GN: conv + GroupNorm in one kernel on the 16x128 level (sdc_conv3x3_row_gn). */
+#define SDC_UNET_FUSE_LN 1
+#define SDC_UNET_FUSE_GN 2
+int sdc_unet_set_flag(sdc_unet* net, int flag, int value);
+
 /* Per-launch profile of the NEXT forward calls: when enabled, every launch is bracketed by CUDA events on `stream` (adds two
  * event records per launch; do not enable inside a graph capture).  After synchronising, read entry i: kernel family name,
  * milliseconds, algorithmic bytes moved (HBM roofline) and FLOPs (tensor roofline) of that launch.  bench.py builds its

@@ -131,6 +131,27 @@ int sdc_linear_attention_fold(int prec, const void* workspace, const float* w_ou
 int sdc_conv1x1_per_sample(int prec, const void* a, int c, const void* w_per_sample, const float* bias, void* out, int operand_out,
                            int B, int H, int W, int Cout, void* stream);
 
+/* PreNorm LayerNorm FOLDED into the qkv projection (FP16 mode; unet.py:65-76 + 189,203): W LN(x) = r (W_g x - mu W_g 1) with
+ * W_g = W diag(g).  Three pieces:
+ *   sdc_gn_silu_rowstats  = sdc_gn_silu(FP16, fp16 x in place, fp16 residual) that also emits rowstats[M][2] = per pixel row
+ *                           (channel mean, 1 / sqrt(var + 1e-5)) of its fp16 OUTPUT (C = 128 or 256);
+ *   sdc_pack_qkv_ln       : w_folded[Cout, Cin] = fp16(w * g), wsum[co] = sum_c float(w_folded[co, c]);
+ *   sdc_conv1x1_qkv_ln    = sdc_conv1x1_qkv on the RAW rows with the folded weights; the epilogue applies r (acc - mu wsum).
+ * The separate LayerNorm pass (one read + one write of the activations) disappears and the normalised rows are never rounded. */
+int sdc_gn_silu_rowstats(const void* x, const double* stats, const float* gamma, const float* beta, const float* scale_shift,
+                         const int32_t* t_index, int64_t ss_stride, const void* residual, void* y, float* rowstats, int B, int HW, int C,
+                         void* stream);
+int sdc_pack_qkv_ln(const float* w, const float* g, void* w_folded, float* wsum, int Cout, int Cin, void* stream);
+int sdc_conv1x1_qkv_ln(const void* a, int c, const void* w_folded, const float* wsum, const float* rowstats, void* q_out, void* kv_out,
+                       int B, int H, int W, int hidden, void* stream);
+
+/* sdc_conv1x1_per_sample (FP16 mode) with LinearAttention's output LayerNorm and the Residual add in its epilogue
+ * (to_out = Conv2d -> LayerNorm, unet.py:190-193, then Residual, :16-22): out = LN(a Wf_b^T + bias) * gain + residual, fp16.
+ * A lane owns an output row in TMEM, so the channel statistics are a per-lane reduction over the accumulator columns (two TMEM
+ * passes, no exchange).  Cout = 128 or 256 (the row must sit in one N tile). */
+int sdc_conv1x1_per_sample_ln(const void* a, int c, const void* w_per_sample, const float* bias, const float* gain, const void* residual,
+                              void* out, int B, int H, int W, int Cout, void* stream);
+
 /* Full softmax attention core (unet.py:239-258) for n <= 32 tokens: out[B*n, 128], an operand. */
 int sdc_attention(int prec, const float* qkv, void* out, int B, int n, void* stream);
 

@@ -63,6 +63,13 @@ struct GemmParams {
                          //      go to a second tensor (map_q, operand precision); columns [q_cols, Cout) go to `out` (fp32, or fp16
                          //      when operand_out is set in FP16 mode: k and v are then read at half the bytes by the context pass)
     int w_sample_rows;   // > 0: per-sample weights -- sample b uses weight rows [b * w_sample_rows, (b + 1) * w_sample_rows)
+    // folded channel LayerNorm of the INPUT rows (PreNorm in front of the qkv projection, unet.py:65-76): the weights were packed as
+    // W * g (sdc_pack_qkv_ln); the epilogue computes r_m * (acc - mu_m * wsum[col]) from per-row (mean, rstd)
+    const float2* ln_rowstats;   // [M] or null
+    const float* ln_wsum;        // [Cout]
+    // channel LayerNorm of the OUTPUT rows + residual (LinearAttention.to_out = conv -> LayerNorm, then Residual, unet.py:190-193,
+    // 16-22): out = LN(acc + bias) * g + residual, fp16; needs the whole row in one N tile (Cout == bn)
+    const float* ln_out_gain;    // [Cout] or null
     const float* bias;       // [Cout] or null
     const void* residual;    // [M, Cout] in the operand precision, or null (added after bias)
     void* out;               // [M, Cout]
@@ -218,14 +225,59 @@ __device__ __forceinline__ void conv_gemm_body(const CUtensorMap& map_a0, const 
             const int m = m_w + lane;
             const bool row_ok = m < p.M;
             float s1 = 0.f, s2 = 0.f;
+            float ln_mu = 0.f, ln_r = 1.f;
+            if (p.ln_rowstats && row_ok) { const float2 rs = __ldg(p.ln_rowstats + m); ln_mu = rs.x; ln_r = rs.y; }
+            if (p.ln_out_gain) {
+                if (m_w < p.M) {
+                    // ---- output LayerNorm: pass 1 over ALL columns of this lane's row (both warps of the quarter, redundantly) ----
+                    const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)buf * acc_cols;
+                    float a1 = 0.f, a2 = 0.f;
+                    for (int c = 0; c < p.bn; c += 32) {
+                        uint32_t r[32];
+                        tmem_ld32(trow + (uint32_t)c, r);
+#pragma unroll
+                        for (int j = 0; j < 32; j += 4) {
+                            const float4 bb = p.bias ? __ldg(reinterpret_cast<const float4*>(p.bias + c + j)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                            const float x0 = __uint_as_float(r[j]) + bb.x, x1 = __uint_as_float(r[j + 1]) + bb.y;
+                            const float x2 = __uint_as_float(r[j + 2]) + bb.z, x3 = __uint_as_float(r[j + 3]) + bb.w;
+                            a1 += (x0 + x1) + (x2 + x3);
+                            a2 = fmaf(x0, x0, a2); a2 = fmaf(x1, x1, a2); a2 = fmaf(x2, x2, a2); a2 = fmaf(x3, x3, a2);
+                        }
+                    }
+                    const float inv_c = 1.0f / (float)p.bn;
+                    const float mean = a1 * inv_c;
+                    const float rstd = rsqrtf(fmaxf(a2 * inv_c - mean * mean, 0.f) + 1e-5f);
+                    // ---- pass 2: this warp's column chunks: normalise, gain, residual, fp16 store ----
+                    for (int c = 32 * half_id; c < p.bn; c += 64) {
+                        uint32_t r[32];
+                        tmem_ld32(trow + (uint32_t)c, r);
+                        float v[32];
+                        const act_t* rrow = resid + (size_t)m * p.Cout + c;
+#pragma unroll
+                        for (int j = 0; j < 32; j += 4) {
+                            const float4 bb = p.bias ? __ldg(reinterpret_cast<const float4*>(p.bias + c + j)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                            const float4 gg = __ldg(reinterpret_cast<const float4*>(p.ln_out_gain + c + j));
+                            const float4 rr = row_ok ? load4_nc(rrow + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+                            v[j] = fmaf((__uint_as_float(r[j]) + bb.x - mean) * rstd, gg.x, rr.x);
+                            v[j + 1] = fmaf((__uint_as_float(r[j + 1]) + bb.y - mean) * rstd, gg.y, rr.y);
+                            v[j + 2] = fmaf((__uint_as_float(r[j + 2]) + bb.z - mean) * rstd, gg.z, rr.z);
+                            v[j + 3] = fmaf((__uint_as_float(r[j + 3]) + bb.w - mean) * rstd, gg.w, rr.w);
+                        }
+                        if (lane == 0) bulk_wait_read<0>();
+                        __syncwarp();
+                        stage_store_half(v, stg, &map_out, c, m_w, lane);
+                    }
+                }
+            } else
             for (int c = 32 * half_id; c < p.bn; c += 64) {
                 const int col = nt * p.bn + c;
                 const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)buf * acc_cols + (uint32_t)c;
                 const act_t* rrow = resid ? resid + (size_t)m * p.Cout + col : nullptr;
+                const float* lw = p.ln_rowstats ? p.ln_wsum + col : nullptr;
                 if (m_w < p.M) {
-                    if (col < p.q_cols) epilogue_chunk_qsoftmax<HALF>(taddr, stg, &map_q, col, m_w, lane, true);
-                    else if (out_half) epilogue_chunk<true, act_t>(taddr, stg, &map_out, col - p.q_cols, m_w, row_ok, p.bias, rrow, false, s1, s2, lane, up, p.W, true, p.stats != nullptr);
-                    else epilogue_chunk<false, act_t>(taddr, stg, &map_out, col - p.q_cols, m_w, row_ok, p.bias, rrow, p.operand_out != 0, s1, s2, lane, up, p.W, true, p.stats != nullptr);
+                    if (col < p.q_cols) epilogue_chunk_qsoftmax<HALF>(taddr, stg, &map_q, col, m_w, lane, true, lw, ln_mu, ln_r);
+                    else if (out_half) epilogue_chunk<true, act_t>(taddr, stg, &map_out, col - p.q_cols, m_w, row_ok, p.bias, rrow, false, s1, s2, lane, up, p.W, true, p.stats != nullptr, lw, ln_mu, ln_r);
+                    else epilogue_chunk<false, act_t>(taddr, stg, &map_out, col - p.q_cols, m_w, row_ok, p.bias, rrow, p.operand_out != 0, s1, s2, lane, up, p.W, true, p.stats != nullptr, lw, ln_mu, ln_r);
                 }
             }
             // accumulator buffer fully read -> hand it back to the MMA warp
@@ -293,9 +345,11 @@ static int encode_act(CUtensorMap* map, const void* a, int kind, int B, int H, i
 
 using namespace sdc;
 
+struct GemmLn { const float* rowstats = nullptr; const float* wsum = nullptr; const float* out_gain = nullptr; };
+
 static int conv_gemm_launch(int prec, int kind, const void* a0, int c0, const void* a1, int c1, const void* w_packed,
                             const float* bias, const void* residual, void* out, double* stats, int operand_out, int B, int H,
-                            int W, int Cout, void* q_out, int q_cols, int per_sample_weights, void* stream) {
+                            int W, int Cout, void* q_out, int q_cols, int per_sample_weights, void* stream, const GemmLn* ln = nullptr) {
     SDC_REQUIRE(prec == SDC_PREC_TF32 || prec == SDC_PREC_F16, "conv_gemm: precision %d", prec);
     const bool half = prec == SDC_PREC_F16;
     const int BK = half ? 64 : 32;
@@ -323,6 +377,12 @@ static int conv_gemm_launch(int prec, int kind, const void* a0, int c0, const vo
     p.kind = kind; p.M = B * H * W; p.Cout = Cout; p.bn = bn; p.H = H; p.W = W; p.bh = bh; p.bb = bb;
     p.c0 = c0; p.c1 = c1; p.operand_out = operand_out; p.hw_per_sample = H * W;
     p.bias = bias; p.residual = residual; p.out = out; p.stats = stats;
+    if (ln) {
+        p.ln_rowstats = (const float2*)ln->rowstats; p.ln_wsum = ln->wsum; p.ln_out_gain = ln->out_gain;
+        SDC_REQUIRE(!ln->rowstats || ln->wsum, "conv_gemm: folded input LayerNorm needs the weight row sums");
+        SDC_REQUIRE(!ln->out_gain || (half && operand_out && residual && Cout == bn && !stats && !q_cols && kind == 0),
+                    "conv_gemm: the fused output LayerNorm needs FP16 mode, an fp16 output, a residual and Cout (%d) in one N tile (128 or 256)", Cout);
+    }
     int n_sm = 148;
     {
         int dev = 0;
@@ -409,6 +469,23 @@ extern "C" int sdc_conv1x1_qkv(int prec, const void* a, int c, const void* w_pac
     SDC_REQUIRE(!kv_operand || prec == SDC_PREC_F16, "conv1x1_qkv: an operand-precision kv tensor exists only in FP16 mode");
     return conv_gemm_launch(prec, 0, a, c, nullptr, 0, w_packed, nullptr, nullptr, kv_out, nullptr, kv_operand ? 1 : 0, B, H, W, 3 * hidden,
                             q_out, hidden, 0, stream);
+}
+
+extern "C" int sdc_conv1x1_qkv_ln(const void* a, int c, const void* w_folded, const float* wsum, const float* rowstats, void* q_out, void* kv_out,
+                                  int B, int H, int W, int hidden, void* stream) {
+    SDC_REQUIRE(hidden > 0 && hidden % 32 == 0 && q_out && kv_out && wsum && rowstats, "conv1x1_qkv_ln: bad arguments");
+    GemmLn ln;
+    ln.rowstats = rowstats; ln.wsum = wsum;
+    return conv_gemm_launch(SDC_PREC_F16, 0, a, c, nullptr, 0, w_folded, nullptr, nullptr, kv_out, nullptr, 1, B, H, W, 3 * hidden, q_out, hidden, 0,
+                            stream, &ln);
+}
+
+extern "C" int sdc_conv1x1_per_sample_ln(const void* a, int c, const void* w_per_sample, const float* bias, const float* gain, const void* residual,
+                                         void* out, int B, int H, int W, int Cout, void* stream) {
+    SDC_REQUIRE(gain && residual, "conv1x1_per_sample_ln: null gain / residual");
+    GemmLn ln;
+    ln.out_gain = gain;
+    return conv_gemm_launch(SDC_PREC_F16, 0, a, c, nullptr, 0, w_per_sample, bias, residual, out, nullptr, 1, B, H, W, Cout, nullptr, 0, 1, stream, &ln);
 }
 
 extern "C" int sdc_conv1x1_per_sample(int prec, const void* a, int c, const void* w_per_sample, const float* bias, void* out,

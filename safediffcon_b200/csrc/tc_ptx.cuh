@@ -152,12 +152,23 @@ template <bool OUT_HALF, typename res_t>
 __device__ __forceinline__ void epilogue_chunk(uint32_t taddr, uint32_t stg, const CUtensorMap* map_out, int col, int row0,
                                                bool row_ok, const float* __restrict__ bias, const res_t* __restrict__ res_row,
                                                bool round, float& s1, float& s2, int lane, int up_phase = -1, int up_w = 0,
-                                               bool wait_stg = false, bool want_stats = true) {
+                                               bool wait_stg = false, bool want_stats = true, const float* __restrict__ ln_wsum = nullptr,
+                                               float ln_mu = 0.f, float ln_r = 1.f) {
     uint32_t r[32];
     tmem_ld32(taddr, r);
     float v[32];
 #pragma unroll
     for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+    if (ln_wsum) {
+        // folded channel LayerNorm of the INPUT row: W (x - mu) r = r (W x - mu * sum_c W[., c]); ln_wsum points at this chunk's columns
+        const float nmr = -ln_mu * ln_r;
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+            const float4 w = __ldg(reinterpret_cast<const float4*>(ln_wsum + j));
+            v[j] = fmaf(nmr, w.x, ln_r * v[j]); v[j + 1] = fmaf(nmr, w.y, ln_r * v[j + 1]);
+            v[j + 2] = fmaf(nmr, w.z, ln_r * v[j + 2]); v[j + 3] = fmaf(nmr, w.w, ln_r * v[j + 3]);
+        }
+    }
     if (bias) {
 #pragma unroll
         for (int j = 0; j < 32; j += 4) {
@@ -247,13 +258,25 @@ __device__ __forceinline__ void stage_store_half(const float (&v)[32], uint32_t 
 // registers and stored in the operand precision (it is the A operand of the folded output projection).
 template <bool OUT_HALF>
 __device__ __forceinline__ void epilogue_chunk_qsoftmax(uint32_t taddr, uint32_t stg, const CUtensorMap* map_q, int col, int row0,
-                                                        int lane, bool wait_stg = false) {
+                                                        int lane, bool wait_stg = false, const float* __restrict__ ln_wsum = nullptr,
+                                                        float ln_mu = 0.f, float ln_r = 1.f) {
     uint32_t r[32];
     tmem_ld32(taddr, r);
     float v[32];
-    float mx = __uint_as_float(r[0]);
 #pragma unroll
-    for (int j = 0; j < 32; ++j) { v[j] = __uint_as_float(r[j]); mx = fmaxf(mx, v[j]); }
+    for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+    if (ln_wsum) {   // folded LayerNorm of the input row (see epilogue_chunk)
+        const float nmr = -ln_mu * ln_r;
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+            const float4 w = __ldg(reinterpret_cast<const float4*>(ln_wsum + j));
+            v[j] = fmaf(nmr, w.x, ln_r * v[j]); v[j + 1] = fmaf(nmr, w.y, ln_r * v[j + 1]);
+            v[j + 2] = fmaf(nmr, w.z, ln_r * v[j + 2]); v[j + 3] = fmaf(nmr, w.w, ln_r * v[j + 3]);
+        }
+    }
+    float mx = v[0];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) mx = fmaxf(mx, v[j]);
     float den = 0.f;
     // ex2.approx (2 ulp) on arguments <= 0: far inside the 2^-11 rounding of the fp16 / tf32 store below
 #pragma unroll

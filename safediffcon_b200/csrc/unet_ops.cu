@@ -5,6 +5,7 @@
 #include "common.cuh"
 #include "../../include/safediffcon_b200_unet.h"
 #include <math.h>
+#include <stdlib.h>
 
 namespace sdc {
 
@@ -273,11 +274,32 @@ __device__ __forceinline__ uint4 pack8(const float* f) {
     for (int k = 0; k < 4; ++k) h[k] = __floats2half2_rn(f[2 * k], f[2 * k + 1]);
     return u;
 }
+// channel mean / rstd of one pixel row held as 8 fp16 values per lane by c8n (16 or 32) adjacent lanes; vector index i = row * c8n + lane.
+// Same two-pass arithmetic as channel_layernorm_h_kernel on the same (rounded) values; the whole warp takes part.
+__device__ __forceinline__ void row_stats8(const uint4& o, int c8n, int C, float2* __restrict__ rs, int i) {
+    float v[8];
+    unpack8(o, v);
+    float sm = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) sm += v[k];
+    for (int m = 1; m < c8n; m <<= 1) sm += __shfl_xor_sync(0xffffffffu, sm, m);
+    const float mean = sm * (1.0f / (float)C);
+    float q = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { const float d = v[k] - mean; q = fmaf(d, d, q); }
+    for (int m = 1; m < c8n; m <<= 1) q += __shfl_xor_sync(0xffffffffu, q, m);
+    if (i % c8n == 0) rs[i / c8n] = make_float2(mean, rsqrtf(q * (1.0f / (float)C) + 1e-5f));
+}
+
+// ROWSTATS: additionally emit, per pixel row of the (fp16-rounded) OUTPUT, the channel mean and 1 / sqrt(var + 1e-5) of the channel
+// LayerNorm that follows in PreNorm(LinearAttention) (unet.py:53-63,65-76): the LayerNorm itself is then folded into the qkv
+// projection (sdc_conv1x1_qkv_ln) and its separate pass over HBM disappears.  A row is owned by C/8 = 16 or 32 adjacent lanes.
+template <bool ROWSTATS>
 __global__ void __launch_bounds__(256) gn_silu_h8_kernel(const __half* __restrict__ x, const double* __restrict__ stats,
                                                          const float* __restrict__ gamma, const float* __restrict__ beta,
                                                          const float* __restrict__ scale_shift, const int32_t* __restrict__ t_index,
                                                          int64_t ss_stride, const __half* __restrict__ residual, __half* __restrict__ y,
-                                                         int HW, int C, int pix_per_cta) {
+                                                         int HW, int C, int pix_per_cta, float2* __restrict__ rowstats) {
     const int b = blockIdx.x;
     const double cnt = (double)HW * (double)C;
     const double mean_d = stats[2 * b] / cnt;
@@ -325,7 +347,9 @@ __global__ void __launch_bounds__(256) gn_silu_h8_kernel(const __half* __restric
                 f[k] = silu_fast(fmaf(f[k], A[k], Bc[k]));
                 if (r8) f[k] += rf[k];
             }
-            y8[i + u * 256] = pack8(f);
+            const uint4 o = pack8(f);
+            y8[i + u * 256] = o;
+            if constexpr (ROWSTATS) row_stats8(o, c8n, C, rowstats + row0, i + u * 256);
         }
     }
     for (; i < total; i += 256) {
@@ -337,7 +361,9 @@ __global__ void __launch_bounds__(256) gn_silu_h8_kernel(const __half* __restric
             f[k] = silu_fast(fmaf(f[k], A[k], Bc[k]));
             if (r8) f[k] += rf[k];
         }
-        y8[i] = pack8(f);
+        const uint4 o = pack8(f);
+        y8[i] = o;
+        if constexpr (ROWSTATS) row_stats8(o, c8n, C, rowstats + row0, i);
     }
 }
 
@@ -1001,6 +1027,73 @@ __global__ void __launch_bounds__(256) linattn_fold_kernel(const float* __restri
     }
 }
 
+// FP16-mode fold on tensor cores: per (sample, head) D[C x 32] = W[:, 32h : 32h + 32] (C x 32) . ctx_{b,h}^T (32 x 32) with
+// mma.sync.m16n8k16, both operands split into fp16 high + low parts (hi*hi + hi*lo + lo*hi: ~2^-21 relative, the accuracy of the
+// fp32 CUDA-core version above, whose 16-channel slabs with two block barriers each made it latency bound: 0.56 ms per step for
+// 6 GFMA).  CTA = (sample, 128 output channels), 8 warps x 16 rows; the sample's four contexts sit in shared memory.
+__device__ __forceinline__ void split_half2(float x, float y, uint32_t& hi, uint32_t& lo) {
+    const __half2 h = __floats2half2_rn(x, y);
+    const float2 hf = __half22float2(h);
+    const __half2 l = __floats2half2_rn(x - hf.x, y - hf.y);
+    hi = *reinterpret_cast<const uint32_t*>(&h);
+    lo = *reinterpret_cast<const uint32_t*>(&l);
+}
+__device__ __forceinline__ void mma16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3]) : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__global__ void __launch_bounds__(256) linattn_fold_mma_kernel(const float* __restrict__ ws, const float* __restrict__ w_out,
+                                                               __half* __restrict__ wf, int Cout) {
+    __shared__ float cs[LA_HEADS][LA_D][LA_D + 8];   // ctx[h][d][e]; rows padded to 40 floats: 8-byte aligned, conflict-free b-fragment reads
+    const int b = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int i = threadIdx.x; i < LA_HEADS * LA_D * LA_D; i += 256)
+        cs[i >> 10][(i >> 5) & 31][i & 31] = ws[((int64_t)b * LA_HEADS + (i >> 10)) * LA_CTX + (i & 1023)];
+    __syncthreads();
+    const int row0 = blockIdx.y * 128 + warp * 16;
+    if (row0 >= Cout) return;
+    const int g = lane >> 2, t4 = lane & 3;
+    const float* wr0 = w_out + (int64_t)(row0 + g) * LA_HID;
+    const float* wr1 = wr0 + 8 * LA_HID;
+    __half* o0 = wf + ((int64_t)b * Cout + row0 + g) * LA_HID;
+    __half* o1 = o0 + 8 * LA_HID;
+#pragma unroll 1
+    for (int h = 0; h < LA_HEADS; ++h) {
+        float d[4][4];
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) { d[nt][0] = d[nt][1] = d[nt][2] = d[nt][3] = 0.f; }
+#pragma unroll
+        for (int ks = 0; ks < 2; ++ks) {
+            // A fragment (W rows g, g + 8; k = e): a0 = (g, 2t..2t+1), a1 = (g+8, 2t..), a2 = (g, 2t+8..), a3 = (g+8, 2t+8..)
+            const int e0 = h * LA_D + ks * 16 + 2 * t4;
+            const float2 w00 = __ldg(reinterpret_cast<const float2*>(wr0 + e0)), w10 = __ldg(reinterpret_cast<const float2*>(wr1 + e0));
+            const float2 w01 = __ldg(reinterpret_cast<const float2*>(wr0 + e0 + 8)), w11 = __ldg(reinterpret_cast<const float2*>(wr1 + e0 + 8));
+            uint32_t ah[4], al[4];
+            split_half2(w00.x, w00.y, ah[0], al[0]);
+            split_half2(w10.x, w10.y, ah[1], al[1]);
+            split_half2(w01.x, w01.y, ah[2], al[2]);
+            split_half2(w11.x, w11.y, ah[3], al[3]);
+#pragma unroll
+            for (int nt = 0; nt < 4; ++nt) {
+                // B fragment (k = e, n = d): b0 = (k 2t..2t+1, n g), b1 = (k 2t+8.., n g); B[k][n] = ctx[d = n][e = k]
+                const float* cr = &cs[h][nt * 8 + g][ks * 16 + 2 * t4];
+                const float2 c0 = *reinterpret_cast<const float2*>(cr), c1 = *reinterpret_cast<const float2*>(cr + 8);
+                uint32_t bh0, bl0, bh1, bl1;
+                split_half2(c0.x, c0.y, bh0, bl0);
+                split_half2(c1.x, c1.y, bh1, bl1);
+                mma16816(d[nt], al, bh0, bh1);
+                mma16816(d[nt], ah, bl0, bl1);
+                mma16816(d[nt], ah, bh0, bh1);
+            }
+        }
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) {
+            const int col = h * LA_D + nt * 8 + 2 * t4;
+            *reinterpret_cast<__half2*>(o0 + col) = __floats2half2_rn(d[nt][0], d[nt][1]);
+            *reinterpret_cast<__half2*>(o1 + col) = __floats2half2_rn(d[nt][2], d[nt][3]);
+        }
+    }
+}
+
 // full softmax attention for n <= 32 tokens: one warp per (b, head), lane = query token
 template <typename T>
 __global__ void __launch_bounds__(128) attention_kernel(const float* __restrict__ qkv, T* __restrict__ out, int n) {
@@ -1259,8 +1352,8 @@ extern "C" int sdc_gn_silu(int prec, const void* xv, int x_operand, const double
     const size_t sm = 2 * C * sizeof(float);
     cudaStream_t st = as_stream(stream);
     if (x_operand) {
-        gn_silu_h8_kernel<<<grid, 256, 0, st>>>((const __half*)xv, stats, gamma, beta, scale_shift, t_index, ss_stride,
-                                                (const __half*)residual, (__half*)y, HW, C, ppc);
+        gn_silu_h8_kernel<false><<<grid, 256, 0, st>>>((const __half*)xv, stats, gamma, beta, scale_shift, t_index, ss_stride,
+                                                       (const __half*)residual, (__half*)y, HW, C, ppc, nullptr);
     } else if (prec == SDC_PREC_F16) {
         if (residual_operand)
             gn_silu_kernel<__half, __half><<<grid, 256, sm, st>>>(x, stats, gamma, beta, scale_shift, t_index, ss_stride,
@@ -1272,6 +1365,46 @@ extern "C" int sdc_gn_silu(int prec, const void* xv, int x_operand, const double
         gn_silu_kernel<float, float><<<grid, 256, sm, st>>>(x, stats, gamma, beta, scale_shift, t_index, ss_stride,
                                                              (const float*)residual, (float*)y, HW, C, ppc);
     }
+    SDC_LAUNCHED();
+    return SDC_OK;
+}
+
+extern "C" int sdc_gn_silu_rowstats(const void* x, const double* stats, const float* gamma, const float* beta, const float* scale_shift,
+                                    const int32_t* t_index, int64_t ss_stride, const void* residual, void* y, float* rowstats, int B,
+                                    int HW, int C, void* stream) {
+    SDC_REQUIRE(x && stats && gamma && beta && y && rowstats && B > 0 && HW > 0, "gn_silu_rowstats: bad arguments");
+    SDC_REQUIRE((C == 128 || C == 256) && HW % 32 == 0, "gn_silu_rowstats: C=%d HW=%d unsupported (C = 128 or 256: a pixel row inside one warp; HW %% 32 == 0)", C, HW);
+    int ppc = HW;
+    while (ppc > 32 && (int64_t)B * (HW / ppc) < 2 * 148 && ppc % 2 == 0) ppc /= 2;
+    while ((int64_t)B * (HW / ppc) < 8 * 3 * 148 && ppc % 64 == 0 && (int64_t)(ppc / 2) * C >= 65536) ppc /= 2;
+    dim3 grid((unsigned)B, (unsigned)((HW + ppc - 1) / ppc));
+    gn_silu_h8_kernel<true><<<grid, 256, 0, as_stream(stream)>>>((const __half*)x, stats, gamma, beta, scale_shift, t_index, ss_stride,
+                                                                  (const __half*)residual, (__half*)y, HW, C, ppc, (float2*)rowstats);
+    SDC_LAUNCHED();
+    return SDC_OK;
+}
+
+namespace sdc {
+// one warp per output row: Wg[co, c] = fp16(W[co, c] * g[c]); wsum[co] = sum_c float(Wg[co, c]) (the ROUNDED weights, so that
+// r * (acc - mu * wsum) equals the projection of the normalised row exactly in terms of what the tensor core multiplies)
+__global__ void pack_qkv_ln_kernel(const float* __restrict__ w, const float* __restrict__ g, __half* __restrict__ wp, float* __restrict__ wsum,
+                                   int Cout, int Cin) {
+    const int co = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (co >= Cout) return;
+    float s = 0.f;
+    for (int c = lane; c < Cin; c += 32) {
+        const __half h = __float2half_rn(w[(int64_t)co * Cin + c] * g[c]);
+        wp[(int64_t)co * Cin + c] = h;
+        s += __half2float(h);
+    }
+    s = warp_sum(s);
+    if (lane == 0) wsum[co] = s;
+}
+}  // namespace sdc
+
+extern "C" int sdc_pack_qkv_ln(const float* w, const float* g, void* w_packed, float* wsum, int Cout, int Cin, void* stream) {
+    SDC_REQUIRE(w && g && w_packed && wsum && Cout > 0 && Cin > 0, "pack_qkv_ln: bad arguments");
+    pack_qkv_ln_kernel<<<(Cout + 7) / 8, 256, 0, as_stream(stream)>>>(w, g, (__half*)w_packed, wsum, Cout, Cin);
     SDC_LAUNCHED();
     return SDC_OK;
 }
@@ -1385,7 +1518,11 @@ extern "C" int sdc_linear_attention_fold(int prec, const void* workspace, const 
     SDC_CHECK_PREC("linear_attention_fold");
     SDC_REQUIRE(workspace && w_out && w_folded && B > 0 && Cout > 0 && Cout % 16 == 0, "linear_attention_fold: Cout %% 16 != 0 or null pointer");
     const unsigned grid = (unsigned)B;
-    if (prec == SDC_PREC_F16)
+    static const bool use_mma = []() { const char* e = getenv("SDC_FOLD_MMA"); return !(e && e[0] == '0'); }();
+    if (prec == SDC_PREC_F16 && use_mma)
+        linattn_fold_mma_kernel<<<dim3(grid, (unsigned)((Cout + 127) / 128)), 256, 0, as_stream(stream)>>>(
+            reinterpret_cast<const float*>(workspace), w_out, (__half*)w_folded, Cout);
+    else if (prec == SDC_PREC_F16)
         linattn_fold_kernel<__half><<<grid, 256, 0, as_stream(stream)>>>(reinterpret_cast<const float*>(workspace), w_out, (__half*)w_folded, Cout);
     else
         linattn_fold_kernel<float><<<grid, 256, 0, as_stream(stream)>>>(reinterpret_cast<const float*>(workspace), w_out, (float*)w_folded, Cout);

@@ -49,6 +49,8 @@ struct AttnP {
     int g_in_i = -1, g_out_i = -1, dim = 0;
     bool full = false;
     float *g_in = nullptr, *g_out = nullptr, *out_w32 = nullptr;
+    void* qkv_ln = nullptr;      // FP16, dim <= 256: qkv weight with the PreNorm gain folded in (sdc_pack_qkv_ln)
+    float* qkv_wsum = nullptr;   // its row sums
     std::string name;
 };
 struct LevelP { BlockP b1, b2; AttnP attn; ConvP resample; bool resamples = false; };
@@ -122,6 +124,7 @@ struct sdc_unet {
     float *film_w = nullptr, *film_b = nullptr, *table = nullptr, *t_arange = nullptr, *emb = nullptr, *th1 = nullptr, *th2 = nullptr;
     float *tw1 = nullptr, *tb1 = nullptr, *tw2 = nullptr, *tb2 = nullptr, *stem_rep = nullptr;
     bool packed = false;
+    bool fuse_ln = false, fuse_gn = false;   // both measured slower than the separate kernels on B200
     // profile
     bool prof_on = false;
     std::vector<ProfEntry> prof;
@@ -198,6 +201,10 @@ void build_attn(sdc_unet* n, AttnP& a, const std::string& name, int dim, bool fu
     }
     a.g_in_i = add_param(n, name + ".fn.norm.g", dim);
     want(n, (void**)&a.g_in, dim * 4);
+    if (!full && n->prec == SDC_PREC_F16 && dim <= 256) {
+        want(n, &a.qkv_ln, (int64_t)3 * HID * dim * 2);
+        want(n, (void**)&a.qkv_wsum, 3 * HID * 4);
+    }
 }
 
 #define PLAN_CUDA(expr)                                                                      \
@@ -300,13 +307,14 @@ void conv(Fwd& f, int kind, const void* a0, int c0, const void* a1, int c1, cons
 
 // EXPERIMENTAL (SDC_FUSE_GN=1): conv + GroupNorm in one kernel on the 16x128 level -- correct but slower on B200 (see conv_row.cu)
 bool gn_fusable(const Fwd& f, const BlockP& p, int c0, int c1, int h, int w) {
-    static const bool on = []() { const char* e = getenv("SDC_FUSE_GN"); return e && e[0] == '1'; }();
-    return on && f.f16 && w == 128 && h % 4 == 0 && h <= 16 && p.cout <= 128 && p.cout % 32 == 0 && c0 % 64 == 0 && c1 % 64 == 0;
+    return f.n->fuse_gn && f.f16 && w == 128 && h % 4 == 0 && h <= 16 && p.cout <= 128 && p.cout % 32 == 0 && c0 % 64 == 0 && c1 % 64 == 0;
 }
 
 // ResnetBlock (unet.py:166-180) on one or two concatenated NHWC inputs -> operand [B*h*w, cout] (nullptr when `head_out`
 // is given: the block is the network's last one and writes eps[B, out_dim, H, W] directly)
-void* resnet(Fwd& f, const BlockP& p, const void* a0, int c0, const void* a1, int c1, int h, int w, float* head_out = nullptr) {
+// rowstats (FP16 compact path only): the block's last GroupNorm apply also emits per-row LayerNorm statistics of its output
+void* resnet(Fwd& f, const BlockP& p, const void* a0, int c0, const void* a1, int c1, int h, int w, float* head_out = nullptr,
+             float* rowstats = nullptr) {
     sdc_unet* n = f.n;
     Range r(f, p.name);
     const int64_t M = (int64_t)f.B * h * w, HW = (int64_t)h * w;
@@ -391,8 +399,12 @@ void* resnet(Fwd& f, const BlockP& p, const void* a0, int c0, const void* a1, in
             f.release(raw2);
             return nullptr;
         }
-        RUN("gn_silu", (double)M * cout * 3.0 * e, 0.0,
-            sdc_gn_silu(f.prec, raw2, 1, s2, p.g2[0], p.g2[1], nullptr, nullptr, 0, res, 1, raw2, f.B, (int)HW, cout, f.stream));
+        if (rowstats)
+            RUN("gn_silu", (double)M * cout * 3.0 * e, 0.0,
+                sdc_gn_silu_rowstats(raw2, s2, p.g2[0], p.g2[1], nullptr, nullptr, 0, res, raw2, rowstats, f.B, (int)HW, cout, f.stream));
+        else
+            RUN("gn_silu", (double)M * cout * 3.0 * e, 0.0,
+                sdc_gn_silu(f.prec, raw2, 1, s2, p.g2[0], p.g2[1], nullptr, nullptr, 0, res, 1, raw2, f.B, (int)HW, cout, f.stream));
         f.release(raw);
         return raw2;
     }
@@ -423,11 +435,34 @@ void* resnet(Fwd& f, const BlockP& p, const void* a0, int c0, const void* a1, in
 }
 
 // Residual(PreNorm(LinearAttention | Attention)) (unet.py:16-22,65-76,182-258); returns a new operand [B*h*w, c]
-void* attention(Fwd& f, const AttnP& p, const void* xin, int c, int h, int w) {
+bool ln_fusable(const Fwd& f, const AttnP& p, int h, int w) {
+    return f.n->fuse_ln && f.f16 && !p.full && p.qkv_ln && (h * w) % 128 == 0 && (p.dim == 128 || p.dim == 256) && !f.n->fuse_gn;
+}
+
+void* attention(Fwd& f, const AttnP& p, const void* xin, int c, int h, int w, const float* rowstats = nullptr) {
     Range r(f, p.name);
     const int64_t M = (int64_t)f.B * h * w;
     const int n = h * w;
     const double e = (double)f.esz;
+    if (rowstats) {
+        // FP16, <= 256 channels: both LayerNorms live in the convolution epilogues (see safediffcon_b200_unet.h)
+        void* qs = f.opd(M, HID);
+        void* kv = f.opd(M, 2 * HID);
+        RUN("conv1x1_qkv", (double)M * (c + 3.0 * HID) * e + (double)M * 8.0, 2.0 * M * 3.0 * HID * c,
+            sdc_conv1x1_qkv_ln(xin, c, p.qkv_ln, p.qkv_wsum, rowstats, qs, kv, f.B, h, w, HID, f.stream));
+        void* ws = f.alloc(sdc_linear_attention_workspace(f.B));
+        RUN("linattn_context", (double)M * 2.0 * HID * e, 2.0 * M * HID * 32.0,
+            sdc_linear_attention_context(kv, (const uint8_t*)kv + HID * f.esz, 2 * HID, 1, ws, f.B, n, f.stream));
+        f.release(kv);
+        void* wf = f.opd((int64_t)f.B * c, HID);
+        RUN("linattn_fold", (double)f.B * c * HID * e, 2.0 * f.B * c * HID * 32.0,
+            sdc_linear_attention_fold(f.prec, ws, p.out_w32, wf, f.B, c, f.stream));
+        void* out = f.opd(M, c);
+        RUN("conv1x1_per_sample_ln", (double)M * (HID + 2.0 * c) * e + (double)f.B * c * HID * e, 2.0 * M * c * HID,
+            sdc_conv1x1_per_sample_ln(qs, HID, wf, p.out.bias, p.g_out, xin, out, f.B, h, w, c, f.stream));
+        f.release(qs); f.release(ws); f.release(wf);
+        return out;
+    }
     void* xn = f.opd(M, c);
     RUN("layernorm", (double)M * c * 2.0 * e, 0.0, sdc_channel_layernorm(f.prec, xin, 1, p.g_in, nullptr, xn, M, c, 1, f.stream));
     if (!p.full && n % 128 == 0) {
@@ -499,9 +534,11 @@ int run_forward(sdc_unet* n, Fwd& f, const float* x, float* eps, int H, int W, u
         void* a = resnet(f, L.b1, cur, c, nullptr, 0, h, w);
         if (cur != r0) f.release(cur);
         skips.push_back({a, c});
-        void* b = resnet(f, L.b2, a, c, nullptr, 0, h, w);
-        void* at = attention(f, L.attn, b, c, h, w);
+        float* rs = (ln_fusable(f, L.attn, h, w) && !gn_fusable(f, L.b2, c, 0, h, w)) ? (float*)f.alloc((int64_t)B * h * w * 8) : nullptr;
+        void* b = resnet(f, L.b2, a, c, nullptr, 0, h, w, nullptr, rs);
+        void* at = attention(f, L.attn, b, c, h, w, rs);
         f.release(b);
+        f.release(rs);
         skips.push_back({at, c});
         const int cout = L.resample.cout;
         Range r(f, "downs." + std::to_string(li) + ".3");
@@ -527,11 +564,13 @@ int run_forward(sdc_unet* n, Fwd& f, const float* x, float* eps, int H, int W, u
         f.release(s.first);
         c = L.b1.cout;
         s = skips.back(); skips.pop_back();
-        void* b = resnet(f, L.b2, a, c, s.first, s.second, h, w);
+        float* rs = (ln_fusable(f, L.attn, h, w) && !gn_fusable(f, L.b2, c, s.second, h, w)) ? (float*)f.alloc((int64_t)B * h * w * 8) : nullptr;
+        void* b = resnet(f, L.b2, a, c, s.first, s.second, h, w, nullptr, rs);
         f.release(a);
         f.release(s.first);
-        void* at = attention(f, L.attn, b, c, h, w);
+        void* at = attention(f, L.attn, b, c, h, w, rs);
         f.release(b);
+        f.release(rs);
         const int cout = L.resample.cout;
         Range r(f, "ups." + std::to_string(li) + ".3");
         void* nxt;
@@ -715,6 +754,7 @@ int pack_attn(sdc_unet* n, AttnP& a, const float* const* params, void* stream) {
         if ((rc = copy_param(n, a.g_out, params, a.g_out_i, st))) return rc;
         if ((rc = copy_param(n, a.out_w32, params, a.out.w, st))) return rc;
     }
+    if (a.qkv_ln && (rc = sdc_pack_qkv_ln(params[a.qkv.w], params[a.g_in_i], a.qkv_ln, a.qkv_wsum, 3 * HID, a.dim, stream))) return rc;
     return SDC_OK;
 }
 }  // namespace
@@ -817,6 +857,14 @@ extern "C" int sdc_unet_forward(sdc_unet* n, const float* x, const int32_t* t_in
     const int rc = run_forward(n, f, x, eps, H, W, nonfinite);
     nvtxRangePop();
     return rc;
+}
+
+extern "C" int sdc_unet_set_flag(sdc_unet* n, int flag, int value) {
+    SDC_REQUIRE(n && (flag == SDC_UNET_FUSE_LN || flag == SDC_UNET_FUSE_GN), "sdc_unet_set_flag: unknown flag %d", flag);
+    if (flag == SDC_UNET_FUSE_LN) n->fuse_ln = value != 0;
+    else n->fuse_gn = value != 0;
+    n->ws_cache.clear();   // the activation layout depends on the schedule
+    return SDC_OK;
 }
 
 extern "C" int sdc_unet_profile_enable(sdc_unet* n, int enable) {

@@ -68,6 +68,11 @@ L.register({
     "sdc_unet_pack_weights": (c_i, [c_p, ctypes.POINTER(c_p), c_i, c_p]),
     "sdc_unet_workspace_bytes": (c_i64, [c_p, c_i, c_i, c_i]),
     "sdc_unet_forward": (c_i, [c_p, c_p, c_p, c_i, c_p, c_i, c_i, c_i, c_p, c_i64, c_p, c_p]),
+    "sdc_unet_set_flag": (c_i, [c_p, c_i, c_i]),
+    "sdc_gn_silu_rowstats": (c_i, [c_p, c_p, c_p, c_p, c_p, c_p, c_i64, c_p, c_p, c_p, c_i, c_i, c_i, c_p]),
+    "sdc_pack_qkv_ln": (c_i, [c_p, c_p, c_p, c_p, c_i, c_i, c_p]),
+    "sdc_conv1x1_qkv_ln": (c_i, [c_p, c_i, c_p, c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_p]),
+    "sdc_conv1x1_per_sample_ln": (c_i, [c_p, c_i, c_p, c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_p]),
     "sdc_unet_profile_enable": (c_i, [c_p, c_i]),
     "sdc_unet_profile_count": (c_i, [c_p]),
     "sdc_unet_profile_entry": (c_i, [c_p, c_i, ctypes.POINTER(ctypes.c_char_p), ctypes.POINTER(c_f), ctypes.POINTER(ctypes.c_double),
@@ -344,6 +349,7 @@ class UnetPlan:
         self.workspaces = {}
         self.nonfinite = None
         self.key = None
+        self.flags = (False, False)   # (fuse_ln, fuse_gn): the handle's defaults
 
     def __del__(self):
         try:
@@ -390,6 +396,13 @@ class UnetPlan:
         L.check(L.lib().sdc_unet_forward(self.handle, L.ptr(x), L.ptr(t_index), int(t_uniform), L.ptr(out), B, H, W, L.ptr(ws), ws.numel(),
                                          L.ptr(self.nonfinite), _st()))
         return out
+
+    FUSE_LN, FUSE_GN = 1, 2
+
+    def set_flag(self, flag, value):
+        """Schedule switches of include/safediffcon_b200_plan.h (SDC_UNET_FUSE_LN, SDC_UNET_FUSE_GN)."""
+        L.check(L.lib().sdc_unet_set_flag(self.handle, int(flag), int(value)))
+        self.workspaces.clear()
 
     def profile(self, enable):
         L.check(L.lib().sdc_unet_profile_enable(self.handle, int(enable)))
@@ -491,6 +504,11 @@ class Unet2D(nn.Module):
         # epilogue (two TMEM passes, cross-cluster exchange of the statistics, SiLU, stores) does not fit into one MMA period
         # (profiles/r02_row_gn_*.txt).  SDC_FUSE_GN=1 enables it.
         self.fuse_groupnorm = os.environ.get("SDC_FUSE_GN", "0") == "1"
+        # EXPERIMENTAL (off): FP16 executor, LinearAttention blocks with <= 256 channels -- both channel LayerNorms folded into the
+        # qkv / output-projection epilogues (sdc_conv1x1_qkv_ln, sdc_conv1x1_per_sample_ln): 1.24 ms of LayerNorm passes disappear
+        # per step at B = 1024, but the 1x1 convolutions are epilogue bound already and lose 1.7 ms (profiles/r02_ln_fusion_ab.txt).
+        # SDC_FUSE_LN=1 enables it.
+        self.fuse_layernorm = os.environ.get("SDC_FUSE_LN", "0") == "1"
         # FP16-range guard (GaussianDiffusion._run_chain): on non-finite eps the chain is repeated with TF32 operands
         self.overflow_fallback = True
 
@@ -558,6 +576,10 @@ class Unet2D(nn.Module):
             dims = [self.downs[i][0].dim_out // self.dim for i in range(1, len(self.downs))] + [self.mid_block1.dim_out // self.dim]
             plan = UnetPlan(self.dim, dims, self.channels, self.out_dim, prec, self.theta, self.table_timesteps)
             c.plan, c.plan_gen = plan, c.plan_gen + 1
+        if (plan.flags != (self.fuse_layernorm, self.fuse_groupnorm)):
+            plan.set_flag(UnetPlan.FUSE_LN, self.fuse_layernorm)
+            plan.set_flag(UnetPlan.FUSE_GN, self.fuse_groupnorm)
+            plan.flags = (self.fuse_layernorm, self.fuse_groupnorm)
         key = self._key()
         if plan.key != key:
             dev = self.init_conv.weight.device

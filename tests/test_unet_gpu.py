@@ -581,3 +581,81 @@ def test_eps_after_adamw_steps_within_1e3():
             eps = net(x.cuda(), t.cuda()).cpu()
             per = [rel(eps[i], ref[i]) for i in range(4)]
             assert max(per) < 1e-3, (prec, per)
+
+
+def test_layernorm_folded_into_attention_projections():
+    """The two fused LayerNorm epilogues of the FP16 LinearAttention path against the separate kernels and torch:
+    (a) sdc_gn_silu_rowstats = sdc_gn_silu + per-row (mean, rstd) of its output; (b) sdc_conv1x1_qkv_ln on raw rows with folded
+    weights == LayerNorm -> sdc_conv1x1_qkv; (c) sdc_conv1x1_per_sample_ln == sdc_conv1x1_per_sample -> LayerNorm + residual."""
+    L, lib = _L()
+    from safediffcon_b200 import unet as U
+    for B, H, W, c in ((3, 16, 128, 128), (75, 8, 64, 256), (2, 4, 32, 256)):
+        g = torch.Generator().manual_seed(B + c)
+        n, M = H * W, B * H * W
+        raw = (torch.randn(M, c, generator=g) * 1.3 + 0.2).half().cuda()
+        res = torch.randn(M, c, generator=g).half().cuda()
+        gamma, beta = (1 + 0.3 * torch.randn(c, generator=g)).cuda(), (0.2 * torch.randn(c, generator=g)).cuda()
+        stats = torch.stack([raw.float().reshape(B, -1).sum(1), (raw.float() ** 2).reshape(B, -1).sum(1)], dim=1).double().contiguous()
+        # (a)
+        y_ref = raw.clone()
+        L.check(lib.sdc_gn_silu(F16, L.ptr(y_ref), 1, L.ptr(stats), L.ptr(gamma), L.ptr(beta), None, None, 0, L.ptr(res), 1, L.ptr(y_ref), B, n, c,
+                                L.stream_ptr()))
+        y = raw.clone()
+        rs = torch.full((M, 2), float("nan")).cuda()
+        L.check(lib.sdc_gn_silu_rowstats(L.ptr(y), L.ptr(stats), L.ptr(gamma), L.ptr(beta), None, None, 0, L.ptr(res), L.ptr(y), L.ptr(rs), B, n, c,
+                                         L.stream_ptr()))
+        assert torch.equal(y, y_ref)
+        yf = y.float()
+        assert torch.allclose(rs[:, 0], yf.mean(1), atol=2e-6, rtol=1e-5)
+        assert torch.allclose(rs[:, 1], (yf.var(1, unbiased=False) + 1e-5).rsqrt(), rtol=2e-5)
+        # (b)
+        wqkv = (torch.randn(384, c, generator=g) * (1.5 / np.sqrt(c))).cuda()
+        g_in = (1 + 0.2 * torch.randn(c, generator=g)).cuda()
+        xn = torch.empty_like(y)
+        L.check(lib.sdc_channel_layernorm(F16, L.ptr(y), 1, L.ptr(g_in), None, L.ptr(xn), M, c, 1, L.stream_ptr()))
+        q_ref, kv_ref = torch.empty(M, 128, dtype=torch.float16).cuda(), torch.empty(M, 256, dtype=torch.float16).cuda()
+        U.conv1x1_qkv(xn, c, U.pack_conv_weight(0, wqkv.reshape(384, c, 1, 1), F16), q_ref, kv_ref, B, H, W, F16)
+        wfold, wsum = torch.empty(384, c, dtype=torch.float16).cuda(), torch.empty(384).cuda()
+        L.check(lib.sdc_pack_qkv_ln(L.ptr(wqkv), L.ptr(g_in), L.ptr(wfold), L.ptr(wsum), 384, c, L.stream_ptr()))
+        assert torch.equal(wfold, (wqkv * g_in).half()) and torch.allclose(wsum, wfold.float().sum(1), rtol=1e-5, atol=1e-5)
+        q, kv = torch.empty_like(q_ref), torch.empty_like(kv_ref)
+        L.check(lib.sdc_conv1x1_qkv_ln(L.ptr(y), c, L.ptr(wfold), L.ptr(wsum), L.ptr(rs), L.ptr(q), L.ptr(kv), B, H, W, 128, L.stream_ptr()))
+        ln = (yf.double() - yf.double().mean(1, keepdim=True)) * (yf.double().var(1, unbiased=False, keepdim=True) + 1e-5).rsqrt() * g_in.double()
+        qkv_t = ln @ wqkv.double().t()
+        q_t = (qkv_t[:, :128].reshape(M, 4, 32).softmax(-1) * 32 ** -0.5).reshape(M, 128)
+        for got, old, want in ((q, q_ref, q_t), (kv, kv_ref, qkv_t[:, 128:])):
+            sc = want.abs().max().item()
+            e_new, e_old = (got.double() - want).abs().max().item() / sc, (old.double() - want).abs().max().item() / sc
+            assert e_new < 2e-3 and e_new < 1.5 * e_old + 2e-4, (B, c, e_new, e_old)   # no worse than LayerNorm -> fp16 -> projection
+        # (c)
+        wf = (torch.randn(B * c, 128, generator=g) / np.sqrt(128)).half().cuda()
+        bout, g_out = torch.randn(c, generator=g).cuda(), (1 + 0.2 * torch.randn(c, generator=g)).cuda()
+        proj = torch.empty(M, c, dtype=torch.float16).cuda()
+        U.conv1x1_per_sample(q_ref, 128, wf, bout, proj, B, H, W, c, F16)
+        o_ref = torch.empty(M, c, dtype=torch.float16).cuda()
+        L.check(lib.sdc_channel_layernorm(F16, L.ptr(proj), 1, L.ptr(g_out), L.ptr(y), L.ptr(o_ref), M, c, 1, L.stream_ptr()))
+        o = torch.full((M, c), float("nan"), dtype=torch.float16).cuda()
+        L.check(lib.sdc_conv1x1_per_sample_ln(L.ptr(q_ref), 128, L.ptr(wf), L.ptr(bout), L.ptr(g_out), L.ptr(y), L.ptr(o), B, H, W, c, L.stream_ptr()))
+        pj = torch.einsum("bnk,bck->bnc", q_ref.double().reshape(B, n, 128), wf.double().reshape(B, c, 128)).reshape(M, c) + bout.double()
+        want = (pj - pj.mean(1, keepdim=True)) * (pj.var(1, unbiased=False, keepdim=True) + 1e-5).rsqrt() * g_out.double() + yf.double()
+        sc = want.abs().max().item()
+        e_new, e_old = (o.double() - want).abs().max().item() / sc, (o_ref.double() - want).abs().max().item() / sc
+        assert torch.isfinite(o.float()).all() and e_new < 2e-3 and e_new < 1.5 * e_old + 2e-4, (B, c, e_new, e_old)
+
+
+def test_fold_on_tensor_cores_matches_fp32():
+    """linattn_fold_mma_kernel (mma.sync, hi/lo split operands) == the fp32 product W_out (x) ctx to fp16 rounding."""
+    L, lib = _L()
+    import safediffcon_b200.unet  # noqa: F401
+    for B, c in ((5, 128), (3, 256), (2, 512), (4, 64)):
+        g = torch.Generator().manual_seed(c)
+        ws = torch.zeros(B, 4, 32 * 32 + 64).cuda()
+        ctx = torch.randn(B, 4, 32, 32, generator=g).cuda() * 0.7
+        ws[:, :, :1024] = ctx.reshape(B, 4, 1024)
+        wout = (torch.randn(c, 128, generator=g) / np.sqrt(128)).cuda()
+        wf = torch.full((B * c, 128), float("nan"), dtype=torch.float16).cuda()
+        L.check(lib.sdc_linear_attention_fold(F16, L.ptr(ws), L.ptr(wout), L.ptr(wf), B, c, L.stream_ptr()))
+        ref = torch.einsum("che,bhde->bchd", wout.double().reshape(c, 4, 32), ctx.double()).reshape(B * c, 128)
+        err = (wf.double() - ref).abs()
+        assert torch.isfinite(wf.float()).all()
+        assert (err <= ref.abs() * 2 ** -10.9 + 1e-6).all(), (c, err.max().item())
