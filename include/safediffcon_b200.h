@@ -42,6 +42,11 @@ int64_t sdc_launch_count(void);
 int sdc_burgers_solve_free(const float* u0, const float* f, float* out, int64_t N, int s, int nt,
                            double visc, double T, double dt, int strict, void* stream);
 
+/* Diagnostics: number of rollouts (all solver entry points, current device) whose final state held NaN/Inf since the last
+ * reset; *count_host receives it (host pointer, may be NULL).  The data path is untouched: non-finite values propagate exactly
+ * as in the reference, this only counts them.  Call after synchronising the stream(s) the rollouts ran on. */
+int sdc_burgers_nonfinite_rollouts(int reset, int64_t* count_host);
+
 /* Cartesian variant, replaces burgers_numeric_solve (generate_burgers.py:113-205):
  * u0:[Nu0,s]  f:[Nf,nt,s]  out:[Nu0,Nf,nt+1,s]. */
 int sdc_burgers_solve_cartesian(const float* u0, const float* f, float* out, int64_t Nu0, int64_t Nf, int s, int nt,

@@ -55,12 +55,20 @@ int64_t sdc_unet_workspace_bytes(const sdc_unet* net, int B, int H, int W);
 int sdc_unet_forward(sdc_unet* net, const float* x, const int32_t* t_index, int t_uniform, float* eps, int B, int H, int W,
                      void* workspace, int64_t workspace_bytes, uint32_t* nonfinite, void* stream);
 
+/* The FiLM table built by sdc_unet_pack_weights: table[t * cols + c], t < rows = table_timesteps, cols = sum of 2 * Cout over the
+ * ResnetBlocks in execution order (scale | shift per block; unet.py:152-155,166-175).  rows / cols receive the shape; if `out`
+ * (device, rows * cols floats) is not NULL the table is copied into it on `stream`. */
+int sdc_unet_film_table(const sdc_unet* net, float* out, int* rows, int* cols, void* stream);
+
 /* Schedule switches, both EXPERIMENTAL and off by default (correct -- tests -- but measured slower than the separate kernels on
  * B200).  SDC_UNET_FUSE_LN: FP16 mode, levels with <= 256 channels -- the PreNorm LayerNorm is folded into the
  * qkv projection and the output LayerNorm + residual into the per-sample projection (sdc_conv1x1_qkv_ln,
  * sdc_conv1x1_per_sample_ln).  SDC_UNET_FUSE_GN: conv + GroupNorm in one kernel on the 16x128 level (sdc_conv3x3_row_gn). */
 #define SDC_UNET_FUSE_LN 1
 #define SDC_UNET_FUSE_GN 2
+/* SDC_UNET_FILM_TC (default 1): build the FiLM table with ONE tcgen05 TF32 GEMM over operands split into high + low parts
+ * (relative error ~1e-6, 0.2 ms) instead of the fp32 CUDA-core loop (9 ms for dim 128); applies to the next sdc_unet_pack_weights. */
+#define SDC_UNET_FILM_TC 3
 int sdc_unet_set_flag(sdc_unet* net, int flag, int value);
 
 /* Per-launch profile of the NEXT forward calls: when enabled, every launch is bracketed by CUDA events on `stream` (adds two

@@ -17,7 +17,7 @@ from .solver import burgers_numeric_solve, burgers_numeric_solve_free, burgers_s
 from .metrics import control_trajectories, evaluate_samples, calculate_safety_metrics, calculate_safety_score  # noqa: F401
 from .guidance import (calculate_guidance, get_finetune_guidance, get_weight, normalize_weights, safety_guidance,  # noqa: F401
                        SafetyGuidance, SCALER)
-from . import conformal, runner  # noqa: F401
+from . import conformal, ops, runner  # noqa: F401  (ops: torch.ops.safediffcon_b200.* registrations)
 from .conformal import ConformalCalculator, kth_select  # noqa: F401
 from .diffusion import GaussianDiffusion, ModelPrediction  # noqa: F401
 from .unet import Unet2D  # noqa: F401

@@ -38,6 +38,7 @@ _SIGS = {
     "sdc_version": (c_i, []),
     "sdc_last_error": (ctypes.c_char_p, []),
     "sdc_launch_count": (c_i64, []),
+    "sdc_burgers_nonfinite_rollouts": (c_i, [c_i, ctypes.POINTER(c_i64)]),
     "sdc_burgers_solve_free": (c_i, [c_p, c_p, c_p, c_i64, c_i, c_i, c_d, c_d, c_d, c_i, c_p]),
     "sdc_burgers_solve_cartesian": (c_i, [c_p, c_p, c_p, c_i64, c_i64, c_i, c_i, c_d, c_d, c_d, c_i, c_p]),
     "sdc_burgers_score": (c_i, [c_p, c_p, c_f, c_i64, c_i, c_i, c_p, c_p, c_p, c_p, c_p]),

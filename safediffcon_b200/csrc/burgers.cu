@@ -106,6 +106,11 @@ __device__ __forceinline__ void count_row(const float (&v)[PPL], float bound, in
     tms += (c > 0) ? 1 : 0;
 }
 
+// Diagnostics (the reference has no failure detection; a diverged rollout silently yields NaN metrics):
+// number of rollouts whose FINAL state holds a non-finite value, per device, since the last reset.  NaN/Inf stay data -- the
+// outputs are exactly the reference's -- this only makes them countable without a pass over the trajectories.
+__device__ unsigned long long g_nonfinite_rollouts = 0ull;
+
 template <int PPL, bool STRICT>
 __global__ void __launch_bounds__(256) burgers_rollout_kernel(BurgersArgs p) {
     const int lane = threadIdx.x & 31;
@@ -126,6 +131,12 @@ __global__ void __launch_bounds__(256) burgers_rollout_kernel(BurgersArgs p) {
         for (int j = 0; j < p.rec; ++j) euler_step<PPL, STRICT>(u, fk, lane, p.a, p.d, p.d2, p.dt);
         if (on) store_row<PPL>(u, on + (int64_t)(k + 1) * S, lane);
         if (score) count_row<PPL>(u, p.u_bound, pts, tms);
+    }
+    {
+        bool bad = false;
+#pragma unroll
+        for (int i = 0; i < PPL; ++i) bad |= !isfinite(u[i]);
+        if (__any_sync(0xffffffffu, bad) && lane == 0) atomicAdd(&g_nonfinite_rollouts, 1ull);
     }
     // reference snapshot k is taken after step (k+1)*rec; steps beyond nt*rec reuse the last forcing row
     // and are not recorded -- the final-state score below therefore uses snapshot nt, like the reference.
@@ -213,6 +224,14 @@ static int launch_rollout(BurgersArgs& a, int s, double visc, double T, double d
 }  // namespace sdc
 
 using namespace sdc;
+
+extern "C" int sdc_burgers_nonfinite_rollouts(int reset, int64_t* count_host) {
+    unsigned long long v = 0ull;
+    SDC_CUDA(cudaMemcpyFromSymbol(&v, g_nonfinite_rollouts, sizeof(v)));   // synchronises with the legacy default stream only
+    if (count_host) *count_host = (int64_t)v;
+    if (reset) { v = 0ull; SDC_CUDA(cudaMemcpyToSymbol(g_nonfinite_rollouts, &v, sizeof(v))); }
+    return SDC_OK;
+}
 
 extern "C" int sdc_burgers_solve_free(const float* u0, const float* f, float* out, int64_t N, int s, int nt, double visc,
                                       double T, double dt, int strict, void* stream) {

@@ -123,7 +123,10 @@ struct sdc_unet {
     std::vector<std::pair<void**, int64_t>> slab_items;   // (where to put the pointer, bytes)
     float *film_w = nullptr, *film_b = nullptr, *table = nullptr, *t_arange = nullptr, *emb = nullptr, *th1 = nullptr, *th2 = nullptr;
     float *tw1 = nullptr, *tb1 = nullptr, *tw2 = nullptr, *tb2 = nullptr, *stem_rep = nullptr;
+    float *film_a3 = nullptr, *film_w3 = nullptr;
+    int table_rows = 0;
     bool packed = false;
+    bool film_tc = true;     // FiLM table GEMM on tcgen05 (TF32, split operands) instead of the fp32 CUDA-core loop
     bool fuse_ln = false, fuse_gn = false;   // both measured slower than the separate kernels on B200
     // profile
     bool prof_on = false;
@@ -686,7 +689,11 @@ extern "C" int sdc_unet_create(sdc_unet** out, int dim, const int* dim_mults, in
     want(n, (void**)&n->tb2, td * 4);
     want(n, (void**)&n->film_w, (int64_t)n->film_total * td * 4);
     want(n, (void**)&n->film_b, (int64_t)n->film_total * 4);
-    want(n, (void**)&n->table, (int64_t)table_timesteps * n->film_total * 4);
+    // FiLM table on the tensor cores (TF32, operands split into high + low parts): table rows padded to a multiple of 128
+    n->table_rows = (table_timesteps + 127) / 128 * 128;
+    want(n, (void**)&n->table, (int64_t)n->table_rows * n->film_total * 4);
+    want(n, (void**)&n->film_a3, (int64_t)n->table_rows * 3 * td * 4);
+    want(n, (void**)&n->film_w3, (int64_t)n->film_total * 3 * td * 4);
     want(n, (void**)&n->t_arange, (int64_t)table_timesteps * 4);
     want(n, (void**)&n->emb, (int64_t)table_timesteps * dim * 4);
     want(n, (void**)&n->th1, (int64_t)table_timesteps * td * 4);
@@ -714,6 +721,25 @@ extern "C" int64_t sdc_unet_param_numel(const sdc_unet* n, int i) {
 }
 
 namespace {
+// out[r, :] = (hi | lo | hi) (w_mode = 0, activations) or (hi | hi | lo) (w_mode = 1, weights) of act(x[r, :]), hi = tf32(x),
+// lo = tf32(x - hi): [a_hi | a_lo | a_hi] . [w_hi | w_hi | w_lo]^T = a_hi w_hi + a_lo w_hi + a_hi w_lo, i.e. the fp32 product to
+// ~2^-21 on TF32 tensor cores.  Rows >= R are zero.  silu: exact expf (this runs once per weight version).
+__global__ void split3_kernel(const float* __restrict__ x, float* __restrict__ out, int R, int rows_out, int K, int w_mode, int silu_in) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (int64_t)rows_out * K) return;
+    const int r = (int)(i / K), k = (int)(i - (int64_t)r * K);
+    float v = 0.f;
+    if (r < R) {
+        v = x[(int64_t)r * K + k];
+        if (silu_in) v = v / (1.0f + expf(-v));
+    }
+    const float hi = to_tf32(v), lo = to_tf32(v - hi);
+    float* o = out + (int64_t)r * 3 * K + k;
+    o[0] = hi;
+    o[K] = w_mode ? hi : lo;
+    o[2 * K] = w_mode ? lo : hi;
+}
+
 __global__ void arange_kernel(float* t, int n) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) t[i] = (float)i;
@@ -809,7 +835,17 @@ extern "C" int sdc_unet_pack_weights(sdc_unet* n, const float* const* params, in
     if ((rc = sdc_sinusoidal_embedding(n->t_arange, n->emb, T, n->dim, n->theta, stream))) return rc;
     if ((rc = sdc_linear_rows(n->emb, n->tw1, n->tb1, n->th1, T, n->dim, td, 0, stream))) return rc;
     if ((rc = sdc_linear_rows(n->th1, n->tw2, n->tb2, n->th2, T, td, td, 2, stream))) return rc;
-    if ((rc = sdc_linear_rows(n->th2, n->film_w, n->film_b, n->table, T, td, n->film_total, 1, stream))) return rc;
+    // every block's SiLU -> Linear for all T times at once: [T, 512] x [512, E] = 8.3 GFLOP for dim 128 -- 9 ms as an fp32 CUDA-core
+    // loop, ~0.2 ms as ONE tcgen05 TF32 GEMM over split operands (paid on every optimiser / EMA step of a fine-tuning loop)
+    if (n->film_tc && td % 32 == 0 && n->film_total % 32 == 0) {
+        const int64_t na = (int64_t)n->table_rows * td, nw = (int64_t)n->film_total * td;
+        split3_kernel<<<(unsigned)((na + 255) / 256), 256, 0, st>>>(n->th2, n->film_a3, T, n->table_rows, td, 0, 1);
+        split3_kernel<<<(unsigned)((nw + 255) / 256), 256, 0, st>>>(n->film_w, n->film_w3, n->film_total, n->film_total, td, 1, 0);
+        g_launches.fetch_add(2);
+        PLAN_CUDA(cudaGetLastError());
+        if ((rc = sdc_conv_gemm(SDC_PREC_TF32, K1, n->film_a3, 3 * td, nullptr, 0, n->film_w3, n->film_b, nullptr, n->table, nullptr, 0,
+                                n->table_rows / 128, 1, 128, n->film_total, stream))) return rc;
+    } else if ((rc = sdc_linear_rows(n->th2, n->film_w, n->film_b, n->table, T, td, n->film_total, 1, stream))) return rc;
     n->packed = true;
     return SDC_OK;
 }
@@ -859,10 +895,22 @@ extern "C" int sdc_unet_forward(sdc_unet* n, const float* x, const int32_t* t_in
     return rc;
 }
 
+extern "C" int sdc_unet_film_table(const sdc_unet* n, float* out, int* rows, int* cols, void* stream) {
+    SDC_REQUIRE(n, "sdc_unet_film_table: null handle");
+    if (rows) *rows = n->table_T;
+    if (cols) *cols = n->film_total;
+    if (out) {
+        SDC_REQUIRE(n->packed, "sdc_unet_film_table: weights not packed");
+        PLAN_CUDA(cudaMemcpyAsync(out, n->table, (size_t)n->table_T * n->film_total * 4, cudaMemcpyDeviceToDevice, as_stream(stream)));
+    }
+    return SDC_OK;
+}
+
 extern "C" int sdc_unet_set_flag(sdc_unet* n, int flag, int value) {
-    SDC_REQUIRE(n && (flag == SDC_UNET_FUSE_LN || flag == SDC_UNET_FUSE_GN), "sdc_unet_set_flag: unknown flag %d", flag);
+    SDC_REQUIRE(n && (flag == SDC_UNET_FUSE_LN || flag == SDC_UNET_FUSE_GN || flag == SDC_UNET_FILM_TC), "sdc_unet_set_flag: unknown flag %d", flag);
     if (flag == SDC_UNET_FUSE_LN) n->fuse_ln = value != 0;
-    else n->fuse_gn = value != 0;
+    else if (flag == SDC_UNET_FUSE_GN) n->fuse_gn = value != 0;
+    else n->film_tc = value != 0;   // takes effect at the next sdc_unet_pack_weights
     n->ws_cache.clear();   // the activation layout depends on the schedule
     return SDC_OK;
 }

@@ -76,3 +76,12 @@ def control_and_score(diffused, target_final, u_bound, nt=11, visc=0.01, T=1.0, 
                                                   float(visc), float(T), float(dt), int(strict), L.ptr(J), L.ptr(pts),
                                                   L.ptr(tms), L.ptr(flg), L.stream_ptr()))
     return out, J, pts, tms, flg
+
+
+def nonfinite_rollouts(reset=True):
+    """Diagnostics: how many rollouts on the current device ended in a non-finite state since the last reset (synchronises)."""
+    torch.cuda.synchronize()
+    n = L.c_i64(0)
+    import ctypes
+    L.check(L.lib().sdc_burgers_nonfinite_rollouts(int(reset), ctypes.byref(n)))
+    return int(n.value)

@@ -69,6 +69,7 @@ L.register({
     "sdc_unet_workspace_bytes": (c_i64, [c_p, c_i, c_i, c_i]),
     "sdc_unet_forward": (c_i, [c_p, c_p, c_p, c_i, c_p, c_i, c_i, c_i, c_p, c_i64, c_p, c_p]),
     "sdc_unet_set_flag": (c_i, [c_p, c_i, c_i]),
+    "sdc_unet_film_table": (c_i, [c_p, c_p, ctypes.POINTER(c_i), ctypes.POINTER(c_i), c_p]),
     "sdc_gn_silu_rowstats": (c_i, [c_p, c_p, c_p, c_p, c_p, c_p, c_i64, c_p, c_p, c_p, c_i, c_i, c_i, c_p]),
     "sdc_pack_qkv_ln": (c_i, [c_p, c_p, c_p, c_p, c_i, c_i, c_p]),
     "sdc_conv1x1_qkv_ln": (c_i, [c_p, c_i, c_p, c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_p]),
@@ -397,7 +398,15 @@ class UnetPlan:
                                          L.ptr(self.nonfinite), _st()))
         return out
 
-    FUSE_LN, FUSE_GN = 1, 2
+    FUSE_LN, FUSE_GN, FILM_TC = 1, 2, 3
+
+    def film_table(self):
+        """Copy of the executor's FiLM table [table_timesteps, E] (tests compare it with the time MLP evaluated by torch)."""
+        rows, cols = c_i(), c_i()
+        L.check(L.lib().sdc_unet_film_table(self.handle, None, ctypes.byref(rows), ctypes.byref(cols), None))
+        out = torch.empty(rows.value, cols.value, dtype=torch.float32, device="cuda")
+        L.check(L.lib().sdc_unet_film_table(self.handle, L.ptr(out), None, None, _st()))
+        return out
 
     def set_flag(self, flag, value):
         """Schedule switches of include/safediffcon_b200_plan.h (SDC_UNET_FUSE_LN, SDC_UNET_FUSE_GN)."""

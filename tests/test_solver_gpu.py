@@ -28,6 +28,21 @@ def test_solve_free_nan_propagation(golden):
     assert np.array_equal(out, golden("solver_free_wild")["traj"], equal_nan=True)
 
 
+def test_nonfinite_rollout_counter(golden):
+    """Diverged rollouts are data (NaN/Inf propagate like the reference) AND countable without a pass over the trajectories."""
+    import safediffcon_b200 as s
+    from safediffcon_b200 import solver
+    solver.nonfinite_rollouts(reset=True)
+    u0, f = fx.solver_inputs(16, seed=0)
+    s.burgers_numeric_solve_free(u0.cuda(), f.cuda(), 0.01, 1.0)
+    assert solver.nonfinite_rollouts(reset=True) == 0
+    u0b, fb = fx.solver_inputs_wild(4, seed=3)
+    out = s.burgers_numeric_solve_free(u0b.cuda(), fb.cuda(), 0.01, 1.0)
+    want = int((~torch.isfinite(out[:, -1])).any(dim=1).sum())
+    assert want > 0 and solver.nonfinite_rollouts(reset=True) == want
+    assert solver.nonfinite_rollouts() == 0
+
+
 def test_solve_cartesian_bit_exact(golden):
     import safediffcon_b200 as s
     u0, f = fx.solver_inputs(3, 5)
