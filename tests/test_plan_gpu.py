@@ -70,10 +70,18 @@ def test_layernorm_fusion_is_a_pure_reformulation():
 
 def test_film_table_on_tensor_cores_matches_the_time_mlp():
     """The executor's FiLM table (split-TF32 tcgen05 GEMM) against the time MLP evaluated by torch in fp64."""
+    import math
+    import torch.nn.functional as F
     net = _net(128, "f16")
     with torch.no_grad():
-        tab = net._plan_ready().film_table()
-        ref = net.double()._film_rows_autograd(1000, torch.arange(1000, device="cuda"), None, torch.device("cuda"))
+        tab = net._plan_ready().film_table().cpu()
+        sd = {k: v.detach().double().cpu() for k, v in net.state_dict().items()}
+        t = torch.arange(1000, dtype=torch.float64)
+        freq = torch.exp(torch.arange(64, dtype=torch.float64) * -(math.log(10000.0) / 63))
+        emb = torch.cat(((t[:, None] * freq).sin(), (t[:, None] * freq).cos()), dim=-1)            # unet.py:81-95
+        h = F.linear(F.gelu(F.linear(emb, sd["time_mlp.1.weight"], sd["time_mlp.1.bias"])), sd["time_mlp.3.weight"], sd["time_mlp.3.bias"])
+        blocks = [k[:-len(".mlp.1.weight")] for k in net.state_dict() if k.endswith(".mlp.1.weight")]   # module order = execution order
+        ref = torch.cat([F.linear(F.silu(h), sd[b + ".mlp.1.weight"], sd[b + ".mlp.1.bias"]) for b in blocks], dim=1)
     assert tab.shape == ref.shape == (1000, 16128)
     assert rel(tab.double(), ref) < 5e-6 and (tab.double() - ref).abs().max().item() < 2e-5
 
