@@ -55,6 +55,17 @@ int64_t sdc_unet_workspace_bytes(const sdc_unet* net, int B, int H, int W);
 int sdc_unet_forward(sdc_unet* net, const float* x, const int32_t* t_index, int t_uniform, float* eps, int B, int H, int W,
                      void* workspace, int64_t workspace_bytes, uint32_t* nonfinite, void* stream);
 
+/* Backward-data pass: eps = Unet2D(x, t) AND grad_x = d<eps, grad_eps>/dx in one call (the VJP with respect to the denoiser input
+ * that the reference obtains by autograd when a guidance callable differentiates eps_theta(x_t, t),
+ * /root/reference/1D/model/diffusion.py:254-262; parameters get no gradient).  Forward with every normalisation input kept, then
+ * the reverse walk: GroupNorm / LayerNorm / attention backward kernels and the same tcgen05 convolutions in TF32 with the
+ * transposed, tap-flipped weights.  Needs SDC_UNET_BACKWARD set before the last sdc_unet_pack_weights.  x, grad_eps, eps, grad_x:
+ * [B, C, H, W] fp32 NCHW.  Workspace: sdc_unet_backward_workspace_bytes (~42 MB per sample for dim 128: all records stay live
+ * until the reverse walk consumes them).  Allocates nothing, never synchronises. */
+int64_t sdc_unet_backward_workspace_bytes(const sdc_unet* net, int B, int H, int W);
+int sdc_unet_backward_data(sdc_unet* net, const float* x, const int32_t* t_index, int t_uniform, const float* grad_eps, float* eps,
+                           float* grad_x, int B, int H, int W, void* workspace, int64_t workspace_bytes, void* stream);
+
 /* The FiLM table built by sdc_unet_pack_weights: table[t * cols + c], t < rows = table_timesteps, cols = sum of 2 * Cout over the
  * ResnetBlocks in execution order (scale | shift per block; unet.py:152-155,166-175).  rows / cols receive the shape; if `out`
  * (device, rows * cols floats) is not NULL the table is copied into it on `stream`. */
@@ -69,6 +80,9 @@ int sdc_unet_film_table(const sdc_unet* net, float* out, int* rows, int* cols, v
 /* SDC_UNET_FILM_TC (default 1): build the FiLM table with ONE tcgen05 TF32 GEMM over operands split into high + low parts
  * (relative error ~1e-6, 0.2 ms) instead of the fp32 CUDA-core loop (9 ms for dim 128); applies to the next sdc_unet_pack_weights. */
 #define SDC_UNET_FILM_TC 3
+/* SDC_UNET_BACKWARD (default 0): sdc_unet_pack_weights also packs the data-gradient weights (transposed, tap-flipped, TF32; a
+ * second device allocation of the size of the fp32 conv weights) that sdc_unet_backward_data needs. */
+#define SDC_UNET_BACKWARD 4
 int sdc_unet_set_flag(sdc_unet* net, int flag, int value);
 
 /* Per-launch profile of the NEXT forward calls: when enabled, every launch is bracketed by CUDA events on `stream` (adds two

@@ -35,6 +35,7 @@ struct ConvP {
     void* packed = nullptr;      // Wp[cout, taps*cin] operand precision
     void* packed_up = nullptr;   // Wp[4*cout, 4*cin]
     float* bias = nullptr;
+    float* wt = nullptr;         // backward-data: Wt[cin, taps*cout] TF32 (sdc_pack_conv_weight_dgrad), packed when SDC_UNET_BACKWARD is set
 };
 struct BlockP {
     int mlp_w, mlp_b, g1w, g1b, g2w, g2b;
@@ -126,6 +127,13 @@ struct sdc_unet {
     float *film_a3 = nullptr, *film_w3 = nullptr;
     int table_rows = 0;
     bool packed = false;
+    bool want_bwd = false;   // SDC_UNET_BACKWARD: also pack the data-gradient weights (second slab, +0.56 GB for dim 128)
+    uint8_t* dslab = nullptr;
+    int64_t dslab_bytes = 0;
+    std::vector<std::pair<void**, int64_t>> dslab_items;
+    float* stem_wt = nullptr;   // [stem_kp2, dim]
+    int stem_kp2 = 0;
+    bool bwd_packed = false;
     bool film_tc = true;     // FiLM table GEMM on tcgen05 (TF32, split operands) instead of the fp32 CUDA-core loop
     bool fuse_ln = false, fuse_gn = false;   // both measured slower than the separate kernels on B200
     // profile
@@ -153,11 +161,13 @@ ConvP make_conv(sdc_unet* n, const std::string& name, int cout, int cin, int kin
     want(n, &c.packed, (int64_t)cout * cin * taps * esz);
     if (up) want(n, &c.packed_up, (int64_t)16 * cout * cin * esz);
     if (bias) want(n, (void**)&c.bias, (int64_t)cout * 4);
+    n->dslab_items.push_back({(void**)&c.wt, (int64_t)cout * cin * taps * 4});
     return c;
 }
 // NOTE: make_conv registers `&c.packed` of a LOCAL; the callers below re-register after the struct has reached its final
 // address (fix_conv), so the slab pointers land in the handle's own members.
 void fix_conv(sdc_unet* n, ConvP& c, size_t& cursor) {
+    n->dslab_items.back().first = (void**)&c.wt;   // (registered by the make_conv call just before)
     n->slab_items[cursor++].first = &c.packed;
     if (c.up) n->slab_items[cursor++].first = &c.packed_up;
     if (c.b >= 0) n->slab_items[cursor++].first = (void**)&c.bias;
@@ -288,21 +298,27 @@ struct Range {   // NVTX range per network block (visible in nsys / ncu --nvtx)
 };
 
 void conv(Fwd& f, int kind, const void* a0, int c0, const void* a1, int c1, const ConvP& cw, const void* wp, const void* residual, void* out,
-          double* st, int operand_out, int h, int w, double algo_k = -1.0) {
+          double* st, int operand_out, int h, int w, double algo_k = -1.0, int prec_override = -1, int cout_override = -1,
+          bool no_bias = false) {
+    const int prec = prec_override >= 0 ? prec_override : f.prec;
+    const int cout = cout_override >= 0 ? cout_override : cw.cout;
+    const float* bias = no_bias ? nullptr : cw.bias;
     const int taps = kind == K3 ? 9 : (kind == K1 ? 1 : 4);
     const double rows = (double)f.B * h * w * (kind == KUP ? 4 : 1);
     const double k = algo_k > 0 ? algo_k : (double)taps * (c0 + c1);
     const double oesz = operand_out ? (double)f.esz : 4.0;
-    const double bytes = (double)f.B * h * w * (kind == KUN ? 4 : 1) * (c0 + c1) * f.esz + rows * cw.cout * oesz + (double)cw.cout * k * f.esz +
-                         (residual ? rows * cw.cout * f.esz : 0.0);
+    const double esz = prec == SDC_PREC_F16 ? 2.0 : 4.0;
+    const double bytes = (double)f.B * h * w * (kind == KUN ? 4 : 1) * (c0 + c1) * esz + rows * cout * (operand_out ? esz : 4.0) + (double)cout * k * esz +
+                         (residual ? rows * cout * esz : 0.0);
+    (void)oesz;
     const char* nm = kind == K3 ? "conv3x3" : (kind == K1 ? "conv1x1" : (kind == KUN ? "conv_unshuffle" : "conv_upsample"));
     int rc = -1;
     if (!f.dry && !f.rc) {
-        f.begin(nm, bytes, 2.0 * rows * cw.cout * k);
-        if (kind == K3 && w == 128 && cw.cout <= 128)
-            rc = sdc_conv3x3_row(f.prec, a0, c0, a1, c1, wp, cw.bias, residual, out, st, operand_out, f.B, h, w, cw.cout, f.stream);
+        f.begin(nm, bytes, 2.0 * rows * cout * k);
+        if (kind == K3 && w == 128 && cout <= 128)
+            rc = sdc_conv3x3_row(prec, a0, c0, a1, c1, wp, bias, residual, out, st, operand_out, f.B, h, w, cout, f.stream);
         if (rc != 0)
-            rc = sdc_conv_gemm(f.prec, kind, a0, c0, a1, c1, wp, cw.bias, residual, out, st, operand_out, f.B, h, w, cw.cout, f.stream);
+            rc = sdc_conv_gemm(prec, kind, a0, c0, a1, c1, wp, bias, residual, out, st, operand_out, f.B, h, w, cout, f.stream);
         f.end();
         if (rc > 0) f.rc = rc;
     }
@@ -613,6 +629,310 @@ int run_forward(sdc_unet* n, Fwd& f, const float* x, float* eps, int H, int W, u
     return f.rc;
 }
 
+
+// ================================================================================================ backward-data pass
+// d<eps, g>/dx (VJP with respect to the denoiser input; the reference reaches it through autograd when a guidance callable
+// differentiates eps_theta(x_t, t), /root/reference/1D/model/diffusion.py:254-262).  run_record = the forward schedule with every
+// normalisation input kept (fp32 convolution outputs, separate attention kernels, unfused upsample); run_backward walks the
+// records in reverse: GroupNorm / LayerNorm / attention backward kernels (csrc/unet_bwd.cu) and the SAME tcgen05 convolution
+// kernels in TF32 with the transposed, tap-flipped weights of sdc_pack_conv_weight_dgrad.  Gradients are fp32 containers,
+// TF32-rounded where they feed a data-gradient convolution.
+struct Rec {
+    int kind;                       // 0 resnet, 1 attn, 2 push, 3 down, 4 up
+    const BlockP* blk = nullptr;
+    const AttnP* att = nullptr;
+    const ConvP* cv = nullptr;
+    int c0 = 0, c1 = 0, c = 0, h = 0, w = 0;
+    bool flag = false;              // down: unshuffle; up: upsample
+    void *raw1 = nullptr, *raw2 = nullptr, *xin = nullptr, *qkv = nullptr, *proj = nullptr, *ws = nullptr;
+    double *s1 = nullptr, *s2 = nullptr;
+    const float* ss = nullptr;
+};
+
+void* resnet_rec(Fwd& f, const BlockP& p, const void* a0, int c0, const void* a1, int c1, int h, int w, std::vector<Rec>& tape) {
+    Range r(f, p.name);
+    const int64_t M = (int64_t)f.B * h * w, HW = (int64_t)h * w;
+    const int cout = p.cout;
+    double* s1 = f.stats + (int64_t)f.stat_i * f.B * 2;
+    double* s2 = f.stats + (int64_t)(f.stat_i + 1) * f.B * 2;
+    f.stat_i += 2;
+    const float* ss = f.film + p.film_off;
+    void* raw1 = f.f32(M, cout);
+    conv(f, K3, a0, c0, a1, c1, p.c1, p.c1.packed, nullptr, raw1, s1, 0, h, w);
+    void* h1 = f.opd(M, cout);
+    RUN("gn_silu", (double)M * cout * (4.0 + f.esz), 0.0,
+        sdc_gn_silu(f.prec, raw1, 0, s1, p.g1[0], p.g1[1], ss, f.t_index, f.E, nullptr, 0, h1, f.B, (int)HW, cout, f.stream));
+    void* raw2 = f.f32(M, cout);
+    conv(f, K3, h1, cout, nullptr, 0, p.c2, p.c2.packed, nullptr, raw2, s2, 0, h, w);
+    f.release(h1);
+    const void* res = a0;
+    void* resbuf = nullptr;
+    int res_operand = 1;
+    if (p.has_res) {
+        resbuf = f.f32(M, cout);
+        conv(f, K1, a0, c0, a1, c1, p.res, p.res.packed, nullptr, resbuf, nullptr, 0, h, w);
+        res = resbuf;
+        res_operand = 0;
+    }
+    void* out = f.opd(M, cout);
+    RUN("gn_silu", (double)M * cout * (8.0 + f.esz), 0.0,
+        sdc_gn_silu(f.prec, raw2, 0, s2, p.g2[0], p.g2[1], nullptr, nullptr, 0, res, res_operand, out, f.B, (int)HW, cout, f.stream));
+    f.release(resbuf);
+    Rec rc;
+    rc.kind = 0; rc.blk = &p; rc.c0 = c0; rc.c1 = c1; rc.h = h; rc.w = w; rc.raw1 = raw1; rc.raw2 = raw2; rc.s1 = s1; rc.s2 = s2; rc.ss = ss;
+    tape.push_back(rc);
+    return out;
+}
+
+void* attention_rec(Fwd& f, const AttnP& p, void* xin, int c, int h, int w, std::vector<Rec>& tape) {
+    Range r(f, p.name);
+    const int64_t M = (int64_t)f.B * h * w;
+    const int n = h * w;
+    void* xn = f.opd(M, c);
+    RUN("layernorm", (double)M * c * 2.0 * f.esz, 0.0, sdc_channel_layernorm(f.prec, xin, 1, p.g_in, nullptr, xn, M, c, 1, f.stream));
+    void* qkv = f.f32(M, 3 * HID);
+    conv(f, K1, xn, c, nullptr, 0, p.qkv, p.qkv.packed, nullptr, qkv, nullptr, 0, h, w);
+    f.release(xn);
+    void* att = f.opd(M, HID);
+    void* out = f.opd(M, c);
+    Rec rc;
+    rc.kind = 1; rc.att = &p; rc.c = c; rc.h = h; rc.w = w; rc.xin = xin; rc.qkv = qkv;
+    if (p.full) {
+        RUN("attention", (double)M * HID * 16.0, 4.0 * M * n * HID, sdc_attention(f.prec, (const float*)qkv, att, f.B, n, f.stream));
+        conv(f, K1, att, HID, nullptr, 0, p.out, p.out.packed, xin, out, nullptr, 1, h, w);
+    } else {
+        void* ws = f.alloc(sdc_linear_attention_workspace(f.B));
+        RUN("linear_attention", (double)M * HID * 16.0, 4.0 * M * HID * 32.0, sdc_linear_attention(f.prec, (const float*)qkv, att, ws, f.B, n, f.stream));
+        void* proj = f.f32(M, c);
+        conv(f, K1, att, HID, nullptr, 0, p.out, p.out.packed, nullptr, proj, nullptr, 0, h, w);
+        RUN("layernorm", (double)M * c * (4.0 + 2.0 * f.esz), 0.0, sdc_channel_layernorm(f.prec, proj, 0, p.g_out, xin, out, M, c, 1, f.stream));
+        rc.ws = ws; rc.proj = proj;
+    }
+    f.release(att);
+    tape.push_back(rc);
+    return out;
+}
+
+// data gradient of convolution `cw` restricted to its input channels [lo, hi): a convolution of g with rows [lo, hi) of Wt
+void* dgrad(Fwd& f, int kind, const void* g, int cin_g, const ConvP& cw, int lo, int hi, const void* residual, int operand_out, int h, int w) {
+    const int taps = kind == K3 ? 9 : 1;
+    const float* wt = cw.wt + (int64_t)lo * taps * cin_g;
+    void* out = f.f32((int64_t)f.B * h * w, hi - lo);
+    conv(f, kind, g, cin_g, nullptr, 0, cw, wt, residual, out, nullptr, operand_out, h, w, -1.0, SDC_PREC_TF32, hi - lo, true);
+    return out;
+}
+
+void* gn_bwd(Fwd& f, const void* dy, const void* raw, const double* stats, float* const* gb, const float* ss, double* sums, int hw, int c) {
+    void* dx = f.f32((int64_t)f.B * hw, c);
+    RUN("gn_silu_bwd", (double)f.B * hw * c * 16.0, 0.0,
+        sdc_gn_silu_bwd((const float*)dy, (const float*)raw, stats, gb[0], gb[1], ss, ss ? f.t_index : nullptr, ss ? f.E : 0, sums, (float*)dx, f.B,
+                        hw, c, f.stream));
+    return dx;
+}
+
+int run_vjp(sdc_unet* n, Fwd& f, const float* x, const float* g_eps, float* eps, float* gx, int H, int W) {
+    const int B = f.B;
+    const int n_gn = 2 * (int)(2 * n->downs.size() + 2 + 2 * n->ups.size() + 1);
+    f.stats = (double*)f.alloc((int64_t)n_gn * B * 2 * sizeof(double));
+    double* sums = (double*)f.alloc((int64_t)B * 2 * sizeof(double));
+    if (f.rc) return f.rc;
+    if (!f.dry) PLAN_CUDA(cudaMemsetAsync(f.stats, 0, (size_t)n_gn * B * 2 * sizeof(double), as_stream(f.stream)));
+    std::vector<Rec> tape;
+    // ---------------- forward with records ----------------
+    int c = n->init_dim, h = H, w = W;
+    void* cur = f.opd((int64_t)B * H * W, c);
+    {
+        void* patches = f.opd((int64_t)B * H * W, n->stem_kp);
+        RUN("stem_im2col", 0.0, 0.0, sdc_stem_im2col(f.prec, x, patches, B, n->channels, H, W, n->stem_kp, f.stream));
+        conv(f, K1, patches, n->stem_kp, nullptr, 0, n->stem, n->stem.packed, nullptr, cur, nullptr, 1, H, W, n->channels * 49.0);
+        f.release(patches);
+    }
+    void* r0 = cur;
+    const int r_c = c;
+    std::vector<std::pair<void*, int>> skips;
+    Rec push; push.kind = 2;
+    for (size_t li = 0; li < n->downs.size(); ++li) {
+        const LevelP& L = n->downs[li];
+        void* a = resnet_rec(f, L.b1, cur, c, nullptr, 0, h, w, tape);
+        skips.push_back({a, c});
+        tape.push_back(push);
+        void* b = resnet_rec(f, L.b2, a, c, nullptr, 0, h, w, tape);
+        void* at = attention_rec(f, L.attn, b, c, h, w, tape);
+        skips.push_back({at, c});
+        tape.push_back(push);
+        const int cout = L.resample.cout;
+        if (L.resamples) { h /= 2; w /= 2; }
+        void* nxt = f.opd((int64_t)B * h * w, cout);
+        conv(f, L.resamples ? KUN : K3, at, c, nullptr, 0, L.resample, L.resample.packed, nullptr, nxt, nullptr, 1, h, w);
+        Rec d; d.kind = 3; d.cv = &L.resample; d.flag = L.resamples; d.c = c; d.h = h; d.w = w;
+        tape.push_back(d);
+        cur = nxt;
+        c = cout;
+    }
+    cur = resnet_rec(f, n->mid1, cur, c, nullptr, 0, h, w, tape);
+    cur = attention_rec(f, n->mid_attn, cur, c, h, w, tape);
+    cur = resnet_rec(f, n->mid2, cur, c, nullptr, 0, h, w, tape);
+    for (size_t li = 0; li < n->ups.size(); ++li) {
+        const LevelP& L = n->ups[li];
+        auto s = skips.back(); skips.pop_back();
+        cur = resnet_rec(f, L.b1, cur, c, s.first, s.second, h, w, tape);
+        c = L.b1.cout;
+        s = skips.back(); skips.pop_back();
+        cur = resnet_rec(f, L.b2, cur, c, s.first, s.second, h, w, tape);
+        cur = attention_rec(f, L.attn, cur, c, h, w, tape);
+        const int cout = L.resample.cout;
+        void* in = cur;
+        if (L.resamples) {
+            void* upb = f.opd((int64_t)B * 4 * h * w, c);
+            RUN("upsample2x", 0.0, 0.0, sdc_upsample2x(f.prec, cur, upb, B, h, w, c, f.stream));
+            h *= 2; w *= 2;
+            in = upb;
+        }
+        void* nxt = f.opd((int64_t)B * h * w, cout);
+        conv(f, K3, in, c, nullptr, 0, L.resample, L.resample.packed, nullptr, nxt, nullptr, 1, h, w);
+        Rec u; u.kind = 4; u.cv = &L.resample; u.flag = L.resamples; u.c = c; u.h = h; u.w = w;
+        tape.push_back(u);
+        cur = nxt;
+        c = cout;
+    }
+    cur = resnet_rec(f, n->fin, cur, c, r0, r_c, h, w, tape);
+    const int cfin = n->fin.cout;
+    RUN("head_conv1", 0.0, 0.0, sdc_head_conv1(f.prec, cur, n->head_w, n->head_b, eps, B, H * W, cfin, n->out_dim, f.stream));
+    // ---------------- backward walk ----------------
+    auto resnet_bwd = [&](const Rec& r, void* g, void*& g0, void*& g1) {
+        const BlockP& p = *r.blk;
+        const int cout = p.cout, hw = r.h * r.w;
+        void* d_raw2 = gn_bwd(f, g, r.raw2, r.s2, p.g2, nullptr, sums, hw, cout);
+        f.release(r.raw2);
+        void* d_h1 = dgrad(f, K3, d_raw2, cout, p.c2, 0, cout, nullptr, 0, r.h, r.w);
+        f.release(d_raw2);
+        void* d_raw1 = gn_bwd(f, d_h1, r.raw1, r.s1, p.g1, r.ss, sums, hw, cout);
+        f.release(d_h1);
+        f.release(r.raw1);
+        void* outs[2] = {nullptr, nullptr};
+        const int lohi[2][2] = {{0, r.c0}, {r.c0, r.c0 + r.c1}};
+        for (int sgm = 0; sgm < 2; ++sgm) {
+            const int lo = lohi[sgm][0], hi = lohi[sgm][1];
+            if (hi == lo) continue;
+            void* side = g;
+            void* side_buf = nullptr;
+            if (p.has_res) { side_buf = dgrad(f, K1, g, cout, p.res, lo, hi, nullptr, 0, r.h, r.w); side = side_buf; }
+            outs[sgm] = dgrad(f, K3, d_raw1, cout, p.c1, lo, hi, side, 1, r.h, r.w);
+            f.release(side_buf);
+        }
+        f.release(d_raw1);
+        g0 = outs[0];
+        g1 = outs[1];
+    };
+    auto attn_bwd = [&](const Rec& r, void* g) -> void* {
+        const AttnP& p = *r.att;
+        const int cc = r.c, nn = r.h * r.w;
+        const int64_t M = (int64_t)B * nn;
+        void* d_qkv = f.f32(M, 3 * HID);
+        if (p.full) {
+            void* d_att = dgrad(f, K1, g, cc, p.out, 0, HID, nullptr, 0, r.h, r.w);
+            RUN("attention_bwd", 0.0, 0.0, sdc_attention_bwd((const float*)r.qkv, (const float*)d_att, (float*)d_qkv, B, nn, f.stream));
+            f.release(d_att);
+        } else {
+            void* d_proj = f.f32(M, cc);
+            RUN("layernorm_bwd", 0.0, 0.0,
+                sdc_channel_layernorm_bwd((const float*)g, r.proj, 0, p.g_out, nullptr, (float*)d_proj, M, cc, 1, f.stream));
+            void* d_att = dgrad(f, K1, d_proj, cc, p.out, 0, HID, nullptr, 0, r.h, r.w);
+            f.release(d_proj);
+            void* wsb = f.alloc(sdc_linear_attention_bwd_workspace(B));
+            RUN("linear_attention_bwd", 0.0, 0.0,
+                sdc_linear_attention_bwd((const float*)r.qkv, (const float*)d_att, r.ws, wsb, (float*)d_qkv, B, nn, f.stream));
+            f.release(d_att); f.release(wsb); f.release(r.ws); f.release(r.proj);
+        }
+        f.release(r.qkv);
+        void* d_xn = dgrad(f, K1, d_qkv, 3 * HID, p.qkv, 0, cc, nullptr, 0, r.h, r.w);
+        f.release(d_qkv);
+        void* d_x = f.f32(M, cc);
+        RUN("layernorm_bwd", 0.0, 0.0,
+            sdc_channel_layernorm_bwd((const float*)d_xn, r.xin, f.f16 ? 1 : 0, p.g_in, (const float*)g, (float*)d_x, M, cc, 1, f.stream));
+        f.release(d_xn);
+        return d_x;
+    };
+    auto add_into = [&](void* a, const void* b, int64_t count) {
+        RUN("add_inplace", 0.0, 0.0, sdc_add_inplace((float*)a, (const float*)b, count, 1, f.stream));
+    };
+    int i = (int)tape.size() - 1;
+    void* g = f.f32((int64_t)B * H * W, cfin);
+    RUN("head_conv1_bwd", 0.0, 0.0, sdc_head_conv1_bwd(g_eps, n->head_w, (float*)g, B, H * W, cfin, n->out_dim, 1, f.stream));
+    void *g_main = nullptr, *g_r = nullptr;
+    resnet_bwd(tape[i], g, g_main, g_r);
+    f.release(g);
+    g = g_main;
+    --i;
+    std::vector<void*> skip_grads;
+    int gc = n->ups.empty() ? cfin : tape[i].cv ? tape[i].cv->cout : cfin;   // channel count of g (tracked below)
+    (void)gc;
+    for (; i >= 0; --i) {
+        const Rec& r = tape[i];
+        if (r.kind == 4) {          // up
+            const ConvP& cw = *r.cv;
+            if (r.flag) {
+                void* g_hi = dgrad(f, K3, g, cw.cout, cw, 0, r.c, nullptr, 0, r.h, r.w);
+                f.release(g);
+                g = f.f32((int64_t)B * (r.h / 2) * (r.w / 2), r.c);
+                RUN("upsample2x_bwd", 0.0, 0.0, sdc_upsample2x_bwd((const float*)g_hi, (float*)g, B, r.h / 2, r.w / 2, r.c, 1, f.stream));
+                f.release(g_hi);
+            } else {
+                void* g2 = dgrad(f, K3, g, cw.cout, cw, 0, r.c, nullptr, 1, r.h, r.w);
+                f.release(g);
+                g = g2;
+            }
+        } else if (r.kind == 1) {   // attention
+            void* g2 = attn_bwd(r, g);
+            f.release(g);
+            g = g2;
+        } else if (r.kind == 0) {   // resnet
+            void *a = nullptr, *b = nullptr;
+            resnet_bwd(r, g, a, b);
+            f.release(g);
+            g = a;
+            if (b) skip_grads.push_back(b);
+        } else if (r.kind == 3) {   // down: the tensor entering it was also pushed as a skip
+            const ConvP& cw = *r.cv;
+            void* sg = skip_grads.back(); skip_grads.pop_back();
+            if (r.flag) {
+                void* t = dgrad(f, K1, g, cw.cout, cw, 0, 4 * r.c, nullptr, 0, r.h, r.w);
+                f.release(g);
+                g = f.f32((int64_t)B * 4 * r.h * r.w, r.c);
+                RUN("pixel_shuffle_bwd", 0.0, 0.0, sdc_pixel_shuffle_bwd((const float*)t, (const float*)sg, (float*)g, B, r.h, r.w, r.c, 1, f.stream));
+                f.release(t);
+            } else {
+                void* g2 = dgrad(f, K3, g, cw.cout, cw, 0, r.c, sg, 1, r.h, r.w);
+                f.release(g);
+                g = g2;
+            }
+            f.release(sg);
+        } else if (r.kind == 2) {   // push: consumed by the following "down" record, else add the skip gradient here
+            if (!(i + 1 < (int)tape.size() && tape[i + 1].kind == 3)) {
+                void* sg = skip_grads.back(); skip_grads.pop_back();
+                const Rec& prev = tape[i - 1];   // the resnet whose output was pushed: its geometry gives the element count
+                add_into(g, sg, (int64_t)B * prev.h * prev.w * prev.blk->cout);
+                f.release(sg);
+            }
+        }
+    }
+    if (!skip_grads.empty()) { set_error("sdc_unet_backward_data: internal skip-gradient mismatch"); return SDC_ERR_STATE; }
+    add_into(g, g_r, (int64_t)B * H * W * n->init_dim);   // the stem output also feeds final_res_block (r = x.clone(), unet.py:393)
+    f.release(g_r);
+    void* t = f.f32((int64_t)B * H * W, n->stem_kp2);
+    {
+        ConvP st = n->stem;
+        if (!f.dry && !f.rc) {
+            f.begin("conv1x1", 0.0, 0.0);
+            const int rc2 = sdc_conv_gemm(SDC_PREC_TF32, K1, g, n->init_dim, nullptr, 0, n->stem_wt, nullptr, nullptr, t, nullptr, 0, B, H, W, n->stem_kp2, f.stream);
+            f.end();
+            if (rc2) f.rc = rc2;
+        }
+    }
+    RUN("stem_col2im", 0.0, 0.0, sdc_stem_col2im((const float*)t, gx, B, n->channels, H, W, n->stem_kp2, f.stream));
+    return f.rc;
+}
+
 }  // namespace
 
 // ------------------------------------------------------------------------------------------------ C ABI
@@ -642,6 +962,8 @@ extern "C" int sdc_unet_create(sdc_unet** out, int dim, const int* dim_mults, in
     want(n, &n->stem.packed, (int64_t)dim * n->stem_kp * esz);
     want(n, (void**)&n->stem.bias, dim * 4);
     want(n, (void**)&n->stem_rep, (int64_t)dim * n->stem_kp * 4);
+    n->stem_kp2 = (k_stem + 63) / 64 * 64;
+    n->dslab_items.push_back({(void**)&n->stem_wt, (int64_t)n->stem_kp2 * dim * 4});
     std::vector<int> dims{dim};
     for (int m : n->mults) dims.push_back(dim * m);
     const int nl = n_mults;
@@ -701,6 +1023,9 @@ extern "C" int sdc_unet_create(sdc_unet** out, int dim, const int* dim_mults, in
     int64_t total = 0;
     for (auto& it : n->slab_items) total += (it.second + 255) / 256 * 256;
     n->slab_bytes = total;
+    total = 0;
+    for (auto& it : n->dslab_items) total += (it.second + 255) / 256 * 256;
+    n->dslab_bytes = total;
     *out = n;
     return SDC_OK;
 }
@@ -708,6 +1033,7 @@ extern "C" int sdc_unet_create(sdc_unet** out, int dim, const int* dim_mults, in
 extern "C" void sdc_unet_destroy(sdc_unet* n) {
     if (!n) return;
     if (n->slab) cudaFree(n->slab);
+    if (n->dslab) cudaFree(n->dslab);
     for (auto& e : n->prof) { cudaEventDestroy(e.e0); cudaEventDestroy(e.e1); }
     delete n;
 }
@@ -752,6 +1078,7 @@ int copy_param(sdc_unet* n, float* dst, const float* const* params, int idx, cud
 int pack_conv(sdc_unet* n, ConvP& c, const float* const* params, void* stream) {
     int rc = sdc_pack_conv_weight(n->prec, c.kind == KUN ? KUN : c.kind, params[c.w], c.packed, c.cout, c.cin, stream);
     if (rc) return rc;
+    if (n->want_bwd && (rc = sdc_pack_conv_weight_dgrad(c.kind == K3 ? 1 : (c.kind == KUN ? 2 : 0), params[c.w], c.wt, c.cout, c.cin, stream))) return rc;
     if (c.up) { rc = sdc_pack_conv_weight(n->prec, KUP, params[c.w], c.packed_up, c.cout, c.cin, stream); if (rc) return rc; }
     if (c.b >= 0) return copy_param(n, c.bias, params, c.b, as_stream(stream));
     return SDC_OK;
@@ -795,7 +1122,18 @@ extern "C" int sdc_unet_pack_weights(sdc_unet* n, const float* const* params, in
         int64_t off = 0;
         for (auto& it : n->slab_items) { *it.first = n->slab + off; off += (it.second + 255) / 256 * 256; }
     }
+    if (n->want_bwd && !n->dslab) {
+        PLAN_CUDA(cudaMalloc((void**)&n->dslab, (size_t)n->dslab_bytes));
+        int64_t off = 0;
+        for (auto& it : n->dslab_items) { *it.first = n->dslab + off; off += (it.second + 255) / 256 * 256; }
+    }
     int rc;
+    if (n->want_bwd) {
+        // stem data gradient: dY[M, c] x W[c, Cin*49] as a 1x1 convolution onto kp2 (zero padded) columns
+        PLAN_CUDA(cudaMemsetAsync(n->stem_wt, 0, (size_t)n->stem_kp2 * n->dim * 4, st));
+        if ((rc = sdc_pack_conv_weight_dgrad(0, params[n->stem.w], n->stem_wt, n->dim, n->channels * 49, stream))) return rc;
+    }
+    n->bwd_packed = n->want_bwd;
     // stem: replicate the 7x7 weight into the (high | low) column ranges, then pack as a 1x1 GEMM operand
     {
         const int c = n->dim, k = n->channels * 49, kp = n->stem_kp;
@@ -895,6 +1233,53 @@ extern "C" int sdc_unet_forward(sdc_unet* n, const float* x, const int32_t* t_in
     return rc;
 }
 
+static int64_t vjp_workspace(const sdc_unet* n, int B, int H, int W) {
+    Fwd f{};
+    f.n = const_cast<sdc_unet*>(n); f.dry = true; f.stream = nullptr; f.B = B; f.prec = n->prec; f.f16 = n->prec == SDC_PREC_F16;
+    f.esz = f.f16 ? 2 : 4;
+    f.ar.reset((void*)(uintptr_t)4096, 0, true);
+    float dummy_film = 0.f;
+    f.film = &dummy_film;
+    if (run_vjp(f.n, f, nullptr, nullptr, (float*)(uintptr_t)4096, (float*)(uintptr_t)4096, H, W)) return 0;
+    return f.ar.high;
+}
+
+extern "C" int64_t sdc_unet_backward_workspace_bytes(const sdc_unet* n, int B, int H, int W) {
+    if (!n || B <= 0 || H <= 0 || W <= 0) return 0;
+    return vjp_workspace(n, B, H, W);
+}
+
+extern "C" int sdc_unet_backward_data(sdc_unet* n, const float* x, const int32_t* t_index, int t_uniform, const float* grad_eps, float* eps,
+                                      float* grad_x, int B, int H, int W, void* workspace, int64_t workspace_bytes, void* stream) {
+    SDC_REQUIRE(n && x && grad_eps && eps && grad_x && workspace, "sdc_unet_backward_data: null arguments");
+    if (!n->packed || !n->bwd_packed) {
+        set_error("sdc_unet_backward_data: set SDC_UNET_BACKWARD and call sdc_unet_pack_weights first (the data-gradient weights are not packed)");
+        return SDC_ERR_STATE;
+    }
+    const int down = 1 << ((int)n->mults.size() - 1);
+    SDC_REQUIRE(B > 0 && H % down == 0 && W % down == 0 && 128 % W == 0 && (H / down) * (W / down) % 32 == 0,
+                "sdc_unet_backward_data: unsupported image size %d x %d", H, W);
+    SDC_REQUIRE(t_index || (t_uniform >= 0 && t_uniform < n->table_T), "sdc_unet_backward_data: diffusion time %d outside the FiLM table", t_uniform);
+    SDC_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 1023) == 0, "sdc_unet_backward_data: workspace must be 1024-byte aligned");
+    const int64_t need = vjp_workspace(n, B, H, W);
+    if (workspace_bytes < need) {
+        set_error("sdc_unet_backward_data: workspace of %lld bytes, need %lld", (long long)workspace_bytes, (long long)need);
+        return SDC_ERR_STATE;
+    }
+    Fwd f{};
+    f.n = n; f.dry = false; f.stream = stream; f.B = B; f.prec = n->prec; f.f16 = n->prec == SDC_PREC_F16;
+    f.esz = f.f16 ? 2 : 4;
+    f.ar.reset(workspace, workspace_bytes, false);
+    f.E = n->film_total;
+    f.t_index = t_index;
+    f.film = t_index ? n->table : n->table + (int64_t)t_uniform * n->film_total;
+    if (n->prof_on) n->prof_used = 0;
+    nvtxRangePushA("sdc_unet_backward_data");
+    const int rc = run_vjp(n, f, x, grad_eps, eps, grad_x, H, W);
+    nvtxRangePop();
+    return rc;
+}
+
 extern "C" int sdc_unet_film_table(const sdc_unet* n, float* out, int* rows, int* cols, void* stream) {
     SDC_REQUIRE(n, "sdc_unet_film_table: null handle");
     if (rows) *rows = n->table_T;
@@ -907,7 +1292,8 @@ extern "C" int sdc_unet_film_table(const sdc_unet* n, float* out, int* rows, int
 }
 
 extern "C" int sdc_unet_set_flag(sdc_unet* n, int flag, int value) {
-    SDC_REQUIRE(n && (flag == SDC_UNET_FUSE_LN || flag == SDC_UNET_FUSE_GN || flag == SDC_UNET_FILM_TC), "sdc_unet_set_flag: unknown flag %d", flag);
+    SDC_REQUIRE(n && flag >= SDC_UNET_FUSE_LN && flag <= SDC_UNET_BACKWARD, "sdc_unet_set_flag: unknown flag %d", flag);
+    if (flag == SDC_UNET_BACKWARD) { n->want_bwd = value != 0; return SDC_OK; }   // takes effect at the next sdc_unet_pack_weights
     if (flag == SDC_UNET_FUSE_LN) n->fuse_ln = value != 0;
     else if (flag == SDC_UNET_FUSE_GN) n->fuse_gn = value != 0;
     else n->film_tc = value != 0;   // takes effect at the next sdc_unet_pack_weights

@@ -69,6 +69,8 @@ L.register({
     "sdc_unet_workspace_bytes": (c_i64, [c_p, c_i, c_i, c_i]),
     "sdc_unet_forward": (c_i, [c_p, c_p, c_p, c_i, c_p, c_i, c_i, c_i, c_p, c_i64, c_p, c_p]),
     "sdc_unet_set_flag": (c_i, [c_p, c_i, c_i]),
+    "sdc_unet_backward_workspace_bytes": (c_i64, [c_p, c_i, c_i, c_i]),
+    "sdc_unet_backward_data": (c_i, [c_p, c_p, c_p, c_i, c_p, c_p, c_p, c_i, c_i, c_i, c_p, c_i64, c_p]),
     "sdc_unet_film_table": (c_i, [c_p, c_p, ctypes.POINTER(c_i), ctypes.POINTER(c_i), c_p]),
     "sdc_gn_silu_rowstats": (c_i, [c_p, c_p, c_p, c_p, c_p, c_p, c_i64, c_p, c_p, c_p, c_i, c_i, c_i, c_p]),
     "sdc_pack_qkv_ln": (c_i, [c_p, c_p, c_p, c_p, c_i, c_i, c_p]),
@@ -351,6 +353,7 @@ class UnetPlan:
         self.nonfinite = None
         self.key = None
         self.flags = (False, False)   # (fuse_ln, fuse_gn): the handle's defaults
+        self.backward = False         # data-gradient weights packed (SDC_UNET_BACKWARD)
 
     def __del__(self):
         try:
@@ -398,7 +401,7 @@ class UnetPlan:
                                          L.ptr(self.nonfinite), _st()))
         return out
 
-    FUSE_LN, FUSE_GN, FILM_TC = 1, 2, 3
+    FUSE_LN, FUSE_GN, FILM_TC, BACKWARD = 1, 2, 3, 4
 
     def film_table(self):
         """Copy of the executor's FiLM table [table_timesteps, E] (tests compare it with the time MLP evaluated by torch)."""
@@ -412,6 +415,19 @@ class UnetPlan:
         """Schedule switches of include/safediffcon_b200_plan.h (SDC_UNET_FUSE_LN, SDC_UNET_FUSE_GN)."""
         L.check(L.lib().sdc_unet_set_flag(self.handle, int(flag), int(value)))
         self.workspaces.clear()
+
+    def vjp(self, x, grad_eps, t_index=None, t_uniform=0):
+        """(eps, d<eps, grad_eps>/dx) through ONE C call (sdc_unet_backward_data); needs the BACKWARD flag set before packing."""
+        B, _, H, W = x.shape
+        need = int(L.lib().sdc_unet_backward_workspace_bytes(self.handle, B, H, W))
+        if need <= 0:
+            L.check(1)
+        ws = torch.empty(need, dtype=torch.uint8, device=x.device)
+        eps = torch.empty(B, self.out_dim, H, W, device=x.device, dtype=torch.float32)
+        gx = torch.empty_like(x)
+        L.check(L.lib().sdc_unet_backward_data(self.handle, L.ptr(x), L.ptr(t_index), int(t_uniform), L.ptr(grad_eps), L.ptr(eps), L.ptr(gx),
+                                               B, H, W, L.ptr(ws), ws.numel(), _st()))
+        return eps, gx
 
     def profile(self, enable):
         L.check(L.lib().sdc_unet_profile_enable(self.handle, int(enable)))
@@ -573,9 +589,9 @@ class Unet2D(nn.Module):
         return True
 
     # ------------------------------------------------------------------ C++ executor (inference)
-    def _plan_ready(self):
+    def _plan_ready(self, backward=False):
         """The C++ executor with weights packed for the current parameter values, or None when this configuration runs on the
-        Python schedule (SDC_NO_PLAN=1, or FP16 with fp32 intermediates)."""
+        Python schedule (SDC_NO_PLAN=1, or FP16 with fp32 intermediates).  backward: also pack the data-gradient weights."""
         if not USE_PLAN or (self.precision == "f16" and not self.compact_intermediates):
             return None
         prec = self._prec()
@@ -589,6 +605,9 @@ class Unet2D(nn.Module):
             plan.set_flag(UnetPlan.FUSE_LN, self.fuse_layernorm)
             plan.set_flag(UnetPlan.FUSE_GN, self.fuse_groupnorm)
             plan.flags = (self.fuse_layernorm, self.fuse_groupnorm)
+        if backward and not plan.backward:
+            plan.set_flag(UnetPlan.BACKWARD, 1)
+            plan.backward, plan.key = True, None   # repack below
         key = self._key()
         if plan.key != key:
             dev = self.init_conv.weight.device
@@ -772,6 +791,18 @@ class Unet2D(nn.Module):
     def vjp(self, x, time, grad_eps):
         """(eps, d<eps, grad_eps>/dx) in one call: forward with saved activations, then the backward-data pass."""
         x = L.dev_f32(x, "x")
+        if self.init_conv.weight.shape[0] == self.dim and (isinstance(time, int) or not torch.is_floating_point(time)):
+            plan = self._plan_ready(backward=True)
+            if plan is not None:   # ONE C call: recording forward + reverse walk inside the executor (sdc_unet_backward_data)
+                with torch.no_grad(), torch.cuda.device(x.device):
+                    g = L.dev_f32(grad_eps, "grad_eps")
+                    if isinstance(time, int):
+                        if not 0 <= time < self.table_timesteps:
+                            raise ValueError(f"safediffcon_b200.Unet2D: diffusion time {time} outside the FiLM table [0, {self.table_timesteps})")
+                        return plan.vjp(x, g, None, time)
+                    if bool(((time < 0) | (time >= self.table_timesteps)).any()):
+                        raise ValueError(f"safediffcon_b200.Unet2D: integer diffusion times must lie in [0, {self.table_timesteps})")
+                    return plan.vjp(x, g, time.to(device=x.device, dtype=torch.int32).reshape(-1).contiguous(), 0)
         tape = []
         with torch.no_grad(), torch.cuda.device(x.device):
             if isinstance(time, int):
