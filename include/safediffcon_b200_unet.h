@@ -236,6 +236,15 @@ int sdc_stem_col2im(const float* t, float* dx, int B, int Cin, int H, int W, int
 int sdc_conv_wgrad(int kind, int a_half, const void* a0, int c0, const void* a1, int c1, const float* dy, float* dw,
                    int B, int H, int W, int Cout, void* stream);
 
+/* The same weight gradient on tcgen05 (kind 0 / 1; Cout, c0, c1 multiples of 128; W in {16, 32, 64, 128}): the PIXEL axis is the
+ * GEMM's K, both operands are read MN-major straight from their pixel-row layout (TMA boxes of dY and of the tap-shifted,
+ * zero-padded activation window; tcgen05.mma.kind::tf32 with MN-major descriptors), fp32 accumulation in TMEM, pixel slices of a
+ * tile added into dw with red.global.add.f32.  fp16 activations are first converted (exactly) to fp32 into `scratch`
+ * (sdc_conv_wgrad_tc_scratch bytes, caller-owned).  Returns -1 (nothing done) for shapes it does not take: use sdc_conv_wgrad. */
+int64_t sdc_conv_wgrad_tc_scratch(int a_half, int c0, int c1, int B, int H, int W);
+int sdc_conv_wgrad_tc(int kind, int a_half, const void* a0, int c0, const void* a1, int c1, const float* dy, float* dw, int B, int H,
+                      int W, int Cout, void* scratch, int64_t scratch_bytes, void* stream);
+
 /* out[c] += sum over the M rows of x[M, C] (conv bias gradient from dY). */
 int sdc_colsum(const float* x, float* out, int64_t M, int C, void* stream);
 

@@ -53,6 +53,8 @@ L.register({
     "sdc_head_conv1_bwd": (c_i, [c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_p]),
     "sdc_stem_col2im": (c_i, [c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_p]),
     "sdc_conv_wgrad": (c_i, [c_i, c_i, c_p, c_i, c_p, c_i, c_p, c_p, c_i, c_i, c_i, c_i, c_p]),
+    "sdc_conv_wgrad_tc_scratch": (c_i64, [c_i, c_i, c_i, c_i, c_i, c_i]),
+    "sdc_conv_wgrad_tc": (c_i, [c_i, c_i, c_p, c_i, c_p, c_i, c_p, c_p, c_i, c_i, c_i, c_i, c_p, c_i64, c_p]),
     "sdc_colsum": (c_i, [c_p, c_p, c_i64, c_i, c_p]),
     "sdc_gn_param_grad": (c_i, [c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_i64, c_p, c_i, c_i, c_i, c_p]),
     "sdc_channel_layernorm_gain_grad": (c_i, [c_p, c_p, c_i, c_p, c_i64, c_i, c_p]),
@@ -243,6 +245,25 @@ def conv_gemm(kind, a0, c0, a1, c1, wp, bias, residual, out, stats, operand_out,
         k_alg = taps * (c0 + c1) if algo_k is None else algo_k
         rows = B * H * W * (4 if kind == KIND_UP2X else 1)
         prof.append((e0, e1, 2.0 * rows * Cout * k_alg, (kind, B, H, W, c0 + c1, Cout)))
+
+
+USE_WGRAD_TC = os.environ.get("SDC_WGRAD_TC", "1") != "0"   # conv weight gradients on tcgen05 where the shape allows
+
+
+def conv_wgrad_any(kind, a0, c0, a1, c1, dy, dw, B, H, W, Cout):
+    """dw += conv weight gradient (OIHW): tcgen05 kernel (pixel axis = K, MN-major operands) when the shape is eligible, else the
+    mma.sync kernel (include/safediffcon_b200_unet.h: sdc_conv_wgrad_tc / sdc_conv_wgrad)."""
+    lib = L.lib()
+    half = int(a0.dtype == torch.float16)
+    if USE_WGRAD_TC:
+        nb = int(lib.sdc_conv_wgrad_tc_scratch(half, c0, c1, B, H, W))
+        scratch = torch.empty(nb, dtype=torch.uint8, device=dy.device) if nb else None
+        rc = lib.sdc_conv_wgrad_tc(kind, half, L.ptr(a0), c0, L.ptr(a1), c1, L.ptr(dy), L.ptr(dw), B, H, W, Cout, L.ptr(scratch), nb, _st())
+        if rc == 0:
+            return
+        if rc > 0:
+            L.check(rc)
+    L.check(lib.sdc_conv_wgrad(kind, half, L.ptr(a0), c0, L.ptr(a1), c1, L.ptr(dy), L.ptr(dw), B, H, W, Cout, _st()))
 
 
 def pack_conv_weight(kind, w, prec=PREC_TF32):
@@ -1157,8 +1178,7 @@ class Unet2D(nn.Module):
             """weight (+ bias) gradient of convolution `cw` from its forward inputs and the gradient of its output"""
             m = cw["mod"]
             dw = torch.zeros(m.weight.shape, device=dev, dtype=torch.float32)
-            L.check(lib.sdc_conv_wgrad(kind, int(a0.dtype == torch.float16), L.ptr(a0), c0, L.ptr(a1), c1, L.ptr(dy), L.ptr(dw),
-                                       B, h, w, cw["cout"], _st()))
+            conv_wgrad_any(kind, a0, c0, a1, c1, dy, dw, B, h, w, cw["cout"])
             acc_grad(m.weight, dw)
             if m.bias is not None:
                 db = torch.zeros(cw["cout"], device=dev, dtype=torch.float32)

@@ -74,6 +74,54 @@ def test_conv_wgrad_vs_autograd(case):
     assert rel(dw.cpu(), 2 * want) < 1e-3
 
 
+TC_CASES = [
+    # kind, half, B, H, W, c0, c1, cout
+    (1, 1, 3, 16, 128, 128, 0, 128),     # full-resolution level, 64-pixel half rows, fp16 activations (converted)
+    (1, 0, 2, 16, 128, 128, 128, 128),   # concat input (two K... two N segments), fp32 activations
+    (1, 1, 5, 8, 64, 256, 128, 256),     # 8x64 level
+    (0, 1, 4, 4, 32, 128, 0, 384),       # qkv projection, 4x32: two rows per pixel tile
+    (1, 1, 6, 2, 16, 512, 0, 128),       # 2x16 level: a pixel tile spans two images
+    (1, 0, 7, 2, 16, 128, 0, 256),       # odd batch: the last tile is half out of range (TMA zero fill)
+    (0, 1, 3, 16, 128, 256, 0, 128),     # 1x1 res_conv
+]
+
+
+@pytest.mark.parametrize("case", TC_CASES, ids=[f"k{c[0]}_h{c[1]}_B{c[2]}_{c[3]}x{c[4]}_c{c[5]}+{c[6]}_o{c[7]}" for c in TC_CASES])
+def test_conv_wgrad_tcgen05_vs_autograd(case):
+    """sdc_conv_wgrad_tc (tcgen05 kind::tf32, MN-major operands, pixel axis = K) against autograd in fp64 and against the mma.sync kernel."""
+    L, lib, U = _L()
+    kind, half, B, H, W, c0, c1, cout = case
+    g = torch.Generator().manual_seed(17 * c0 + cout + H)
+    cin = c0 + c1
+    ksz = 3 if kind == 1 else 1
+    adt = torch.float16 if half else torch.float32
+    x = torch.randn(B, cin, H, W, generator=g).to(adt)
+    if not half:
+        x = (x.view(torch.int32) & ~0x1FFF).view(torch.float32)   # TF32-representable (what an fp32 operand tensor holds)
+    gy = torch.randn(B, cout, H, W, generator=g)
+    gy = (gy.view(torch.int32) & ~0x1FFF).view(torch.float32)     # dY arrives TF32-rounded from the backward-data pass
+    w = torch.zeros((cout, cin, ksz, ksz), dtype=torch.float64, requires_grad=True)
+    y = F.conv2d(x.double(), w, padding=1 if kind == 1 else 0)
+    (want,) = torch.autograd.grad(y, w, gy.double())
+    rows = nhwc_rows(x).cuda()
+    a0 = rows[:, :c0].contiguous()
+    a1 = rows[:, c0:].contiguous() if c1 else None
+    dy = nhwc_rows(gy).cuda()
+    dw = torch.zeros((cout, cin, ksz, ksz), device="cuda")
+    nb = int(lib.sdc_conv_wgrad_tc_scratch(half, c0, c1, B, H, W))
+    scratch = torch.empty(max(nb, 16), dtype=torch.uint8, device="cuda")
+    rc = lib.sdc_conv_wgrad_tc(kind, half, L.ptr(a0), c0, L.ptr(a1), c1, L.ptr(dy), L.ptr(dw), B, H, W, cout, L.ptr(scratch), nb, L.stream_ptr())
+    assert rc == 0, rc
+    torch.cuda.synchronize()
+    err = rel(dw.cpu(), want)
+    assert err < 2e-5, err          # exact TF32 products, fp32 accumulation
+    old = torch.zeros_like(dw)
+    L.check(lib.sdc_conv_wgrad(kind, half, L.ptr(a0), c0, L.ptr(a1), c1, L.ptr(dy), L.ptr(old), B, H, W, cout, L.stream_ptr()))
+    assert rel(dw, old) < 2e-5
+    rc = lib.sdc_conv_wgrad_tc(kind, half, L.ptr(a0), c0, L.ptr(a1), c1, L.ptr(dy), L.ptr(dw), B, H, W, cout, L.ptr(scratch), nb, L.stream_ptr())
+    assert rc == 0 and rel(dw.cpu(), 2 * want) < 2e-5     # accumulation semantics
+
+
 def test_colsum_and_head_wgrad():
     L, lib, U = _L()
     g = torch.Generator().manual_seed(3)
