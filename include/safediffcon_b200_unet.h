@@ -84,6 +84,14 @@ int sdc_stem_conv7(int prec, const float* x, const float* w, const float* bias, 
  * the product sees x to ~2^-22 with fp16 / tf32 operands. */
 int sdc_stem_im2col(int prec, const float* x, void* a, int B, int Cin, int H, int W, int kp, void* stream);
 
+/* The whole stem in ONE tcgen05 kernel (FP16 mode, W = 128, Cout = 128, Cin <= 3): the [128 px x 320] patch tile of an image row is
+ * written by the kernel's own warps into shared memory in the K-major SWIZZLE_128B operand layout (high | low split as in
+ * sdc_stem_im2col) and multiplied against the resident weight matrix -- the patch matrix never exists in HBM (round 1: 1.3 GB
+ * written and read back per evaluation at B = 1024).  w_packed: sdc_pack_conv_weight(kind 0) of the [Cout, 320] matrix holding the
+ * stem weight at columns 0 and 160.  out: NHWC fp16 [B*H*W, Cout] (+ bias).  Returns -1 (nothing done) for other shapes. */
+int sdc_stem_conv7_tc(const float* x, const void* w_packed, const float* bias, void* out, int B, int Cin, int H, int W, int Cout, int kp,
+                      void* stream);
+
 /* GroupNorm(1, C) apply + FiLM + SiLU (+ residual), Block.forward (unet.py:138-147) and ResnetBlock's sum (:180):
  * y = silu(((x - mean_b) * rstd_b * gamma_c + beta_c) * (scale_bc + 1) + shift_bc) + res ; mean/rstd from
  * stats[b] = (sum, sumsq) over C*HW elements, eps 1e-5, biased variance.  scale_shift: [n_t, 2C] rows

@@ -539,11 +539,20 @@ int run_forward(sdc_unet* n, Fwd& f, const float* x, float* eps, int H, int W, u
     void* cur = f.opd((int64_t)B * H * W, c);
     {
         Range r(f, "init_conv");
-        void* patches = f.opd((int64_t)B * H * W, n->stem_kp);
-        RUN("stem_im2col", (double)B * H * W * (n->channels * 4.0 + n->stem_kp * (double)f.esz), 0.0,
-            sdc_stem_im2col(f.prec, x, patches, B, n->channels, H, W, n->stem_kp, f.stream));
-        conv(f, K1, patches, n->stem_kp, nullptr, 0, n->stem, n->stem.packed, nullptr, cur, nullptr, 1, H, W, n->channels * 49.0);
-        f.release(patches);
+        static const bool stem_tc = []() { const char* e = getenv("SDC_STEM_TC"); return !(e && e[0] == '0'); }();
+        int rc = -1;
+        if (f.f16 && stem_tc && W == 128 && n->init_dim == 128 && n->stem_kp == 320 && n->channels <= 3) {
+            rc = 0;   // (eligibility mirrors sdc_stem_conv7_tc, so that the dry run lays out the same buffers)
+            RUN("stem_conv7", (double)B * H * W * (n->channels * 4.0 + c * 2.0), 2.0 * B * H * W * c * n->channels * 49.0,
+                sdc_stem_conv7_tc(x, n->stem.packed, n->stem.bias, cur, B, n->channels, H, W, c, n->stem_kp, f.stream));
+        }
+        if (rc != 0) {
+            void* patches = f.opd((int64_t)B * H * W, n->stem_kp);
+            RUN("stem_im2col", (double)B * H * W * (n->channels * 4.0 + n->stem_kp * (double)f.esz), 0.0,
+                sdc_stem_im2col(f.prec, x, patches, B, n->channels, H, W, n->stem_kp, f.stream));
+            conv(f, K1, patches, n->stem_kp, nullptr, 0, n->stem, n->stem.packed, nullptr, cur, nullptr, 1, H, W, n->channels * 49.0);
+            f.release(patches);
+        }
     }
     void* r0 = cur;
     const int r_c = c;

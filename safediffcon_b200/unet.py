@@ -26,6 +26,7 @@ L.register({
     "sdc_conv3x3_row_gn_head": (c_i, [c_p, c_i, c_p, c_i, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_p]),
     "sdc_stem_conv7": (c_i, [c_i, c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_p]),
     "sdc_stem_im2col": (c_i, [c_i, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_p]),
+    "sdc_stem_conv7_tc": (c_i, [c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_i, c_p]),
     "sdc_gn_silu": (c_i, [c_i, c_p, c_i, c_p, c_p, c_p, c_p, c_p, c_i64, c_p, c_i, c_p, c_i, c_i, c_i, c_p]),
     "sdc_gn_silu_head": (c_i, [c_p, c_p, c_p, c_p, c_p, c_i, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_p]),
     "sdc_channel_layernorm": (c_i, [c_i, c_p, c_i, c_p, c_p, c_p, c_i64, c_i, c_i, c_p]),
@@ -247,6 +248,7 @@ def conv_gemm(kind, a0, c0, a1, c1, wp, bias, residual, out, stats, operand_out,
         prof.append((e0, e1, 2.0 * rows * Cout * k_alg, (kind, B, H, W, c0 + c1, Cout)))
 
 
+USE_STEM_TC = os.environ.get("SDC_STEM_TC", "1") != "0"     # the stem as one tcgen05 kernel (csrc/stem_conv.cu)
 USE_WGRAD_TC = os.environ.get("SDC_WGRAD_TC", "1") != "0"   # conv weight gradients on tcgen05 where the shape allows
 
 
@@ -1042,10 +1044,16 @@ class Unet2D(nn.Module):
 
         c = self.init_conv.weight.shape[0]
         cur = opd(B * H * W, c)
-        patches = opd(B * H * W, pk["stem"]["kp"])
-        L.check(lib.sdc_stem_im2col(prec, L.ptr(x), L.ptr(patches), B, Cin, H, W, pk["stem"]["kp"], _st()))
-        conv(KIND_1x1, patches, pk["stem"]["kp"], None, 0, pk["stem"], None, cur, None, True, H, W, algo_k=Cin * 49)
-        del patches
+        rc = -1
+        if prec == PREC_F16 and USE_STEM_TC:   # the whole stem in one tcgen05 kernel (no patch matrix in HBM)
+            rc = lib.sdc_stem_conv7_tc(L.ptr(x), L.ptr(pk["stem"]["w"]), L.ptr(pk["stem"]["b"]), L.ptr(cur), B, Cin, H, W, c, pk["stem"]["kp"], _st())
+            if rc > 0:
+                L.check(rc)
+        if rc != 0:
+            patches = opd(B * H * W, pk["stem"]["kp"])
+            L.check(lib.sdc_stem_im2col(prec, L.ptr(x), L.ptr(patches), B, Cin, H, W, pk["stem"]["kp"], _st()))
+            conv(KIND_1x1, patches, pk["stem"]["kp"], None, 0, pk["stem"], None, cur, None, True, H, W, algo_k=Cin * 49)
+            del patches
         r, r_c = cur, c
         h, w = H, W
         skips = []

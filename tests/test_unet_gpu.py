@@ -167,6 +167,34 @@ def test_stem_tensor_core_vs_torch(prec):
         assert (out.double() - ref).abs().max().item() < 2e-5 * ref.abs().max().item()
 
 
+@pytest.mark.parametrize("B", [1, 3, 37, 300])
+def test_stem_one_kernel_vs_torch(B):
+    """sdc_stem_conv7_tc (operand tile built in shared memory by the kernel itself, resident weights) == the 7x7 pad-3 convolution
+    with fp16-rounded weights on the fp32 input (high + low split), fp16 NHWC output, and == the im2col + GEMM pair."""
+    L, lib = _L()
+    from safediffcon_b200 import unet as U
+    cout, kp = 128, 320
+    g = torch.Generator().manual_seed(B)
+    x = (torch.randn(B, 3, 16, 128, generator=g) * 1.3).cuda()
+    w = (torch.randn(cout, 3, 7, 7, generator=g) * 0.1).cuda()
+    b = torch.randn(cout, generator=g).cuda()
+    wrep = torch.zeros(cout, kp).cuda()
+    wrep[:, :147] = w.reshape(cout, 147)
+    wrep[:, 160:307] = w.reshape(cout, 147)
+    wp = U.pack_conv_weight(0, wrep.reshape(cout, kp, 1, 1), F16)
+    out = torch.full((B * 2048, cout), float("nan"), dtype=torch.float16).cuda()
+    assert lib.sdc_stem_conv7_tc(L.ptr(x), L.ptr(wp), L.ptr(b), L.ptr(out), B, 3, 16, 128, cout, kp, L.stream_ptr()) == 0
+    torch.cuda.synchronize()
+    ref = nhwc(F.conv2d(x.double(), quant(w.cpu(), F16).cuda().double(), b.double(), padding=3)).reshape(-1, cout)
+    assert torch.isfinite(out.float()).all()
+    assert (out.double() - ref).abs().max().item() < 6e-4 * ref.abs().max().item()      # fp16 rounding of the output only
+    patches = torch.empty(B * 2048, kp, dtype=torch.float16).cuda()
+    L.check(lib.sdc_stem_im2col(F16, L.ptr(x), L.ptr(patches), B, 3, 16, 128, kp, L.stream_ptr()))
+    old = torch.empty(B * 2048, cout, dtype=torch.float16).cuda()
+    U.conv_gemm(0, patches, kp, None, 0, wp, b, None, old, None, True, B, 16, 128, cout, F16)
+    assert (out.float() - old.float()).abs().max().item() <= 2 ** -9 * ref.abs().max().item()   # same products, fp32 sum order differs
+
+
 @pytest.mark.parametrize("prec", [TF32, F16])
 def test_gn_silu_vs_torch(prec):
     L, lib = _L()
