@@ -34,10 +34,11 @@ namespace sdc {
 // ------------------------------------------------------------------------------------------ kernel
 constexpr int BM = 128;        // output pixels per tile (= UMMA M)
 constexpr int A_BYTES = BM * 128;   // one K block of activations: 128 rows of 128 bytes (32 TF32 or 64 FP16 channels)
-constexpr int EPI_WARPS = 8;   // two warps per TMEM lane quarter, alternating 32-column chunks
-constexpr int GEMM_THREADS = 64 + 32 * EPI_WARPS;
-constexpr int STG_BUF = 4096;  // one epilogue staging buffer: 32 rows x 128 bytes (TMA-store box)
-constexpr int STG_BYTES = EPI_WARPS * STG_BUF;   // one buffer per epilogue warp
+// Epilogue warps: EPI = 8 (two per TMEM lane quarter, alternating 32-column chunks) for the tensor-bound convolutions; EPI = 16
+// (four per quarter) for the 1x1 projections with a short K loop, whose epilogue is the whole kernel: with two warps per scheduler
+// the per-chunk chain (TMEM load -> ~250 instructions -> shared -> TMA store) kept the issue slots 40 % busy and the qkv projection
+// at 0.64 of the copy peak (profiles/r02_ncu_full_B1024.summary.txt).
+constexpr int STG_BUF = 4096;  // one epilogue staging buffer per epilogue warp: 32 rows x 128 bytes (TMA-store box)
 
 struct GemmParams {
     int kind;            // 0: 1x1, 1: 3x3 pad 1, 2: 2x2 stride-2 (pixel-unshuffle + 1x1), 3: nearest-upsample x2 + 3x3 pad 1
@@ -85,12 +86,14 @@ struct GemmParams {
 // drops from 16 KB + BN*128 B to 16 KB + BN*64 B, which is what bounds the 1-CTA kernel.  Barriers: TMA of both CTAs
 // credits the leader's `full`; the MMA commit multicasts to both CTAs' `empty` / `acc_full`; both epilogues arrive on
 // the leader's `acc_empty`.
-template <bool HALF, bool PAIR>
+template <bool HALF, bool PAIR, int EPI_WARPS>
 __device__ __forceinline__ void conv_gemm_body(const CUtensorMap& map_a0, const CUtensorMap& map_a1, const CUtensorMap& map_w,
                                                const CUtensorMap& map_out, const CUtensorMap& map_q, const GemmParams& p) {
     using Op = Operand<HALF>;
     using act_t = typename ActT<HALF>::type;
     constexpr int BK = Op::kBK;
+    constexpr int STG_BYTES = EPI_WARPS * STG_BUF;
+    constexpr int COL_STEP = 32 * (EPI_WARPS / 4);   // column stride of one epilogue warp: the warps of a quarter interleave 32-column chunks
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     const int b_rows = PAIR ? p.bn / 2 : p.bn;            // weight rows staged by this CTA
@@ -135,25 +138,25 @@ __device__ __forceinline__ void conv_gemm_body(const CUtensorMap& map_a0, const 
 
     if (warp == 0) {
         if (lane == 0) {
-            int g = 0;  // running K-block counter across tiles (smem ring position)
+            int s = 0;          // smem ring position across tiles
+            uint32_t ph = 0;    // its phase parity
+            // tile id = (mq * phases + phase) * tiles_n + nt, walked incrementally (no per-tile integer divisions)
+            int mq = tile_lo / tiles_pn, phase = (tile_lo - mq * tiles_pn) / p.tiles_n, nt = tile_lo - mq * tiles_pn - phase * p.tiles_n;
             for (int tile = tile_lo; tile < tile_hi; ++tile) {
-                const int mq = tile / tiles_pn, pn = tile - mq * tiles_pn;
-                const int phase = pn / p.tiles_n, nt = pn - phase * p.tiles_n;
                 const int mt = PAIR ? 2 * mq + (int)rank : mq;
                 // tile origin in (image, row); tiles always span full rows (bw == W)
                 const int pix0 = mt * BM;
                 const int b0 = pix0 / p.hw_per_sample;
                 const int h0 = (pix0 - b0 * p.hw_per_sample) / p.W;
-                for (int kb = 0; kb < num_kb; ++kb, ++g) {
-                    const int s = g % p.stages;
-                    const uint32_t ph = (uint32_t)(g / p.stages) & 1u;
+                // ring position (s, ph), tap and channel chunk advance incrementally: this single thread's instruction stream is
+                // the critical path of the short-K 1x1 convolutions (2 K blocks per tile), integer divisions do not belong in it
+                for (int kb = 0, tap = 0, ck = 0; kb < num_kb; ++kb) {
                     mbar_wait(&empty_bar[s], ph ^ 1u);
                     uint8_t* sa = smem + s * stage_bytes;
                     uint8_t* sb = sa + A_BYTES;
                     if constexpr (PAIR) { if (leader) mbar_expect_tx(&full_bar[s], (uint32_t)(2 * stage_bytes)); }   // bytes of BOTH CTAs
                     else mbar_expect_tx(&full_bar[s], (uint32_t)stage_bytes);
-                    const int tap = kb / chunks;
-                    const int cc = (kb - tap * chunks) * BK;          // channel offset in the concatenated input
+                    const int cc = ck * BK;          // channel offset in the concatenated input
                     const bool second = cc >= p.c0;
                     const CUtensorMap* ma = second ? &map_a1 : &map_a0;
                     const int cseg = second ? cc - p.c0 : cc;
@@ -164,7 +167,7 @@ __device__ __forceinline__ void conv_gemm_body(const CUtensorMap& map_a0, const 
                         else tma_load_5d(sa, ma, &full_bar[s], (tap & 1) * cin + cseg, 0, tap >> 1, h0, b0);
                     } else {
                         int dy = 0, dx = 0;
-                        if (p.kind == 1) { dy = tap / 3 - 1; dx = tap % 3 - 1; }
+                        if (p.kind == 1) { const int ty = (tap * 11) >> 5; dy = ty - 1; dx = tap - 3 * ty - 1; }   // tap / 3 for tap < 9
                         else if (p.kind == 3) { dy = (phase >> 1) - 1 + (tap >> 1); dx = (phase & 1) - 1 + (tap & 1); }
                         if constexpr (PAIR) tma_load_4d_2sm(sa, ma, &full_bar[s], cseg, dx, h0 + dy, b0);
                         else tma_load_4d(sa, ma, &full_bar[s], cseg, dx, h0 + dy, b0);
@@ -173,21 +176,23 @@ __device__ __forceinline__ void conv_gemm_body(const CUtensorMap& map_a0, const 
                     const int wrow = nt * p.bn + b0 * p.w_sample_rows + phase * p.Cout;
                     if constexpr (PAIR) tma_load_2d_2sm(sb, &map_w, &full_bar[s], tap * ctot + cc, wrow + (int)rank * b_rows);
                     else tma_load_2d(sb, &map_w, &full_bar[s], tap * ctot + cc, wrow);
+                    if (++ck == chunks) { ck = 0; ++tap; }
+                    if (++s == p.stages) { s = 0; ph ^= 1u; }
                 }
+                if (++nt == p.tiles_n) { nt = 0; if (++phase == p.phases) { phase = 0; ++mq; } }
             }
         }
     } else if (warp == 1) {
         if (leader) {   // whole warp walks the loops (uniform control flow); one elected lane issues the MMAs and commits
             const uint32_t idesc = Op::idesc(p.bn, PAIR ? 2 * BM : BM);
-            int g = 0, it = 0;
+            int s = 0, it = 0;
+            uint32_t ph = 0;
             for (int tile = tile_lo; tile < tile_hi; ++tile, ++it) {
                 const int buf = it & 1;
                 mbar_wait(&acc_empty[buf], ((uint32_t)(it >> 1) & 1u) ^ 1u);   // epilogue(s) drained this buffer
                 tc_fence_after();
                 const uint32_t tmem_d = tmem_base + (uint32_t)buf * acc_cols;
-                for (int kb = 0; kb < num_kb; ++kb, ++g) {
-                    const int s = g % p.stages;
-                    const uint32_t ph = (uint32_t)(g / p.stages) & 1u;
+                for (int kb = 0; kb < num_kb; ++kb) {
                     mbar_wait(&full_bar[s], ph);
                     tc_fence_after();
                     const uint32_t sa = smem_u32(smem + s * stage_bytes);
@@ -203,19 +208,19 @@ __device__ __forceinline__ void conv_gemm_body(const CUtensorMap& map_a0, const 
                         if (kb == num_kb - 1) { if constexpr (PAIR) umma_commit_2sm(&acc_full[buf]); else umma_commit(&acc_full[buf]); }
                     }
                     __syncwarp();
+                    if (++s == p.stages) { s = 0; ph ^= 1u; }
                 }
             }
         }
     } else {
         // ---- epilogue: warp w may only touch TMEM lanes [32*(w%4), 32*(w%4)+32); lane = accumulator row ----
-        const int q = warp & 3, half_id = (warp - 2) >> 2;   // TMEM lane quarter; which of the two column-chunk parities
+        const int q = warp & 3, half_id = (warp - 2) >> 2;   // TMEM lane quarter; which of the EPI_WARPS / 4 interleaved column-chunk sets
         const uint32_t stg = smem_u32(staging + (warp - 2) * STG_BUF);
         const act_t* resid = reinterpret_cast<const act_t*>(p.residual);
         const bool out_half = HALF && p.operand_out;
         int it = 0;
+        int mq = tile_lo / tiles_pn, phase = (tile_lo - mq * tiles_pn) / p.tiles_n, nt = tile_lo - mq * tiles_pn - phase * p.tiles_n;
         for (int tile = tile_lo; tile < tile_hi; ++tile, ++it) {
-            const int mq = tile / tiles_pn, pn = tile - mq * tiles_pn;
-            const int phase = pn / p.tiles_n, nt = pn - phase * p.tiles_n;
             const int up = p.kind == 3 ? phase : -1;
             const int mt = PAIR ? 2 * mq + (int)rank : mq;
             const int buf = it & 1;
@@ -248,7 +253,7 @@ __device__ __forceinline__ void conv_gemm_body(const CUtensorMap& map_a0, const 
                     const float mean = a1 * inv_c;
                     const float rstd = rsqrtf(fmaxf(a2 * inv_c - mean * mean, 0.f) + 1e-5f);
                     // ---- pass 2: this warp's column chunks: normalise, gain, residual, fp16 store ----
-                    for (int c = 32 * half_id; c < p.bn; c += 64) {
+                    for (int c = 32 * half_id; c < p.bn; c += COL_STEP) {
                         uint32_t r[32];
                         tmem_ld32(trow + (uint32_t)c, r);
                         float v[32];
@@ -269,7 +274,7 @@ __device__ __forceinline__ void conv_gemm_body(const CUtensorMap& map_a0, const 
                     }
                 }
             } else
-            for (int c = 32 * half_id; c < p.bn; c += 64) {
+            for (int c = 32 * half_id; c < p.bn; c += COL_STEP) {
                 const int col = nt * p.bn + c;
                 const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)buf * acc_cols + (uint32_t)c;
                 const act_t* rrow = resid ? resid + (size_t)m * p.Cout + col : nullptr;
@@ -294,6 +299,7 @@ __device__ __forceinline__ void conv_gemm_body(const CUtensorMap& map_a0, const 
                     atomicAdd(p.stats + 2 * b + 1, (double)s2);
                 }
             }
+            if (++nt == p.tiles_n) { nt = 0; if (++phase == p.phases) { phase = 0; ++mq; } }
         }
         if (lane == 0) bulk_wait<0>();   // all output stores complete before the CTA's shared memory goes away
         tc_fence_before();
@@ -307,19 +313,19 @@ __device__ __forceinline__ void conv_gemm_body(const CUtensorMap& map_a0, const 
     }
 }
 
-template <bool HALF>
-__global__ void __launch_bounds__(GEMM_THREADS, 1)
+template <bool HALF, int EPI_WARPS = 8>
+__global__ void __launch_bounds__(64 + 32 * EPI_WARPS, 1)
 conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ CUtensorMap map_a1,
                  const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUtensorMap map_out,
                  const __grid_constant__ CUtensorMap map_q, const GemmParams p) {
-    conv_gemm_body<HALF, false>(map_a0, map_a1, map_w, map_out, map_q, p);
+    conv_gemm_body<HALF, false, EPI_WARPS>(map_a0, map_a1, map_w, map_out, map_q, p);
 }
-template <bool HALF>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
+template <bool HALF, int EPI_WARPS = 8>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(64 + 32 * EPI_WARPS, 1)
 conv_gemm2_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ CUtensorMap map_a1,
                   const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUtensorMap map_out,
                   const __grid_constant__ CUtensorMap map_q, const GemmParams p) {
-    conv_gemm_body<HALF, true>(map_a0, map_a1, map_w, map_out, map_q, p);
+    conv_gemm_body<HALF, true, EPI_WARPS>(map_a0, map_a1, map_w, map_out, map_q, p);
 }
 
 // ------------------------------------------------------------------------------------------ host side
@@ -396,10 +402,18 @@ static int conv_gemm_launch(int prec, int kind, const void* a0, int c0, const vo
     SDC_REQUIRE(!per_sample_weights || (H * W) % BM == 0, "conv_gemm: per-sample weights need H*W %% 128 == 0");
     const bool pair = allow_pair && ((tiles_m + 1) / 2) * (Cout / bn) * p.phases >= n_sm / 2 && (!per_sample_weights || (H * W) % (2 * BM) == 0);
     const int stage_bytes = A_BYTES + (pair ? bn / 2 : bn) * 128;
-    int stages = (190 * 1024) / stage_bytes;
+    // 16 epilogue warps when the epilogue is the kernel: 1x1 convolutions with at most 4 K blocks (FP16 mode; SDC_EPI16=0 restores 8)
+    static const bool allow_epi16 = []() { const char* e = getenv("SDC_EPI16"); return !(e && e[0] == '0'); }();
+    // (measured: +10-15 % on the qkv and per-sample projections with K = 128; the plain 1x1 convolutions already stream at 0.9+ of the
+    // copy peak with 8 warps and lose 10 % to the smaller register budget)
+    const bool epi16 = allow_epi16 && half && kind == 0 && (c0 + c1) / BK <= 2 && (q_cols > 0 || per_sample_weights) && !(ln && ln->out_gain);
+    const int epi_warps = epi16 ? 16 : 8;
+    const int stg_bytes = epi_warps * STG_BUF;
+    int stages = (222 * 1024 - stg_bytes) / stage_bytes;
     if (stages > 8) stages = 8;
+    if (epi16 && stages > 6) stages = 6;   // short K loops: a deeper ring holds nothing
     p.stages = stages;
-    const int smem_bytes = stages * stage_bytes + STG_BYTES + (2 * stages + 4) * 8 + 16 + 1024;
+    const int smem_bytes = stages * stage_bytes + stg_bytes + (2 * stages + 4) * 8 + 16 + 1024;
     p.tiles_n = Cout / bn;
     p.tiles_total = (pair ? (tiles_m + 1) / 2 : tiles_m) * p.tiles_n * p.phases;
     const int workers = pair ? n_sm / 2 : n_sm;
@@ -441,16 +455,21 @@ static int conv_gemm_launch(int prec, int kind, const void* a0, int c0, const vo
         SDC_CUDA(cudaFuncSetAttribute(conv_gemm2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         SDC_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         SDC_CUDA(cudaFuncSetAttribute(conv_gemm2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        SDC_CUDA(cudaFuncSetAttribute((conv_gemm_kernel<true, 16>), cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        SDC_CUDA(cudaFuncSetAttribute((conv_gemm2_kernel<true, 16>), cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         attr_set = true;
     }
     const int grid = (p.tiles_total + p.tiles_per_cta - 1) / p.tiles_per_cta;
     cudaStream_t st = as_stream(stream);
+    const int threads = 64 + 32 * epi_warps;
     if (pair) {
-        if (half) conv_gemm2_kernel<true><<<2 * grid, GEMM_THREADS, smem_bytes, st>>>(ma0, ma1, mw, mo, mq, p);
-        else conv_gemm2_kernel<false><<<2 * grid, GEMM_THREADS, smem_bytes, st>>>(ma0, ma1, mw, mo, mq, p);
+        if (epi16) conv_gemm2_kernel<true, 16><<<2 * grid, threads, smem_bytes, st>>>(ma0, ma1, mw, mo, mq, p);
+        else if (half) conv_gemm2_kernel<true><<<2 * grid, threads, smem_bytes, st>>>(ma0, ma1, mw, mo, mq, p);
+        else conv_gemm2_kernel<false><<<2 * grid, threads, smem_bytes, st>>>(ma0, ma1, mw, mo, mq, p);
     } else {
-        if (half) conv_gemm_kernel<true><<<grid, GEMM_THREADS, smem_bytes, st>>>(ma0, ma1, mw, mo, mq, p);
-        else conv_gemm_kernel<false><<<grid, GEMM_THREADS, smem_bytes, st>>>(ma0, ma1, mw, mo, mq, p);
+        if (epi16) conv_gemm_kernel<true, 16><<<grid, threads, smem_bytes, st>>>(ma0, ma1, mw, mo, mq, p);
+        else if (half) conv_gemm_kernel<true><<<grid, threads, smem_bytes, st>>>(ma0, ma1, mw, mo, mq, p);
+        else conv_gemm_kernel<false><<<grid, threads, smem_bytes, st>>>(ma0, ma1, mw, mo, mq, p);
     }
     SDC_LAUNCHED();
     return SDC_OK;

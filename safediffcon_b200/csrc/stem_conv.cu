@@ -34,6 +34,12 @@ struct StemParams {
     const float* bias;
 };
 
+__device__ __forceinline__ float lds32(uint32_t addr) {
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr) : "memory");
+    return v;
+}
+
 __global__ void __launch_bounds__(ST_THREADS, 1)
 stem_conv7_tc_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUtensorMap map_out, const StemParams p) {
     extern __shared__ uint8_t smem_raw[];
@@ -149,39 +155,48 @@ stem_conv7_tc_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_con
             asm volatile("cp.async.commit_group;" ::: "memory");
         };
         if (tile_lo < tile_hi) prefetch(tile_lo, 0);
-        const int ch = bt & 7, r0 = bt >> 3;   // 16-byte chunk of a K block; rows r0, r0 + 64
-        int off[ST_KB][8];                     // window offsets of this thread's 8 patch columns in every K block (-1 = padding)
+        // Work item = (16-byte chunk c of the 20 high-part chunks, pixel row r): the thread loads the 8 patch values ONCE and writes both
+        // the high chunk c and the low chunk c + 20 (the kernel is shared-memory-bandwidth bound: window reads + operand writes +
+        // the tensor core's own operand reads; one thread per (chunk, row) of the 40 chunks read every window value twice).
+        // Lanes = 32 consecutive rows of one chunk: window reads are consecutive floats, the swizzled 16-byte stores conflict free.
+        const int r = bt & 127, c0 = bt >> 7;   // chunks c0, c0 + 4, .., c0 + 16
+        int off[5][8];                         // window offsets of the 8 patch columns of every chunk (-1 = padding column)
 #pragma unroll
-        for (int kb = 0; kb < ST_KB; ++kb)
+        for (int i = 0; i < 5; ++i)
 #pragma unroll
-            for (int e = 0; e < 8; ++e) off[kb][e] = koff[(kb * 8 + ch) * 8 + e];
+            for (int e = 0; e < 8; ++e) off[i][e] = koff[(c0 + 4 * i) * 8 + e];
+        const uint32_t row_off = (uint32_t)((r >> 3) * 1024 + (r & 7) * 128);
         int it = 0;
         for (int tile = tile_lo; tile < tile_hi; ++tile, ++it) {
             asm volatile("cp.async.wait_group 0;" ::: "memory");
             asm volatile("bar.sync 2, 512;" ::: "memory");          // every builder's copies of this tile have landed
             if (tile + 1 < tile_hi) prefetch(tile + 1, (it + 1) & 1);
-            const float* win = xs + (it & 1) * (4 * 7 * ST_WP);
+            // explicit shared-window loads: `xs` descends from the re-aligned dynamic-smem base, so plain dereferences compile to
+            // generic LD.E (64-bit addressing, long scoreboard) -- ld.shared through a 32-bit address instead
+            const uint32_t win = smem_u32(xs + (it & 1) * (4 * 7 * ST_WP) + r);
+            uint32_t waited = 0;   // K blocks whose release by the previous tile's MMAs this thread has already observed
 #pragma unroll
-            for (int kb = 0; kb < ST_KB; ++kb) {
-                mbar_wait(&a_empty[kb], ((uint32_t)it & 1u) ^ 1u);   // the MMAs of the previous tile have read this K block
-                const bool low = kb * 8 + ch >= 20;      // chunk index over the 320 columns: < 20 high part, >= 20 low part
-                const uint32_t blk = smem_u32(a_tile + kb * ST_KBLK);
+            for (int i = 0; i < 5; ++i) {
+                const int c = c0 + 4 * i;
+                const int kb_h = c >> 3, kb_l = (c + 20) >> 3;
+                if (!(waited >> kb_h & 1u)) { mbar_wait(&a_empty[kb_h], ((uint32_t)it & 1u) ^ 1u); waited |= 1u << kb_h; }
+                if (!(waited >> kb_l & 1u)) { mbar_wait(&a_empty[kb_l], ((uint32_t)it & 1u) ^ 1u); waited |= 1u << kb_l; }
+                uint32_t hv[4], lv[4];
 #pragma unroll
-                for (int j = 0; j < 2; ++j) {
-                    const int r = r0 + 64 * j;
-                    uint32_t wv[4];
-#pragma unroll
-                    for (int e = 0; e < 4; ++e) {
-                        const float v0 = off[kb][2 * e] >= 0 ? win[off[kb][2 * e] + r] : 0.f;
-                        const float v1 = off[kb][2 * e + 1] >= 0 ? win[off[kb][2 * e + 1] + r] : 0.f;
-                        __half2 h2 = __floats2half2_rn(v0, v1);
-                        if (low) { const float2 f2 = __half22float2(h2); h2 = __floats2half2_rn(v0 - f2.x, v1 - f2.y); }
-                        wv[e] = *reinterpret_cast<const uint32_t*>(&h2);
-                    }
-                    // K-major SWIZZLE_128B: row r at (r / 8) * 1024 + (r % 8) * 128, 16-byte chunk ch at ((ch ^ (r % 8)) * 16)
-                    const uint32_t dst = blk + (uint32_t)((r >> 3) * 1024 + (r & 7) * 128 + ((ch ^ (r & 7)) << 4));
-                    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(wv[0]), "r"(wv[1]), "r"(wv[2]), "r"(wv[3]) : "memory");
+                for (int e = 0; e < 4; ++e) {
+                    const float v0 = off[i][2 * e] >= 0 ? lds32(win + 4u * (uint32_t)off[i][2 * e]) : 0.f;
+                    const float v1 = off[i][2 * e + 1] >= 0 ? lds32(win + 4u * (uint32_t)off[i][2 * e + 1]) : 0.f;
+                    const __half2 h2 = __floats2half2_rn(v0, v1);
+                    const float2 f2 = __half22float2(h2);
+                    const __half2 l2 = __floats2half2_rn(v0 - f2.x, v1 - f2.y);
+                    hv[e] = *reinterpret_cast<const uint32_t*>(&h2);
+                    lv[e] = *reinterpret_cast<const uint32_t*>(&l2);
                 }
+                // K-major SWIZZLE_128B: row r at (r / 8) * 1024 + (r % 8) * 128, 16-byte chunk ch at ((ch ^ (r % 8)) * 16)
+                const uint32_t dh = smem_u32(a_tile + kb_h * ST_KBLK) + row_off + (uint32_t)(((c & 7) ^ (r & 7)) << 4);
+                const uint32_t dl = smem_u32(a_tile + kb_l * ST_KBLK) + row_off + (uint32_t)((((c + 20) & 7) ^ (r & 7)) << 4);
+                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dh), "r"(hv[0]), "r"(hv[1]), "r"(hv[2]), "r"(hv[3]) : "memory");
+                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dl), "r"(lv[0]), "r"(lv[1]), "r"(lv[2]), "r"(lv[3]) : "memory");
             }
             fence_proxy_async();   // generic-proxy writes -> visible to the tensor core's async-proxy reads
             __syncwarp();

@@ -277,13 +277,28 @@ __device__ __forceinline__ void epilogue_chunk_qsoftmax(uint32_t taddr, uint32_t
     float mx = v[0];
 #pragma unroll
     for (int j = 0; j < 32; ++j) mx = fmaxf(mx, v[j]);
-    float den = 0.f;
+    // exp(v - mx) = ex2(v * log2e - mx * log2e): one packed FFMA2 + two MUFU per element pair, packed adds / scaling (sm_100 f32x2
+    // arithmetic halves the FP32 issue slots of this chunk, which is issue bound: 4 epilogue warps per scheduler share them).
     // ex2.approx (2 ulp) on arguments <= 0: far inside the 2^-11 rounding of the fp16 / tf32 store below
+    const float l2e = 1.4426950408889634f;
+    const float2 k2 = make_float2(l2e, l2e), nm2 = make_float2(-mx * l2e, -mx * l2e);
+    float2 den2 = make_float2(0.f, 0.f);
 #pragma unroll
-    for (int j = 0; j < 32; ++j) { v[j] = __expf(v[j] - mx); den += v[j]; }
-    const float sc = 0.17677669529663687f / den;
+    for (int j = 0; j < 32; j += 2) {
+        const float2 a = __ffma2_rn(make_float2(v[j], v[j + 1]), k2, nm2);
+        float2 e;
+        asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e.x) : "f"(a.x));
+        asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e.y) : "f"(a.y));
+        den2 = __fadd2_rn(den2, e);
+        v[j] = e.x; v[j + 1] = e.y;
+    }
+    const float sc = 0.17677669529663687f / (den2.x + den2.y);
+    const float2 sc2 = make_float2(sc, sc);
 #pragma unroll
-    for (int j = 0; j < 32; ++j) v[j] *= sc;
+    for (int j = 0; j < 32; j += 2) {
+        const float2 o = __fmul2_rn(make_float2(v[j], v[j + 1]), sc2);
+        v[j] = o.x; v[j + 1] = o.y;
+    }
     if (wait_stg) {
         if (lane == 0) bulk_wait_read<0>();
         __syncwarp();
