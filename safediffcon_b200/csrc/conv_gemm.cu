@@ -400,7 +400,12 @@ static int conv_gemm_launch(int prec, int kind, const void* a0, int c0, const vo
     // CTA pairs (cta_group::2) whenever there are at least as many 256-row pair tiles as SM pairs
     // per-sample weights: every (pair) tile must lie inside one sample
     SDC_REQUIRE(!per_sample_weights || (H * W) % BM == 0, "conv_gemm: per-sample weights need H*W %% 128 == 0");
-    const bool pair = allow_pair && ((tiles_m + 1) / 2) * (Cout / bn) * p.phases >= n_sm / 2 && (!per_sample_weights || (H * W) % (2 * BM) == 0);
+    // ... or, with fewer tiles than that, when the contraction is long (>= 32 K blocks) and the tile count even enough: such launches
+    // (the 2x16 / 4x32 levels at the reference's batch sizes) are bound by each SM re-reading the weight slab from L2, which a pair halves
+    static const int pair_long_k = []() { const char* e = getenv("SDC_PAIR_LONGK"); return e ? atoi(e) : 32; }();
+    const int taps_ = kind == 1 ? 9 : (kind >= 2 ? 4 : 1);
+    const bool long_k = pair_long_k > 0 && taps_ * ((c0 + c1) / BK) >= pair_long_k && tiles_m >= 2 && tiles_m * (Cout / bn) * p.phases <= n_sm;
+    const bool pair = allow_pair && (((tiles_m + 1) / 2) * (Cout / bn) * p.phases >= n_sm / 2 || long_k) && (!per_sample_weights || (H * W) % (2 * BM) == 0);
     const int stage_bytes = A_BYTES + (pair ? bn / 2 : bn) * 128;
     // 16 epilogue warps when the epilogue is the kernel: 1x1 convolutions with at most 4 K blocks (FP16 mode; SDC_EPI16=0 restores 8)
     static const bool allow_epi16 = []() { const char* e = getenv("SDC_EPI16"); return !(e && e[0] == '0'); }();

@@ -295,7 +295,7 @@ __device__ __forceinline__ void row_stats8(const uint4& o, int c8n, int C, float
 // LayerNorm that follows in PreNorm(LinearAttention) (unet.py:53-63,65-76): the LayerNorm itself is then folded into the qkv
 // projection (sdc_conv1x1_qkv_ln) and its separate pass over HBM disappears.  A row is owned by C/8 = 16 or 32 adjacent lanes.
 template <bool ROWSTATS>
-__global__ void __launch_bounds__(256) gn_silu_h8_kernel(const __half* __restrict__ x, const double* __restrict__ stats,
+__global__ void __launch_bounds__(256, ROWSTATS ? 2 : 4) gn_silu_h8_kernel(const __half* __restrict__ x, const double* __restrict__ stats,
                                                          const float* __restrict__ gamma, const float* __restrict__ beta,
                                                          const float* __restrict__ scale_shift, const int32_t* __restrict__ t_index,
                                                          int64_t ss_stride, const __half* __restrict__ residual, __half* __restrict__ y,
