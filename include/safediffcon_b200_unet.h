@@ -45,7 +45,10 @@ int sdc_conv_gemm(int prec, int kind, const void* a0, int c0, const void* a1, in
 
 /* Same contract as sdc_conv_gemm(kind = 3x3) for the full-resolution level: W == 128 and Cout <= 128.  One CTA computes
  * two image rows and loads the activation halo once per 128-byte channel chunk (the 9 taps are shifted UMMA descriptor
- * views of it), cutting L2->SMEM operand traffic ~2.8x.  Returns -1 (and does nothing) when the shape is not eligible. */
+ * views of it), cutting L2->SMEM operand traffic ~2.8x.  W == 64 (H % 8 == 0, at least one 8-row item per SM pair): a CTA pair
+ * computes eight image rows from one 6-row x 64-pixel activation box per channel chunk and HORIZONTAL tap (TMA does that
+ * shift), the vertical taps being row-shifted descriptor views of the box (csrc/conv_row64.cu): half the operand traffic of
+ * the generic kernel.  Returns -1 (and does nothing) when the shape is not eligible. */
 int sdc_conv3x3_row(int prec, const void* a0, int c0, const void* a1, int c1, const void* w_packed, const float* bias,
                     const void* residual, void* out, double* stats, int operand_out, int B, int H, int W, int Cout,
                     void* stream);

@@ -63,6 +63,7 @@ struct GemmParams {
     int q_cols;          // > 0: LinearAttention qkv mode -- output columns [0, q_cols) get softmax_d * 32^-0.5 per 32-column head and
                          //      go to a second tensor (map_q, operand precision); columns [q_cols, Cout) go to `out` (fp32, or fp16
                          //      when operand_out is set in FP16 mode: k and v are then read at half the bytes by the context pass)
+    int chunk_major;     // 3x3: K order (chunk, dx, dy) instead of (tap, chunk); see the producer loop
     int w_sample_rows;   // > 0: per-sample weights -- sample b uses weight rows [b * w_sample_rows, (b + 1) * w_sample_rows)
     // folded channel LayerNorm of the INPUT rows (PreNorm in front of the qkv projection, unet.py:65-76): the weights were packed as
     // W * g (sdc_pack_qkv_ln); the epilogue computes r_m * (acc - mu_m * wsum[col]) from per-row (mean, rstd)
@@ -150,7 +151,10 @@ __device__ __forceinline__ void conv_gemm_body(const CUtensorMap& map_a0, const 
                 const int h0 = (pix0 - b0 * p.hw_per_sample) / p.W;
                 // ring position (s, ph), tap and channel chunk advance incrementally: this single thread's instruction stream is
                 // the critical path of the short-K 1x1 convolutions (2 K blocks per tile), integer divisions do not belong in it
-                for (int kb = 0, tap = 0, ck = 0; kb < num_kb; ++kb) {
+                // K order: kinds 0, 2, 3 walk the channel chunks of a tap, then the next tap.  3x3 (kind 1): chunk-major with the taps
+                // of a chunk in the order (dx, dy) -- the order of conv_row64.cu, so that a sample's result does not depend on which of
+                // the two kernels the batch size selects (same fp32 accumulation sequence; tests/test_full_size_gpu.py)
+                for (int kb = 0, tap = 0, ck = 0, t_dx = 0, t_dy = 0; kb < num_kb; ++kb) {
                     mbar_wait(&empty_bar[s], ph ^ 1u);
                     uint8_t* sa = smem + s * stage_bytes;
                     uint8_t* sb = sa + A_BYTES;
@@ -176,7 +180,10 @@ __device__ __forceinline__ void conv_gemm_body(const CUtensorMap& map_a0, const 
                     const int wrow = nt * p.bn + b0 * p.w_sample_rows + phase * p.Cout;
                     if constexpr (PAIR) tma_load_2d_2sm(sb, &map_w, &full_bar[s], tap * ctot + cc, wrow + (int)rank * b_rows);
                     else tma_load_2d(sb, &map_w, &full_bar[s], tap * ctot + cc, wrow);
-                    if (++ck == chunks) { ck = 0; ++tap; }
+                    if (p.chunk_major) {
+                        if (++t_dy == 3) { t_dy = 0; if (++t_dx == 3) { t_dx = 0; ++ck; } }
+                        tap = t_dy * 3 + t_dx;
+                    } else if (++ck == chunks) { ck = 0; ++tap; }
                     if (++s == p.stages) { s = 0; ph ^= 1u; }
                 }
                 if (++nt == p.tiles_n) { nt = 0; if (++phase == p.phases) { phase = 0; ++mq; } }
@@ -378,6 +385,8 @@ static int conv_gemm_launch(int prec, int kind, const void* a0, int c0, const vo
                 "conv_gemm: qkv mode needs q_out, q_cols %% 32 == 0 and a kv output that is plain fp32 or (FP16 mode) an operand");
     GemmParams p{};
     p.q_cols = q_cols;
+    static const bool chunk_major = []() { const char* e = getenv("SDC_KORDER"); return !(e && e[0] == '0'); }();
+    p.chunk_major = kind == 1 && chunk_major;
     p.w_sample_rows = per_sample_weights ? Cout : 0;
     p.phases = kind == 3 ? 4 : 1;
     p.kind = kind; p.M = B * H * W; p.Cout = Cout; p.bn = bn; p.H = H; p.W = W; p.bh = bh; p.bb = bb;

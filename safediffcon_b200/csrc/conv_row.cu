@@ -500,6 +500,10 @@ struct RowGn {
     void* slots; const float* head_w; const float* head_b; float* head_out; int head_cout;
 };
 
+// W = 64 variant (conv_row64.cu): one activation box per horizontal tap, vertical taps as row-shifted views
+int conv3x3_row64_launch(int prec, const void* a0, int c0, const void* a1, int c1, const void* w_packed, const float* bias,
+                         const void* residual, void* out, double* stats, int operand_out, int B, int H, int W, int Cout, void* stream);
+
 // Returns SDC_OK when the problem was handled here, -1 when the shape is not eligible (caller uses conv_gemm).
 static int conv3x3_row_launch(int prec, const void* a0, int c0, const void* a1, int c1, const void* w_packed, const float* bias,
                               const void* residual, void* out, double* stats, int operand_out, int B, int H, int W, int Cout,
@@ -507,6 +511,7 @@ static int conv3x3_row_launch(int prec, const void* a0, int c0, const void* a1, 
     SDC_REQUIRE(prec == SDC_PREC_TF32 || prec == SDC_PREC_F16, "conv3x3_row: precision %d", prec);
     const bool half = prec == SDC_PREC_F16;
     const int BK = half ? 64 : 32;
+    if (W == 64 && !gn) return conv3x3_row64_launch(prec, a0, c0, a1, c1, w_packed, bias, residual, out, stats, operand_out, B, H, W, Cout, stream);
     if (W != RW || Cout > 128 || Cout % 32 != 0 || c0 % BK != 0 || c1 % BK != 0 || c0 <= 0) return -1;
     SDC_REQUIRE(a0 && w_packed && out && B > 0 && H > 0 && (c1 == 0 || a1), "conv3x3_row: bad arguments");
     RowParams p{};

@@ -315,7 +315,7 @@ void conv(Fwd& f, int kind, const void* a0, int c0, const void* a1, int c1, cons
     int rc = -1;
     if (!f.dry && !f.rc) {
         f.begin(nm, bytes, 2.0 * rows * cout * k);
-        if (kind == K3 && w == 128 && cout <= 128)
+        if (kind == K3 && (w == 128 || w == 64) && cout <= 128)
             rc = sdc_conv3x3_row(prec, a0, c0, a1, c1, wp, bias, residual, out, st, operand_out, f.B, h, w, cout, f.stream);
         if (rc != 0)
             rc = sdc_conv_gemm(prec, kind, a0, c0, a1, c1, wp, bias, residual, out, st, operand_out, f.B, h, w, cout, f.stream);

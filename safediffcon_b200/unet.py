@@ -229,7 +229,7 @@ def conv_gemm(kind, a0, c0, a1, c1, wp, bias, residual, out, stats, operand_out,
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
     rc = -1
-    if kind == KIND_3x3 and USE_ROW_KERNEL and W == 128 and Cout <= 128:
+    if kind == KIND_3x3 and USE_ROW_KERNEL and W in (128, 64) and Cout <= 128:
         rc = L.lib().sdc_conv3x3_row(prec, L.ptr(a0), c0, L.ptr(a1), c1, L.ptr(wp), L.ptr(bias), L.ptr(residual), L.ptr(out),
                                      L.ptr(stats), int(operand_out), B, H, W, Cout, _st())
         if rc > 0:

@@ -67,6 +67,9 @@ CONV_CASES = [
     (1, 600, 2, 16, 32, 32, 96, True, False, True, False),     # CTA-pair, N tile 32 -> half tiles of 16 rows
     (1, 80, 6, 128, 32, 32, 64, True, True, True, True),       # row kernel, CTA pairs, H=6: phantom rows in the 2nd CTA
     (1, 160, 16, 128, 128, 0, 128, True, False, True, False),  # row kernel, CTA pairs, production shape
+    (1, 150, 8, 64, 128, 0, 128, True, False, True, True),     # W = 64 row kernel (conv_row64.cu): production shape, 2+ items per cluster
+    (1, 80, 8, 64, 64, 64, 96, True, True, True, True),        # W = 64 row kernel: two segments, residual, N = 96
+    (1, 75, 16, 64, 32, 32, 64, False, False, True, False),    # W = 64 row kernel: two 8-row items per image, TF32 chunks of 32
 ]
 
 
