@@ -87,10 +87,11 @@ int sdc_stem_conv7(int prec, const float* x, const float* w, const float* bias, 
  * the product sees x to ~2^-22 with fp16 / tf32 operands. */
 int sdc_stem_im2col(int prec, const float* x, void* a, int B, int Cin, int H, int W, int kp, void* stream);
 
-/* The whole stem in ONE tcgen05 kernel (FP16 mode, W = 128, Cout = 128, Cin <= 3): the [128 px x 320] patch tile of an image row is
- * written by the kernel's own warps into shared memory in the K-major SWIZZLE_128B operand layout (high | low split as in
- * sdc_stem_im2col) and multiplied against the resident weight matrix -- the patch matrix never exists in HBM (round 1: 1.3 GB
- * written and read back per evaluation at B = 1024).  w_packed: sdc_pack_conv_weight(kind 0) of the [Cout, 320] matrix holding the
+/* The whole stem in ONE tcgen05 kernel (FP16 mode, W = 128, Cout = 128, Cin <= 3).  Per image row the kernel's own warps write ONE
+ * operand tile T[w' = 0..133][(ci, ky)] = x[ci, h + ky - 3, w' - 3] (high | low fp16 split as in sdc_stem_im2col, zero = padding) into
+ * shared memory in the K-major SWIZZLE_128B layout; the seven horizontal taps are row-shifted UMMA views of it, multiplied against
+ * seven resident [Cout x 64] weight tiles -- no patch matrix in HBM (round 1: 1.3 GB written and read back per evaluation at
+ * B = 1024) and none in shared memory either.  w_packed: sdc_pack_conv_weight(kind 0) of the [Cout, 320] matrix holding the
  * stem weight at columns 0 and 160.  out: NHWC fp16 [B*H*W, Cout] (+ bias).  Returns -1 (nothing done) for other shapes. */
 int sdc_stem_conv7_tc(const float* x, const void* w_packed, const float* bias, void* out, int B, int Cin, int H, int W, int Cout, int kp,
                       void* stream);
