@@ -9,7 +9,7 @@ import os
 import torch
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_PKG, "libsafediffcon_b200.so")
+LIB_PATH = os.environ.get("SDC_LIB_PATH") or os.path.join(_PKG, "libsafediffcon_b200.so")   # override: A/B of two builds (scripts/)
 _lib = None
 
 c_f = ctypes.c_float
