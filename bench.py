@@ -46,8 +46,9 @@ CHAIN_STEPS = 1000
 CONV_GFLOP_PER_SAMPLE = 27.811 - 0.0771 - 0.0016  # tcgen05 convs only: minus the 7x7 stem and the 3-channel head
 W_SCORE, U_BOUND, Q_GUIDE = 500.0, 0.8, 0.0
 # mean dram__bytes_read.sum + dram__bytes_write.sum per conv launch of one step at B=1024, from the ncu pass over THIS code
-# (profiles/r02_per_launch_metrics_B1024.csv: 74 launches, 41.06 GB; summary in profiles/r02_launches_B1024.summary.txt)
-TRAFFIC_BYTES_PER_LAUNCH = 554.8e6
+# (profiles/r02b_per_launch_metrics_B1024.csv: 73 tcgen05 launches incl. the stem, 39.54 GB; summary in
+# profiles/r02b_launches_B1024.summary.txt)
+TRAFFIC_BYTES_PER_LAUNCH = 541.6e6
 CAL_STATES = 2048   # config 4 slice (whole job, sharded over the ranks)
 FP32_PEAK_TFLOPS = 148 * 128 * 2 * 1.965e9 / 1e12   # 74.5: FMA pipe at the maximum SM clock (solver roofline)
 

@@ -374,7 +374,7 @@ __global__ void __launch_bounds__(256, ROWSTATS ? 2 : 4) gn_silu_h8_kernel(const
 // x: fp32 conv output (C = 128); residual: fp16 or fp32.  16 lanes per pixel (8 channels each), a warp covers 2 pixels; the
 // (<= 4) dot products are reduced with a transposing butterfly: 5 shuffles instead of 16.
 template <typename TR>
-__global__ void __launch_bounds__(256) gn_silu_head_kernel(const float* __restrict__ x, const double* __restrict__ stats,
+__global__ void __launch_bounds__(256, 3) gn_silu_head_kernel(const float* __restrict__ x, const double* __restrict__ stats,
                                                            const float* __restrict__ gamma, const float* __restrict__ beta,
                                                            const TR* __restrict__ residual, const float* __restrict__ hw,
                                                            const float* __restrict__ hb, float* __restrict__ out, int HW, int Cout,
@@ -697,7 +697,7 @@ __global__ void __launch_bounds__(256) linattn_context_kernel(const TK* __restri
 // chunk a thread converts 4 rows x 8 channels (always the same channels: their running sums stay in registers), the four
 // warps each multiply a 32-pixel quarter, the 32 x 32 partial contexts are reduced through shared memory at the end.
 // ek = exp(k - max_d + 8 ln 2): the factor 256 keeps small weights out of the fp16 subnormal range and cancels in ctx = acc / ksum.
-constexpr int LC_CH = 128, LC_LD = 40;
+constexpr int LC_LD = 40;
 __device__ __forceinline__ void ldsm_x4_trans(uint32_t (&r)[4], uint32_t addr) {
     asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0, %1, %2, %3}, [%4];"
                  : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
@@ -715,47 +715,63 @@ __device__ __forceinline__ uint32_t hmax2_u32(uint32_t a, uint32_t b) {
     const __half2 r = __hmax2(*reinterpret_cast<const __half2*>(&a), *reinterpret_cast<const __half2*>(&b));
     return *reinterpret_cast<const uint32_t*>(&r);
 }
+// Round 2: the four warps of a CTA are INDEPENDENT streams.  Warp w takes the 32-pixel blocks w, w + 4, ... of the (sample, head)
+// and keeps its own running column maximum, channel sums and 32 x 32 accumulator; the lanes that loaded a block are the lanes whose
+// MMAs consume it (rows of the block = rows of the warp's shared-memory tile), so the loop needs no block barrier at all -- the
+// previous version met four __syncthreads per 128 pixels (maximum exchange, rescale factors, tiles written, tiles consumed) and was
+// latency bound at 0.57 of the copy peak inside the step.  k rows of the next block are requested into registers and the next v
+// block goes global -> shared (cp.async, double buffered) before the MMAs of the current one; accumulators are only rescaled when a
+// column maximum actually rose (warp vote).  The four partial contexts are merged at the end like split-K softmax partials.
 __global__ void __launch_bounds__(128) linattn_context_mma_kernel(const __half* __restrict__ kbase, const __half* __restrict__ vbase,
                                                                   int ld, float* __restrict__ ctx, int n) {
-    __shared__ __align__(16) __half tiles[2 * LC_CH * LC_LD];   // ek | v, 10 KB each; reused for the final reduction (16 KB)
-    __shared__ float red[4][LA_D];
-    __shared__ float kmax[LA_D];
-    __shared__ float rescale[LA_D];
-    __half* ek = tiles;
-    __half* vs = tiles + LC_CH * LC_LD;
+    constexpr int TILE = 32 * LC_LD;                            // halves per 32-pixel tile (80-byte rows: conflict-free ldmatrix)
+    __shared__ __align__(16) __half tiles[4 * 3 * TILE];        // per warp: ek | v (two buffers); reused for the merge (16 KB of floats)
+    __shared__ float wres[4][LA_D];                             // per warp: rescale factors of the current block
+    __shared__ float wmax[4][LA_D], wsum[4][LA_D];
     const int b = blockIdx.x / LA_HEADS, h = blockIdx.x % LA_HEADS;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const __half* kp = kbase + (int64_t)b * n * ld + h * LA_D;
     const __half* vp = vbase + (int64_t)b * n * ld + h * LA_D;
-    const int cg = tid & 3, pr = tid >> 2;   // loader role: channels 8 cg .. 8 cg + 7 of chunk rows pr, pr + 32, pr + 64, pr + 96
-    if (tid < LA_D) kmax[tid] = -INFINITY;
+    const int cg = lane & 3, pr = lane >> 2;   // loader role: channels 8 cg .. 8 cg + 7 of block rows pr, pr + 8, pr + 16, pr + 24
+    __half* ek = tiles + warp * 3 * TILE;
+    const uint32_t ek_s = (uint32_t)__cvta_generic_to_shared(ek), vs_s = ek_s + 2u * TILE;
     float acc[2][4][4];
 #pragma unroll
     for (int i = 0; i < 2; ++i)
 #pragma unroll
-        for (int j = 0; j < 4; ++j)
+        for (int jj = 0; jj < 4; ++jj)
 #pragma unroll
-            for (int k = 0; k < 4; ++k) acc[i][j][k] = 0.f;
-    float ksum[8];
+            for (int k = 0; k < 4; ++k) acc[i][jj][k] = 0.f;
+    float ksum[8], kmx[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) ksum[j] = 0.f;
+    for (int jj = 0; jj < 8; ++jj) { ksum[jj] = 0.f; kmx[jj] = -INFINITY; }
     constexpr float LOG2E = 1.4426950408889634f;
-    const uint32_t ek_s = (uint32_t)__cvta_generic_to_shared(ek), vs_s = (uint32_t)__cvta_generic_to_shared(vs);
-    // Software pipeline: the k rows of chunk i+1 are requested (into the registers chunk i has just finished with) before the
-    // MMAs of chunk i, and v goes global -> shared with cp.async (zero fill past the end) while the maxima / exponentials run.
+    const int blocks = (n + 31) / 32;
     uint4 kr[4];
-    auto load_k = [&](int n0) {
-        const int cnt = min(LC_CH, n - n0);
+    auto load_k = [&](int blk) {
+        const int n0 = blk * 32;
 #pragma unroll
         for (int rr = 0; rr < 4; ++rr) {
-            const int r = pr + 32 * rr;
+            const int r = n0 + pr + 8 * rr;
             kr[rr] = make_uint4(0xFC00FC00u, 0xFC00FC00u, 0xFC00FC00u, 0xFC00FC00u);   // -inf: exp = 0, rows past the end add nothing
-            if (r < cnt) kr[rr] = __ldcs(reinterpret_cast<const uint4*>(kp + (int64_t)(n0 + r) * ld + cg * 8));
+            if (r < n) kr[rr] = __ldcs(reinterpret_cast<const uint4*>(kp + (int64_t)r * ld + cg * 8));
         }
     };
-    load_k(0);
-    for (int n0 = 0; n0 < n; n0 += LC_CH) {
-        const int cnt = min(LC_CH, n - n0);
+    auto load_v = [&](int blk, int buf) {
+        const int n0 = blk * 32;
+#pragma unroll
+        for (int rr = 0; rr < 4; ++rr) {
+            const int rl = pr + 8 * rr, r = n0 + rl;
+            const __half* src = vp + (int64_t)min(r, n - 1) * ld + cg * 8;   // clamped address, 0 source bytes past the end
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(vs_s + 2u * (uint32_t)(buf * TILE + rl * LC_LD + cg * 8)), "l"(src),
+                         "r"(r < n ? 16 : 0) : "memory");
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    if (warp < blocks) { load_k(warp); load_v(warp, 0); }
+    int it = 0;
+    for (int blk = warp; blk < blocks; blk += 4, ++it) {
+        // column maxima of this block: over the thread's four rows, then over the eight row groups of the warp
         uint32_t m2[4] = {kr[0].x, kr[0].y, kr[0].z, kr[0].w};
 #pragma unroll
         for (int rr = 1; rr < 4; ++rr) {
@@ -765,82 +781,85 @@ __global__ void __launch_bounds__(128) linattn_context_mma_kernel(const __half* 
 #pragma unroll
         for (int o = 4; o < 32; o <<= 1) {
 #pragma unroll
-            for (int j = 0; j < 4; ++j) m2[j] = hmax2_u32(m2[j], __shfl_xor_sync(0xffffffffu, m2[j], o));
+            for (int jj = 0; jj < 4; ++jj) m2[jj] = hmax2_u32(m2[jj], __shfl_xor_sync(0xffffffffu, m2[jj], o));
         }
-        __syncthreads();   // the previous chunk's tiles, maxima and rescale factors are consumed
+        float mn[8];
+        bool rose = false;
 #pragma unroll
-        for (int rr = 0; rr < 4; ++rr) {
-            const int r = pr + 32 * rr;
-            const __half* src = vp + (int64_t)(n0 + min(r, cnt - 1)) * ld + cg * 8;   // clamped address, 0 source bytes past the end
-            asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(vs_s + 2u * (uint32_t)(r * LC_LD + cg * 8)), "l"(src),
-                         "r"(r < cnt ? 16 : 0) : "memory");
+        for (int jj = 0; jj < 4; ++jj) {
+            const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&m2[jj]));
+            mn[2 * jj] = fmaxf(kmx[2 * jj], f.x);
+            mn[2 * jj + 1] = fmaxf(kmx[2 * jj + 1], f.y);
+            rose |= mn[2 * jj] != kmx[2 * jj] || mn[2 * jj + 1] != kmx[2 * jj + 1];
         }
-        asm volatile("cp.async.commit_group;" ::: "memory");
-        if (lane < 4) {
+        if (__any_sync(0xffffffffu, rose)) {   // warp-uniform: every lane with the same cg holds the same maxima
+            float sc[8];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&m2[j]));
-                red[warp][cg * 8 + 2 * j] = f.x;
-                red[warp][cg * 8 + 2 * j + 1] = f.y;
+            for (int jj = 0; jj < 8; ++jj) {
+                sc[jj] = (kmx[jj] == mn[jj]) ? 1.0f : __expf(kmx[jj] - mn[jj]);   // first block: exp(-inf) = 0 on zero accumulators
+                ksum[jj] *= sc[jj];
+                kmx[jj] = mn[jj];
             }
+            if (pr == 0) {
+                *reinterpret_cast<float4*>(&wres[warp][cg * 8]) = make_float4(sc[0], sc[1], sc[2], sc[3]);
+                *reinterpret_cast<float4*>(&wres[warp][cg * 8 + 4]) = make_float4(sc[4], sc[5], sc[6], sc[7]);
+            }
+            __syncwarp();
+            const int g = lane >> 2;
+#pragma unroll
+            for (int mt = 0; mt < 2; ++mt) {
+                const float s0 = wres[warp][mt * 16 + g], s1 = wres[warp][mt * 16 + g + 8];
+#pragma unroll
+                for (int nt = 0; nt < 4; ++nt) { acc[mt][nt][0] *= s0; acc[mt][nt][1] *= s0; acc[mt][nt][2] *= s1; acc[mt][nt][3] *= s1; }
+            }
+            __syncwarp();
         }
-        __syncthreads();
-        if (tid < LA_D) {
-            const float t = fmaxf(fmaxf(red[0][tid], red[1][tid]), fmaxf(red[2][tid], red[3][tid]));
-            const float mo = kmax[tid], mn = fmaxf(mo, t);
-            rescale[tid] = (mo == mn) ? 1.0f : __expf(mo - mn);   // first chunk: exp(-inf) = 0 on zero accumulators
-            kmax[tid] = mn;
-        }
-        __syncthreads();
         {
             float off[8];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                off[j] = fmaf(-kmax[cg * 8 + j], LOG2E, 8.0f);
-                ksum[j] *= rescale[cg * 8 + j];
-            }
+            for (int jj = 0; jj < 8; ++jj) off[jj] = fmaf(-kmx[jj], LOG2E, 8.0f);
 #pragma unroll
             for (int rr = 0; rr < 4; ++rr) {
                 float f[8];
                 unpack8(kr[rr], f);
 #pragma unroll
-                for (int j = 0; j < 8; ++j) f[j] = ex2_approx(fmaf(f[j], LOG2E, off[j]));
+                for (int jj = 0; jj < 8; ++jj) f[jj] = ex2_approx(fmaf(f[jj], LOG2E, off[jj]));
                 const uint4 e8 = pack8(f);
                 unpack8(e8, f);   // the sums use the values the tensor cores see
 #pragma unroll
-                for (int j = 0; j < 8; ++j) ksum[j] += f[j];
-                *reinterpret_cast<uint4*>(ek + (pr + 32 * rr) * LC_LD + cg * 8) = e8;
-            }
-            const int g = lane >> 2;
-#pragma unroll
-            for (int mt = 0; mt < 2; ++mt) {
-                const float s0 = rescale[mt * 16 + g], s1 = rescale[mt * 16 + g + 8];
-#pragma unroll
-                for (int nt = 0; nt < 4; ++nt) { acc[mt][nt][0] *= s0; acc[mt][nt][1] *= s0; acc[mt][nt][2] *= s1; acc[mt][nt][3] *= s1; }
+                for (int jj = 0; jj < 8; ++jj) ksum[jj] += f[jj];
+                *reinterpret_cast<uint4*>(ek + (pr + 8 * rr) * LC_LD + cg * 8) = e8;
             }
         }
-        if (n0 + LC_CH < n) load_k(n0 + LC_CH);   // prefetch: in flight across the barrier and the MMAs below
-        asm volatile("cp.async.wait_all;" ::: "memory");
-        __syncthreads();
+        const int buf = it & 1;
+        if (blk + 4 < blocks) {   // the warp's next block: k rows into the registers just consumed, v into the other buffer
+            load_k(blk + 4);
+            load_v(blk + 4, buf ^ 1);
+            asm volatile("cp.async.wait_group 1;" ::: "memory");
+        } else {
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
+        }
+        __syncwarp();
 #pragma unroll
         for (int ks = 0; ks < 2; ++ks) {
-            const int k0 = warp * 32 + ks * 16;
+            const int k0 = ks * 16;
             uint32_t a[2][4], bb[2][4];
 #pragma unroll
             for (int mt = 0; mt < 2; ++mt)
                 ldsm_x4_trans(a[mt], ek_s + 2u * (uint32_t)((k0 + (lane & 7) + ((lane >> 4) << 3)) * LC_LD + mt * 16 + (((lane >> 3) & 1) << 3)));
 #pragma unroll
             for (int np = 0; np < 2; ++np)
-                ldsm_x4_trans(bb[np], vs_s + 2u * (uint32_t)((k0 + (lane & 7) + (((lane >> 3) & 1) << 3)) * LC_LD + np * 16 + ((lane >> 4) << 3)));
+                ldsm_x4_trans(bb[np], vs_s + 2u * (uint32_t)(buf * TILE + (k0 + (lane & 7) + (((lane >> 3) & 1) << 3)) * LC_LD + np * 16 + ((lane >> 4) << 3)));
 #pragma unroll
             for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
                 for (int nt = 0; nt < 4; ++nt) mma_f16_16x8x16(acc[mt][nt], a[mt], bb[nt >> 1][(nt & 1) * 2], bb[nt >> 1][(nt & 1) * 2 + 1]);
         }
+        __syncwarp();   // the tile is rewritten by other lanes in the next iteration
     }
-    // reduce the four warps' partial contexts and channel sums
+    // merge the four warps' partials: maxima, channel sums, contexts
     __syncthreads();
-    float* racc = reinterpret_cast<float*>(tiles);   // [4][32][32] floats = 16 KB
+    float* racc = reinterpret_cast<float*>(tiles);   // [4][32][32] floats = 16 KB (the tile memory holds 30 KB)
     {
         const int g = lane >> 2, c2 = 2 * (lane & 3);
 #pragma unroll
@@ -852,27 +871,40 @@ __global__ void __launch_bounds__(128) linattn_context_mma_kernel(const __half* 
                 *reinterpret_cast<float2*>(o + 8 * LA_D) = make_float2(acc[mt][nt][2], acc[mt][nt][3]);
             }
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            float t = ksum[j];
+        for (int jj = 0; jj < 8; ++jj) {
+            float t = ksum[jj];
 #pragma unroll
             for (int o = 4; o < 32; o <<= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
-            ksum[j] = t;
+            ksum[jj] = t;
         }
-        if (lane < 4) {
+        if (pr == 0) {
 #pragma unroll
-            for (int j = 0; j < 8; ++j) red[warp][cg * 8 + j] = ksum[j];
+            for (int jj = 0; jj < 8; ++jj) { wsum[warp][cg * 8 + jj] = ksum[jj]; wmax[warp][cg * 8 + jj] = kmx[jj]; }
         }
+    }
+    __syncthreads();
+    if (tid < LA_D) {   // per channel d: global maximum and the factor that brings each warp's partial to it (0 for a warp without blocks)
+        const float M = fmaxf(fmaxf(wmax[0][tid], wmax[1][tid]), fmaxf(wmax[2][tid], wmax[3][tid]));
+        float ks = 0.f;
+#pragma unroll
+        for (int w = 0; w < 4; ++w) {
+            const float f = wmax[w][tid] == -INFINITY ? 0.f : __expf(wmax[w][tid] - M);
+            wres[w][tid] = f;
+            ks = fmaf(wsum[w][tid], f, ks);
+        }
+        wmax[0][tid] = M;
+        wsum[0][tid] = ks;
     }
     __syncthreads();
     float* cb = ctx + (int64_t)blockIdx.x * LA_CTX;
     for (int i = tid; i < LA_D * LA_D; i += 128) {
         const int d = i >> 5;
-        const float ks = (red[0][d] + red[1][d]) + (red[2][d] + red[3][d]);
-        cb[i] = ((racc[i] + racc[1024 + i]) + (racc[2048 + i] + racc[3072 + i])) / ks;
+        const float t = fmaf(racc[i], wres[0][d], racc[1024 + i] * wres[1][d]) + fmaf(racc[2048 + i], wres[2][d], racc[3072 + i] * wres[3][d]);
+        cb[i] = t / wsum[0][d];
     }
     if (tid < LA_D) {
-        cb[LA_D * LA_D + tid] = kmax[tid];
-        cb[LA_D * LA_D + LA_D + tid] = ((red[0][tid] + red[1][tid]) + (red[2][tid] + red[3][tid])) * (1.0f / 256.0f);
+        cb[LA_D * LA_D + tid] = wmax[0][tid];
+        cb[LA_D * LA_D + LA_D + tid] = wsum[0][tid] * (1.0f / 256.0f);
     }
 }
 
