@@ -74,7 +74,7 @@ int sdc_unet_film_table(const sdc_unet* net, float* out, int* rows, int* cols, v
 /* Schedule switches, both EXPERIMENTAL and off by default (correct -- tests -- but measured slower than the separate kernels on
  * B200).  SDC_UNET_FUSE_LN: FP16 mode, levels with <= 256 channels -- the PreNorm LayerNorm is folded into the
  * qkv projection and the output LayerNorm + residual into the per-sample projection (sdc_conv1x1_qkv_ln,
- * sdc_conv1x1_per_sample_ln).  SDC_UNET_FUSE_GN: conv + GroupNorm in one kernel on the 16x128 level (sdc_conv3x3_row_gn). */
+ * sdc_conv1x1_per_sample_ln); value 2 folds the PreNorm only (output LayerNorm as a separate kernel).  SDC_UNET_FUSE_GN: conv + GroupNorm in one kernel on the 16x128 level (sdc_conv3x3_row_gn). */
 #define SDC_UNET_FUSE_LN 1
 #define SDC_UNET_FUSE_GN 2
 /* SDC_UNET_FILM_TC (default 1): build the FiLM table with ONE tcgen05 TF32 GEMM over operands split into high + low parts

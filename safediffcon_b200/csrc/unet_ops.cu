@@ -275,27 +275,28 @@ __device__ __forceinline__ uint4 pack8(const float* f) {
     return u;
 }
 // channel mean / rstd of one pixel row held as 8 fp16 values per lane by c8n (16 or 32) adjacent lanes; vector index i = row * c8n + lane.
-// Same two-pass arithmetic as channel_layernorm_h_kernel on the same (rounded) values; the whole warp takes part.
+// One pass (sum and sum of squares reduced side by side: two independent shuffle chains of log2(c8n) steps instead of two dependent
+// passes) on the ROUNDED values the projection will read; fp32 is ample for <= 256 values of O(1).  The whole warp takes part.
 __device__ __forceinline__ void row_stats8(const uint4& o, int c8n, int C, float2* __restrict__ rs, int i) {
     float v[8];
     unpack8(o, v);
-    float sm = 0.f;
+    float sm = 0.f, q = 0.f;
 #pragma unroll
-    for (int k = 0; k < 8; ++k) sm += v[k];
-    for (int m = 1; m < c8n; m <<= 1) sm += __shfl_xor_sync(0xffffffffu, sm, m);
-    const float mean = sm * (1.0f / (float)C);
-    float q = 0.f;
-#pragma unroll
-    for (int k = 0; k < 8; ++k) { const float d = v[k] - mean; q = fmaf(d, d, q); }
-    for (int m = 1; m < c8n; m <<= 1) q += __shfl_xor_sync(0xffffffffu, q, m);
-    if (i % c8n == 0) rs[i / c8n] = make_float2(mean, rsqrtf(q * (1.0f / (float)C) + 1e-5f));
+    for (int k = 0; k < 8; ++k) { sm += v[k]; q = fmaf(v[k], v[k], q); }
+    for (int m = 1; m < c8n; m <<= 1) {
+        sm += __shfl_xor_sync(0xffffffffu, sm, m);
+        q += __shfl_xor_sync(0xffffffffu, q, m);
+    }
+    const float inv = 1.0f / (float)C;
+    const float mean = sm * inv;
+    if (i % c8n == 0) rs[i / c8n] = make_float2(mean, rsqrtf(fmaxf(fmaf(-mean, mean, q * inv), 0.f) + 1e-5f));
 }
 
 // ROWSTATS: additionally emit, per pixel row of the (fp16-rounded) OUTPUT, the channel mean and 1 / sqrt(var + 1e-5) of the channel
 // LayerNorm that follows in PreNorm(LinearAttention) (unet.py:53-63,65-76): the LayerNorm itself is then folded into the qkv
 // projection (sdc_conv1x1_qkv_ln) and its separate pass over HBM disappears.  A row is owned by C/8 = 16 or 32 adjacent lanes.
 template <bool ROWSTATS>
-__global__ void __launch_bounds__(256, ROWSTATS ? 2 : 4) gn_silu_h8_kernel(const __half* __restrict__ x, const double* __restrict__ stats,
+__global__ void __launch_bounds__(256, ROWSTATS ? 3 : 4) gn_silu_h8_kernel(const __half* __restrict__ x, const double* __restrict__ stats,
                                                          const float* __restrict__ gamma, const float* __restrict__ beta,
                                                          const float* __restrict__ scale_shift, const int32_t* __restrict__ t_index,
                                                          int64_t ss_stride, const __half* __restrict__ residual, __half* __restrict__ y,

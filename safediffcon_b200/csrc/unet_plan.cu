@@ -135,7 +135,8 @@ struct sdc_unet {
     int stem_kp2 = 0;
     bool bwd_packed = false;
     bool film_tc = true;     // FiLM table GEMM on tcgen05 (TF32, split operands) instead of the fp32 CUDA-core loop
-    bool fuse_ln = false, fuse_gn = false;   // both measured slower than the separate kernels on B200
+    int fuse_ln = 0;         // 0: separate LayerNorm kernels; 1: both LayerNorms of LinearAttention in the projection epilogues; 2: PreNorm only
+    bool fuse_gn = false;    // (value 1 and fuse_gn measured slower than the separate kernels on B200)
     // profile
     bool prof_on = false;
     std::vector<ProfEntry> prof;
@@ -476,6 +477,16 @@ void* attention(Fwd& f, const AttnP& p, const void* xin, int c, int h, int w, co
         void* wf = f.opd((int64_t)f.B * c, HID);
         RUN("linattn_fold", (double)f.B * c * HID * e, 2.0 * f.B * c * HID * 32.0,
             sdc_linear_attention_fold(f.prec, ws, p.out_w32, wf, f.B, c, f.stream));
+        if (f.n->fuse_ln == 2) {
+            // PreNorm folded into the qkv projection only; output projection + LayerNorm + residual as separate kernels
+            void* proj = f.opd(M, c);
+            RUN("conv1x1_per_sample", (double)M * HID * e + (double)M * c * 2.0 + (double)f.B * c * HID * e, 2.0 * M * c * HID,
+                sdc_conv1x1_per_sample(f.prec, qs, HID, wf, p.out.bias, proj, 1, f.B, h, w, c, f.stream));
+            void* out = f.opd(M, c);
+            RUN("layernorm", (double)M * c * (2.0 + 2.0 * e), 0.0, sdc_channel_layernorm(f.prec, proj, 1, p.g_out, xin, out, M, c, 1, f.stream));
+            f.release(qs); f.release(ws); f.release(wf); f.release(proj);
+            return out;
+        }
         void* out = f.opd(M, c);
         RUN("conv1x1_per_sample_ln", (double)M * (HID + 2.0 * c) * e + (double)f.B * c * HID * e, 2.0 * M * c * HID,
             sdc_conv1x1_per_sample_ln(qs, HID, wf, p.out.bias, p.g_out, xin, out, f.B, h, w, c, f.stream));
@@ -1303,7 +1314,7 @@ extern "C" int sdc_unet_film_table(const sdc_unet* n, float* out, int* rows, int
 extern "C" int sdc_unet_set_flag(sdc_unet* n, int flag, int value) {
     SDC_REQUIRE(n && flag >= SDC_UNET_FUSE_LN && flag <= SDC_UNET_BACKWARD, "sdc_unet_set_flag: unknown flag %d", flag);
     if (flag == SDC_UNET_BACKWARD) { n->want_bwd = value != 0; return SDC_OK; }   // takes effect at the next sdc_unet_pack_weights
-    if (flag == SDC_UNET_FUSE_LN) n->fuse_ln = value != 0;
+    if (flag == SDC_UNET_FUSE_LN) n->fuse_ln = value < 0 ? 0 : (value > 2 ? 2 : value);
     else if (flag == SDC_UNET_FUSE_GN) n->fuse_gn = value != 0;
     else n->film_tc = value != 0;   // takes effect at the next sdc_unet_pack_weights
     n->ws_cache.clear();   // the activation layout depends on the schedule

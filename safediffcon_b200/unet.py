@@ -556,7 +556,7 @@ class Unet2D(nn.Module):
         # qkv / output-projection epilogues (sdc_conv1x1_qkv_ln, sdc_conv1x1_per_sample_ln): 1.24 ms of LayerNorm passes disappear
         # per step at B = 1024, but the 1x1 convolutions are epilogue bound already and lose 1.7 ms (profiles/r02_ln_fusion_ab.txt).
         # SDC_FUSE_LN=1 enables it.
-        self.fuse_layernorm = os.environ.get("SDC_FUSE_LN", "0") == "1"
+        self.fuse_layernorm = int(os.environ.get("SDC_FUSE_LN", "0"))   # 0 off, 1 both LayerNorms, 2 PreNorm only
         # FP16-range guard (GaussianDiffusion._run_chain): on non-finite eps the chain is repeated with TF32 operands
         self.overflow_fallback = True
 
@@ -625,7 +625,7 @@ class Unet2D(nn.Module):
             plan = UnetPlan(self.dim, dims, self.channels, self.out_dim, prec, self.theta, self.table_timesteps)
             c.plan, c.plan_gen = plan, c.plan_gen + 1
         if (plan.flags != (self.fuse_layernorm, self.fuse_groupnorm)):
-            plan.set_flag(UnetPlan.FUSE_LN, self.fuse_layernorm)
+            plan.set_flag(UnetPlan.FUSE_LN, int(self.fuse_layernorm))
             plan.set_flag(UnetPlan.FUSE_GN, self.fuse_groupnorm)
             plan.flags = (self.fuse_layernorm, self.fuse_groupnorm)
         if backward and not plan.backward:
