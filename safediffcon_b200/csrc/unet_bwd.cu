@@ -289,101 +289,126 @@ __global__ void __launch_bounds__(256) linattn_bwd_reduce_kernel(const float* __
 }
 
 // per pixel: dq, dk, dv -> dqkv[B*n, 384] (TF32-rounded operand of the qkv dgrad)      grid = (B*heads, ceil(n/128)), 128 threads
+// One thread owns one pixel of one head (three 32 x 32 matrix-vector products in registers).  Its 128-byte slices of q, k, v, dO
+// and of the three results sit 1536 / 512 bytes apart from its neighbour's, so direct per-thread accesses cost 32 sectors per
+// warp instruction (round 2 profile: 5.0 ms per 16x128-level call at B = 1024 against ~1.3 ms of HBM time).  All global traffic
+// therefore goes through two shared-memory tiles with COALESCED 16-byte accesses (8 lanes per pixel row); the per-thread row
+// reads / writes use a 33-float pitch (conflict free).
+constexpr int LB_PITCH = LB_D + 1;
+__device__ __forceinline__ void lb_tile_load(float* tile, const float* __restrict__ src, int64_t row_stride, int rows, int tid) {
+    // tile[r][0..31] <- src[r * row_stride + 0..31], r < rows (zero beyond); 128 threads: 16 rows per pass
+    const int c4 = (tid & 7) * 4, r0 = tid >> 3;
+#pragma unroll
+    for (int rr = 0; rr < 128; rr += 16) {
+        const int r = rr + r0;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (r < rows) v = *reinterpret_cast<const float4*>(src + (int64_t)r * row_stride + c4);
+        float* d = tile + r * LB_PITCH + c4;
+        d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
+    }
+}
+__device__ __forceinline__ void lb_tile_store(const float* tile, float* __restrict__ dst, int64_t row_stride, int rows, int tid) {
+    const int c4 = (tid & 7) * 4, r0 = tid >> 3;
+#pragma unroll
+    for (int rr = 0; rr < 128; rr += 16) {
+        const int r = rr + r0;
+        if (r < rows) {
+            const float* t = tile + r * LB_PITCH + c4;
+            store_operand4(dst + (int64_t)r * row_stride + c4, make_float4(t[0], t[1], t[2], t[3]));
+        }
+    }
+}
 __global__ void __launch_bounds__(128) linattn_bwd_apply_kernel(const float* __restrict__ qkv, const float* __restrict__ dout,
                                                                 const float* __restrict__ fwd_ws, const float* __restrict__ dctx,
                                                                 float* __restrict__ dqkv, int n) {
     __shared__ __align__(16) float cs[LB_D][LB_D];    // ctx[d][e]
     __shared__ __align__(16) float dcs[LB_D][LB_D];   // dctx[d][e]
     __shared__ float kmax[LB_D], kinv[LB_D], cdot[LB_D];
+    __shared__ float t0[128 * LB_PITCH], t1[128 * LB_PITCH];
     const int b = blockIdx.x / LB_HEADS, h = blockIdx.x % LB_HEADS;
+    const int tid = threadIdx.x;
     const float* ws = fwd_ws + (int64_t)blockIdx.x * LB_CTX;
-    for (int i = threadIdx.x; i < LB_D * LB_D; i += blockDim.x) {
+    const int p0 = blockIdx.y * 128;
+    const int rows = min(128, n - p0);
+    const int64_t pix0 = (int64_t)b * n + p0;
+    const float* qbase = qkv + pix0 * LB_QKV + h * LB_D;
+    float* obase = dqkv + pix0 * LB_QKV + h * LB_D;
+    lb_tile_load(t0, qbase, LB_QKV, rows, tid);                                   // q
+    lb_tile_load(t1, dout + pix0 * LB_HID + h * LB_D, LB_HID, rows, tid);         // dO
+    for (int i = tid; i < LB_D * LB_D; i += 128) {
         cs[i >> 5][i & 31] = ws[i];
         dcs[i >> 5][i & 31] = dctx[(int64_t)blockIdx.x * LB_D * LB_D + i];
     }
-    if (threadIdx.x < LB_D) {
-        kmax[threadIdx.x] = ws[LB_D * LB_D + threadIdx.x];
-        kinv[threadIdx.x] = 1.0f / ws[LB_D * LB_D + LB_D + threadIdx.x];
+    if (tid < LB_D) {
+        kmax[tid] = ws[LB_D * LB_D + tid];
+        kinv[tid] = 1.0f / ws[LB_D * LB_D + LB_D + tid];
     }
     __syncthreads();
-    if (threadIdx.x < LB_D) {
+    if (tid < LB_D) {
         float a = 0.f;
-        for (int e = 0; e < LB_D; ++e) a = fmaf(dcs[threadIdx.x][e], cs[threadIdx.x][e], a);
-        cdot[threadIdx.x] = a;   // = sum_n ks[d,n] dks[d,n]
+        for (int e = 0; e < LB_D; ++e) a = fmaf(dcs[tid][e], cs[tid][e], a);
+        cdot[tid] = a;   // = sum_n ks[d,n] dks[d,n]
     }
-    __syncthreads();
-    const int i = blockIdx.y * 128 + threadIdx.x;
-    if (i >= n) return;
-    const int64_t pix = (int64_t)b * n + i;
-    const float* base = qkv + pix * LB_QKV + h * LB_D;
-    float* obase = dqkv + pix * LB_QKV + h * LB_D;
     float a[LB_D], g[LB_D];
+    float* my0 = t0 + tid * LB_PITCH;
+    float* my1 = t1 + tid * LB_PITCH;
     {   // ---- dq = p * (dp - sum p dp), p = softmax_d(q), dp[d] = 32^-0.5 * sum_e ctx[d,e] dO[e]
-        const float* dop = dout + pix * LB_HID + h * LB_D;
 #pragma unroll
-        for (int j = 0; j < LB_D; j += 4) {
-            const float4 t = *reinterpret_cast<const float4*>(base + j);
-            a[j] = t.x; a[j + 1] = t.y; a[j + 2] = t.z; a[j + 3] = t.w;
-            const float4 u = *reinterpret_cast<const float4*>(dop + j);
-            g[j] = u.x; g[j + 1] = u.y; g[j + 2] = u.z; g[j + 3] = u.w;
-        }
+        for (int j = 0; j < LB_D; ++j) { a[j] = my0[j]; g[j] = my1[j]; }
         float mx = a[0];
 #pragma unroll
         for (int j = 1; j < LB_D; ++j) mx = fmaxf(mx, a[j]);
         float den = 0.f;
 #pragma unroll
-        for (int j = 0; j < LB_D; ++j) { a[j] = expf(a[j] - mx); den += a[j]; }
+        for (int j = 0; j < LB_D; ++j) { a[j] = __expf(a[j] - mx); den += a[j]; }
         const float inv = 1.0f / den;
         float dot = 0.f;
         float dpv[LB_D];
 #pragma unroll
         for (int d = 0; d < LB_D; ++d) {
-            float s = 0.f;
+            float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;   // four independent chains (a single 32-deep FMA chain per d is latency bound)
 #pragma unroll
             for (int e = 0; e < LB_D; e += 4) {
                 const float4 c4 = *reinterpret_cast<const float4*>(&cs[d][e]);
-                s = fmaf(c4.x, g[e], s); s = fmaf(c4.y, g[e + 1], s); s = fmaf(c4.z, g[e + 2], s); s = fmaf(c4.w, g[e + 3], s);
+                s0 = fmaf(c4.x, g[e], s0); s1 = fmaf(c4.y, g[e + 1], s1); s2 = fmaf(c4.z, g[e + 2], s2); s3 = fmaf(c4.w, g[e + 3], s3);
             }
+            const float s = (s0 + s1) + (s2 + s3);
             a[d] *= inv;
             dpv[d] = s * 0.17677669529663687f;
             dot = fmaf(a[d], dpv[d], dot);
         }
 #pragma unroll
-        for (int d = 0; d < LB_D; d += 4)
-            store_operand4(obase + d, make_float4(a[d] * (dpv[d] - dot), a[d + 1] * (dpv[d + 1] - dot), a[d + 2] * (dpv[d + 2] - dot),
-                                                  a[d + 3] * (dpv[d + 3] - dot)));
+        for (int d = 0; d < LB_D; ++d) my0[d] = a[d] * (dpv[d] - dot);   // own row only: nobody else reads it before the barrier
     }
+    __syncthreads();   // dq rows complete, dO rows consumed, cdot visible
+    lb_tile_store(t0, obase, LB_QKV, rows, tid);                      // dq out
+    lb_tile_load(t0, qbase + 2 * LB_HID, LB_QKV, rows, tid);          // v  (same thread <-> element mapping as the store above)
+    lb_tile_load(t1, qbase + LB_HID, LB_QKV, rows, tid);              // k
+    __syncthreads();
     {   // ---- dk[d] = ks[d] (sum_e dctx[d,e] v[e] - cdot[d]),  dv[e] = sum_d ks[d] dctx[d,e],  ks = exp(k - kmax) / ksum
 #pragma unroll
-        for (int j = 0; j < LB_D; j += 4) {
-            const float4 t = *reinterpret_cast<const float4*>(base + LB_HID + j);
-            a[j] = expf(t.x - kmax[j]) * kinv[j]; a[j + 1] = expf(t.y - kmax[j + 1]) * kinv[j + 1];
-            a[j + 2] = expf(t.z - kmax[j + 2]) * kinv[j + 2]; a[j + 3] = expf(t.w - kmax[j + 3]) * kinv[j + 3];
-            const float4 u = *reinterpret_cast<const float4*>(base + 2 * LB_HID + j);
-            g[j] = u.x; g[j + 1] = u.y; g[j + 2] = u.z; g[j + 3] = u.w;
-        }
+        for (int j = 0; j < LB_D; ++j) { a[j] = expf(my1[j] - kmax[j]) * kinv[j]; g[j] = my0[j]; }
         float dv[LB_D];
 #pragma unroll
         for (int e = 0; e < LB_D; ++e) dv[e] = 0.f;
-        float dk[LB_D];
 #pragma unroll
         for (int d = 0; d < LB_D; ++d) {
-            float s = 0.f;
+            float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
 #pragma unroll
             for (int e = 0; e < LB_D; e += 4) {
                 const float4 c4 = *reinterpret_cast<const float4*>(&dcs[d][e]);
-                s = fmaf(c4.x, g[e], s); s = fmaf(c4.y, g[e + 1], s); s = fmaf(c4.z, g[e + 2], s); s = fmaf(c4.w, g[e + 3], s);
+                s0 = fmaf(c4.x, g[e], s0); s1 = fmaf(c4.y, g[e + 1], s1); s2 = fmaf(c4.z, g[e + 2], s2); s3 = fmaf(c4.w, g[e + 3], s3);
                 dv[e] = fmaf(a[d], c4.x, dv[e]); dv[e + 1] = fmaf(a[d], c4.y, dv[e + 1]);
                 dv[e + 2] = fmaf(a[d], c4.z, dv[e + 2]); dv[e + 3] = fmaf(a[d], c4.w, dv[e + 3]);
             }
-            dk[d] = a[d] * (s - cdot[d]);
+            my1[d] = a[d] * (((s0 + s1) + (s2 + s3)) - cdot[d]);   // dk
         }
 #pragma unroll
-        for (int d = 0; d < LB_D; d += 4) {
-            store_operand4(obase + LB_HID + d, make_float4(dk[d], dk[d + 1], dk[d + 2], dk[d + 3]));
-            store_operand4(obase + 2 * LB_HID + d, make_float4(dv[d], dv[d + 1], dv[d + 2], dv[d + 3]));
-        }
+        for (int e = 0; e < LB_D; ++e) my0[e] = dv[e];
     }
+    __syncthreads();
+    lb_tile_store(t1, obase + LB_HID, LB_QKV, rows, tid);
+    lb_tile_store(t0, obase + 2 * LB_HID, LB_QKV, rows, tid);
 }
 
 // ---------------------------------------------------------------------------------------------- full attention backward (n <= 32)
