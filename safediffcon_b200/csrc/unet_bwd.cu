@@ -289,22 +289,61 @@ __global__ void __launch_bounds__(256) linattn_bwd_reduce_kernel(const float* __
 }
 
 // per pixel: dq, dk, dv -> dqkv[B*n, 384] (TF32-rounded operand of the qkv dgrad)      grid = (B*heads, ceil(n/128)), 128 threads
-// One thread owns one pixel of one head (three 32 x 32 matrix-vector products in registers).  Its 128-byte slices of q, k, v, dO
-// and of the three results sit 1536 / 512 bytes apart from its neighbour's, so direct per-thread accesses cost 32 sectors per
-// warp instruction (round 2 profile: 5.0 ms per 16x128-level call at B = 1024 against ~1.3 ms of HBM time).  All global traffic
-// therefore goes through two shared-memory tiles with COALESCED 16-byte accesses (8 lanes per pixel row); the per-thread row
-// reads / writes use a 33-float pitch (conflict free).
-constexpr int LB_PITCH = LB_D + 1;
-__device__ __forceinline__ void lb_tile_load(float* tile, const float* __restrict__ src, int64_t row_stride, int rows, int tid) {
-    // tile[r][0..31] <- src[r * row_stride + 0..31], r < rows (zero beyond); 128 threads: 16 rows per pass
+//   dq = p (dp - <p, dp>),  p = softmax_d(q),  dp = 32^-0.5 dO C^T          (C = ctx[d][e] of the forward)
+//   dk = ks (S - cdot),     ks = exp(k - kmax) / ksum,  S = v D^T            (D = dctx[d][e], cdot[d] = <C[d], D[d]>)
+//   dv = ks D
+// Round-2 history: (1) one thread per pixel with three 32 x 32 matrix-vector products in registers and per-thread global accesses:
+// 5.0 ms per 16x128-level call at B = 1024; (2) coalesced shared-memory staging: 4.1 ms -- the profile then showed the kernel bound by
+// the broadcast LDS.128 that feed the matrix rows (one per 4-8 FMA: 512 B of register-file return traffic each).  (3) This version:
+// the three products are [128 px x 32] x [32 x 32] GEMMs on mma.sync.m16n8k8 TF32 (operands rounded to nearest like every other
+// tensor-core operand of the backward pass, fp32 accumulate); a warp owns 32 pixel rows (two M tiles); softmax / Jacobian algebra runs
+// on the accumulator fragments (a pixel's 32 channels sit in the 4 lanes of a quad: two shuffles per reduction).  All global traffic
+// goes through two shared-memory tiles with coalesced 16-byte accesses; 36-float pitch = conflict-free fragment loads.
+constexpr int LB_TP = LB_D + 4;
+__device__ __forceinline__ uint32_t lb_tf32(float x) {
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+    return r;
+}
+__device__ __forceinline__ void lb_mma(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3]) : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+// acc[nt] (16 x 8 each, nt = 0..3) = A[16 x 32] * B with A = rows r0 .. r0 + 15 of `tile` and B[k][n] = m[n][k] (both pitch LB_TP)
+__device__ __forceinline__ void lb_gemm(float (&acc)[4][4], const float* tile, int r0, const float* m, int lane) {
+    const int g = lane >> 2, t = lane & 3;
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt) { acc[nt][0] = 0.f; acc[nt][1] = 0.f; acc[nt][2] = 0.f; acc[nt][3] = 0.f; }
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks) {
+        const float* ar = tile + (r0 + g) * LB_TP + 8 * ks + t;
+        const uint32_t a[4] = {lb_tf32(ar[0]), lb_tf32(ar[8 * LB_TP]), lb_tf32(ar[4]), lb_tf32(ar[8 * LB_TP + 4])};
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) {
+            const float* br = m + (8 * nt + g) * LB_TP + 8 * ks + t;
+            lb_mma(acc[nt], a, lb_tf32(br[0]), lb_tf32(br[4]));
+        }
+    }
+}
+// tile[r][0..31] <- f(src[r * row_stride + 0..31]), r < rows (zero beyond); 128 threads: 16 rows per pass, 8 lanes per row
+template <bool KS>
+__device__ __forceinline__ void lb_tile_load(float* tile, const float* __restrict__ src, int64_t row_stride, int rows, int tid,
+                                             const float* kmax, const float* kinv) {
     const int c4 = (tid & 7) * 4, r0 = tid >> 3;
+    float m4[4] = {0.f, 0.f, 0.f, 0.f}, i4[4] = {1.f, 1.f, 1.f, 1.f};
+    if constexpr (KS) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) { m4[k] = kmax[c4 + k]; i4[k] = kinv[c4 + k]; }
+    }
 #pragma unroll
     for (int rr = 0; rr < 128; rr += 16) {
         const int r = rr + r0;
         float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (r < rows) v = *reinterpret_cast<const float4*>(src + (int64_t)r * row_stride + c4);
-        float* d = tile + r * LB_PITCH + c4;
-        d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
+        if (r < rows) {
+            v = *reinterpret_cast<const float4*>(src + (int64_t)r * row_stride + c4);
+            if constexpr (KS) v = make_float4(__expf(v.x - m4[0]) * i4[0], __expf(v.y - m4[1]) * i4[1], __expf(v.z - m4[2]) * i4[2], __expf(v.w - m4[3]) * i4[3]);
+        }
+        *reinterpret_cast<float4*>(tile + r * LB_TP + c4) = v;
     }
 }
 __device__ __forceinline__ void lb_tile_store(const float* tile, float* __restrict__ dst, int64_t row_stride, int rows, int tid) {
@@ -312,32 +351,30 @@ __device__ __forceinline__ void lb_tile_store(const float* tile, float* __restri
 #pragma unroll
     for (int rr = 0; rr < 128; rr += 16) {
         const int r = rr + r0;
-        if (r < rows) {
-            const float* t = tile + r * LB_PITCH + c4;
-            store_operand4(dst + (int64_t)r * row_stride + c4, make_float4(t[0], t[1], t[2], t[3]));
-        }
+        if (r < rows) store_operand4(dst + (int64_t)r * row_stride + c4, *reinterpret_cast<const float4*>(tile + r * LB_TP + c4));
     }
 }
 __global__ void __launch_bounds__(128) linattn_bwd_apply_kernel(const float* __restrict__ qkv, const float* __restrict__ dout,
                                                                 const float* __restrict__ fwd_ws, const float* __restrict__ dctx,
                                                                 float* __restrict__ dqkv, int n) {
-    __shared__ __align__(16) float cs[LB_D][LB_D];    // ctx[d][e]
-    __shared__ __align__(16) float dcs[LB_D][LB_D];   // dctx[d][e]
+    __shared__ __align__(16) float m0[LB_D * LB_TP];   // phase A: ctx[d][e];  phase B: dctx transposed, [e][d]
+    __shared__ __align__(16) float m1[LB_D * LB_TP];   // dctx[d][e]
     __shared__ float kmax[LB_D], kinv[LB_D], cdot[LB_D];
-    __shared__ float t0[128 * LB_PITCH], t1[128 * LB_PITCH];
+    __shared__ __align__(16) float t0[128 * LB_TP], t1[128 * LB_TP];
     const int b = blockIdx.x / LB_HEADS, h = blockIdx.x % LB_HEADS;
-    const int tid = threadIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int g = lane >> 2, t = lane & 3;
     const float* ws = fwd_ws + (int64_t)blockIdx.x * LB_CTX;
     const int p0 = blockIdx.y * 128;
     const int rows = min(128, n - p0);
     const int64_t pix0 = (int64_t)b * n + p0;
     const float* qbase = qkv + pix0 * LB_QKV + h * LB_D;
     float* obase = dqkv + pix0 * LB_QKV + h * LB_D;
-    lb_tile_load(t0, qbase, LB_QKV, rows, tid);                                   // q
-    lb_tile_load(t1, dout + pix0 * LB_HID + h * LB_D, LB_HID, rows, tid);         // dO
+    lb_tile_load<false>(t0, qbase, LB_QKV, rows, tid, nullptr, nullptr);                                   // q
+    lb_tile_load<false>(t1, dout + pix0 * LB_HID + h * LB_D, LB_HID, rows, tid, nullptr, nullptr);         // dO
     for (int i = tid; i < LB_D * LB_D; i += 128) {
-        cs[i >> 5][i & 31] = ws[i];
-        dcs[i >> 5][i & 31] = dctx[(int64_t)blockIdx.x * LB_D * LB_D + i];
+        m0[(i >> 5) * LB_TP + (i & 31)] = ws[i];
+        m1[(i >> 5) * LB_TP + (i & 31)] = dctx[(int64_t)blockIdx.x * LB_D * LB_D + i];
     }
     if (tid < LB_D) {
         kmax[tid] = ws[LB_D * LB_D + tid];
@@ -346,65 +383,89 @@ __global__ void __launch_bounds__(128) linattn_bwd_apply_kernel(const float* __r
     __syncthreads();
     if (tid < LB_D) {
         float a = 0.f;
-        for (int e = 0; e < LB_D; ++e) a = fmaf(dcs[tid][e], cs[tid][e], a);
+        for (int e = 0; e < LB_D; ++e) a = fmaf(m1[tid * LB_TP + e], m0[tid * LB_TP + e], a);
         cdot[tid] = a;   // = sum_n ks[d,n] dks[d,n]
     }
-    float a[LB_D], g[LB_D];
-    float* my0 = t0 + tid * LB_PITCH;
-    float* my1 = t1 + tid * LB_PITCH;
-    {   // ---- dq = p * (dp - sum p dp), p = softmax_d(q), dp[d] = 32^-0.5 * sum_e ctx[d,e] dO[e]
+    // ---- phase A: dq (this warp's 32 rows, two M tiles) ----
 #pragma unroll
-        for (int j = 0; j < LB_D; ++j) { a[j] = my0[j]; g[j] = my1[j]; }
-        float mx = a[0];
+    for (int mt = 0; mt < 2; ++mt) {
+        const int r0 = warp * 32 + mt * 16;
+        float dp[4][4];
+        lb_gemm(dp, t1, r0, m0, lane);   // dO C^T: columns = d
+        float* q0 = t0 + (r0 + g) * LB_TP + 2 * t;   // accumulator layout: rows r0 + g, r0 + g + 8; columns 8 nt + 2 t, + 1
+        float* q1 = q0 + 8 * LB_TP;
+        float p[4][4];
+        float mx0 = -INFINITY, mx1 = -INFINITY;
 #pragma unroll
-        for (int j = 1; j < LB_D; ++j) mx = fmaxf(mx, a[j]);
-        float den = 0.f;
-#pragma unroll
-        for (int j = 0; j < LB_D; ++j) { a[j] = __expf(a[j] - mx); den += a[j]; }
-        const float inv = 1.0f / den;
-        float dot = 0.f;
-        float dpv[LB_D];
-#pragma unroll
-        for (int d = 0; d < LB_D; ++d) {
-            float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;   // four independent chains (a single 32-deep FMA chain per d is latency bound)
-#pragma unroll
-            for (int e = 0; e < LB_D; e += 4) {
-                const float4 c4 = *reinterpret_cast<const float4*>(&cs[d][e]);
-                s0 = fmaf(c4.x, g[e], s0); s1 = fmaf(c4.y, g[e + 1], s1); s2 = fmaf(c4.z, g[e + 2], s2); s3 = fmaf(c4.w, g[e + 3], s3);
-            }
-            const float s = (s0 + s1) + (s2 + s3);
-            a[d] *= inv;
-            dpv[d] = s * 0.17677669529663687f;
-            dot = fmaf(a[d], dpv[d], dot);
+        for (int nt = 0; nt < 4; ++nt) {
+            const float2 u = *reinterpret_cast<const float2*>(q0 + 8 * nt), w = *reinterpret_cast<const float2*>(q1 + 8 * nt);
+            p[nt][0] = u.x; p[nt][1] = u.y; p[nt][2] = w.x; p[nt][3] = w.y;
+            mx0 = fmaxf(mx0, fmaxf(u.x, u.y));
+            mx1 = fmaxf(mx1, fmaxf(w.x, w.y));
         }
+        mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1)); mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
+        mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1)); mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
+        float d0 = 0.f, d1 = 0.f;
 #pragma unroll
-        for (int d = 0; d < LB_D; ++d) my0[d] = a[d] * (dpv[d] - dot);   // own row only: nobody else reads it before the barrier
+        for (int nt = 0; nt < 4; ++nt) {
+            p[nt][0] = __expf(p[nt][0] - mx0); p[nt][1] = __expf(p[nt][1] - mx0);
+            p[nt][2] = __expf(p[nt][2] - mx1); p[nt][3] = __expf(p[nt][3] - mx1);
+            d0 += p[nt][0] + p[nt][1];
+            d1 += p[nt][2] + p[nt][3];
+        }
+        d0 += __shfl_xor_sync(0xffffffffu, d0, 1); d0 += __shfl_xor_sync(0xffffffffu, d0, 2);
+        d1 += __shfl_xor_sync(0xffffffffu, d1, 1); d1 += __shfl_xor_sync(0xffffffffu, d1, 2);
+        const float i0 = 1.0f / d0, i1 = 1.0f / d1;
+        float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) {
+            p[nt][0] *= i0; p[nt][1] *= i0; p[nt][2] *= i1; p[nt][3] *= i1;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) dp[nt][k] *= 0.17677669529663687f;
+            s0 += p[nt][0] * dp[nt][0] + p[nt][1] * dp[nt][1];
+            s1 += p[nt][2] * dp[nt][2] + p[nt][3] * dp[nt][3];
+        }
+        s0 += __shfl_xor_sync(0xffffffffu, s0, 1); s0 += __shfl_xor_sync(0xffffffffu, s0, 2);
+        s1 += __shfl_xor_sync(0xffffffffu, s1, 1); s1 += __shfl_xor_sync(0xffffffffu, s1, 2);
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) {   // own rows, own elements: each q element was read by exactly this lane
+            *reinterpret_cast<float2*>(q0 + 8 * nt) = make_float2(p[nt][0] * (dp[nt][0] - s0), p[nt][1] * (dp[nt][1] - s0));
+            *reinterpret_cast<float2*>(q1 + 8 * nt) = make_float2(p[nt][2] * (dp[nt][2] - s1), p[nt][3] * (dp[nt][3] - s1));
+        }
     }
-    __syncthreads();   // dq rows complete, dO rows consumed, cdot visible
-    lb_tile_store(t0, obase, LB_QKV, rows, tid);                      // dq out
-    lb_tile_load(t0, qbase + 2 * LB_HID, LB_QKV, rows, tid);          // v  (same thread <-> element mapping as the store above)
-    lb_tile_load(t1, qbase + LB_HID, LB_QKV, rows, tid);              // k
+    __syncthreads();   // dq rows complete, dO rows and ctx consumed, cdot visible
+    lb_tile_store(t0, obase, LB_QKV, rows, tid);                                           // dq out
+    lb_tile_load<false>(t0, qbase + 2 * LB_HID, LB_QKV, rows, tid, nullptr, nullptr);       // v  (same thread <-> element mapping as the store above)
+    lb_tile_load<true>(t1, qbase + LB_HID, LB_QKV, rows, tid, kmax, kinv);                  // ks = exp(k - kmax) / ksum
+    for (int i = tid; i < LB_D * LB_D; i += 128) m0[(i & 31) * LB_TP + (i >> 5)] = m1[(i >> 5) * LB_TP + (i & 31)];   // m0[e][d] = dctx[d][e]
     __syncthreads();
-    {   // ---- dk[d] = ks[d] (sum_e dctx[d,e] v[e] - cdot[d]),  dv[e] = sum_d ks[d] dctx[d,e],  ks = exp(k - kmax) / ksum
+    // ---- phase B: dk, dv ----
 #pragma unroll
-        for (int j = 0; j < LB_D; ++j) { a[j] = expf(my1[j] - kmax[j]) * kinv[j]; g[j] = my0[j]; }
-        float dv[LB_D];
+    for (int mt = 0; mt < 2; ++mt) {
+        const int r0 = warp * 32 + mt * 16;
+        float sv[4][4], dv[4][4];
+        lb_gemm(sv, t0, r0, m1, lane);   // v D^T: columns = d
+        lb_gemm(dv, t1, r0, m0, lane);   // ks D:  columns = e
+        float* k0 = t1 + (r0 + g) * LB_TP + 2 * t;
+        float* k1 = k0 + 8 * LB_TP;
+        float* v0 = t0 + (r0 + g) * LB_TP + 2 * t;
+        float* v1 = v0 + 8 * LB_TP;
+        float dk[4][4];
 #pragma unroll
-        for (int e = 0; e < LB_D; ++e) dv[e] = 0.f;
-#pragma unroll
-        for (int d = 0; d < LB_D; ++d) {
-            float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
-#pragma unroll
-            for (int e = 0; e < LB_D; e += 4) {
-                const float4 c4 = *reinterpret_cast<const float4*>(&dcs[d][e]);
-                s0 = fmaf(c4.x, g[e], s0); s1 = fmaf(c4.y, g[e + 1], s1); s2 = fmaf(c4.z, g[e + 2], s2); s3 = fmaf(c4.w, g[e + 3], s3);
-                dv[e] = fmaf(a[d], c4.x, dv[e]); dv[e + 1] = fmaf(a[d], c4.y, dv[e + 1]);
-                dv[e + 2] = fmaf(a[d], c4.z, dv[e + 2]); dv[e + 3] = fmaf(a[d], c4.w, dv[e + 3]);
-            }
-            my1[d] = a[d] * (((s0 + s1) + (s2 + s3)) - cdot[d]);   // dk
+        for (int nt = 0; nt < 4; ++nt) {
+            const float2 u = *reinterpret_cast<const float2*>(k0 + 8 * nt), w = *reinterpret_cast<const float2*>(k1 + 8 * nt);
+            const float c0 = cdot[8 * nt + 2 * t], c1 = cdot[8 * nt + 2 * t + 1];
+            dk[nt][0] = u.x * (sv[nt][0] - c0); dk[nt][1] = u.y * (sv[nt][1] - c1);
+            dk[nt][2] = w.x * (sv[nt][2] - c0); dk[nt][3] = w.y * (sv[nt][3] - c1);
         }
+        __syncwarp();   // every lane's fragment reads of these 16 rows of ks / v are done before they are overwritten
 #pragma unroll
-        for (int e = 0; e < LB_D; ++e) my0[e] = dv[e];
+        for (int nt = 0; nt < 4; ++nt) {
+            *reinterpret_cast<float2*>(k0 + 8 * nt) = make_float2(dk[nt][0], dk[nt][1]);
+            *reinterpret_cast<float2*>(k1 + 8 * nt) = make_float2(dk[nt][2], dk[nt][3]);
+            *reinterpret_cast<float2*>(v0 + 8 * nt) = make_float2(dv[nt][0], dv[nt][1]);
+            *reinterpret_cast<float2*>(v1 + 8 * nt) = make_float2(dv[nt][2], dv[nt][3]);
+        }
     }
     __syncthreads();
     lb_tile_store(t1, obase + LB_HID, LB_QKV, rows, tid);

@@ -21,3 +21,7 @@ tot = sum(e.device_time_total for e in rows)
 print(f"B={B}: device time {tot / 1e3:.2f} ms over {sum(e.count for e in rows)} kernels")
 for e in rows[:28]:
     print(f"  {e.key[:70]:70s} n={e.count:3d} {e.device_time_total / 1e3:8.3f} ms  max {max(1, e.device_time_total) / e.count / 1e3:7.3f} ms avg")
+if len(sys.argv) > 2:   # per-launch durations of the kernels whose name contains argv[2]
+    for e in prof.events():
+        if sys.argv[2] in e.name:
+            print(f"    {e.name[:60]:60s} {e.device_time / 1e3:8.3f} ms")
