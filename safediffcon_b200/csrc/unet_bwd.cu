@@ -9,12 +9,15 @@
 // backward kernels: GroupNorm+FiLM+SiLU, channel LayerNorm, linear / full attention, pixel-(un)shuffle, nearest-upsample,
 // the 3-channel head and the col2im of the 7x7 stem.  All tensors are NHWC pixel rows [B*H*W, C].
 #include "common.cuh"
+#include <stdlib.h>
 #include "../../include/safediffcon_b200_unet.h"
 #include <math.h>
 
 namespace sdc {
 
-__device__ __forceinline__ float sigmoidf_(float v) { return 1.0f / (1.0f + expf(-v)); }
+// MUFU.EX2 + MUFU.RCP (relative error ~1e-6; every consumer rounds to TF32 afterwards).  With expf and an IEEE division the two
+// GroupNorm backward passes were issue bound, not HBM bound (ncu: 3.4 TB/s at 46 % warp occupancy, ~70 instructions per element).
+__device__ __forceinline__ float sigmoidf_(float v) { return __fdividef(1.0f, 1.0f + __expf(-v)); }
 // d silu(z) / dz
 __device__ __forceinline__ float dsilu(float z) {
     const float s = sigmoidf_(z);
@@ -152,6 +155,134 @@ __global__ void __launch_bounds__(256) gn_silu_bwd_apply_kernel(const float* __r
         }
         store_operand4(o + 4 * (int64_t)i, make_float4(r[0], r[1], r[2], r[3]));
     }
+}
+
+// Both passes in ONE kernel (round 2): a cluster of CL CTAs owns one sample.  Pass 1 reads dy and x from HBM and leaves them in L2;
+// the per-CTA partial sums meet through distributed shared memory (fixed summation order: deterministic, no atomics); pass 2
+// re-reads the same lines while they are still L2 resident (2 CTAs of 512 threads per SM: at most 37 samples x 2 MB in flight at
+// the 16x128 level, against 126 MB of L2) and writes dx.  HBM traffic per element: 8 B read + 4 B written instead of 16 + 4 for the
+// two-kernel version above (the backward-data pass spent 16.5 ms of 118 ms in those 76 launches at B = 1024).
+__device__ __forceinline__ double ld_cluster_f64(const double* local, uint32_t rank) {
+    const uint32_t a = (uint32_t)__cvta_generic_to_shared(local);
+    uint32_t ra;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(a), "r"(rank));
+    double v;
+    asm volatile("ld.shared::cluster.f64 %0, [%1];" : "=d"(v) : "r"(ra) : "memory");
+    return v;
+}
+__device__ __forceinline__ void cluster_barrier() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+template <int CL>
+__global__ void __launch_bounds__(512, 2) gn_silu_bwd_fused_kernel(const float* __restrict__ dy, const float* __restrict__ x,
+                                                                   const double* __restrict__ stats, const float* __restrict__ gamma,
+                                                                   const float* __restrict__ beta, const float* __restrict__ scale_shift,
+                                                                   const int32_t* __restrict__ t_index, int64_t ss_stride,
+                                                                   double* __restrict__ sums, float* __restrict__ dx, int HW, int C) {
+    extern __shared__ float coef[];
+    __shared__ float red[2][16];
+    __shared__ double part[2];   // this CTA's (S1, S2): read by every CTA of the cluster
+    __shared__ float tot[2];
+    const int b = blockIdx.x / CL, rank = blockIdx.x % CL;   // 1-D clusters of CL consecutive CTAs
+    const GnCoef g = gn_prepare(coef, stats, gamma, beta, scale_shift, t_index, ss_stride, b, HW, C);
+    const int c4n = C / 4;
+    const int ppc = (HW + CL - 1) / CL;
+    const int rows = max(0, min(ppc, HW - rank * ppc));
+    const int64_t row0 = (int64_t)b * HW + (int64_t)rank * ppc;
+    const float4* x4 = reinterpret_cast<const float4*>(x + row0 * C);
+    const float4* d4 = reinterpret_cast<const float4*>(dy + row0 * C);
+    const int total = rows * c4n;
+    const float inv_rstd = 1.0f / g.rstd;
+    // 512 % c4n == 0 for every channel count of the network: a thread always meets the same four channels
+    const bool fixed_c = (512 % c4n) == 0;
+    float a4[4], b4[4];
+    {
+        const int c = (threadIdx.x % c4n) * 4;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { a4[j] = coef[c + j]; b4[j] = coef[C + c + j]; }
+    }
+    float s1 = 0.f, s2 = 0.f;
+    for (int i0 = threadIdx.x; i0 < total; i0 += 2 * 512) {
+        float4 xv[2], dv[2];
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            const int i = i0 + u * 512;
+            if (i < total) { xv[u] = x4[i]; dv[u] = d4[i]; }
+        }
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            const int i = i0 + u * 512;
+            if (i < total) {
+                if (!fixed_c) {
+                    const int c = (i % c4n) * 4;
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) { a4[j] = coef[c + j]; b4[j] = coef[C + c + j]; }
+                }
+                const float xs[4] = {xv[u].x, xv[u].y, xv[u].z, xv[u].w}, ds[4] = {dv[u].x, dv[u].y, dv[u].z, dv[u].w};
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const float z = fmaf(xs[j], a4[j], b4[j]);
+                    const float dxh = ds[j] * dsilu(z) * a4[j] * inv_rstd;
+                    s1 += dxh;
+                    s2 += dxh * (xs[j] - g.mean) * g.rstd;
+                }
+            }
+        }
+    }
+    s1 = warp_sum(s1);
+    s2 = warp_sum(s2);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (lane == 0) { red[0][warp] = s1; red[1][warp] = s2; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double a = 0.0, c = 0.0;
+        for (int w = 0; w < 16; ++w) { a += (double)red[0][w]; c += (double)red[1][w]; }
+        part[0] = a;
+        part[1] = c;
+    }
+    if constexpr (CL > 1) cluster_barrier(); else __syncthreads();
+    if (threadIdx.x == 0) {
+        double a = 0.0, c = 0.0;
+        if constexpr (CL > 1) {
+            for (uint32_t r = 0; r < (uint32_t)CL; ++r) { a += ld_cluster_f64(&part[0], r); c += ld_cluster_f64(&part[1], r); }
+        } else { a = part[0]; c = part[1]; }
+        const double cnt = (double)HW * (double)C;
+        tot[0] = (float)(a / cnt) * g.rstd;
+        tot[1] = (float)(c / cnt) * g.rstd;
+        if (rank == 0) { sums[2 * b] = a; sums[2 * b + 1] = c; }
+    }
+    __syncthreads();
+    const float m1 = tot[0], m2 = tot[1];
+    float* o = dx + row0 * C;
+    for (int i0 = threadIdx.x; i0 < total; i0 += 2 * 512) {
+        float4 xv[2], dv[2];
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            const int i = i0 + u * 512;
+            if (i < total) { xv[u] = __ldcs(x4 + i); dv[u] = __ldcs(d4 + i); }   // last use: evict first
+        }
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            const int i = i0 + u * 512;
+            if (i < total) {
+                if (!fixed_c) {
+                    const int c = (i % c4n) * 4;
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) { a4[j] = coef[c + j]; b4[j] = coef[C + c + j]; }
+                }
+                const float xs[4] = {xv[u].x, xv[u].y, xv[u].z, xv[u].w}, ds[4] = {dv[u].x, dv[u].y, dv[u].z, dv[u].w};
+                float r[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const float z = fmaf(xs[j], a4[j], b4[j]);
+                    r[j] = ds[j] * dsilu(z) * a4[j] - m1 - (xs[j] - g.mean) * g.rstd * m2;
+                }
+                store_operand4(o + 4 * (int64_t)i, make_float4(r[0], r[1], r[2], r[3]));
+            }
+        }
+    }
+    if constexpr (CL > 1) cluster_barrier();   // no CTA leaves while a partner may still read its shared memory
 }
 
 // ---------------------------------------------------------------------------------------------- channel LayerNorm backward
@@ -669,11 +800,41 @@ extern "C" int sdc_gn_silu_bwd(const float* dy, const float* x, const double* st
                                int HW, int C, void* stream) {
     SDC_REQUIRE(dy && x && stats && gamma && beta && sums && dx && B > 0 && HW > 0, "gn_silu_bwd: bad arguments");
     SDC_REQUIRE(C % 4 == 0 && C <= 4096, "gn_silu_bwd: C=%d unsupported", C);
+    const size_t sm = 2 * C * sizeof(float);
+    cudaStream_t st = as_stream(stream);
+    static const bool fused = []() { const char* e = getenv("SDC_GN_BWD_FUSED"); return !(e && e[0] == '0'); }();
+    if (fused) {
+        // one kernel: a cluster of 16 / 8 CTAs per sample when a sample is large enough to feed them (>= 256 K / 128 K elements: at most
+        // 18 x 2 MB / 37 x 1 MB of dy + x in flight between the passes), else one CTA per sample
+        static const int max_cl = []() { const char* e = getenv("SDC_GN_BWD_CL"); return e ? atoi(e) : 8; }();   // 16 (non-portable) measured slower: 1.38 vs 1.10 ms per 16x128-level call
+        const int64_t ne = (int64_t)HW * C;
+        const int cl = (ne >= 262144 && HW % 16 == 0 && max_cl >= 16) ? 16 : ((ne >= 131072 && HW % 8 == 0 && max_cl >= 8) ? 8 : 1);
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3((unsigned)(B * cl));
+        cfg.blockDim = dim3(512);
+        cfg.dynamicSmemBytes = sm;
+        cfg.stream = st;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = cl;
+        attr[0].val.clusterDim.y = 1;
+        attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        static bool np_set = false;
+        if (!np_set) {
+            SDC_CUDA(cudaFuncSetAttribute(gn_silu_bwd_fused_kernel<16>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+            np_set = true;
+        }
+        if (cl == 16) SDC_CUDA(cudaLaunchKernelEx(&cfg, gn_silu_bwd_fused_kernel<16>, dy, x, stats, gamma, beta, scale_shift, t_index, ss_stride, sums, dx, HW, C));
+        else if (cl == 8) SDC_CUDA(cudaLaunchKernelEx(&cfg, gn_silu_bwd_fused_kernel<8>, dy, x, stats, gamma, beta, scale_shift, t_index, ss_stride, sums, dx, HW, C));
+        else SDC_CUDA(cudaLaunchKernelEx(&cfg, gn_silu_bwd_fused_kernel<1>, dy, x, stats, gamma, beta, scale_shift, t_index, ss_stride, sums, dx, HW, C));
+        SDC_LAUNCHED();
+        return SDC_OK;
+    }
     int ppc = HW;
     while (ppc > 32 && (int64_t)B * (HW / ppc) < 2 * 148 && ppc % 2 == 0) ppc /= 2;
     dim3 grid((unsigned)B, (unsigned)((HW + ppc - 1) / ppc));
-    const size_t sm = 2 * C * sizeof(float);
-    cudaStream_t st = as_stream(stream);
     SDC_CUDA(cudaMemsetAsync(sums, 0, (size_t)B * 2 * sizeof(double), st));
     gn_silu_bwd_reduce_kernel<<<grid, 256, sm, st>>>(dy, x, stats, gamma, beta, scale_shift, t_index, ss_stride, sums, HW, C, ppc);
     SDC_LAUNCHED();
