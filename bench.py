@@ -541,6 +541,35 @@ def main():
                 "config4": config4, "config5": config5,
                 "e2e": e2e if e2e is not None else {"value": None, "unit": "samples/s", "h2d_bytes_per_step": 0,
                                                     "d2h_bytes_per_step": 0, "skipped": True}}
+        if ws == 1:
+            # backward-data pass (guidance gradient through the denoiser): recording forward + reverse walk in one C call,
+            # per-launch CUDA events of the executor (a reported extra: the headline chain uses the closed-form guidance and never calls it)
+            try:
+                Bv = 256
+                xv = torch.randn(Bv, 3, 16, 128, device=dev)
+                gv = torch.randn(Bv, 3, 16, 128, device=dev)
+                for _ in range(2):
+                    net.vjp(xv, 500, gv)
+                torch.cuda.synchronize()
+                planv = net._plan_ready(backward=True)
+                planv.profile(True)
+                net.vjp(xv, 500, gv)
+                torch.cuda.synchronize()
+                ents = planv.profile_entries()
+                planv.profile(False)
+                fam = {}
+                for nm, ms_, _, fl in ents:
+                    d = fam.setdefault(nm, [0, 0.0, 0.0])
+                    d[0] += 1; d[1] += ms_; d[2] += fl
+                line["backward_data"] = {"what": "Unet2D.vjp = sdc_unet_backward_data: d<eps, g>/dx_t, FP16 recording forward + TF32 data-gradient walk",
+                                         "batch": Bv, "launches": len(ents), "ms": sum(e[1] for e in ents),
+                                         "by_family_ms": {k: round(v[1], 3) for k, v in sorted(fam.items(), key=lambda kv: -kv[1][1])[:8]},
+                                         "conv_tflops": sum(v[2] for k, v in fam.items() if k.startswith("conv")) /
+                                                        max(1e-9, sum(v[1] for k, v in fam.items() if k.startswith("conv"))) / 1e9}
+                del xv, gv
+                torch.cuda.empty_cache()
+            except Exception as ex:   # a reported extra: never lose the bench line over it
+                line["backward_data"] = {"error": repr(ex)[:200]}
         if not args.no_cpu and ws == 1:
             # the CPU leg runs at N = 1 only: under torchrun the other ranks would sit in a barrier while rank 0 fights them for cores
             line["cpu_baseline"] = cpu_baseline_obj()

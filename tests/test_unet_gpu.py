@@ -690,3 +690,29 @@ def test_fold_on_tensor_cores_matches_fp32():
         err = (wf.double() - ref).abs()
         assert torch.isfinite(wf.float()).all()
         assert (err <= ref.abs() * 2 ** -10.9 + 1e-6).all(), (c, err.max().item())
+
+
+def test_row64_kernel_declines_ineligible_shapes():
+    """sdc_conv3x3_row with W = 64 hands the problem back (-1, nothing launched) when an image is not a whole number of 8-row items or when
+    there are fewer items than SM pairs; U.conv_gemm then runs the generic kernel, whose result the W = 64 kernel reproduces bitwise."""
+    L, lib = _L()
+    from safediffcon_b200 import unet as U
+    g = torch.Generator().manual_seed(64)
+    cout, c0 = 128, 128
+    w = (torch.randn(cout, c0, 3, 3, generator=g) / 34.0).cuda()
+    wp = U.pack_conv_weight(1, w, F16)
+    for B, H, want in ((80, 4, -1), (8, 8, -1), (80, 8, 0)):
+        x = torch.randn(B * H * 64, c0, generator=g).half().cuda()
+        out = torch.zeros(B * H * 64, cout, dtype=torch.float16).cuda()
+        stats = torch.zeros(B, 2, dtype=torch.float64).cuda()
+        rc = lib.sdc_conv3x3_row(F16, L.ptr(x), c0, None, 0, L.ptr(wp), None, None, L.ptr(out), L.ptr(stats), 1, B, H, 64, cout, L.stream_ptr())
+        torch.cuda.synchronize()
+        assert rc == want, (B, H, rc)
+        if rc == 0:
+            ref, rstats = torch.zeros_like(out), torch.zeros_like(stats)
+            L.check(lib.sdc_conv_gemm(F16, 1, L.ptr(x), c0, None, 0, L.ptr(wp), None, None, L.ptr(ref), L.ptr(rstats), 1, B, H, 64, cout, L.stream_ptr()))
+            torch.cuda.synchronize()
+            assert torch.equal(out, ref)
+            assert torch.allclose(stats, rstats, rtol=1e-12, atol=1e-9)   # same fp32 partials, double atomics in a different order
+        else:
+            assert not out.any()
