@@ -542,6 +542,28 @@ def main():
                 "e2e": e2e if e2e is not None else {"value": None, "unit": "samples/s", "h2d_bytes_per_step": 0,
                                                     "d2h_bytes_per_step": 0, "skipped": True}}
         if ws == 1:
+            # the reference's own batch sizes (test batch 50, calibration batch 250): guided DDIM chains from the captured graph;
+            # latency-bound territory (~145 launches per step on a mostly empty GPU), reported next to the B = 1024 headline
+            try:
+                gd50 = mk(50)
+                rb = {}
+                for Bs in (50, 250):
+                    z = torch.zeros(Bs, 128, device=dev)
+                    kw = dict(batch_size=Bs, u_init=z, u_final=z, guidance_u0=True, nablaJ=guide, enable_grad=False, seed=1)
+                    gd50.sample(**kw)
+                    torch.cuda.synchronize()
+                    ea, eb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    ea.record()
+                    gd50.sample(**kw)
+                    eb.record()
+                    torch.cuda.synchronize()
+                    ms_s = ea.elapsed_time(eb) / 50.0
+                    rb[f"B{Bs}"] = {"ms_per_step": ms_s, "ddim200_chain_ms": 200.0 * ms_s, "samples_per_s_ddim200": Bs / (0.2 * ms_s)}
+                line["reference_batches"] = {"what": "guided DDIM chain (50 steps timed, eta 1) at the reference's test / calibration batch sizes, "
+                                                     "one captured CUDA graph per reverse step", **rb}
+                del gd50
+            except Exception as ex:   # a reported extra: never lose the bench line over it
+                line["reference_batches"] = {"error": repr(ex)[:200]}
             # backward-data pass (guidance gradient through the denoiser): recording forward + reverse walk in one C call,
             # per-launch CUDA events of the executor (a reported extra: the headline chain uses the closed-form guidance and never calls it)
             try:
